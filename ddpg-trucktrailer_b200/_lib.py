@@ -1,0 +1,123 @@
+"""ctypes binding of libtt_b200.so (include/tt_b200.h).  There is no CPU fallback: if the library cannot be
+built/loaded, or no CUDA device is visible when a compute object is created, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+TT_OBS_DIM = 23
+TT_NCOMP = 10
+TT_NSTATS = 16
+TT_PREC_FP32, TT_PREC_BF16 = 0, 1
+
+COMP_NAMES = ("distance_reward", "progress_reward", "heading_reward", "orientation_reward", "staged_success",
+              "safety_penalty", "exploration_bonus", "final_success_bonus", "backward_penalty", "smoothness_penalty")
+VIOLATION_NAMES = ("none", "jackknife", "jackknife_warning", "major_boundary", "minor_boundary", "past_the_goal",
+                   "max_step", "excessive_backward")
+FLAG_NAMES = ("jackknife", "out_of_map", "max_steps_reached", "goal_reached", "goal_passed", "excessive_backward")
+STAT_NAMES = ("steps", "episodes", "successes", "return_sum", "return_sq_sum", "reward_sum") + tuple("term_" + f for f in FLAG_NAMES)
+
+
+class EnvCfg(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "L1", "L2", "v1x", "dt", "map_min", "map_max", "max_hitch", "steer_max", "pos_thr", "ori_thr", "step_len",
+        "start_x_lo", "start_x_hi", "start_y_lo", "start_y_hi", "start_yaw_lo", "start_yaw_hi",
+        "goal_x", "goal_y", "goal_yaw")]
+
+
+class StepInfo(C.Structure):
+    _fields_ = [("d_comps", C.c_void_p), ("d_violation", C.c_void_p), ("d_flags", C.c_void_p), ("d_success", C.c_void_p)]
+
+
+class RolloutBufs(C.Structure):
+    _fields_ = [("d_obs_cur", C.c_void_p), ("d_obs_next", C.c_void_p), ("ld_obs", C.c_int64), ("d_ou_x", C.c_void_p),
+                ("d_action", C.c_void_p), ("d_scaled", C.c_void_p), ("d_reward", C.c_void_p), ("d_done", C.c_void_p),
+                ("d_state_mem", C.c_void_p), ("d_action_mem", C.c_void_p), ("d_reward_mem", C.c_void_p),
+                ("d_new_state_mem", C.c_void_p), ("d_terminal_mem", C.c_void_p), ("mem_size", C.c_int64),
+                ("mem_cntr", C.c_int64)]
+
+
+_P, _I64, _I32, _U64, _U32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32
+
+# every symbol include/tt_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "tt_last_error": (C.c_char_p, []),
+    "tt_abi_version": (C.c_int, []),
+    "tt_device_count": (C.c_int, []),
+    "tt_launch_count": (_U64, []),
+    "tt_env_default_cfg": (C.c_int, [C.POINTER(EnvCfg)]),
+    "tt_env_workspace_bytes": (C.c_size_t, [_I64]),
+    "tt_env_create": (C.c_int, [C.POINTER(_P), C.POINTER(EnvCfg), _I64, _U64, _U64, _P, C.c_size_t]),
+    "tt_env_destroy": (C.c_int, [_P]),
+    "tt_env_seed": (C.c_int, [_P, _U64, _P]),
+    "tt_env_reset": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "tt_env_step": (C.c_int, [_P, _P, _P, _I64, _P, _P, C.POINTER(StepInfo), _P]),
+    "tt_env_step_k": (C.c_int, [_P, _P, _I32, _I32, _P, _I64, _P, _P, C.POINTER(StepInfo), _P]),
+    "tt_env_set_state": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _I64, _P]),
+    "tt_env_get_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "tt_env_tick": (C.c_int, [_P, _U32, _P]),
+    "tt_env_iter_ptr": (_P, [_P]),
+    "tt_env_seed_value": (_U64, [_P]),
+    "tt_env_global_offset": (_U64, [_P]),
+    "tt_env_num_envs": (_I64, [_P]),
+    "tt_env_stats_read": (C.c_int, [_P, _P, _I32, _P]),
+    "tt_ou_step": (C.c_int, [_P, _P, _P, _I64, _U64, _U64, _P, _P]),
+    "tt_actor_workspace_bytes": (C.c_size_t, [_I32, _I32, _I32]),
+    "tt_actor_create": (C.c_int, [C.POINTER(_P), _I32, _I32, _I32, _P, C.c_size_t]),
+    "tt_actor_destroy": (C.c_int, [_P]),
+    "tt_actor_load": (C.c_int, [_P] + [_P] * 10 + [_P]),
+    "tt_actor_forward": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, _P]),
+    "tt_scale_action": (C.c_int, [_P, _P, _I64, _P]),
+    "tt_replay_store": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P]),
+    "tt_replay_gather": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "tt_rollout_step": (C.c_int, [_P, _P, C.POINTER(RolloutBufs), _I32, _I32, _P]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if stale and nvcc is present) libtt_b200.so and bind every symbol."""
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)          # AttributeError here = the .so does not export what the header declares
+            fn.restype, fn.argtypes = res, args
+        if L.tt_abi_version() != 1:
+            raise RuntimeError("libtt_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+class TTError(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise TTError(f"libtt_b200 error {rc}: {load().tt_last_error().decode()}")
+
+
+def require_cuda() -> None:
+    """The product path has no CPU fallback: fail loudly when the CUDA side is unavailable."""
+    if load().tt_device_count() <= 0:
+        raise TTError("no CUDA device visible to libtt_b200.so -- this package has no CPU fallback")
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

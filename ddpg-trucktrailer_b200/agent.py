@@ -1,0 +1,199 @@
+"""Vectorised DDPG agent rollout side: ``Agent.choose_action / remember / noise.reset`` of
+DDPG/DDPG_agent.py:9-52 for N observations at once.
+
+The actor forward (DDPG/networks.py:138-147), the per-env Ornstein-Uhlenbeck noise (DDPG/noise.py) and the
+replay store run as CUDA kernels behind the C ABI.  ``learn()`` (DDPG_agent.py:72-106) is the learner and
+not part of this path; it is provided as a plain torch step on the device ring
+so that the reference driver loop runs end to end.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TT_OBS_DIM, TT_PREC_BF16, TT_PREC_FP32, check, ptr, stream_ptr
+from .replay import DeviceReplayBuffer
+
+ACTOR_KEYS = ("fc1.weight", "fc1.bias", "bn1.weight", "bn1.bias", "fc2.weight", "fc2.bias", "bn2.weight", "bn2.bias",
+              "mu.weight", "mu.bias")
+
+
+def init_actor_state_dict(input_dims=TT_OBS_DIM, fc1_dims=400, fc2_dims=300, n_actions=1, seed=None):
+    """Initial actor parameters with the reference's distributions and draw order (networks.py:110-131):
+    fc1/fc2 U(+-1/sqrt(out_features)) (the reference uses weight.size()[0]), mu U(+-0.003), LayerNorm (1, 0).
+    Built on the CPU generator so that ``torch.manual_seed(s)`` gives the same tensors as the reference."""
+    import torch.nn as nn
+    if seed is not None:
+        torch.manual_seed(seed)
+    fc1 = nn.Linear(input_dims, fc1_dims)
+    fc2 = nn.Linear(fc1_dims, fc2_dims)
+    bn1, bn2 = nn.LayerNorm(fc1_dims), nn.LayerNorm(fc2_dims)
+    mu = nn.Linear(fc2_dims, n_actions)
+    f2 = 1.0 / np.sqrt(fc2.weight.data.size()[0])
+    fc2.weight.data.uniform_(-f2, f2); fc2.bias.data.uniform_(-f2, f2)
+    f1 = 1.0 / np.sqrt(fc1.weight.data.size()[0])
+    fc1.weight.data.uniform_(-f1, f1); fc1.bias.data.uniform_(-f1, f1)
+    mu.weight.data.uniform_(-0.003, 0.003); mu.bias.data.uniform_(-0.003, 0.003)
+    mods = {"fc1": fc1, "bn1": bn1, "fc2": fc2, "bn2": bn2, "mu": mu}
+    return {k: getattr(mods[k.split(".")[0]], k.split(".")[1]).data.clone() for k in ACTOR_KEYS}
+
+
+class CudaActor:
+    """Packed device copy of an ``ActorNetwork`` state_dict + the forward kernels."""
+
+    def __init__(self, input_dims=TT_OBS_DIM, fc1_dims=400, fc2_dims=300, device=None):
+        _lib.require_cuda()
+        self.L = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.dims = (int(input_dims), int(fc1_dims), int(fc2_dims))
+        with torch.cuda.device(self.device):
+            nbytes = self.L.tt_actor_workspace_bytes(*self.dims)
+            self._ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+            h = C.c_void_p()
+            check(self.L.tt_actor_create(C.byref(h), *self.dims, (self._ws.data_ptr() + 255) // 256 * 256, nbytes))
+            self._h = h
+        self._sd = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self.L.tt_actor_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def load_state_dict(self, sd):
+        """``sd``: reference ActorNetwork state_dict (torch tensors or numpy arrays, any device)."""
+        i, h1, h2 = self.dims
+        shapes = {"fc1.weight": (h1, i), "fc1.bias": (h1,), "bn1.weight": (h1,), "bn1.bias": (h1,), "fc2.weight": (h2, h1),
+                  "fc2.bias": (h2,), "bn2.weight": (h2,), "bn2.bias": (h2,), "mu.weight": (1, h2), "mu.bias": (1,)}
+        dev = {}
+        for k in ACTOR_KEYS:
+            t = torch.as_tensor(sd[k]).detach().to(device=self.device, dtype=torch.float32).contiguous()
+            if tuple(t.shape) != shapes[k]:
+                raise ValueError(f"{k}: expected shape {shapes[k]}, got {tuple(t.shape)}")
+            dev[k] = t
+        with torch.cuda.device(self.device):
+            check(self.L.tt_actor_load(self._h, *[dev[k].data_ptr() for k in ACTOR_KEYS], stream_ptr()))
+        self._sd = dev
+
+    def state_dict(self):
+        return {k: v.clone() for k, v in self._sd.items()}
+
+    def forward(self, obs, out=None, precision="fp32"):
+        """tanh(mu(relu(LN(fc2(relu(LN(fc1(obs)))))))) -> [n] float32 (networks.py:138-147)."""
+        with torch.cuda.device(self.device):
+            if obs.dim() == 1:
+                obs = obs.reshape(1, -1)
+            if obs.dtype != torch.float32 or obs.stride(1) != 1 or obs.device != self.device:
+                obs = obs.to(device=self.device, dtype=torch.float32).contiguous()
+            n = obs.shape[0]
+            if out is None:
+                out = torch.empty(n, dtype=torch.float32, device=self.device)
+            prec = TT_PREC_BF16 if precision in ("bf16", TT_PREC_BF16) else TT_PREC_FP32
+            check(self.L.tt_actor_forward(self._h, obs.data_ptr(), obs.stride(0), n, out.data_ptr(), prec, stream_ptr()))
+        return out
+
+
+class OUNoiseState:
+    """Per-env ``OUActionNoise`` (DDPG/noise.py:4-20): theta 0.2, sigma 0.15, dt 1e-2, mu 0; Philox normals
+    keyed by (seed, global env id, iteration)."""
+
+    def __init__(self, num_envs, device, seed=27, global_env_offset=0):
+        self.x_prev = torch.zeros(num_envs, dtype=torch.float32, device=device)
+        self.seed, self.global_env_offset = int(seed), int(global_env_offset)
+        self._iter = torch.zeros(1, dtype=torch.int32, device=device)     # used when no env supplies the counter
+        self.iter_ptr = self._iter.data_ptr()
+        self._own_iter = True
+
+    def bind_env(self, env):
+        """Share the env's device-side iteration counter and seed (the reference's noise stream is a function
+        of the episode seed, DDPG/trainv2.py:489 + noise.py:14)."""
+        self.iter_ptr = env.L.tt_env_iter_ptr(env._h)
+        self.seed, self.global_env_offset = env.seed_value, env.global_env_offset
+        self._own_iter = False
+
+    def reset(self, mask=None):
+        """noise.py:19-20 (``agent.noise.reset()``, trainv2.py:492); ``mask`` restricts it to finished envs."""
+        if mask is None:
+            self.x_prev.zero_()
+        else:
+            self.x_prev.masked_fill_(mask.bool(), 0.0)
+
+
+class VecAgent:
+    """``Agent`` (DDPG/DDPG_agent.py:9-52) for ``num_envs`` environments; same constructor arguments."""
+
+    def __init__(self, alpha, beta, input_dims, tau, n_actions, gamma=0.99, max_size=1000000, fc1_dims=400, fc2_dims=300,
+                 batch_size=64, num_envs=1, device=None, seed=27, global_env_offset=0, precision="fp32", actor_seed=None):
+        _lib.require_cuda()
+        self.L = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.gamma, self.tau, self.batch_size, self.alpha, self.beta = gamma, tau, batch_size, alpha, beta
+        in_dim = int(input_dims[0]) if isinstance(input_dims, (tuple, list)) else int(input_dims)
+        if n_actions != 1:
+            raise ValueError("the CUDA actor is specialised to n_actions == 1 (simv2 action space)")
+        self.num_envs = int(num_envs)
+        self.precision = precision
+        self.memory = DeviceReplayBuffer(max_size, (in_dim,), n_actions, device=self.device)
+        self.noise = OUNoiseState(self.num_envs, self.device, seed, global_env_offset)
+        self.actor = CudaActor(in_dim, fc1_dims, fc2_dims, device=self.device)
+        self.actor.load_state_dict(init_actor_state_dict(in_dim, fc1_dims, fc2_dims, n_actions, seed=actor_seed))
+        self._action = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+        self._learner = None
+
+    def choose_action(self, observation, evaluate=False):
+        """DDPG_agent.py:36-49: mu(obs) + OU noise (unless ``evaluate``); returns the UNCLIPPED action [N,1]."""
+        with torch.cuda.device(self.device):
+            obs = torch.as_tensor(observation, device=self.device)
+            single = obs.dim() == 1
+            mu = self.actor.forward(obs, out=self._action, precision=self.precision)
+            if not evaluate:
+                n = self.noise
+                check(self.L.tt_ou_step(n.x_prev.data_ptr(), mu.data_ptr(), None, mu.numel(), n.seed, n.global_env_offset,
+                                        n.iter_ptr, stream_ptr()))
+                if n._own_iter:
+                    n._iter += 1
+        return mu.reshape(-1) if single else mu.reshape(-1, 1)
+
+    @staticmethod
+    def scale_action(action, high=0.78539819):
+        """trainv2.py:516: clip(action, -1, 1) * env.action_space.high"""
+        return torch.clamp(action, -1.0, 1.0) * high
+
+    def remember(self, state, action, reward, state_, done):
+        """DDPG_agent.py:51-52 for a batch of transitions."""
+        self.memory.store_transition(state, action, reward, state_, done)
+
+    def load_actor_state_dict(self, sd):
+        self.actor.load_state_dict(sd)
+
+    def learn(self):
+        """Learner step (DDPG_agent.py:72-106), not part of the B200 hot path: plain torch on the device ring."""
+        from .learner import TorchLearner
+        if self._learner is None:
+            self._learner = TorchLearner(self)
+        return self._learner.learn()
+
+
+class Agent(VecAgent):
+    """N=1 numpy-facing agent with the reference's exact call contract (DDPG_agent.py:36-52):
+    ``choose_action(obs(23,)) -> np.float32 (1,)``; ``remember`` takes numpy/python scalars."""
+
+    def __init__(self, alpha, beta, input_dims, tau, n_actions, gamma=0.99, max_size=1000000, fc1_dims=400, fc2_dims=300,
+                 batch_size=64, **kw):
+        super().__init__(alpha, beta, input_dims, tau, n_actions, gamma, max_size, fc1_dims, fc2_dims, batch_size, num_envs=1, **kw)
+
+    def choose_action(self, observation, evaluate=False):
+        obs = torch.from_numpy(np.asarray(observation, np.float32)).to(self.device)
+        return super().choose_action(obs, evaluate).cpu().numpy().reshape(1).astype(np.float32)
+
+    def remember(self, state, action, reward, state_, done):
+        dev = self.device
+        t = lambda x, dt: torch.as_tensor(np.asarray(x), dtype=dt).reshape(1, -1).to(dev)
+        super().remember(t(state, torch.float32), t(action, torch.float32).reshape(-1), t(reward, torch.float32).reshape(-1),
+                         t(state_, torch.float32), t(done, torch.uint8).reshape(-1))

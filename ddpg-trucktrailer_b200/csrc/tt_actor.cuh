@@ -1,0 +1,54 @@
+// tt_actor.cuh -- packed device weights of the actor (ActorNetwork, DDPG/networks.py:98-147) shared by the
+// fp32 CUDA-core kernel (tt_agent.cu) and the bf16 tcgen05 kernel (tt_actor_tc.cu).
+//
+// Layouts inside the caller-provided workspace (all 256 B aligned):
+//   w1t  f32 [k1p][h1p]   fc1.weight transposed (k-major), zero padded; k1p = in_dim rounded up to 8
+//   w2t  f32 [h1p][h2p]   fc2.weight transposed (k-major), zero padded; h*p = h* rounded up to 32
+//   b1 g1 be1 [h1p], b2 g2 be2 w3 [h2p], b3 [1]            (padded entries are 0)
+//   w1b  bf16 [h1p][kb1]  fc1.weight, K padded to kb1 = 64, row-major (N x K, "K-major" UMMA B operand)
+//   w2b  bf16 [h2p][h1p]  fc2.weight, row-major (N x K); h1p is a multiple of 32
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+struct tt_actor_dev {
+    int in_dim, h1, h2;
+    int k1p, h1p, h2p, kb1;
+    float *w1t, *w2t, *b1, *g1, *be1, *b2, *g2, *be2, *w3, *b3;
+    __nv_bfloat16 *w1b, *w2b;
+};
+
+struct tt_actor {
+    tt_actor_dev dev;
+    bool loaded;
+};
+
+static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d, char *base) {
+    const int k1p = (in_dim + 7) / 8 * 8, h1p = (h1 + 31) / 32 * 32, h2p = (h2 + 31) / 32 * 32, kb1 = 64;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+    const size_t o_w1t = take(sizeof(float) * k1p * h1p), o_w2t = take(sizeof(float) * h1p * h2p);
+    const size_t o_b1 = take(sizeof(float) * h1p), o_g1 = take(sizeof(float) * h1p), o_be1 = take(sizeof(float) * h1p);
+    const size_t o_b2 = take(sizeof(float) * h2p), o_g2 = take(sizeof(float) * h2p), o_be2 = take(sizeof(float) * h2p);
+    const size_t o_w3 = take(sizeof(float) * h2p), o_b3 = take(sizeof(float));
+    const size_t o_w1b = take(sizeof(__nv_bfloat16) * h1p * kb1), o_w2b = take(sizeof(__nv_bfloat16) * h2p * h1p);
+    if (d) {
+        d->in_dim = in_dim; d->h1 = h1; d->h2 = h2; d->k1p = k1p; d->h1p = h1p; d->h2p = h2p; d->kb1 = kb1;
+        auto f = [&](size_t o) { return reinterpret_cast<float *>(base + o); };
+        d->w1t = f(o_w1t); d->w2t = f(o_w2t); d->b1 = f(o_b1); d->g1 = f(o_g1); d->be1 = f(o_be1);
+        d->b2 = f(o_b2); d->g2 = f(o_g2); d->be2 = f(o_be2); d->w3 = f(o_w3); d->b3 = f(o_b3);
+        d->w1b = reinterpret_cast<__nv_bfloat16 *>(base + o_w1b); d->w2b = reinterpret_cast<__nv_bfloat16 *>(base + o_w2b);
+    }
+    return off;
+}
+
+namespace tt {
+int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, cudaStream_t s);
+int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, cudaStream_t s);
+int actor_pack_tc(tt_actor *a, const float *d_fc1_w, const float *d_fc2_w, cudaStream_t s);
+int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
+                 uint64_t gid0, const uint32_t *d_iter, int evaluate, cudaStream_t s);
+int launch_ou_zero(float *d_x, const uint8_t *d_mask, int64_t n, cudaStream_t s);
+}  // namespace tt

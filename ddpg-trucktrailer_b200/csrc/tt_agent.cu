@@ -1,0 +1,347 @@
+// tt_agent.cu -- kernels (b) OU noise and (c) the batched actor forward (fp32 CUDA-core path), plus the
+// weight re-packing.  Replaces Agent.choose_action (DDPG/DDPG_agent.py:36-49), OUActionNoise
+// (DDPG/noise.py:12-20) and ActorNetwork.forward (DDPG/networks.py:138-147) for N observations at once.
+// The tcgen05 (bf16 tensor-core) actor lives in tt_actor_tc.cu and shares tt_actor with this file.
+#include <new>
+#include "tt_actor.cuh"
+#include "tt_common.cuh"
+#include "tt_env_math.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kPiOver4F = 0.78539819f;       // float32(pi/4) == env.action_space.high[0] (simv2.py:86-91)
+
+// ---------------------------------------------------------------------------------------------------------
+// (b) OU noise, DDPG/noise.py:12-17 with theta=0.2, sigma=0.15, dt=1e-2, mu=0; optional fused
+//     "mu + noise" (DDPG_agent.py:41-43) and "clip(a,-1,1) * pi/4" (trainv2.py:516)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) ou_kernel(float *__restrict__ x, float *__restrict__ action,
+                                                      float *__restrict__ scaled, const uint8_t *__restrict__ reset_mask,
+                                                      int64_t n, uint64_t seed, uint64_t gid0,
+                                                      const uint32_t *__restrict__ iter, int evaluate) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float a = action ? action[i] : 0.0f;
+    if (!evaluate) {
+        float xp = x[i];
+        if (reset_mask && reset_mask[i]) xp = 0.0f;                      // trainv2.py:492 agent.noise.reset()
+        const float nrm = ttm::rng_normal(seed, (uint32_t)(gid0 + i), *iter);
+        const float xn = xp + 0.2f * (0.0f - xp) * 0.01f + 0.15f * 0.1f * nrm;
+        x[i] = xn;
+        a += xn;
+        if (action) action[i] = a;
+    }
+    if (scaled) scaled[i] = fminf(fmaxf(a, -1.0f), 1.0f) * kPiOver4F;
+}
+
+__global__ void __launch_bounds__(kThreads) ou_zero_kernel(float *__restrict__ x, const uint8_t *__restrict__ mask, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n && mask[i]) x[i] = 0.0f;
+}
+
+__global__ void __launch_bounds__(kThreads) scale_kernel(const float *__restrict__ a, float *__restrict__ s, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) s[i] = fminf(fmaxf(a[i], -1.0f), 1.0f) * kPiOver4F;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight packing: reference state_dict layout -> kernel layouts (see tt_actor.cuh)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void pack_fp32_kernel(tt_actor_dev A, const float *fc1_w, const float *fc1_b, const float *g1, const float *be1,
+                                 const float *fc2_w, const float *fc2_b, const float *g2, const float *be2,
+                                 const float *mu_w, const float *mu_b) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int v = tid; v < A.k1p * A.h1p; v += nth) {                    // W1T[k][c] = fc1.weight[c][k]
+        const int k = v / A.h1p, c = v - k * A.h1p;
+        A.w1t[v] = (k < A.in_dim && c < A.h1) ? fc1_w[c * A.in_dim + k] : 0.0f;
+    }
+    for (int v = tid; v < A.h1p * A.h2p; v += nth) {                    // W2T[k][c] = fc2.weight[c][k]
+        const int k = v / A.h2p, c = v - k * A.h2p;
+        A.w2t[v] = (k < A.h1 && c < A.h2) ? fc2_w[c * A.h1 + k] : 0.0f;
+    }
+    for (int c = tid; c < A.h1p; c += nth) {
+        const bool in = c < A.h1;
+        A.b1[c] = in ? fc1_b[c] : 0.0f; A.g1[c] = in ? g1[c] : 0.0f; A.be1[c] = in ? be1[c] : 0.0f;
+    }
+    for (int c = tid; c < A.h2p; c += nth) {
+        const bool in = c < A.h2;
+        A.b2[c] = in ? fc2_b[c] : 0.0f; A.g2[c] = in ? g2[c] : 0.0f; A.be2[c] = in ? be2[c] : 0.0f;
+        A.w3[c] = in ? mu_w[c] : 0.0f;
+    }
+    if (tid == 0) A.b3[0] = mu_b[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// (c) actor forward, fp32 on the CUDA cores.  One CTA = 64 observation rows per tile, persistent over tiles.
+// Warp w owns rows 8w..8w+7; lane l owns output columns l, l+32, ...  Activations live in shared memory
+// transposed ([k][row], row stride 68 floats) so that the 8 row operands of one k are two broadcast LDS.128;
+// the k-major (pre-transposed) weights stream through a cp.async double buffer in chunks of 16 k.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TM = 64, RS = 68, KC = 16;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// acc[r][j] += sum_k act[k][row0w + r] * wT[k][lane + 32 j]  for k in [0, K); weights streamed from global
+template <int CJ, bool kGuard>
+__device__ __forceinline__ void gemm_stream(float (&acc)[8][CJ], const float *__restrict__ act /*smem [K][RS]*/,
+                                            const float *__restrict__ wT /*global [K][WP]*/, int K, int WP,
+                                            float *wbuf /*smem 2*KC*WP*/, int warp, int lane) {
+    const int tid = threadIdx.x;
+    const int nchunks = (K + KC - 1) / KC;
+    auto issue = [&](int ch, int buf) {
+        const int k0 = ch * KC, kn = min(KC, K - k0);
+        const int vec = kn * WP / 4;                         // WP % 32 == 0 -> rows are 16 B multiples
+        const float4 *src = reinterpret_cast<const float4 *>(wT + (size_t)k0 * WP);
+        float4 *dst = reinterpret_cast<float4 *>(wbuf + (size_t)buf * KC * WP);
+        for (int v = tid; v < vec; v += kThreads) cp_async16(dst + v, src + v);
+        cp_async_commit();
+    };
+    issue(0, 0);
+    for (int ch = 0; ch < nchunks; ch++) {
+        if (ch + 1 < nchunks) { issue(ch + 1, (ch + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        const float *wb = wbuf + (size_t)(ch & 1) * KC * WP;
+        const int k0 = ch * KC, kn = min(KC, K - k0);
+#pragma unroll 4
+        for (int kk = 0; kk < kn; kk++) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(act + (size_t)(k0 + kk) * RS + warp * 8);
+            const float4 a1 = *reinterpret_cast<const float4 *>(act + (size_t)(k0 + kk) * RS + warp * 8 + 4);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float w[CJ];
+#pragma unroll
+            for (int j = 0; j < CJ; j++) w[j] = (!kGuard || lane + 32 * j < WP) ? wb[kk * WP + lane + 32 * j] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int j = 0; j < CJ; j++) acc[r][j] = fmaf(a[r], w[j], acc[r][j]);
+        }
+        __syncthreads();
+    }
+}
+
+// bias + LayerNorm (eps 1e-5, biased variance: torch.nn.LayerNorm) + ReLU on a warp-distributed row block
+template <int CJ, bool kGuard>
+__device__ __forceinline__ void bias_ln_relu(float (&acc)[8][CJ], const float *__restrict__ bias, const float *__restrict__ g,
+                                             const float *__restrict__ be, int H, int HP, int lane) {
+    float bj[CJ], gj[CJ], bej[CJ];
+#pragma unroll
+    for (int j = 0; j < CJ; j++) {
+        const int c = lane + 32 * j;
+        const bool in = !kGuard || c < HP;
+        bj[j] = in ? bias[c] : 0.f; gj[j] = in ? g[c] : 0.f; bej[j] = in ? be[c] : 0.f;
+    }
+    const float invH = 1.0f / (float)H;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < CJ; j++) { acc[r][j] += bj[j]; s += acc[r][j]; }      // padded columns are exactly 0
+        const float mean = warp_sum_f(s) * invH;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < CJ; j++) { const float d = (lane + 32 * j < H) ? acc[r][j] - mean : 0.f; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum_f(q) * invH + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < CJ; j++) acc[r][j] = fmaxf(fmaf((acc[r][j] - mean) * rstd, gj[j], bej[j]), 0.f);   // pad: g=be=0 -> 0
+    }
+}
+
+template <int CJ1, int CJ2, bool kGuard>
+__global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A, const float *__restrict__ obs, int64_t ld,
+                                                                int64_t n, float *__restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    float *xs = smem;                                   // [k1p][RS]
+    float *hs = xs + A.k1p * RS;                        // [h1p][RS]
+    float *wbuf = hs + A.h1p * RS;                      // max(k1p*h1p, 2*KC*max(h1p,h2p))
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (n + TM - 1) / TM;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * TM;
+        const int rows = (int)min((int64_t)TM, n - row0);
+        // ---- observation tile -> xs[k][r] (zero-padded) ----
+        for (int v = threadIdx.x; v < A.k1p * RS; v += kThreads) xs[v] = 0.f;
+        __syncthreads();
+        if (ld == A.in_dim) {
+            const float *src = obs + row0 * ld;
+            for (int v = threadIdx.x; v < rows * A.in_dim; v += kThreads) {
+                const int r = v / A.in_dim, k = v - r * A.in_dim;
+                xs[k * RS + r] = __ldcs(src + v);
+            }
+        } else {
+            for (int v = threadIdx.x; v < rows * A.in_dim; v += kThreads) {
+                const int r = v / A.in_dim, k = v - r * A.in_dim;
+                xs[k * RS + r] = __ldcs(obs + (row0 + r) * ld + k);
+            }
+        }
+        __syncthreads();
+        // ---- layer 1: fc1 -> LN -> ReLU (networks.py:139-141) ----
+        {
+            float acc[8][CJ1];
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int j = 0; j < CJ1; j++) acc[r][j] = 0.f;
+            gemm_stream<CJ1, kGuard>(acc, xs, A.w1t, A.k1p, A.h1p, wbuf, warp, lane);
+            bias_ln_relu<CJ1, kGuard>(acc, A.b1, A.g1, A.be1, A.h1, A.h1p, lane);
+#pragma unroll
+            for (int j = 0; j < CJ1; j++) {
+                const int c = lane + 32 * j;
+                if (c < A.h1p) {
+                    *reinterpret_cast<float4 *>(hs + (size_t)c * RS + warp * 8) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+                    *reinterpret_cast<float4 *>(hs + (size_t)c * RS + warp * 8 + 4) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- layer 2: fc2 -> LN -> ReLU -> mu -> tanh (networks.py:142-145) ----
+        {
+            float acc[8][CJ2];
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int j = 0; j < CJ2; j++) acc[r][j] = 0.f;
+            gemm_stream<CJ2, kGuard>(acc, hs, A.w2t, A.h1, A.h2p, wbuf, warp, lane);
+            bias_ln_relu<CJ2, kGuard>(acc, A.b2, A.g2, A.be2, A.h2, A.h2p, lane);
+            float w3[CJ2];
+#pragma unroll
+            for (int j = 0; j < CJ2; j++) w3[j] = (!kGuard || lane + 32 * j < A.h2p) ? A.w3[lane + 32 * j] : 0.f;
+            const float b3 = A.b3[0];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < CJ2; j++) s = fmaf(acc[r][j], w3[j], s);
+                s = warp_sum_f(s);
+                const int row = warp * 8 + r;
+                if (lane == 0 && row < rows) out[row0 + row] = tanhf(s + b3);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+size_t actor_fp32_smem(const tt_actor_dev &A) {
+    const int wmax = A.h1p > A.h2p ? A.h1p : A.h2p;
+    size_t wb = (size_t)2 * KC * wmax;
+    return sizeof(float) * ((size_t)A.k1p * RS + (size_t)A.h1p * RS + wb);
+}
+
+}  // namespace
+
+namespace tt {
+
+int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, cudaStream_t s) {
+    const tt_actor_dev &A = a->dev;
+    const size_t smem = actor_fp32_smem(A);
+    const int64_t ntiles = (n + TM - 1) / TM;
+    const int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
+    const int cj1 = A.h1p / 32, cj2 = A.h2p / 32;
+    if (cj1 == 13 && cj2 == 10) {
+        auto kern = actor_fp32_kernel<13, 10, false>;
+        TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu);
+    } else if (cj1 <= 16 && cj2 <= 16) {
+        auto kern = actor_fp32_kernel<16, 16, true>;
+        TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu);
+    } else {
+        set_error("actor: hidden sizes above 512 are not supported (h1=%d h2=%d)", A.h1, A.h2);
+        return TT_ERR_INVALID;
+    }
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
+}
+
+int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
+                 uint64_t gid0, const uint32_t *d_iter, int evaluate, cudaStream_t s) {
+    ou_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(d_x, d_action, d_scaled, d_reset_mask, n, seed,
+                                                                            gid0, d_iter, evaluate);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
+}
+
+int launch_ou_zero(float *d_x, const uint8_t *d_mask, int64_t n, cudaStream_t s) {
+    ou_zero_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(d_x, d_mask, n);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
+}
+
+}  // namespace tt
+
+extern "C" {
+
+int tt_ou_step(float *d_x, float *d_action, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
+               uint64_t global_env_offset, const uint32_t *d_iter, tt_stream_t stream) {
+    TT_REQUIRE(d_x && d_iter && n > 0, "bad argument");
+    return tt::launch_noise(d_x, d_action, nullptr, d_reset_mask, n, seed, global_env_offset, d_iter, 0, tt::as_stream(stream));
+}
+
+int tt_scale_action(const float *d_action, float *d_scaled, int64_t n, tt_stream_t stream) {
+    TT_REQUIRE(d_action && d_scaled && n > 0, "bad argument");
+    scale_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, tt::as_stream(stream)>>>(d_action, d_scaled, n);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
+}
+
+size_t tt_actor_workspace_bytes(int32_t in_dim, int32_t h1, int32_t h2) {
+    if (in_dim <= 0 || h1 <= 0 || h2 <= 0) return 0;
+    return tt_actor_layout(in_dim, h1, h2, nullptr, nullptr);
+}
+
+int tt_actor_create(tt_actor **out, int32_t in_dim, int32_t h1, int32_t h2, void *d_workspace, size_t workspace_bytes) {
+    TT_REQUIRE(out && d_workspace, "NULL argument");
+    TT_REQUIRE(in_dim > 0 && in_dim <= 32 && h1 > 0 && h1 <= 512 && h2 > 0 && h2 <= 512, "unsupported layer sizes");
+    if ((reinterpret_cast<uintptr_t>(d_workspace) & 255) != 0 || workspace_bytes < tt_actor_workspace_bytes(in_dim, h1, h2)) {
+        tt::set_error("tt_actor_create: workspace must be 256 B aligned and >= %zu bytes", tt_actor_workspace_bytes(in_dim, h1, h2));
+        return TT_ERR_WORKSPACE;
+    }
+    if (tt_device_count() <= 0) { tt::set_error("tt_actor_create: no CUDA device (there is no CPU fallback)"); return TT_ERR_CUDA; }
+    tt_actor *a = new (std::nothrow) tt_actor;
+    TT_REQUIRE(a, "out of host memory");
+    tt_actor_layout(in_dim, h1, h2, &a->dev, static_cast<char *>(d_workspace));
+    a->loaded = false;
+    *out = a;
+    return TT_OK;
+}
+
+int tt_actor_destroy(tt_actor *a) { delete a; return TT_OK; }
+
+int tt_actor_load(tt_actor *a, const float *d_fc1_w, const float *d_fc1_b, const float *d_ln1_g, const float *d_ln1_b,
+                  const float *d_fc2_w, const float *d_fc2_b, const float *d_ln2_g, const float *d_ln2_b,
+                  const float *d_mu_w, const float *d_mu_b, tt_stream_t stream) {
+    TT_REQUIRE(a && d_fc1_w && d_fc1_b && d_ln1_g && d_ln1_b && d_fc2_w && d_fc2_b && d_ln2_g && d_ln2_b && d_mu_w && d_mu_b,
+               "NULL argument");
+    cudaStream_t s = tt::as_stream(stream);
+    pack_fp32_kernel<<<64, 256, 0, s>>>(a->dev, d_fc1_w, d_fc1_b, d_ln1_g, d_ln1_b, d_fc2_w, d_fc2_b, d_ln2_g, d_ln2_b,
+                                        d_mu_w, d_mu_b);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    int rc = tt::actor_pack_tc(a, d_fc1_w, d_fc2_w, s);
+    if (rc != TT_OK) return rc;
+    a->loaded = true;
+    return TT_OK;
+}
+
+int tt_actor_forward(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n, float *d_mu, int32_t precision,
+                     tt_stream_t stream) {
+    TT_REQUIRE(a && d_obs && d_mu, "NULL argument");
+    TT_REQUIRE(a->loaded, "tt_actor_load has not been called");
+    TT_REQUIRE(n > 0 && ld_obs >= a->dev.in_dim, "bad n / ld_obs");
+    if (precision == TT_PREC_FP32) return tt::actor_forward_fp32(a, d_obs, ld_obs, n, d_mu, tt::as_stream(stream));
+    if (precision == TT_PREC_BF16) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, tt::as_stream(stream));
+    tt::set_error("tt_actor_forward: unknown precision %d", precision);
+    return TT_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing: one process per GPU, environments sharded by global id, no data-path collective.
+
+The path shards trivially: rank r owns global envs [r*n, (r+1)*n); the Philox streams
+are keyed by (seed, global id), so a given environment's trajectory is the same for any GPU count.  The
+only collectives are latency-bound and go through ``torch.distributed`` (NCCL over NVLink on the GPU box,
+gloo in the CPU tests): a sum all-reduce of the 16-word statistics vector per iteration and a broadcast of
+the 131 601 actor parameters from the learner rank after each update.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+from ._lib import STAT_NAMES, TT_NSTATS
+
+ACTOR_KEYS = ("fc1.weight", "fc1.bias", "bn1.weight", "bn1.bias", "fc2.weight", "fc2.bias", "bn2.weight", "bn2.bias",
+              "mu.weight", "mu.bias")
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns (rank, world,
+    local_rank).  Single-process runs (no WORLD_SIZE) return (0, 1, 0) without creating a group."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard(num_envs_total: int, rank: int, world: int):
+    """Global env range of `rank`: (offset, count); remainders go to the lowest ranks."""
+    base, rem = divmod(int(num_envs_total), world)
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+def all_reduce_stats(stats: torch.Tensor) -> torch.Tensor:
+    """Sum the per-rank statistics vector (float64[16]) over ranks, in place."""
+    assert stats.numel() == TT_NSTATS
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+def summarize(stats: torch.Tensor) -> dict:
+    v = stats.detach().cpu().tolist()
+    d = dict(zip(STAT_NAMES, v))
+    ep = max(d["episodes"], 1.0)
+    d["mean_return"] = d["return_sum"] / ep
+    d["std_return"] = max(d["return_sq_sum"] / ep - d["mean_return"] ** 2, 0.0) ** 0.5
+    d["success_rate"] = d["successes"] / ep
+    return d
+
+
+def flatten_actor(sd: dict, device=None) -> torch.Tensor:
+    return torch.cat([torch.as_tensor(sd[k], dtype=torch.float32, device=device).reshape(-1) for k in ACTOR_KEYS])
+
+
+def unflatten_actor(flat: torch.Tensor, like: dict) -> dict:
+    out, o = {}, 0
+    for k in ACTOR_KEYS:
+        n = like[k].numel()
+        out[k] = flat[o:o + n].reshape(like[k].shape)
+        o += n
+    return out
+
+
+def broadcast_actor(sd: dict, src: int = 0, device=None) -> dict:
+    """Broadcast an actor state_dict from `src` as ONE flat float32 message (526 404 B)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return sd
+    flat = flatten_actor(sd, device=device)
+    dist.broadcast(flat, src=src)
+    return unflatten_actor(flat, sd)

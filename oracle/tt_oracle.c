@@ -76,7 +76,6 @@ static void kin(const tto_cfg *c, const double *x, double delta, double *xd) {
 }
 
 /* scipy rk.py:541-550 */
-static const double RK_C[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1};
 static const double RK_A[6][5] = {
     {0, 0, 0, 0, 0},
     {1.0 / 5, 0, 0, 0, 0},

@@ -1,0 +1,121 @@
+"""Actor forward / OU noise / action scaling kernels vs the reference torch outputs (golden) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _sets(g):
+    w0 = {k[3:]: g[k] for k in g.files if k.startswith("w0/")}
+    w1 = {k: v.copy() for k, v in w0.items()}
+    w1["mu.weight"] = w1["mu.weight"] * np.float32(60.0)
+    w1["mu.bias"] = w1["mu.bias"] + np.float32(0.05)
+    w1["fc2.weight"] = w1["fc2.weight"] * np.float32(2.0)
+    for k in ("bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias"):
+        w1[k] = g["w1/" + k]
+    return w0, w1
+
+
+@pytest.mark.parametrize("ld", [23, 24])
+def test_actor_fp32_matches_reference_torch(golden_dir, ld):
+    """ActorNetwork.forward (networks.py:138-147): fp32 kernel within 1e-5 of the reference torch forward."""
+    import ddpg_trucktrailer_b200 as tt
+    g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
+    obs = torch.zeros(len(g["obs"]), ld, device="cuda")
+    obs[:, :23] = torch.from_numpy(g["obs"]).cuda()
+    actor = tt.agent.CudaActor()
+    for w, ref in zip(_sets(g), (g["out0"], g["out1"])):
+        actor.load_state_dict(w)
+        out = actor.forward(obs[:, :23]).cpu().numpy()
+        assert np.abs(out - ref).max() < 1e-5
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 20000])
+def test_actor_fp32_ragged_sizes_vs_oracle(golden_dir, n):
+    import ddpg_trucktrailer_b200 as tt
+    from oracle import oracle as orc
+    g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
+    _, w1 = _sets(g)
+    obs = np.random.default_rng(n).uniform(-1, 1, (n, 23)).astype(np.float32)
+    actor = tt.agent.CudaActor(); actor.load_state_dict(w1)
+    out = actor.forward(torch.from_numpy(obs).cuda()).cpu().numpy()
+    assert np.abs(out - orc.OracleActor(w1).forward(obs)).max() < 1e-5
+
+
+def test_actor_other_hidden_sizes():
+    """fc1_dims / fc2_dims are constructor arguments of the reference Agent (DDPG_agent.py:10-12)."""
+    import ddpg_trucktrailer_b200 as tt
+    from oracle import oracle as orc
+    sd = tt.init_actor_state_dict(23, 256, 128, 1, seed=3)
+    sd["mu.weight"] *= 50
+    actor = tt.agent.CudaActor(23, 256, 128); actor.load_state_dict(sd)
+    obs = np.random.default_rng(0).uniform(-1, 1, (777, 23)).astype(np.float32)
+    out = actor.forward(torch.from_numpy(obs).cuda()).cpu().numpy()
+    ref = orc.OracleActor({k: v.numpy() for k, v in sd.items()}).forward(obs)
+    assert np.abs(out - ref).max() < 1e-5
+
+
+def test_init_matches_reference_distributions():
+    import ddpg_trucktrailer_b200 as tt
+    sd = tt.init_actor_state_dict(seed=0)
+    assert sd["fc1.weight"].abs().max() <= 1 / np.sqrt(400) and sd["fc2.weight"].abs().max() <= 1 / np.sqrt(300)
+    assert sd["mu.weight"].abs().max() <= 0.003 and (sd["bn1.weight"] == 1).all() and (sd["bn2.bias"] == 0).all()
+
+
+def test_init_equals_reference_seed0(golden_dir):
+    """Same draw order as networks.py:110-131 -> torch.manual_seed(0) reproduces the reference's weights."""
+    import ddpg_trucktrailer_b200 as tt
+    g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
+    sd = tt.init_actor_state_dict(seed=0)
+    for k in tt.ACTOR_KEYS:
+        assert np.array_equal(sd[k].numpy(), g["w0/" + k]), k
+
+
+def test_ou_noise_vs_oracle_and_moments():
+    """noise.py:12-17 with Philox normals: matches the oracle restatement; stationary moments are right."""
+    import ddpg_trucktrailer_b200 as tt
+    from oracle import oracle as orc
+    from ddpg_trucktrailer_b200 import _lib
+    L = _lib.load()
+    n = 1 << 16
+    x = torch.zeros(n, device="cuda"); act = torch.full((n,), 0.25, device="cuda")
+    it = torch.tensor([7], dtype=torch.int32, device="cuda")
+    xo = np.zeros(n, np.float32); ao = np.full(n, 0.25, np.float32)
+    for t in (7, 8, 9):
+        it.fill_(t)
+        _lib.check(L.tt_ou_step(x.data_ptr(), act.data_ptr(), None, n, 99, 1000, it.data_ptr(), _lib.stream_ptr()))
+        orc.ou_step(xo, ao, None, 99, 1000, t)
+    assert np.abs(x.cpu().numpy() - xo).max() < 2e-6 and np.abs(act.cpu().numpy() - ao).max() < 5e-6
+    # reset mask zeroes the state first (agent.noise.reset(), trainv2.py:492)
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda"); mask[::2] = 1
+    it.fill_(10)
+    _lib.check(L.tt_ou_step(x.data_ptr(), None, mask.data_ptr(), n, 99, 1000, it.data_ptr(), _lib.stream_ptr()))
+    m = mask.cpu().numpy().astype(np.uint8)
+    orc.ou_step(xo, None, m, 99, 1000, 10)
+    assert np.abs(x.cpu().numpy() - xo).max() < 2e-6
+    inc = x.cpu().numpy()[::2]                      # one step from 0: N(0, (0.15*0.1)^2)
+    assert abs(inc.mean()) < 3e-4 and abs(inc.std() - 0.015) < 3e-4
+
+
+def test_choose_action_and_scaling():
+    """Agent.choose_action (DDPG_agent.py:36-49): mu + noise unclipped; evaluate=True skips noise;
+    trainv2.py:516 scaling."""
+    import ddpg_trucktrailer_b200 as tt
+    from ddpg_trucktrailer_b200 import _lib
+    N = 5000
+    ag = tt.VecAgent(1e-4, 1e-3, (23,), 1e-3, 1, num_envs=N, max_size=1 << 14, actor_seed=0)
+    obs = torch.empty(N, 23, device="cuda").uniform_(-1, 1)
+    mu = ag.choose_action(obs, evaluate=True).clone()
+    assert mu.shape == (N, 1)
+    a1 = ag.choose_action(obs).clone()
+    assert torch.allclose(a1 - mu, ag.noise.x_prev.reshape(-1, 1), atol=1e-7) and (a1 != mu).any()
+    scaled = torch.empty(N, device="cuda")
+    big = (a1 * 100).reshape(-1).contiguous()
+    _lib.check(_lib.load().tt_scale_action(big.data_ptr(), scaled.data_ptr(), N, _lib.stream_ptr()))
+    ref = np.clip(big.cpu().numpy(), -1, 1) * np.float32(0.78539819)
+    assert np.array_equal(scaled.cpu().numpy(), ref.astype(np.float32))
+    ag.noise.reset()
+    assert (ag.noise.x_prev == 0).all()
