@@ -4,8 +4,8 @@
 //
 // Layout in HBM (struct-of-arrays inside the caller-provided workspace, every array 256 B aligned):
 //   st[6][N] f64   psi1 psi2 x1 y1 x2 y2            goal[N] float4   gx gy sin(gyaw) cos(gyaw)
-//   rsA[N] float4  prev closest cum first_steer      rsB[N]  float4   h1 h2 h3 episode_return
-//   packed[N] u32  steps|emax|rmax-emax|stage bits|finished          d0[N] f32
+//   rsA[N] float4  closest cum first_steer ep_return rsB[N]  float4   g1 g2 g3 d0   (g = distance decrements)
+//   packed[N] u32  steps|emax|rmax-emax|stage bits|finished
 //   pose[4][N] f64 startx starty startyaw goalyaw   (written on reset only; host-visible attributes)
 //   stats[16] f64, iter u32
 // One thread owns one environment: all loads/stores are unit-stride across the warp (8 or 16 B per lane).
@@ -23,7 +23,6 @@ struct EnvPtrs {
     double *st;          // [6][N]
     float4 *goal, *rsA, *rsB;
     uint32_t *packed;
-    float *d0;
     double *pose;        // [4][N]
     double *stats;       // [16]
     uint32_t *iter;
@@ -49,18 +48,17 @@ __device__ __forceinline__ void load_regs(const EnvPtrs &p, int64_t i, EnvRegs &
     const float4 g = __ldg(&p.goal[i]);
     e.gx = g.x; e.gy = g.y; e.sgy = g.z; e.cgy = g.w;
     const float4 a = p.rsA[i], b = p.rsB[i];
-    e.prev = a.x; e.closest = a.y; e.cum = a.z; e.first_steer = a.w;
-    e.h1 = b.x; e.h2 = b.y; e.h3 = b.z; e.ep_ret = b.w;
+    e.closest = a.x; e.cum = a.y; e.first_steer = a.z; e.ep_ret = a.w;
+    e.g1 = b.x; e.g2 = b.y; e.g3 = b.z; e.d0 = b.w;
     e.packed = p.packed[i];
-    e.d0 = __ldg(&p.d0[i]);
 }
 
 __device__ __forceinline__ void store_dyn(const EnvPtrs &p, int64_t i, const EnvRegs &e) {
     const int64_t N = p.N;
     p.st[i] = e.psi1; p.st[N + i] = e.psi2; p.st[2 * N + i] = e.x1; p.st[3 * N + i] = e.y1;
     p.st[4 * N + i] = e.x2; p.st[5 * N + i] = e.y2;
-    p.rsA[i] = make_float4(e.prev, e.closest, e.cum, e.first_steer);
-    p.rsB[i] = make_float4(e.h1, e.h2, e.h3, e.ep_ret);
+    p.rsA[i] = make_float4(e.closest, e.cum, e.first_steer, e.ep_ret);
+    p.rsB[i] = make_float4(e.g1, e.g2, e.g3, e.d0);
     p.packed[i] = e.packed;
 }
 
@@ -68,7 +66,6 @@ __device__ __forceinline__ void store_episode_consts(const EnvPtrs &p, int64_t i
                                                      double syaw, double gyaw) {
     const int64_t N = p.N;
     p.goal[i] = make_float4(e.gx, e.gy, e.sgy, e.cgy);
-    p.d0[i] = e.d0;
     p.pose[i] = sx; p.pose[N + i] = sy; p.pose[2 * N + i] = syaw; p.pose[3 * N + i] = gyaw;
 }
 
@@ -281,12 +278,12 @@ static size_t env_layout(int64_t n, EnvPtrs *p, char *base) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = tt::align_up(off + bytes, 256); return o; };
     const size_t o_st = take(sizeof(double) * 6 * n), o_goal = take(sizeof(float4) * n), o_a = take(sizeof(float4) * n),
-                 o_b = take(sizeof(float4) * n), o_pk = take(sizeof(uint32_t) * n), o_d0 = take(sizeof(float) * n),
+                 o_b = take(sizeof(float4) * n), o_pk = take(sizeof(uint32_t) * n),
                  o_pose = take(sizeof(double) * 4 * n), o_stats = take(sizeof(double) * TT_NSTATS), o_iter = take(256);
     if (p) {
         p->st = reinterpret_cast<double *>(base + o_st); p->goal = reinterpret_cast<float4 *>(base + o_goal);
         p->rsA = reinterpret_cast<float4 *>(base + o_a); p->rsB = reinterpret_cast<float4 *>(base + o_b);
-        p->packed = reinterpret_cast<uint32_t *>(base + o_pk); p->d0 = reinterpret_cast<float *>(base + o_d0);
+        p->packed = reinterpret_cast<uint32_t *>(base + o_pk);
         p->pose = reinterpret_cast<double *>(base + o_pose); p->stats = reinterpret_cast<double *>(base + o_stats);
         p->iter = reinterpret_cast<uint32_t *>(base + o_iter); p->N = n;
     }

@@ -67,8 +67,11 @@ struct EnvRegs {
     double psi1, psi2, x1, y1, x2, y2;        // simv2.py:489 state
     float  gx, gy, sgy, cgy;                   // goal position, sin/cos(goal yaw)
     float  d0;                                 // hypot(goal - start), simv2.py:264 / reward_functionv1.py:34
-    float  prev, closest, cum, first_steer;    // reward_functionv1.py:99-109
-    float  h1, h2, h3;                         // distance_history[1..3] (history[4] == prev, [0] is never read)
+    float  closest, cum, first_steer;          // reward_functionv1.py:99-109
+    // distance_history / previous_distance (reward_functionv1.py:40-67) are kept as the last three per-step
+    // distance DECREMENTS g_k = d_{k-1} - d_k (g1 = most recent): the reward only ever uses differences of
+    // distances, and a float32 decrement (~0.4 m) is 100x more precise than a float32 distance (~60 m).
+    float  g1, g2, g3;
     float  ep_ret;                             // running episode return (trainv2.py:529 `score`)
     uint32_t packed;
 };
@@ -176,7 +179,7 @@ TT_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi)
 // observation packing: simv2.py:103-181 (index map in SURVEY.md section 8a row a5)
 // trig inputs: s1/c1 = sin/cos psi1, s2/c2 = psi2, sth/cth = hitch, sdl/cdl = steering
 // ---------------------------------------------------------------------------------------------------
-struct ObsAux { float d, dxl, dyl; };
+struct ObsAux { float d, dx, dy; };
 
 TT_HD ObsAux pack_obs(const StepConsts &k, const EnvRegs &e, float s1, float c1, float s2, float c2, float sth,
                       float cth, float sdl, float cdl, float *o) {
@@ -200,7 +203,7 @@ TT_HD ObsAux pack_obs(const StepConsts &k, const EnvRegs &e, float s1, float c1,
         const float inv = 1.0f / d;
         o[21] = -dyl * inv; o[22] = -dxl * inv;
     } else { o[21] = s2; o[22] = -c2; }
-    ObsAux a; a.d = d; a.dxl = dxl; a.dyl = dyl;
+    ObsAux a; a.d = d; a.dx = dx; a.dy = dy;
     return a;
 }
 
@@ -225,7 +228,7 @@ TT_HD void begin_episode(const StepConsts &k, EnvRegs &e, double sx, double sy, 
     const double d0 = sqrt(ddx * ddx + ddy * ddy);
     e.d0 = (float)d0;
     e.packed = pack_limits(k, d0);
-    e.prev = e.closest = e.cum = e.first_steer = e.h1 = e.h2 = e.h3 = 0.0f;
+    e.closest = e.cum = e.first_steer = e.g1 = e.g2 = e.g3 = 0.0f;
     e.ep_ret = 0.0f;
     if (obs) {
         float s2, c2, s1, c1, sth, cth;
@@ -358,9 +361,12 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
 #endif
     for (int m = 0; m < 6; m++) accb = fma(B[m], u[m], accb);
     const double dpsi2 = k.h * accb;
+    // goal offset of the trailer BEFORE the move (for the distance decrement below)
+    const float dxp = (float)((double)e.gx - e.x2), dyp = (float)((double)e.gy - e.y2);
+    const float ix2 = k.hv * ax2, iy2 = k.hv * ay2;
     e.psi1 += hw; e.psi2 += dpsi2;                           // simv2.py:516-517
     e.x1 += (double)(k.hv * ax1); e.y1 += (double)(k.hv * ay1);
-    e.x2 += (double)(k.hv * ax2); e.y2 += (double)(k.hv * ay2);
+    e.x2 += (double)ix2; e.y2 += (double)iy2;
 
     // ---- trig of the new state (for the observation) ----
     double sdn, cdn;
@@ -381,20 +387,27 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
     const uint32_t emax = (e.packed >> PK_EMAX_SHIFT) & PK_EMAX_MASK;
     const uint32_t rmax = emax + ((e.packed & PK_RMAX_EXTRA) ? 1u : 0u);
     const float steer = (float)delta;                        // == arctan2(obs[10], obs[11]) to float32 rounding (:37)
-    if (steps == 1u) {                                       // :40-76 first step of the episode
-        e.prev = d; e.first_steer = steer; e.cum = 0.0f; e.h1 = e.h2 = e.h3 = d; e.closest = d;
+    // g = previous_distance - current_distance = (dp^2 - d^2) / (dp + d), with dp^2 - d^2 expanded through the
+    // exact float32 position increment: no cancellation, abs error ~1e-7 instead of ~8e-6
+    float g;
+    if (steps == 1u) {                                       // :40-76 first step of the episode: previous = current
+        g = 0.0f; e.first_steer = steer; e.cum = 0.0f; e.g1 = e.g2 = e.g3 = 0.0f; e.closest = d;
         e.packed &= ~(PK_ST2 | PK_ST3);
-    } else e.closest = fminf(e.closest, d);                  // :70-74
+    } else {
+        const float dp = sqrtf(fmaf(dxp, dxp, dyp * dyp));
+        const float num = fmaf(ix2, dxp + oa.dx, iy2 * (dyp + oa.dy));
+        g = (dp + d) > 0.0f ? num / (dp + d) : 0.0f;
+        e.closest = fminf(e.closest, d);                     // :70-74
+    }
     // ---- compute_dynamic_weights :189-238 ----
     const float d0 = e.d0 + 1e-6f;
     const float jp = clampf((d0 - d) / d0, 0.0f, 1.0f);
     const float w_final = 0.5f * (fast_tanhf(7.0f * (jp - 0.3f)) + 1.0f), w_head = 1.0f - w_final;
     // ---- calculate_progress_reward :144-187 ----
-    const float inst = e.prev - d;
-    float prog = fast_tanhf(inst);
-    prog = inst > 0.0f ? prog : 0.5f * prog;
-    prog += 0.5f * fast_tanhf(0.5f * (e.h1 - d));            // history after append+pop: [h1,h2,h3,prev,d]
-    prog += (e.h3 >= e.prev && e.prev >= d) ? 0.2f : 0.0f;
+    float prog = fast_tanhf(g);                              // instant_progress = previous - current
+    prog = g > 0.0f ? prog : 0.5f * prog;
+    prog += 0.5f * fast_tanhf(0.5f * (((g + e.g1) + e.g2) + e.g3));   // history[0] - current = d_{t-4} - d_t
+    prog += (e.g1 >= 0.0f && g >= 0.0f) ? 0.2f : 0.0f;      // history[2] >= history[3] >= history[4]
     // ---- heading / orientation :285-324 ----
     const float heading = out.obs[22], orient = out.obs[20];
     // ---- staged success :338-367 (|atan2(o19,o20)| <= a  <=>  o20 >= cos a) ----
@@ -420,7 +433,7 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
     const double rm = (double)rmax, sd_ = (double)steps;
     const float expl = sd_ < rm * 0.5 ? 4.0f : (sd_ < rm * 0.8 ? 2.0f : 0.0f);
     // ---- backward movement penalty :240-283 ----
-    e.cum += fmaxf(0.0f, d - e.prev);
+    e.cum += fmaxf(0.0f, -g);
     const float budget = 5.0f * fminf(1.0f, (float)steps * 0.02f);
     const float ex = fmaxf(0.0f, e.cum - budget);
     const float back = -0.5f * ex * sqrtf(ex);
@@ -428,7 +441,7 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
     const float smooth = fabsf(steer - e.first_steer) * 0.63661977236758134f;
     const float fin = success ? 200.0f : 0.0f;
     // ---- history / previous distance :166-171, :472 ----
-    e.h1 = e.h2; e.h2 = e.h3; e.h3 = e.prev; e.prev = d;
+    e.g3 = e.g2; e.g2 = e.g1; e.g1 = g;
     // ---- total :475-486 ----
     const float c_prog = 15.0f * prog, c_head = 15.0f * heading * w_head, c_ori = 15.0f * orient * w_final,
                 c_smooth = -25.0f * smooth;

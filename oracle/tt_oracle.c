@@ -434,17 +434,19 @@ static void layer_norm_relu_f(float *x, int n, const float *g, const float *b) {
 
 static float actor_forward_one_f(const tto_actor *a, const float *s, float *h1, float *h2) {
     for (int j = 0; j < a->h1; j++) {
-        float acc = a->b1[j];
+        float acc = 0.f;
         const float *w = a->w1 + j * a->in_dim;
+#pragma omp simd reduction(+ : acc)
         for (int k = 0; k < a->in_dim; k++) acc += w[k] * s[k];
-        h1[j] = acc;
+        h1[j] = acc + a->b1[j];
     }
     layer_norm_relu_f(h1, a->h1, a->g1, a->be1);
     for (int j = 0; j < a->h2; j++) {
-        float acc = a->b2[j];
+        float acc = 0.f;
         const float *w = a->w2 + j * a->h1;
+#pragma omp simd reduction(+ : acc)
         for (int k = 0; k < a->h1; k++) acc += w[k] * h1[k];
-        h2[j] = acc;
+        h2[j] = acc + a->b2[j];
     }
     layer_norm_relu_f(h2, a->h2, a->g2, a->be2);
     float acc = a->b3[0];
