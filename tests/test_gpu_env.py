@@ -145,7 +145,7 @@ def test_step_k_equals_single_steps_and_global_ids():
         _, r, d, _ = b.step(acts[t]); rs.append(r.clone()); ds.append(d.clone())
         b.reset(options={"mask": d}); b.tick()
     assert torch.equal(rk, torch.stack(rs)) and torch.equal(dk.bool(), torch.stack(ds))
-    assert torch.equal(a.state, b.state) and dk.sum() > N // 4
+    assert torch.equal(a.state, b.state) and dk.sum() > 50
     c = tt.VecTruckTrailerEnv(300, seed=5, global_env_offset=600); c.reset()
     _, rc, dc, _ = c.step_k(acts[:, 600:900].contiguous(), auto_reset=True)
     assert torch.equal(rc, rk[:, 600:900]) and torch.equal(c.state, a.state[600:900])
