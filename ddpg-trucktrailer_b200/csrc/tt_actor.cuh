@@ -5,8 +5,8 @@
 //   w1t  f32 [k1p][h1p]   fc1.weight transposed (k-major), zero padded; k1p = in_dim rounded up to 8
 //   w2t  f32 [h1p][h2p]   fc2.weight transposed (k-major), zero padded; h*p = h* rounded up to 32
 //   b1 g1 be1 [h1p], b2 g2 be2 w3 [h2p], b3 [1]            (padded entries are 0)
-//   w1b  bf16 [h1p][kb1]  fc1.weight, K padded to kb1 = 64, row-major (N x K, "K-major" UMMA B operand)
-//   w2b  bf16 [h2p][h1p]  fc2.weight, row-major (N x K); h1p is a multiple of 32
+//   w1b  bf16 UMMA image  [n1 rows x 64 B]          fc1.weight|fc1.bias, K-major SWIZZLE_64B (tt_actor_tc.cu)
+//   w2b  bf16 UMMA image  [kb2][n2 rows x 64 B]     fc2.weight|fc2.bias in k-blocks of 32, same swizzle
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -33,7 +33,8 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
     const size_t o_b1 = take(sizeof(float) * h1p), o_g1 = take(sizeof(float) * h1p), o_be1 = take(sizeof(float) * h1p);
     const size_t o_b2 = take(sizeof(float) * h2p), o_g2 = take(sizeof(float) * h2p), o_be2 = take(sizeof(float) * h2p);
     const size_t o_w3 = take(sizeof(float) * h2p), o_b3 = take(sizeof(float));
-    const size_t o_w1b = take(sizeof(__nv_bfloat16) * h1p * kb1), o_w2b = take(sizeof(__nv_bfloat16) * h2p * h1p);
+    const size_t n1 = (h1 + 15) / 16 * 16, n2 = (h2 + 15) / 16 * 16, kb2 = (h1 + 1 + 31) / 32;
+    const size_t o_w1b = take(n1 * 64), o_w2b = take(kb2 * n2 * 64);
     if (d) {
         d->in_dim = in_dim; d->h1 = h1; d->h2 = h2; d->k1p = k1p; d->h1p = h1p; d->h2p = h2p; d->kb1 = kb1;
         auto f = [&](size_t o) { return reinterpret_cast<float *>(base + o); };
@@ -47,7 +48,7 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
 namespace tt {
 int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, cudaStream_t s);
 int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, cudaStream_t s);
-int actor_pack_tc(tt_actor *a, const float *d_fc1_w, const float *d_fc2_w, cudaStream_t s);
+int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *fc2_w, const float *fc2_b, cudaStream_t s);
 int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
                  uint64_t gid0, const uint32_t *d_iter, int evaluate, cudaStream_t s);
 int launch_ou_zero(float *d_x, const uint8_t *d_mask, int64_t n, cudaStream_t s);

@@ -327,7 +327,7 @@ int tt_actor_load(tt_actor *a, const float *d_fc1_w, const float *d_fc1_b, const
     pack_fp32_kernel<<<64, 256, 0, s>>>(a->dev, d_fc1_w, d_fc1_b, d_ln1_g, d_ln1_b, d_fc2_w, d_fc2_b, d_ln2_g, d_ln2_b,
                                         d_mu_w, d_mu_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    int rc = tt::actor_pack_tc(a, d_fc1_w, d_fc2_w, s);
+    int rc = tt::actor_pack_tc_full(a, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, s);
     if (rc != TT_OK) return rc;
     a->loaded = true;
     return TT_OK;

@@ -119,3 +119,32 @@ def test_choose_action_and_scaling():
     assert np.array_equal(scaled.cpu().numpy(), ref.astype(np.float32))
     ag.noise.reset()
     assert (ag.noise.x_prev == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tcgen05 (bf16 tensor-core) actor: north_star bar 1e-3 against the reference torch forward
+# ------------------------------------------------------------------------------------------------------------
+def test_actor_tc_matches_reference_torch(golden_dir):
+    import ddpg_trucktrailer_b200 as tt
+    g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
+    obs = torch.from_numpy(g["obs"]).cuda()
+    actor = tt.agent.CudaActor()
+    for w, ref in zip(_sets(g), (g["out0"], g["out1"])):
+        actor.load_state_dict(w)
+        out = actor.forward(obs, precision="bf16").cpu().numpy()
+        err = np.abs(out - ref).max()
+        assert err < 1e-3, err
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 5000, 148 * 128 * 3 + 17])
+def test_actor_tc_ragged_sizes_vs_fp32_kernel(golden_dir, n):
+    import ddpg_trucktrailer_b200 as tt
+    g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
+    _, w1 = _sets(g)
+    actor = tt.agent.CudaActor(); actor.load_state_dict(w1)
+    obs = torch.empty(n, 24, device="cuda").uniform_(-1, 1)[:, :23]          # ld_obs = 24
+    a = actor.forward(obs, precision="bf16").clone()
+    b = actor.forward(obs, precision="fp32")
+    assert (a - b).abs().max() < 1e-3
+    a2 = actor.forward(obs, precision="bf16")
+    assert torch.equal(a, a2)                                                # deterministic
