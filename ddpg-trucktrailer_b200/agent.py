@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import TT_OBS_DIM, TT_PREC_BF16, TT_PREC_FP32, check, ptr, stream_ptr
+from ._lib import PRECISIONS, TT_OBS_DIM, check, ptr, stream_ptr
 from .replay import DeviceReplayBuffer
 
 ACTOR_KEYS = ("fc1.weight", "fc1.bias", "bn1.weight", "bn1.bias", "fc2.weight", "fc2.bias", "bn2.weight", "bn2.bias",
@@ -85,7 +85,9 @@ class CudaActor:
         return {k: v.clone() for k, v in self._sd.items()}
 
     def forward(self, obs, out=None, precision="fp32"):
-        """tanh(mu(relu(LN(fc2(relu(LN(fc1(obs)))))))) -> [n] float32 (networks.py:138-147)."""
+        """tanh(mu(relu(LN(fc2(relu(LN(fc1(obs)))))))) -> [n] float32 (networks.py:138-147).
+        precision: "fp32" (CUDA cores, <=1e-5), "f16" (tcgen05, fp16 operands + exact first layer, <=1e-3) or
+        "bf16" (tcgen05, plain bf16 operands)."""
         with torch.cuda.device(self.device):
             if obs.dim() == 1:
                 obs = obs.reshape(1, -1)
@@ -94,7 +96,7 @@ class CudaActor:
             n = obs.shape[0]
             if out is None:
                 out = torch.empty(n, dtype=torch.float32, device=self.device)
-            prec = TT_PREC_BF16 if precision in ("bf16", TT_PREC_BF16) else TT_PREC_FP32
+            prec = PRECISIONS[precision]
             check(self.L.tt_actor_forward(self._h, obs.data_ptr(), obs.stride(0), n, out.data_ptr(), prec, stream_ptr()))
         return out
 

@@ -5,8 +5,8 @@
 //   w1t  f32 [k1p][h1p]   fc1.weight transposed (k-major), zero padded; k1p = in_dim rounded up to 8
 //   w2t  f32 [h1p][h2p]   fc2.weight transposed (k-major), zero padded; h*p = h* rounded up to 32
 //   b1 g1 be1 [h1p], b2 g2 be2 w3 [h2p], b3 [1]            (padded entries are 0)
-//   w1b  bf16 UMMA image  [n1 rows x 64 B]          fc1.weight|fc1.bias, K-major SWIZZLE_64B (tt_actor_tc.cu)
-//   w2b  bf16 UMMA image  [kb2][n2 rows x 64 B]     fc2.weight|fc2.bias in k-blocks of 32, same swizzle
+//   w1_{f16,bf16}  UMMA image [hi | lo][n1 rows x 64 B]   fc1.weight|fc1.bias, K-major SWIZZLE_64B (tt_actor_tc.cu)
+//   w2_{f16,bf16}  UMMA image [kb2][n2 rows x 64 B]       fc2.weight|fc2.bias in k-blocks of 32, same swizzle
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -17,7 +17,7 @@ struct tt_actor_dev {
     int in_dim, h1, h2;
     int k1p, h1p, h2p, kb1;
     float *w1t, *w2t, *b1, *g1, *be1, *b2, *g2, *be2, *w3, *b3;
-    __nv_bfloat16 *w1b, *w2b;
+    void *w1_f16, *w2_f16, *w1_bf16, *w2_bf16;     // UMMA operand images (tt_actor_tc.cu)
 };
 
 struct tt_actor {
@@ -34,20 +34,20 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
     const size_t o_b2 = take(sizeof(float) * h2p), o_g2 = take(sizeof(float) * h2p), o_be2 = take(sizeof(float) * h2p);
     const size_t o_w3 = take(sizeof(float) * h2p), o_b3 = take(sizeof(float));
     const size_t n1 = (h1 + 15) / 16 * 16, n2 = (h2 + 15) / 16 * 16, kb2 = (h1 + 1 + 31) / 32;
-    const size_t o_w1b = take(n1 * 64), o_w2b = take(kb2 * n2 * 64);
+    const size_t o_w1h = take(2 * n1 * 64), o_w2h = take(kb2 * n2 * 64), o_w1b = take(2 * n1 * 64), o_w2b = take(kb2 * n2 * 64);
     if (d) {
         d->in_dim = in_dim; d->h1 = h1; d->h2 = h2; d->k1p = k1p; d->h1p = h1p; d->h2p = h2p; d->kb1 = kb1;
         auto f = [&](size_t o) { return reinterpret_cast<float *>(base + o); };
         d->w1t = f(o_w1t); d->w2t = f(o_w2t); d->b1 = f(o_b1); d->g1 = f(o_g1); d->be1 = f(o_be1);
         d->b2 = f(o_b2); d->g2 = f(o_g2); d->be2 = f(o_be2); d->w3 = f(o_w3); d->b3 = f(o_b3);
-        d->w1b = reinterpret_cast<__nv_bfloat16 *>(base + o_w1b); d->w2b = reinterpret_cast<__nv_bfloat16 *>(base + o_w2b);
+        d->w1_f16 = base + o_w1h; d->w2_f16 = base + o_w2h; d->w1_bf16 = base + o_w1b; d->w2_bf16 = base + o_w2b;
     }
     return off;
 }
 
 namespace tt {
 int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, cudaStream_t s);
-int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, cudaStream_t s);
+int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, cudaStream_t s);
 int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *fc2_w, const float *fc2_b, cudaStream_t s);
 int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
                  uint64_t gid0, const uint32_t *d_iter, int evaluate, cudaStream_t s);

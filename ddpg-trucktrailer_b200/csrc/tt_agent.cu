@@ -339,7 +339,7 @@ int tt_actor_forward(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n,
     TT_REQUIRE(a->loaded, "tt_actor_load has not been called");
     TT_REQUIRE(n > 0 && ld_obs >= a->dev.in_dim, "bad n / ld_obs");
     if (precision == TT_PREC_FP32) return tt::actor_forward_fp32(a, d_obs, ld_obs, n, d_mu, tt::as_stream(stream));
-    if (precision == TT_PREC_BF16) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, tt::as_stream(stream));
+    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, tt::as_stream(stream));
     tt::set_error("tt_actor_forward: unknown precision %d", precision);
     return TT_ERR_INVALID;
 }

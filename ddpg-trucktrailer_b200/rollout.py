@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import TT_PREC_BF16, TT_PREC_FP32, check, ptr, stream_ptr
+from ._lib import PRECISIONS, check, ptr, stream_ptr
 
 
 class RolloutEngine:
@@ -47,7 +47,7 @@ class RolloutEngine:
                                  m.reward_memory.data_ptr() if self.store else None,
                                  m.new_state_memory.data_ptr() if self.store else None,
                                  m.terminal_memory.data_ptr() if self.store else None, m.mem_size, m.mem_cntr)
-            prec = TT_PREC_BF16 if self.precision in ("bf16", TT_PREC_BF16) else TT_PREC_FP32
+            prec = PRECISIONS[self.precision]
             check(self.L.tt_rollout_step(env._h, ag.actor._h, C.byref(b), prec, int(self.evaluate), stream_ptr()))
             if self.store:
                 m.mem_cntr += env.num_envs

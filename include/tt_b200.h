@@ -142,7 +142,11 @@ int tt_ou_step(float *d_x, float *d_action, const uint8_t *d_reset_mask, int64_t
 
 /* ---- actor: ActorNetwork.forward (DDPG/networks.py:138-147) ---- */
 typedef struct tt_actor tt_actor;     /* opaque: packed device weights */
-enum { TT_PREC_FP32 = 0, TT_PREC_BF16 = 1 };
+/* TT_PREC_FP32: CUDA-core fp32 (<= 1e-5 of torch fp32, any layer sizes).  Tensor-core paths (tcgen05, layer sizes
+ * 23-400-300): TT_PREC_F16 = fp16 operands with an exact (split hi/lo) first layer, fp32 accumulation (<= 1e-3 even
+ * for strongly amplified trained weights); TT_PREC_BF16 = plain bf16 operands (fastest; <= 1e-3 for reference-scale
+ * weights). */
+enum { TT_PREC_FP32 = 0, TT_PREC_BF16 = 1, TT_PREC_F16 = 2 };
 size_t tt_actor_workspace_bytes(int32_t in_dim, int32_t h1, int32_t h2);
 int tt_actor_create(tt_actor **out, int32_t in_dim, int32_t h1, int32_t h2, void *d_workspace,
                     size_t workspace_bytes);
@@ -154,8 +158,7 @@ int tt_actor_load(tt_actor *a, const float *d_fc1_w, const float *d_fc1_b, const
                   const float *d_ln1_b, const float *d_fc2_w, const float *d_fc2_b, const float *d_ln2_g,
                   const float *d_ln2_b, const float *d_mu_w, const float *d_mu_b, tt_stream_t stream);
 /* d_mu[n] = tanh(mu(relu(LN(fc2(relu(LN(fc1(obs)))))))).  If d_scaled != NULL it also receives
- * clip(mu, -1, 1) * float32(pi/4) (trainv2.py:516).  precision: TT_PREC_FP32 (<=1e-5 of torch fp32) or
- * TT_PREC_BF16 (tcgen05 tensor cores, <=1e-3). */
+ * clip(mu, -1, 1) * float32(pi/4) (trainv2.py:516).  precision: one of TT_PREC_*. */
 int tt_actor_forward(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n, float *d_mu,
                      int32_t precision, tt_stream_t stream);
 
