@@ -168,6 +168,17 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, f
     return *reinterpret_cast<uint32_t *>(&p);
 }
 
+// round two floats to the operand type and apply ReLU on the packed pair (exactly relu-then-round: rounding is monotonic)
+template <typename OpT> __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2_relu<__half>(float lo, float hi) {
+    __half2 p = __hmax2(__floats2half2_rn(lo, hi), __float2half2_rn(0.f));
+    return *reinterpret_cast<uint32_t *>(&p);
+}
+template <> __device__ __forceinline__ uint32_t pack2_relu<__nv_bfloat16>(float lo, float hi) {
+    __nv_bfloat162 p = __hmax2(__floats2bfloat162_rn(lo, hi), __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<uint32_t *>(&p);
+}
+
 template <bool kSplit>
 struct Plan {
     static constexpr int kXBlocks = kSplit ? 2 : 1;
@@ -192,7 +203,8 @@ enum { B_W1 = 0, B_XFULL, B_H1FULL, B_A2FULL, B_H2FULL, B_TMEMFREE, B_W2FULL, B_
 template <typename OpT, bool kSplit, int kGroups>
 __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const char *__restrict__ w1img, const char *__restrict__ w2img,
                                                                          tt_actor_dev A, const float *__restrict__ obs, int64_t ld,
-                                                                         int64_t n, float *__restrict__ out) {
+                                                                         int64_t n, float *__restrict__ out,
+                                                                         unsigned long long *__restrict__ dbg) {
     using P = Plan<kSplit>;
     constexpr int kEpiThreads = 128 * kGroups, kThreads = kEpiThreads + 64;
     constexpr int kMmaWarp = 4 * kGroups, kProdWarp = kMmaWarp + 1;
@@ -268,11 +280,14 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
             constexpr int nA = 256, nB = N1 - 256, mA = 256, mB = N2 - 256;
             const uint32_t id1a = make_idesc(nA, kFmt), id1b = make_idesc(nB, kFmt), id2a = make_idesc(mA, kFmt), id2b = make_idesc(mB, kFmt);
             uint32_t it = 0, tcount = 0;
+            long long t_x = 0, t_a2 = 0, t_w2 = 0, t0;
             mbar_wait(bar(B_W1), 0);
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
                 const uint32_t ph = tcount & 1u;
+                t0 = clock64();
                 mbar_wait(bar(B_XFULL), ph);
                 mbar_wait(bar(B_TMEMFREE), ph ^ 1u);                      // previous tile's accumulators drained
+                t_x += clock64() - t0;
                 tc_fence_after();
                 // layer 1: (X_hi, W_hi) [+ (X_lo, W_hi) + (X_hi, W_lo)], each K = 32 = 2 x UMMA_K
                 constexpr int npairs = kSplit ? 3 : 1;
@@ -288,11 +303,15 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
                     }
                 }
                 umma_commit(bar(B_H1FULL));
+                t0 = clock64();
                 mbar_wait(bar(B_A2FULL), ph);
+                t_a2 += clock64() - t0;
                 tc_fence_after();
                 for (int kb = 0; kb < KB2; kb++, it++) {
                     const uint32_t slot = it % P::kSlots, wph = (it / P::kSlots) & 1u;
+                    t0 = clock64();
                     mbar_wait(bar(B_W2FULL + slot), wph);
+                    t_w2 += clock64() - t0;
                     tc_fence_after();
                     const uint32_t wb = sW2 + slot * P::kW2Slot, ab = sA2 + (uint32_t)kb * kTileM * kRowB;
 #pragma unroll
@@ -306,6 +325,7 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
                 }
                 umma_commit(bar(B_H2FULL));
             }
+            if (dbg && blockIdx.x == 0) { dbg[0] = t_x; dbg[1] = t_a2; dbg[2] = t_w2; dbg[3] = tcount; }
         }
     } else {
         // ================= epilogue warps: thread = (row, column group) =================
@@ -314,36 +334,62 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
         const int et = threadIdx.x;                                       // 0 .. kEpiThreads-1
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t xsw = (((uint32_t)r >> 1) & 3u);
+        constexpr int kXPer = (kTileM * IN + kEpiThreads - 1) / kEpiThreads;
+        float xreg[kXPer];
+        auto load_x = [&](int64_t t) {
+            const int64_t r0 = t * kTileM;
+#pragma unroll
+            for (int i = 0; i < kXPer; i++) {
+                const int v = et + i * kEpiThreads;
+                const int rr = v / IN, k = v - rr * IN;
+                xreg[i] = (v < kTileM * IN && r0 + rr < n) ? __ldcs(obs + (r0 + rr) * ld + k) : 0.f;
+            }
+        };
+        load_x(blockIdx.x);
         uint32_t tcount = 0;
+        long long e_x = 0, e_w1 = 0, e_1 = 0, e_w2 = 0, e_2 = 0, t0 = clock64(), t1;
+        const long long t_begin = t0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
             const uint32_t ph = tcount & 1u;
             const int64_t row0 = tile * kTileM;
             const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
-            // ---- observation tile -> 16-bit (hi [+ lo residual]), swizzled.  X may be overwritten here: the layer-1
-            //      MMAs of the previous tile completed before its H1FULL, which every epilogue thread has waited on. ----
-            for (int v = et; v < kTileM * IN; v += kEpiThreads) {
-                const int rr = v / IN, k = v - rr * IN;
-                const float x = rr < rows ? __ldcs(obs + (row0 + rr) * ld + k) : 0.f;
-                const OpT hi = to_op<OpT>(x);
-                *reinterpret_cast<OpT *>(sm + P::x + sw64_off(rr, k)) = hi;
-                if (kSplit) *reinterpret_cast<OpT *>(sm + P::x + kTileM * kRowB + sw64_off(rr, k)) = to_op<OpT>(x - op_to_float(hi));
+            // ---- observation tile (prefetched into registers one tile ahead) -> 16-bit hi [+ lo residual], swizzled.
+            //      X may be overwritten here: the layer-1 MMAs of the previous tile completed before its H1FULL, which
+            //      every epilogue thread has waited on. ----
+#pragma unroll
+            for (int i = 0; i < kXPer; i++) {
+                const int v = et + i * kEpiThreads;
+                if (v < kTileM * IN) {
+                    const int rr = v / IN, k = v - rr * IN;
+                    const float x = xreg[i];
+                    const OpT hi = to_op<OpT>(x);
+                    *reinterpret_cast<OpT *>(sm + P::x + sw64_off(rr, k)) = hi;
+                    if (kSplit) *reinterpret_cast<OpT *>(sm + P::x + kTileM * kRowB + sw64_off(rr, k)) = to_op<OpT>(x - op_to_float(hi));
+                }
             }
             fence_proxy_async();
             mbar_arrive(bar(B_XFULL));
+            load_x(tile + gridDim.x);                                     // in flight during this tile's epilogues
+            t1 = clock64(); e_x += t1 - t0; t0 = t1;
             // ---- epilogue 1: LayerNorm + ReLU over H1 columns -> A2 (16-bit, UMMA image) ----
             mbar_wait(bar(B_H1FULL), ph);
+            t1 = clock64(); e_w1 += t1 - t0; t0 = t1;
             tc_fence_after();
             uint32_t v[32];
-            float sum = 0.f, sq = 0.f;
+            float sum, sq;
+            float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ch = 0; ch < NCH1; ch++) {
                 if (ch % kGroups != grp) continue;
                 tmem_ld_chunk<N1>(trow, ch, v);
                 tmem_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j++) { const float x = __uint_as_float(v[j]); sum += x; sq = fmaf(x, x, sq); }   // columns >= N1 read as 0
+                for (int j = 0; j < 16; j++) {                             // packed fp32x2 (FADD2 / FFMA2); columns >= N1 read as 0
+                    const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    s2 = __fadd2_rn(s2, x); q2 = __ffma2_rn(x, x, q2);
+                }
             }
-            red1[grp * kTileM + r] = make_float2(sum, sq);
+            red1[grp * kTileM + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
             named_bar_sync(1, kEpiThreads);
             sum = 0.f; sq = 0.f;
 #pragma unroll
@@ -351,6 +397,7 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
             float mean = sum * (1.0f / H1);
             float rstd = rsqrtf(fmaxf(sq * (1.0f / H1) - mean * mean, 0.f) + 1e-5f);
             float nmr = -mean * rstd;
+            float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
 #pragma unroll
             for (int ch = 0; ch < NCH1; ch++) {
                 if (ch % kGroups != grp) continue;
@@ -361,32 +408,41 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
                 for (int q = 0; q < 4; q++) {                             // 4 chunks of 8 columns = 16 B each
                     const float4 g0 = *reinterpret_cast<const float4 *>(pg1 + ch * 32 + q * 8), g1 = *reinterpret_cast<const float4 *>(pg1 + ch * 32 + q * 8 + 4);
                     const float4 e0 = *reinterpret_cast<const float4 *>(pbe1 + ch * 32 + q * 8), e1 = *reinterpret_cast<const float4 *>(pbe1 + ch * 32 + q * 8 + 4);
-                    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-                    float y[8];
+                    const float2 gg[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+                    const float2 ee[4] = {make_float2(e0.x, e0.y), make_float2(e0.z, e0.w), make_float2(e1.x, e1.y), make_float2(e1.z, e1.w)};
+                    uint32_t pk4[4];
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        y[j] = fmaxf(fmaf(fmaf(__uint_as_float(v[q * 8 + j]), rstd, nmr), gg[j], ee[j]), 0.f);
+                    for (int j = 0; j < 4; j++) {                          // y = relu(((x - mean) rstd) g + be): 2 x FFMA2, pack, packed max
+                        const float2 x = make_float2(__uint_as_float(v[q * 8 + 2 * j]), __uint_as_float(v[q * 8 + 2 * j + 1]));
+                        const float2 y = __ffma2_rn(__ffma2_rn(x, rstd2, nmr2), gg[j], ee[j]);
+                        pk4[j] = pack2_relu<OpT>(y.x, y.y);
+                    }
                     uint4 pk;
-                    pk.x = pack2<OpT>(y[0], y[1]); pk.y = pack2<OpT>(y[2], y[3]); pk.z = pack2<OpT>(y[4], y[5]); pk.w = pack2<OpT>(y[6], y[7]);
+                    pk.x = pk4[0]; pk.y = pk4[1]; pk.z = pk4[2]; pk.w = pk4[3];
                     *reinterpret_cast<uint4 *>(blk + (((uint32_t)q ^ xsw) << 4)) = pk;
                 }
             }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar(B_A2FULL));
+            t1 = clock64(); e_1 += t1 - t0; t0 = t1;
             // ---- epilogue 2: LayerNorm + ReLU over H2 columns, dot with mu.weight, tanh ----
             mbar_wait(bar(B_H2FULL), ph);
+            t1 = clock64(); e_w2 += t1 - t0; t0 = t1;
             tc_fence_after();
-            sum = 0.f; sq = 0.f;
+            s2 = make_float2(0.f, 0.f); q2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ch = 0; ch < NCH2; ch++) {
                 if (ch % kGroups != grp) continue;
                 tmem_ld_chunk<N2>(trow, ch, v);
                 tmem_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j++) { const float x = __uint_as_float(v[j]); sum += x; sq = fmaf(x, x, sq); }   // pad columns are exactly 0
+                for (int j = 0; j < 16; j++) {                             // pad columns are exactly 0
+                    const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    s2 = __fadd2_rn(s2, x); q2 = __ffma2_rn(x, x, q2);
+                }
             }
-            red2[grp * kTileM + r] = make_float2(sum, sq);
+            red2[grp * kTileM + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
             named_bar_sync(1, kEpiThreads);
             sum = 0.f; sq = 0.f;
 #pragma unroll
@@ -394,7 +450,8 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
             mean = sum * (1.0f / H2);
             rstd = rsqrtf(fmaxf(sq * (1.0f / H2) - mean * mean, 0.f) + 1e-5f);
             nmr = -mean * rstd;
-            float dot = 0.f;
+            rstd2 = make_float2(rstd, rstd); nmr2 = make_float2(nmr, nmr);
+            float2 dot2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ch = 0; ch < NCH2; ch++) {
                 if (ch % kGroups != grp) continue;
@@ -404,12 +461,16 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
                 for (int q = 0; q < 8; q++) {
                     const float4 g0 = *reinterpret_cast<const float4 *>(pg2 + ch * 32 + q * 4), e0 = *reinterpret_cast<const float4 *>(pbe2 + ch * 32 + q * 4),
                                  w0 = *reinterpret_cast<const float4 *>(pw3 + ch * 32 + q * 4);
-                    dot = fmaf(fmaxf(fmaf(fmaf(__uint_as_float(v[q * 4 + 0]), rstd, nmr), g0.x, e0.x), 0.f), w0.x, dot);
-                    dot = fmaf(fmaxf(fmaf(fmaf(__uint_as_float(v[q * 4 + 1]), rstd, nmr), g0.y, e0.y), 0.f), w0.y, dot);
-                    dot = fmaf(fmaxf(fmaf(fmaf(__uint_as_float(v[q * 4 + 2]), rstd, nmr), g0.z, e0.z), 0.f), w0.z, dot);
-                    dot = fmaf(fmaxf(fmaf(fmaf(__uint_as_float(v[q * 4 + 3]), rstd, nmr), g0.w, e0.w), 0.f), w0.w, dot);
+                    const float2 xa = make_float2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]));
+                    const float2 xb = make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                    float2 ya = __ffma2_rn(__ffma2_rn(xa, rstd2, nmr2), make_float2(g0.x, g0.y), make_float2(e0.x, e0.y));
+                    float2 yb = __ffma2_rn(__ffma2_rn(xb, rstd2, nmr2), make_float2(g0.z, g0.w), make_float2(e0.z, e0.w));
+                    ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
+                    dot2 = __ffma2_rn(ya, make_float2(w0.x, w0.y), dot2);
+                    dot2 = __ffma2_rn(yb, make_float2(w0.z, w0.w), dot2);
                 }
             }
+            const float dot = dot2.x + dot2.y;
             tc_fence_before();
             mbar_arrive(bar(B_TMEMFREE));
             red3[grp * kTileM + r] = dot;
@@ -420,6 +481,10 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
                 for (int g = 0; g < kGroups; g++) d += red3[g * kTileM + r];
                 out[row0 + r] = tanhf(d);
             }
+            t1 = clock64(); e_2 += t1 - t0; t0 = t1;
+        }
+        if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+            dbg[4] = e_x; dbg[5] = e_w1; dbg[6] = e_1; dbg[7] = e_w2; dbg[8] = e_2; dbg[9] = clock64() - t_begin;
         }
     }
     // ---------------- teardown ----------------
@@ -431,6 +496,8 @@ __global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const c
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
     }
 }
+
+unsigned long long *g_tc_dbg = nullptr;      // optional device buffer for the per-phase cycle counters (tt_debug_set_tc_profile)
 
 template <typename OpT, bool kSplit, int kGroups>
 int launch_tc(const char *w1img, const char *w2img, const tt_actor_dev &A, const float *d_obs, int64_t ld, int64_t n, float *d_mu,
@@ -445,7 +512,7 @@ int launch_tc(const char *w1img, const char *w2img, const tt_actor_dev &A, const
     }
     const int64_t ntiles = (n + kTileM - 1) / kTileM;
     const int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
-    kern<<<grid, 128 * kGroups + 64, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu);
+    kern<<<grid, 128 * kGroups + 64, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, g_tc_dbg);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
@@ -453,6 +520,8 @@ int launch_tc(const char *w1img, const char *w2img, const tt_actor_dev &A, const
 }  // namespace
 
 namespace tt {
+
+void set_tc_profile_buffer(unsigned long long *d) { g_tc_dbg = d; }
 
 bool actor_tc_supported(const tt_actor_dev &A) { return A.in_dim == IN && A.h1 == H1 && A.h2 == H2; }
 
@@ -478,3 +547,7 @@ int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t 
 }
 
 }  // namespace tt
+
+// Debug hook (not part of the public header): per-phase cycle counters of block 0 of the tensor-core actor.
+// d_buf: device buffer of >= 16 uint64, or NULL to switch profiling off.
+extern "C" void tt_debug_set_tc_profile(unsigned long long *d_buf) { tt::set_tc_profile_buffer(d_buf); }
