@@ -21,7 +21,7 @@ def hm():
     deps = [SRC, os.path.join(HERE, "..", "ddpg-trucktrailer_b200", "csrc", "tt_env_math.cuh"),
             os.path.join(HERE, "..", "ddpg-trucktrailer_b200", "csrc", "tt_consts.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-mavx2 -mfma", "-ffp-contract=fast", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"])
+        subprocess.check_call(["g++", "-O2", "-mavx2", "-mfma", "-ffp-contract=fast", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"])
     L = C.CDLL(LIB)
     L.hm_rng_normal.restype = C.c_float
     L.hm_rng_normal.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
