@@ -12,6 +12,7 @@
 // The 23-float observation rows ([N, ld_obs] row-major, the layout the actor and the replay ring consume)
 // are transposed through shared memory so that the global stores are coalesced.
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include "tt_common.cuh"
 #include "tt_consts.h"
@@ -40,6 +41,9 @@ struct tt_env {
 namespace {
 
 constexpr int kBlock = 128;
+#ifndef TT_ENV_MINBLOCKS_DEFAULT
+#define TT_ENV_MINBLOCKS_DEFAULT 4
+#endif
 
 __device__ __forceinline__ void load_regs(const EnvPtrs &p, int64_t i, EnvRegs &e) {
     const int64_t N = p.N;
@@ -96,8 +100,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // K env steps per launch; state stays in registers across the K steps.
-template <bool kInfo>
-__global__ void __launch_bounds__(kBlock) env_step_kernel(EnvPtrs p, StepConsts k, const float *__restrict__ actions,
+template <bool kInfo, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p, StepConsts k, const float *__restrict__ actions,
                                                           int K, int auto_reset, float *__restrict__ obs, int64_t ld,
                                                           float *__restrict__ reward, uint8_t *__restrict__ done,
                                                           tt_step_info info, uint64_t seed, uint64_t gid0) {
@@ -344,14 +348,19 @@ int tt_env_step_k(tt_env *env, const float *d_actions, int32_t K, int32_t auto_r
     tt_step_info inf;
     memset(&inf, 0, sizeof inf);
     const bool want = info && (info->d_comps || info->d_violation || info->d_flags || info->d_success);
+    // occupancy knob (registers per thread): TT_ENV_MINBLOCKS = 4 (128 regs) | 5 (96) | 6 (80) | 8 (64, spills)
+    static const int variant = [] { const char *e = getenv("TT_ENV_MINBLOCKS"); return e ? atoi(e) : TT_ENV_MINBLOCKS_DEFAULT; }();
+#define TT_LAUNCH_STEP(INFO, MB)                                                                                          \
+    env_step_kernel<INFO, MB><<<grid, kBlock, 0, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs, ld_obs, d_reward, \
+                                                      d_done, inf, env->seed, env->gid0)
     if (want) {
         inf = *info;
-        env_step_kernel<true><<<grid, kBlock, 0, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs, ld_obs, d_reward,
-                                                      d_done, inf, env->seed, env->gid0);
-    } else {
-        env_step_kernel<false><<<grid, kBlock, 0, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs, ld_obs, d_reward,
-                                                       d_done, inf, env->seed, env->gid0);
-    }
+        TT_LAUNCH_STEP(true, 4);
+    } else if (variant == 5) TT_LAUNCH_STEP(false, 5);
+    else if (variant == 6) TT_LAUNCH_STEP(false, 6);
+    else if (variant == 8) TT_LAUNCH_STEP(false, 8);
+    else TT_LAUNCH_STEP(false, 4);
+#undef TT_LAUNCH_STEP
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     if (auto_reset) { tick_kernel<<<1, 1, 0, s>>>(env->p.iter, (uint32_t)K); TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK(); }
     return TT_OK;

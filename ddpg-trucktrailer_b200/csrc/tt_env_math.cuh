@@ -35,6 +35,42 @@
 namespace ttm {
 
 // ---------------------------------------------------------------------------------------------------
+// float64 literals.  As immediates every double costs two UMOV (32-bit halves) in front of the DFMA that uses
+// it, which doubled the instruction count of the float64 polynomial sections; from __constant__ memory the
+// DFMA reads them as a constant-bank operand for free.  The host build uses the same values from a plain array.
+// ---------------------------------------------------------------------------------------------------
+#define TTM_F64_TABLE                                                                                                  \
+    /* 0..5   fdlibm __kernel_sin S1..S6 */                                                                             \
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,  \
+    -2.50507602534068634195e-08, 1.58969099521155010221e-10,                                                           \
+    /* 6..11  fdlibm __kernel_cos C1..C6 */                                                                             \
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,  \
+    2.08757232129817482790e-09, -1.13596475577881948265e-11,                                                           \
+    /* 12..14 2/pi, pi/2 hi, pi/2 lo */                                                                                 \
+    6.36619772367581382433e-01, 1.57079632679489655800e+00, 6.12323399573676603587e-17,                                \
+    /* 15..18 Taylor sin: -1/3!, 1/5!, -1/7!, 1/9! */                                                                   \
+    -1.6666666666666666e-01, 8.3333333333333332e-03, -1.9841269841269841e-04, 2.7557319223985893e-06,                  \
+    /* 19..22 Taylor cos: -1/2!, 1/4!, -1/6!, 1/8! */                                                                   \
+    -0.5, 4.1666666666666664e-02, -1.3888888888888889e-03, 2.4801587301587302e-05,                                     \
+    /* 23..37 Dormand-Prince a21 | a31 a32 | a41 a42 a43 | a51..a54 | a61..a65 (scipy rk.py:541-549) */                 \
+    1.0 / 5, 3.0 / 40, 9.0 / 40, 44.0 / 45, -56.0 / 15, 32.0 / 9, 19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561,     \
+    -212.0 / 729, 9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656,                              \
+    /* 38..42 c2..c6 */                                                                                                  \
+    1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0,                                                                            \
+    /* 43..48 b1..b6 (rk.py:550) */                                                                                      \
+    35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84
+static const double kF64Host[] = {TTM_F64_TABLE};
+#if defined(__CUDACC__)
+static __constant__ double kF64Dev[] = {TTM_F64_TABLE};
+#endif
+#if defined(__CUDA_ARCH__)
+#define TTM_K(i) kF64Dev[i]
+#else
+#define TTM_K(i) kF64Host[i]
+#endif
+enum { K_S = 0, K_C = 6, K_2OPI = 12, K_PIO2H = 13, K_PIO2L = 14, K_TS = 15, K_TC = 19, K_A = 23, K_CN = 38, K_B = 43 };
+
+// ---------------------------------------------------------------------------------------------------
 // constants derived once on the host from tt_env_cfg (passed to kernels by value -> constant bank)
 // ---------------------------------------------------------------------------------------------------
 struct StepConsts {
@@ -91,26 +127,26 @@ struct StepOut {
 // float64 sin/cos on |r| <= pi/4 (fdlibm __kernel_sin/__kernel_cos minimax coefficients, < 1 ulp)
 TT_HD void sincos_pio4_f64(double r, double &s, double &c) {
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, TTM_K(K_S + 5), TTM_K(K_S + 4));
+    ps = fma(z, ps, TTM_K(K_S + 3));
+    ps = fma(z, ps, TTM_K(K_S + 2));
+    ps = fma(z, ps, TTM_K(K_S + 1));
+    ps = fma(z, ps, TTM_K(K_S + 0));
     s = fma(r * z, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, TTM_K(K_C + 5), TTM_K(K_C + 4));
+    pc = fma(z, pc, TTM_K(K_C + 3));
+    pc = fma(z, pc, TTM_K(K_C + 2));
+    pc = fma(z, pc, TTM_K(K_C + 1));
+    pc = fma(z, pc, TTM_K(K_C + 0));
     c = fma(z * z, pc, fma(z, -0.5, 1.0));
 }
 
 // reduce x to r in [-pi/4, pi/4], quadrant q (x = r + q*pi/2); |x| up to ~1e5 keeps < 1e-15 error
 TT_HD double reduce_pio2(double x, int &q) {
-    const double k = rint(x * 6.36619772367581382433e-01);
+    const double k = rint(x * TTM_K(K_2OPI));
     q = (int)k;
-    double r = fma(-k, 1.57079632679489655800e+00, x);
-    return fma(-k, 6.12323399573676603587e-17, r);
+    double r = fma(-k, TTM_K(K_PIO2H), x);
+    return fma(-k, TTM_K(K_PIO2L), r);
 }
 
 TT_HD void sincos_f64(double x, double &s, double &c) {
@@ -142,13 +178,13 @@ TT_HD void sincos_f32_of_f64(double x, float &s, float &c) {
 // Taylor sin/cos of a SMALL float64 angle (|d| <~ 0.3; truncation < 4e-14 there, < 2e-17 at 0.15)
 TT_HD void sincos_small_f64(double d, double &s, double &c) {
     const double z = d * d;
-    double ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);
-    ps = fma(z, ps, 8.3333333333333332e-03);
-    ps = fma(z, ps, -1.6666666666666666e-01);
+    double ps = fma(z, TTM_K(K_TS + 3), TTM_K(K_TS + 2));
+    ps = fma(z, ps, TTM_K(K_TS + 1));
+    ps = fma(z, ps, TTM_K(K_TS + 0));
     s = fma(d * z, ps, d);
-    double pc = fma(z, 2.4801587301587302e-05, -1.3888888888888889e-03);
-    pc = fma(z, pc, 4.1666666666666664e-02);
-    pc = fma(z, pc, -0.5);
+    double pc = fma(z, TTM_K(K_TC + 3), TTM_K(K_TC + 2));
+    pc = fma(z, pc, TTM_K(K_TC + 1));
+    pc = fma(z, pc, TTM_K(K_TC + 0));
     c = fma(z, pc, 1.0);
 }
 
@@ -300,8 +336,13 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
     double delta = (double)action;
     delta = delta < -k.steer_max ? -k.steer_max : (delta > k.steer_max ? k.steer_max : delta);
     double sdl, cdl;
-    sincos_f64(delta, sdl, cdl);
-    const double hw = k.h * (k.vL1 * (sdl / cdl));          // psi1 increment: psi1' = (v/L1) tan(delta) is constant
+    sincos_pio4_f64(delta, sdl, cdl);                        // |delta| <= steer_max <= pi/4: no range reduction
+    // tan(delta) = sdl / cdl without a float64 division: float32 quotient refined by one Newton step (err ~1e-14)
+    const float cf = (float)cdl;
+    const float t0f = (float)sdl / cf;
+    const double t0 = (double)t0f;
+    const double tand = fma(fma(-t0, cdl, sdl), (double)(1.0f / cf), t0);
+    const double hw = k.h * (k.vL1 * tand);                  // psi1 increment: psi1' = (v/L1) tan(delta) is constant
 
     // ---- base trig ----
     double S0, C0;
@@ -310,23 +351,13 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
     sincos_f32_of_f64(e.psi2, s2b, c2b);
     const float S0f = (float)S0, C0f = (float)C0;
 
-    // ---- Dormand-Prince 5 (scipy rk.py:541-550 tableau), theta/psi2 in float64, positions in float32 ----
-    const double A[6][5] = {
-        {0, 0, 0, 0, 0},
-        {1.0 / 5, 0, 0, 0, 0},
-        {3.0 / 40, 9.0 / 40, 0, 0, 0},
-        {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0},
-        {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0},
-        {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656}};
-    const double Cn[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1};
-    const double B[6] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
-
+    // ---- Dormand-Prince 5 (scipy rk.py:541-550 tableau, TTM_K), theta/psi2 in float64, positions in float32 ----
     double u[6];                                             // psi2' at the stages = (v/L2) sin(theta_j)
     u[0] = k.vL2 * S0;
     float ax1, ay1, ax2, ay2;                                // sum_j b_j * (unit velocity components)
     {
         const float s1b = fmaf(S0f, c2b, C0f * s2b), c1b = fmaf(C0f, c2b, -S0f * s2b);
-        const float b = (float)B[0];
+        const float b = (float)(35.0 / 384);
         ax1 = b * c1b; ay1 = b * s1b; ax2 = b * (C0f * c2b); ay2 = b * (C0f * s2b);
     }
 #if defined(__CUDA_ARCH__)
@@ -337,20 +368,20 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int m = 0; m < j; m++) acc = fma(A[j][m], u[m], acc);
+        for (int m = 0; m < j; m++) acc = fma(TTM_K(K_A + j * (j - 1) / 2 + m), u[m], acc);
         const double dpsi2 = k.h * acc;
-        const double dth = fma(Cn[j], hw, -dpsi2);
+        const double dth = fma(TTM_K(K_CN + j - 1), hw, -dpsi2);
         double sd, cd;
         sincos_small_f64(dth, sd, cd);
         const double sth = fma(S0, cd, C0 * sd);
         u[j] = k.vL2 * sth;
-        if (B[j] != 0.0) {
+        if (j != 1) {                                        // b2 = 0: stage 2 does not enter the position quadrature
             const float cthf = (float)fma(C0, cd, -S0 * sd), sthf = (float)sth;
             float sp, cp;
             sincos_small_f32((float)dpsi2, sp, cp);
             const float s2j = fmaf(s2b, cp, c2b * sp), c2j = fmaf(c2b, cp, -s2b * sp);
             const float s1j = fmaf(sthf, c2j, cthf * s2j), c1j = fmaf(cthf, c2j, -sthf * s2j);
-            const float b = (float)B[j];
+            const float b = j == 2 ? (float)(500.0 / 1113) : j == 3 ? (float)(125.0 / 192) : j == 4 ? (float)(-2187.0 / 6784) : (float)(11.0 / 84);
             ax1 = fmaf(b, c1j, ax1); ay1 = fmaf(b, s1j, ay1);
             ax2 = fmaf(b, cthf * c2j, ax2); ay2 = fmaf(b, cthf * s2j, ay2);
         }
@@ -359,7 +390,7 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int m = 0; m < 6; m++) accb = fma(B[m], u[m], accb);
+    for (int m = 0; m < 6; m++) if (m != 1) accb = fma(TTM_K(K_B + m), u[m], accb);
     const double dpsi2 = k.h * accb;
     // goal offset of the trailer BEFORE the move (for the distance decrement below)
     const float dxp = (float)((double)e.gx - e.x2), dyp = (float)((double)e.gy - e.y2);
