@@ -28,7 +28,12 @@ static inline ttm::StepConsts tt_make_consts(const tt_env_cfg &c) {
     k.sy_lo = c.start_y_lo; k.sy_w = c.start_y_hi - c.start_y_lo;
     k.syaw_lo = c.start_yaw_lo; k.syaw_w = c.start_yaw_hi - c.start_yaw_lo;
     k.gx = c.goal_x; k.gy = c.goal_y; k.gyaw = c.goal_yaw;
-    k.hv = (float)(c.dt * c.v1x);
+    k.hv_fix = (float)(c.dt * c.v1x * ttm::kPosScale);
+    k.pos_inv = (float)(1.0 / ttm::kPosScale); k.pos_scale_d = ttm::kPosScale;
+    k.map_min_fix = ttm::pos_from_double(c.map_min); k.map_max_fix = ttm::pos_from_double(c.map_max);
+    k.maj_lo_fix = ttm::pos_from_double(c.map_min - 2.0); k.maj_hi_fix = ttm::pos_from_double(c.map_max + 2.0);
+    k.gx_fix = ttm::pos_from_double(c.goal_x); k.gy_fix = ttm::pos_from_double(c.goal_y);
+    k.sgy0 = (float)sin(c.goal_yaw); k.cgy0 = (float)cos(c.goal_yaw);
     const double w = c.map_max - c.map_min;
     k.mid = (float)((c.map_max + c.map_min) / 2.0); k.inv_half = (float)(2.0 / w);
     k.inv_maxd = (float)(1.0 / sqrt(w * w + w * w));

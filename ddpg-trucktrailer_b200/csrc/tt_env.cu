@@ -2,15 +2,21 @@
 // reset / state injection / readback / statistics.  Replaces Truck_trailer_Env_2.reset/step
 // (truck_trailer_sim/simv2.py:459-545) and RewardFunction (reward_functionv1.py) for the whole batch.
 //
-// Layout in HBM (struct-of-arrays inside the caller-provided workspace, every array 256 B aligned):
-//   st[6][N] f64   psi1 psi2 x1 y1 x2 y2            goal[N] float4   gx gy sin(gyaw) cos(gyaw)
-//   rsA[N] float4  closest cum first_steer ep_return rsB[N]  float4   g1 g2 g3 d0   (g = distance decrements)
-//   packed[N] u32  steps|emax|rmax-emax|stage bits|finished
-//   pose[4][N] f64 startx starty startyaw goalyaw   (written on reset only; host-visible attributes)
+// Layout in HBM (struct-of-arrays inside the caller-provided workspace, every array 256 B aligned; one 16 B
+// vector per env and array, so a warp touches 512 contiguous bytes per access):
+//   psi[N]  double2  psi1 psi2 (float64: the unstable hitch dynamics need it, see tt_env_math.cuh)
+//   pos[N]  int4     x1 y1 x2 y2 in 2^-25 m fixed point
+//   rsA[N]  float4   closest cum first_steer episode_return
+//   rsB[N]  float4   g1 g2 g3 d0                (g = per-step distance decrements)
+//   packed[N] u32    steps | emax | rmax-emax | stage bits | finished
+//   goal[N] int4     gx gy (fixed point) sin/cos(gyaw) bits -- only READ when per-env goals were injected
+//   pose[4][N] f64   startx starty startyaw goalyaw (written on reset only; host-visible attributes)
 //   stats[16] f64, iter u32
-// One thread owns one environment: all loads/stores are unit-stride across the warp (8 or 16 B per lane).
-// The 23-float observation rows ([N, ld_obs] row-major, the layout the actor and the replay ring consume)
-// are transposed through shared memory so that the global stores are coalesced.
+// One thread owns one environment.  The step kernel is persistent: a CTA walks over 128-env tiles and issues
+// the loads of its NEXT tile before computing the current one (register double buffer), so the DRAM latency
+// is hidden behind ~1.2 k instructions of arithmetic instead of relying on occupancy.  The 23-float
+// observation rows ([N, ld_obs] row-major, the layout the actor and the replay ring consume) are transposed
+// through shared memory so that the global stores are coalesced 16 B vectors.
 #include <new>
 #include <stdlib.h>
 #include <string.h>
@@ -21,9 +27,11 @@
 using namespace ttm;
 
 struct EnvPtrs {
-    double *st;          // [6][N]
-    float4 *goal, *rsA, *rsB;
+    double2 *psi;
+    int4 *pos;
+    float4 *rsA, *rsB;
     uint32_t *packed;
+    int4 *goal;
     double *pose;        // [4][N]
     double *stats;       // [16]
     uint32_t *iter;
@@ -36,6 +44,7 @@ struct tt_env {
     EnvPtrs p;
     uint64_t seed;
     uint64_t gid0;
+    bool per_env_goal;
 };
 
 namespace {
@@ -45,22 +54,37 @@ constexpr int kBlock = 128;
 #define TT_ENV_MINBLOCKS_DEFAULT 4
 #endif
 
-__device__ __forceinline__ void load_regs(const EnvPtrs &p, int64_t i, EnvRegs &e) {
-    const int64_t N = p.N;
-    e.psi1 = p.st[i]; e.psi2 = p.st[N + i]; e.x1 = p.st[2 * N + i]; e.y1 = p.st[3 * N + i];
-    e.x2 = p.st[4 * N + i]; e.y2 = p.st[5 * N + i];
-    const float4 g = __ldg(&p.goal[i]);
-    e.gx = g.x; e.gy = g.y; e.sgy = g.z; e.cgy = g.w;
-    const float4 a = p.rsA[i], b = p.rsB[i];
-    e.closest = a.x; e.cum = a.y; e.first_steer = a.z; e.ep_ret = a.w;
-    e.g1 = b.x; e.g2 = b.y; e.g3 = b.z; e.d0 = b.w;
-    e.packed = p.packed[i];
+// raw per-env words as they sit in HBM (the prefetch buffer)
+struct EnvRaw {
+    double2 psi;
+    int4 pos;
+    float4 a, b;
+    int4 goal;
+    uint32_t packed;
+    float action;
+};
+
+template <bool kGoal>
+__device__ __forceinline__ void load_raw(const EnvPtrs &p, int64_t i, const float *__restrict__ actions, EnvRaw &r) {
+    r.psi = p.psi[i]; r.pos = p.pos[i]; r.a = p.rsA[i]; r.b = p.rsB[i]; r.packed = p.packed[i];
+    if (kGoal) r.goal = __ldg(&p.goal[i]);
+    r.action = __ldcs(&actions[i]);
+}
+
+template <bool kGoal>
+__device__ __forceinline__ void unpack(const StepConsts &k, const EnvRaw &r, EnvRegs &e) {
+    e.psi1 = r.psi.x; e.psi2 = r.psi.y;
+    e.x1 = r.pos.x; e.y1 = r.pos.y; e.x2 = r.pos.z; e.y2 = r.pos.w;
+    e.closest = r.a.x; e.cum = r.a.y; e.first_steer = r.a.z; e.ep_ret = r.a.w;
+    e.g1 = r.b.x; e.g2 = r.b.y; e.g3 = r.b.z; e.d0 = r.b.w;
+    e.packed = r.packed;
+    if (kGoal) { e.gx = r.goal.x; e.gy = r.goal.y; e.sgy = __int_as_float(r.goal.z); e.cgy = __int_as_float(r.goal.w); }
+    else { e.gx = k.gx_fix; e.gy = k.gy_fix; e.sgy = k.sgy0; e.cgy = k.cgy0; }
 }
 
 __device__ __forceinline__ void store_dyn(const EnvPtrs &p, int64_t i, const EnvRegs &e) {
-    const int64_t N = p.N;
-    p.st[i] = e.psi1; p.st[N + i] = e.psi2; p.st[2 * N + i] = e.x1; p.st[3 * N + i] = e.y1;
-    p.st[4 * N + i] = e.x2; p.st[5 * N + i] = e.y2;
+    p.psi[i] = make_double2(e.psi1, e.psi2);
+    p.pos[i] = make_int4(e.x1, e.y1, e.x2, e.y2);
     p.rsA[i] = make_float4(e.closest, e.cum, e.first_steer, e.ep_ret);
     p.rsB[i] = make_float4(e.g1, e.g2, e.g3, e.d0);
     p.packed[i] = e.packed;
@@ -69,7 +93,7 @@ __device__ __forceinline__ void store_dyn(const EnvPtrs &p, int64_t i, const Env
 __device__ __forceinline__ void store_episode_consts(const EnvPtrs &p, int64_t i, const EnvRegs &e, double sx, double sy,
                                                      double syaw, double gyaw) {
     const int64_t N = p.N;
-    p.goal[i] = make_float4(e.gx, e.gy, e.sgy, e.cgy);
+    p.goal[i] = make_int4(e.gx, e.gy, __float_as_int(e.sgy), __float_as_int(e.cgy));
     p.pose[i] = sx; p.pose[N + i] = sy; p.pose[2 * N + i] = syaw; p.pose[3 * N + i] = gyaw;
 }
 
@@ -99,99 +123,140 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// K env steps per launch; state stays in registers across the K steps.
-template <bool kInfo, int kMinBlocks>
+// K env steps per launch; state stays in registers across the K steps; persistent over 128-env tiles.
+// kMinBlocks == 7 is a memory-traffic-only probe (no arithmetic) used for roofline analysis.
+template <bool kInfo, bool kGoal, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p, StepConsts k, const float *__restrict__ actions,
-                                                          int K, int auto_reset, float *__restrict__ obs, int64_t ld,
-                                                          float *__restrict__ reward, uint8_t *__restrict__ done,
-                                                          tt_step_info info, uint64_t seed, uint64_t gid0) {
-    __shared__ __align__(16) float tile[kBlock * TT_OBS_DIM];
-    __shared__ float sstat[12][kBlock / 32];
+                                                                      int K, int auto_reset, float *__restrict__ obs, int64_t ld,
+                                                                      float *__restrict__ reward, uint8_t *__restrict__ done,
+                                                                      tt_step_info info, uint64_t seed, uint64_t gid0) {
+    // observation tiles: double buffered; full tiles leave through the bulk-copy engine (cp.async.bulk shared ->
+    // global), which drains them while the CTA already computes its next tile
+    __shared__ __align__(128) float tiles[2][kBlock * TT_OBS_DIM];
+    uint32_t tbuf = 0;
+    const bool bulk_ok = obs != nullptr && ld == TT_OBS_DIM && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
     const int64_t N = p.N;
-    const int64_t row0 = (int64_t)blockIdx.x * kBlock;
-    const int64_t i = row0 + threadIdx.x;
-    const bool active = i < N;
-    const int rows = (int)((N - row0) < kBlock ? (N - row0) : kBlock);
+    const int64_t ntiles = (N + kBlock - 1) / kBlock;
     const uint32_t t0 = *p.iter;
-
-    EnvRegs e;
-    if (active) load_regs(p, i, e);
     StatAcc sa;
     sa.steps = sa.episodes = sa.successes = sa.ret = sa.ret2 = sa.rew = 0.f;
 #pragma unroll
     for (int f = 0; f < 6; f++) sa.fl[f] = 0.f;
 
-    for (int j = 0; j < K; j++) {
-        StepOut o;
-        if (active) {
-            if (e.packed & PK_FINISHED) {
-                // frozen: no reset since `done` -> reward 0, done 1, observation of the frozen state, steering 0
-                float s2, c2, s1, c1;
-                sincos_f32_of_f64(e.psi2, s2, c2);
-                sincos_f32_of_f64(e.psi1, s1, c1);
-                pack_obs(k, e, s1, c1, s2, c2, fmaf(s1, c2, -c1 * s2), fmaf(c1, c2, s1 * s2), 0.0f, 1.0f, o.obs);
-                o.reward = 0.f; o.done = true; o.success = false; o.flags = 0u; o.viol = 0u;
+    EnvRaw nxt;
+    {
+        const int64_t i0 = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+        if (i0 < N) load_raw<kGoal>(p, i0, actions, nxt);
+    }
+    for (int64_t tileidx = blockIdx.x; tileidx < ntiles; tileidx += gridDim.x) {
+        const int64_t row0 = tileidx * kBlock;
+        const int64_t i = row0 + threadIdx.x;
+        const bool active = i < N;
+        const int rows = (int)((N - row0) < kBlock ? (N - row0) : kBlock);
+        const EnvRaw cur = nxt;
+        {   // prefetch the next tile of this CTA: in flight during the whole computation below
+            const int64_t in = i + (int64_t)gridDim.x * kBlock;
+            if (in < N) load_raw<kGoal>(p, in, actions, nxt);
+        }
+        EnvRegs e;
+        if (active) unpack<kGoal>(k, cur, e);
+
+        for (int j = 0; j < K; j++) {
+            StepOut o;
+            if (active) {
+                if (e.packed & PK_FINISHED) {
+                    // frozen: no reset since `done` -> reward 0, done 1, observation of the frozen state, steering 0
+                    float s2, c2, s1, c1;
+                    sincos_f32_of_f64(e.psi2, s2, c2);
+                    sincos_f32_of_f64(e.psi1, s1, c1);
+                    pack_obs(k, e, s1, c1, s2, c2, fmaf(s1, c2, -c1 * s2), fmaf(c1, c2, s1 * s2), 0.0f, 1.0f, o.obs);
+                    o.reward = 0.f; o.done = true; o.success = false; o.flags = 0u; o.viol = 0u;
 #pragma unroll
-                for (int c = 0; c < TT_NCOMP; c++) o.comps[c] = 0.f;
-            } else {
-                const float a = __ldcs(&actions[(int64_t)j * N + i]);
-                env_step<kInfo>(k, e, a, o);
-                sa.steps += 1.f; sa.rew += o.reward;
-                if (o.done) {
-                    sa.episodes += 1.f; sa.successes += o.success ? 1.f : 0.f;
-                    sa.ret += e.ep_ret; sa.ret2 += e.ep_ret * e.ep_ret;
+                    for (int c = 0; c < TT_NCOMP; c++) o.comps[c] = 0.f;
+                } else {
+                    const float a = j == 0 ? cur.action : __ldcs(&actions[(int64_t)j * N + i]);
+                    if (kMinBlocks == 7) {
+                        e.psi1 += a; e.psi2 += a; e.x1 += 1; e.y1 += 2; e.x2 += 3; e.y2 += e.gx;
+                        e.closest += a; e.cum += e.sgy; e.first_steer += e.cgy; e.g1 += a; e.g2 += a; e.g3 += a; e.packed += 1;
 #pragma unroll
-                    for (int f = 0; f < 6; f++) sa.fl[f] += (o.flags >> f) & 1u ? 1.f : 0.f;
+                        for (int c = 0; c < TT_OBS_DIM; c++) o.obs[c] = (float)e.x1 + (float)c;
+                        o.reward = e.closest; o.done = false; o.success = false; o.flags = 0; o.viol = 0;
+                    } else
+                        env_step<kInfo>(k, e, a, o);
+                    sa.steps += 1.f; sa.rew += o.reward;
+                    if (o.done) {
+                        sa.episodes += 1.f; sa.successes += o.success ? 1.f : 0.f;
+                        sa.ret += e.ep_ret; sa.ret2 += e.ep_ret * e.ep_ret;
+#pragma unroll
+                        for (int f = 0; f < 6; f++) sa.fl[f] += (o.flags >> f) & 1u ? 1.f : 0.f;
+                    }
                 }
-            }
-            const int64_t oi = (int64_t)j * N + i;
-            if (reward) __stcs(&reward[oi], o.reward);
-            if (done) done[oi] = o.done ? 1 : 0;
-            if (kInfo) {
-                if (info.d_comps) {
+                const int64_t oi = (int64_t)j * N + i;
+                if (reward) __stcs(&reward[oi], o.reward);
+                if (done) done[oi] = o.done ? 1 : 0;
+                if (kInfo) {
+                    if (info.d_comps) {
 #pragma unroll
-                    for (int c = 0; c < TT_NCOMP; c++) info.d_comps[((int64_t)j * TT_NCOMP + c) * N + i] = o.comps[c];
+                        for (int c = 0; c < TT_NCOMP; c++) info.d_comps[((int64_t)j * TT_NCOMP + c) * N + i] = o.comps[c];
+                    }
+                    if (info.d_violation) info.d_violation[oi] = (uint8_t)o.viol;
+                    if (info.d_flags) info.d_flags[oi] = (uint8_t)o.flags;
+                    if (info.d_success) info.d_success[oi] = o.success ? 1 : 0;
                 }
-                if (info.d_violation) info.d_violation[oi] = (uint8_t)o.viol;
-                if (info.d_flags) info.d_flags[oi] = (uint8_t)o.flags;
-                if (info.d_success) info.d_success[oi] = o.success ? 1 : 0;
+                if (o.done && !(e.packed & PK_FINISHED)) {
+                    if (auto_reset) {
+                        double sx, sy, syaw;
+                        rng_pose(k, seed, (uint32_t)(gid0 + i), t0 + (uint32_t)j, sx, sy, syaw);
+                        reset_from_pose(k, e, sx, sy, syaw, k.gx, k.gy, k.gyaw, nullptr);
+                        store_episode_consts(p, i, e, sx, sy, syaw, k.gyaw);
+                    } else e.packed |= PK_FINISHED;
+                }
             }
             if (obs) {
+                float *tile = tiles[tbuf];
+                __syncthreads();                 // thread 0 has waited for the bulk store that last read this buffer
+                if (active) {
 #pragma unroll
-                for (int c = 0; c < TT_OBS_DIM; c++) tile[threadIdx.x * TT_OBS_DIM + c] = o.obs[c];
-            }
-            if (o.done && !(e.packed & PK_FINISHED)) {
-                if (auto_reset) {
-                    double sx, sy, syaw;
-                    rng_pose(k, seed, (uint32_t)(gid0 + i), t0 + (uint32_t)j, sx, sy, syaw);
-                    reset_from_pose(k, e, sx, sy, syaw, k.gx, k.gy, k.gyaw, nullptr);
-                    store_episode_consts(p, i, e, sx, sy, syaw, k.gyaw);
-                } else e.packed |= PK_FINISHED;
+                    for (int c = 0; c < TT_OBS_DIM; c++) tile[threadIdx.x * TT_OBS_DIM + c] = o.obs[c];
+                }
+                float *dst = obs + (int64_t)j * N * ld;
+                if (bulk_ok && rows == kBlock) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(dst + row0 * TT_OBS_DIM), "r"(src), "r"((uint32_t)(kBlock * TT_OBS_DIM * sizeof(float))) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the OTHER buffer is free again
+                    }
+                } else {
+                    __syncthreads();
+                    store_obs_tile(tile, dst, ld, row0, rows);
+                }
+                tbuf ^= 1u;
             }
         }
-        if (obs) {
-            __syncthreads();
-            store_obs_tile(tile, obs + (int64_t)j * N * ld, ld, row0, rows);
-            __syncthreads();
-        }
+        if (active) store_dyn(p, i, e);
     }
-    if (active) store_dyn(p, i, e);
 
-    // block-level statistics -> 12 atomics per block
-    float v[12] = {sa.steps, sa.episodes, sa.successes, sa.ret, sa.ret2, sa.rew,
-                   sa.fl[0], sa.fl[1], sa.fl[2], sa.fl[3], sa.fl[4], sa.fl[5]};
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all bulk stores complete
+
+    // statistics: steps and reward every launch, the episode counters only in warps that finished an episode
+    // (one warp-shuffle tree each; one double atomic per warp and statistic).  All lanes of the warp get here.
+    const int lane = threadIdx.x & 31;
+    {
+        const float rs = warp_sum(sa.rew), st = warp_sum(sa.steps);
+        if (lane == 0 && st != 0.f) { atomicAdd(&p.stats[0], (double)st); atomicAdd(&p.stats[5], (double)rs); }
+        if (__any_sync(0xffffffffu, sa.episodes != 0.f)) {
+            float v[10] = {sa.episodes, sa.successes, sa.ret, sa.ret2, sa.fl[0], sa.fl[1], sa.fl[2], sa.fl[3], sa.fl[4], sa.fl[5]};
+            const int slot[10] = {1, 2, 3, 4, 6, 7, 8, 9, 10, 11};
 #pragma unroll
-    for (int s = 0; s < 12; s++) {
-        const float r = warp_sum(v[s]);
-        if (lane == 0) sstat[s][wid] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) {
-        double tot = 0.0;
-#pragma unroll
-        for (int w = 0; w < kBlock / 32; w++) tot += (double)sstat[threadIdx.x][w];
-        if (tot != 0.0) atomicAdd(&p.stats[threadIdx.x], tot);
+            for (int s = 0; s < 10; s++) {
+                const float r = warp_sum(v[s]);
+                if (lane == 0 && r != 0.f) atomicAdd(&p.stats[slot[s]], (double)r);
+            }
+        }
     }
 }
 
@@ -226,8 +291,9 @@ __global__ void __launch_bounds__(kBlock) env_set_state_kernel(EnvPtrs p, StepCo
     const int64_t i = idx ? idx[j] : j;
     if (i < 0 || i >= p.N) return;
     EnvRegs e;
-    e.psi1 = state[6 * j]; e.psi2 = state[6 * j + 1]; e.x1 = state[6 * j + 2]; e.y1 = state[6 * j + 3];
-    e.x2 = state[6 * j + 4]; e.y2 = state[6 * j + 5];
+    e.psi1 = state[6 * j]; e.psi2 = state[6 * j + 1];
+    e.x1 = pos_from_double(state[6 * j + 2]); e.y1 = pos_from_double(state[6 * j + 3]);
+    e.x2 = pos_from_double(state[6 * j + 4]); e.y2 = pos_from_double(state[6 * j + 5]);
     float o[TT_OBS_DIM];
     begin_episode(k, e, start[3 * j], start[3 * j + 1], goal[3 * j], goal[3 * j + 1], goal[3 * j + 2], obs ? o : nullptr);
     store_dyn(p, i, e);
@@ -245,17 +311,25 @@ __global__ void __launch_bounds__(kBlock) env_get_state_kernel(EnvPtrs p, double
     const int64_t N = p.N;
     if (i >= N) return;
     if (state) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) state[6 * i + c] = p.st[c * N + i];
+        const double2 a = p.psi[i];
+        const int4 q = p.pos[i];
+        state[6 * i] = a.x; state[6 * i + 1] = a.y;
+        state[6 * i + 2] = pos_to_double(q.x); state[6 * i + 3] = pos_to_double(q.y);
+        state[6 * i + 4] = pos_to_double(q.z); state[6 * i + 5] = pos_to_double(q.w);
     }
     if (start) { start[3 * i] = p.pose[i]; start[3 * i + 1] = p.pose[N + i]; start[3 * i + 2] = p.pose[2 * N + i]; }
-    if (goal) { const float4 g = p.goal[i]; goal[3 * i] = g.x; goal[3 * i + 1] = g.y; goal[3 * i + 2] = p.pose[3 * N + i]; }
+    if (goal) { const int4 g = p.goal[i]; goal[3 * i] = pos_to_double(g.x); goal[3 * i + 1] = pos_to_double(g.y); goal[3 * i + 2] = p.pose[3 * N + i]; }
     const uint32_t pk = p.packed[i];
     if (steps) steps[i] = (int32_t)(pk & PK_STEPS_MASK);
     if (max_steps) max_steps[i] = (int32_t)((pk >> PK_EMAX_SHIFT) & PK_EMAX_MASK);
 }
 
 __global__ void tick_kernel(uint32_t *iter, uint32_t by) { *iter += by; }
+
+__global__ void __launch_bounds__(kBlock) env_init_goal_kernel(EnvPtrs p, StepConsts k) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < p.N) p.goal[i] = make_int4(k.gx_fix, k.gy_fix, __float_as_int(k.sgy0), __float_as_int(k.cgy0));
+}
 
 __global__ void stats_read_kernel(double *stats, double *out, int clear) {
     const int t = threadIdx.x;
@@ -281,13 +355,13 @@ int tt_env_default_cfg(tt_env_cfg *cfg) {
 static size_t env_layout(int64_t n, EnvPtrs *p, char *base) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = tt::align_up(off + bytes, 256); return o; };
-    const size_t o_st = take(sizeof(double) * 6 * n), o_goal = take(sizeof(float4) * n), o_a = take(sizeof(float4) * n),
-                 o_b = take(sizeof(float4) * n), o_pk = take(sizeof(uint32_t) * n),
+    const size_t o_psi = take(sizeof(double2) * n), o_pos = take(sizeof(int4) * n), o_a = take(sizeof(float4) * n),
+                 o_b = take(sizeof(float4) * n), o_pk = take(sizeof(uint32_t) * n), o_goal = take(sizeof(int4) * n),
                  o_pose = take(sizeof(double) * 4 * n), o_stats = take(sizeof(double) * TT_NSTATS), o_iter = take(256);
     if (p) {
-        p->st = reinterpret_cast<double *>(base + o_st); p->goal = reinterpret_cast<float4 *>(base + o_goal);
+        p->psi = reinterpret_cast<double2 *>(base + o_psi); p->pos = reinterpret_cast<int4 *>(base + o_pos);
         p->rsA = reinterpret_cast<float4 *>(base + o_a); p->rsB = reinterpret_cast<float4 *>(base + o_b);
-        p->packed = reinterpret_cast<uint32_t *>(base + o_pk);
+        p->packed = reinterpret_cast<uint32_t *>(base + o_pk); p->goal = reinterpret_cast<int4 *>(base + o_goal);
         p->pose = reinterpret_cast<double *>(base + o_pose); p->stats = reinterpret_cast<double *>(base + o_stats);
         p->iter = reinterpret_cast<uint32_t *>(base + o_iter); p->N = n;
     }
@@ -308,10 +382,14 @@ int tt_env_create(tt_env **out, const tt_env_cfg *cfg, int64_t n_envs, uint64_t 
     if (tt_device_count() <= 0) { tt::set_error("tt_env_create: no CUDA device (there is no CPU fallback)"); return TT_ERR_CUDA; }
     tt_env *e = new (std::nothrow) tt_env;
     TT_REQUIRE(e, "out of host memory");
-    e->cfg = *cfg; e->k = tt_make_consts(*cfg); e->seed = seed; e->gid0 = global_env_offset;
+    e->cfg = *cfg; e->k = tt_make_consts(*cfg); e->seed = seed; e->gid0 = global_env_offset; e->per_env_goal = false;
     env_layout(n_envs, &e->p, static_cast<char *>(d_workspace));
     cudaError_t err = cudaMemset(d_workspace, 0, tt_env_workspace_bytes(n_envs));
     if (err != cudaSuccess) { delete e; return tt::cuda_fail(err, "cudaMemset(workspace)"); }
+    env_init_goal_kernel<<<(unsigned)grid_for(n_envs), kBlock>>>(e->p, e->k);      // default goal everywhere
+    TT_COUNT_LAUNCH();
+    err = cudaGetLastError();
+    if (err != cudaSuccess) { delete e; return tt::cuda_fail(err, "env_init_goal_kernel"); }
     *out = e;
     return TT_OK;
 }
@@ -344,22 +422,30 @@ int tt_env_step_k(tt_env *env, const float *d_actions, int32_t K, int32_t auto_r
     TT_REQUIRE(K >= 1, "K < 1");
     TT_REQUIRE(!d_obs || ld_obs >= TT_OBS_DIM, "ld_obs < 23");
     cudaStream_t s = tt::as_stream(stream);
-    const unsigned grid = (unsigned)grid_for(env->p.N);
     tt_step_info inf;
     memset(&inf, 0, sizeof inf);
     const bool want = info && (info->d_comps || info->d_violation || info->d_flags || info->d_success);
-    // occupancy knob (registers per thread): TT_ENV_MINBLOCKS = 4 (128 regs) | 5 (96) | 6 (80) | 8 (64, spills)
+    // occupancy knob (registers per thread): TT_ENV_MINBLOCKS = 4 (128 regs) | 5 (96) | 6 (80) | 7 (traffic-only probe)
     static const int variant = [] { const char *e = getenv("TT_ENV_MINBLOCKS"); return e ? atoi(e) : TT_ENV_MINBLOCKS_DEFAULT; }();
-#define TT_LAUNCH_STEP(INFO, MB)                                                                                          \
-    env_step_kernel<INFO, MB><<<grid, kBlock, 0, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs, ld_obs, d_reward, \
-                                                      d_done, inf, env->seed, env->gid0)
+    const int64_t ntiles = grid_for(env->p.N);
+#define TT_LAUNCH_STEP(INFO, GOAL, MB)                                                                                          \
+    do {                                                                                                                        \
+        auto kern = env_step_kernel<INFO, GOAL, MB>;                                                                            \
+        static int per_sm = 0;                                                                                                  \
+        if (per_sm == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0) != cudaSuccess) per_sm = 4;  \
+        const int64_t cap = (int64_t)tt::sm_count() * (per_sm > 0 ? per_sm : 4);                                                \
+        kern<<<(unsigned)(ntiles < cap ? ntiles : cap), kBlock, 0, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs, ld_obs, \
+                                                                      d_reward, d_done, inf, env->seed, env->gid0);            \
+    } while (0)
+    const bool goal = env->per_env_goal;
     if (want) {
         inf = *info;
-        TT_LAUNCH_STEP(true, 4);
-    } else if (variant == 5) TT_LAUNCH_STEP(false, 5);
-    else if (variant == 6) TT_LAUNCH_STEP(false, 6);
-    else if (variant == 8) TT_LAUNCH_STEP(false, 8);
-    else TT_LAUNCH_STEP(false, 4);
+        if (goal) TT_LAUNCH_STEP(true, true, 4); else TT_LAUNCH_STEP(true, false, 4);
+    } else if (goal) TT_LAUNCH_STEP(false, true, 4);
+    else if (variant == 5) TT_LAUNCH_STEP(false, false, 5);
+    else if (variant == 6) TT_LAUNCH_STEP(false, false, 6);
+    else if (variant == 7) TT_LAUNCH_STEP(false, false, 7);
+    else TT_LAUNCH_STEP(false, false, 4);
 #undef TT_LAUNCH_STEP
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     if (auto_reset) { tick_kernel<<<1, 1, 0, s>>>(env->p.iter, (uint32_t)K); TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK(); }
@@ -383,6 +469,7 @@ int tt_env_set_state(tt_env *env, const int64_t *d_idx, int64_t n, const double 
     TT_REQUIRE(env && d_state && d_start && d_goal, "NULL argument");
     TT_REQUIRE(n > 0 && n <= env->p.N, "n out of range");
     TT_REQUIRE(!d_obs || ld_obs >= TT_OBS_DIM, "ld_obs < 23");
+    env->per_env_goal = true;      // injected goals may differ from the configured one: the step kernel reads goal[]
     env_set_state_kernel<<<(unsigned)grid_for(n), kBlock, 0, tt::as_stream(stream)>>>(env->p, env->k, d_idx, n, d_state,
                                                                                      d_start, d_goal, d_obs, ld_obs);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();

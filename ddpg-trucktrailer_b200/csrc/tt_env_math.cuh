@@ -11,7 +11,9 @@
 //     therefore end up far outside the 1e-4 parity bar, while errors in the position integrals are not fed
 //     back at all.  So the 1-D theta ODE (psi1' is constant within a step) is integrated in float64 with
 //     short polynomial rotations of (sin theta0, cos theta0) -- no libm call, ~215 DFMA-class ops -- and
-//     the four position integrals use float32 stage values accumulated into the float64 state.
+//     the four position integrals use float32 stage values; the positions themselves are kept as 32-bit FIXED
+//     POINT (2^-25 m = 3e-8 m steps over +-64 m): uniformly finer than float32 at map scale, half the bytes of
+//     float64, exact integer differences/comparisons, and no float64 arithmetic on the position path.
 //   * All sines/cosines of the stage angles and of the new state come from rotating one base pair per
 //     angle by the (small) stage increment; the observation needs no further trig and no atan2:
 //     sin/cos(heading_error) = -dy_local/d, -dx_local/d and the orientation tests compare cosines.
@@ -25,6 +27,11 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#if !defined(__CUDACC__)
+#include <algorithm>
+using std::max;
+using std::min;
+#endif
 
 #if defined(__CUDACC__)
 #define TT_HD __host__ __device__ __forceinline__
@@ -84,7 +91,12 @@ struct StepConsts {
     double L2;
     double sx_lo, sx_w, sy_lo, sy_w, syaw_lo, syaw_w;   // start-pose box   simv2.py:331-333
     double gx, gy, gyaw;        // default goal                             simv2.py:335-337
-    float  hv;                  // dt * v1x
+    float  hv_fix;              // dt * v1x * 2^25   (position increment in fixed-point units)
+    float  pos_inv;             // 2^-25
+    double pos_scale_d;         // 2^25
+    int32_t map_min_fix, map_max_fix, maj_lo_fix, maj_hi_fix;   // map bounds and the +-2 m "major" band, fixed point
+    int32_t gx_fix, gy_fix;     // default goal, fixed point
+    float  sgy0, cgy0;          // sin / cos of the default goal yaw
     float  mid, inv_half;       // map centre, 2 / width                    simv2.py:109-114
     float  inv_maxd;            // 1 / max_expected_distance                simv2.py:57
     float  pos_thr;             // 0.5                                      simv2.py:97
@@ -100,8 +112,10 @@ enum : uint32_t {
 
 // per-env persistent state, as held in registers
 struct EnvRegs {
-    double psi1, psi2, x1, y1, x2, y2;        // simv2.py:489 state
-    float  gx, gy, sgy, cgy;                   // goal position, sin/cos(goal yaw)
+    double psi1, psi2;                         // simv2.py:489 state: headings (float64) ...
+    int32_t x1, y1, x2, y2;                    // ... and positions (fixed point, 2^-25 m)
+    int32_t gx, gy;                            // goal position (fixed point)
+    float  sgy, cgy;                           // sin/cos(goal yaw)
     float  d0;                                 // hypot(goal - start), simv2.py:264 / reward_functionv1.py:34
     float  closest, cum, first_steer;          // reward_functionv1.py:99-109
     // distance_history / previous_distance (reward_functionv1.py:40-67) are kept as the last three per-step
@@ -211,6 +225,21 @@ TT_HD float fast_tanhf(float x) {   // 1 - 2/(e^{2x}+1); abs error ~1e-7, exact 
 
 TT_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
+// fixed-point positions
+constexpr double kPosScale = 33554432.0;        // 2^25
+TT_HD int32_t pos_from_double(double x) {
+    const double v = rint(x * kPosScale);
+    return v > 2147483520.0 ? 2147483520 : (v < -2147483520.0 ? -2147483520 : (int32_t)v);
+}
+TT_HD double pos_to_double(int32_t x) { return (double)x * (1.0 / kPosScale); }
+TT_HD int32_t f2i_rn(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rn(x);
+#else
+    return (int32_t)lrintf(x);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // observation packing: simv2.py:103-181 (index map in SURVEY.md section 8a row a5)
 // trig inputs: s1/c1 = sin/cos psi1, s2/c2 = psi2, sth/cth = hitch, sdl/cdl = steering
@@ -219,15 +248,15 @@ struct ObsAux { float d, dx, dy; };
 
 TT_HD ObsAux pack_obs(const StepConsts &k, const EnvRegs &e, float s1, float c1, float s2, float c2, float sth,
                       float cth, float sdl, float cdl, float *o) {
-    const float dx = (float)((double)e.gx - e.x2), dy = (float)((double)e.gy - e.y2);
+    const float dx = (float)(e.gx - e.x2) * k.pos_inv, dy = (float)(e.gy - e.y2) * k.pos_inv;   // exact integer differences
     const float d = sqrtf(fmaf(dx, dx, dy * dy));
     const float dxl = fmaf(dx, c2, dy * s2), dyl = fmaf(dy, c2, -dx * s2);
-    o[0] = ((float)e.x1 - k.mid) * k.inv_half;  o[1] = ((float)e.y1 - k.mid) * k.inv_half;
+    o[0] = ((float)e.x1 * k.pos_inv - k.mid) * k.inv_half;  o[1] = ((float)e.y1 * k.pos_inv - k.mid) * k.inv_half;
     o[2] = s1;  o[3] = c1;
-    o[4] = ((float)e.x2 - k.mid) * k.inv_half;  o[5] = ((float)e.y2 - k.mid) * k.inv_half;
+    o[4] = ((float)e.x2 * k.pos_inv - k.mid) * k.inv_half;  o[5] = ((float)e.y2 * k.pos_inv - k.mid) * k.inv_half;
     o[6] = s2;  o[7] = c2;
     o[8] = sth; o[9] = cth; o[10] = sdl; o[11] = cdl;
-    o[12] = (e.gx - k.mid) * k.inv_half; o[13] = (e.gy - k.mid) * k.inv_half;
+    o[12] = ((float)e.gx * k.pos_inv - k.mid) * k.inv_half; o[13] = ((float)e.gy * k.pos_inv - k.mid) * k.inv_half;
     o[14] = e.sgy; o[15] = e.cgy;
     o[16] = clampf(d * k.inv_maxd, 0.0f, 1.0f);
     o[17] = clampf(dxl * k.inv_maxd, -1.0f, 1.0f);
@@ -259,7 +288,7 @@ TT_HD void begin_episode(const StepConsts &k, EnvRegs &e, double sx, double sy, 
                          float *obs) {
     float sg, cg;
     sincos_f32_of_f64(gyaw, sg, cg);
-    e.gx = (float)gx; e.gy = (float)gy; e.sgy = sg; e.cgy = cg;
+    e.gx = pos_from_double(gx); e.gy = pos_from_double(gy); e.sgy = sg; e.cgy = cg;
     const double ddx = gx - sx, ddy = gy - sy;
     const double d0 = sqrt(ddx * ddx + ddy * ddy);
     e.d0 = (float)d0;
@@ -281,8 +310,8 @@ TT_HD void reset_from_pose(const StepConsts &k, EnvRegs &e, double sx, double sy
     double sn, cs;
     sincos_f64(syaw, sn, cs);
     e.psi1 = e.psi2 = (double)(float)syaw;
-    e.x1 = (double)(float)fma(k.L2, cs, sx); e.y1 = (double)(float)fma(k.L2, sn, sy);
-    e.x2 = (double)(float)sx; e.y2 = (double)(float)sy;
+    e.x1 = pos_from_double((double)(float)fma(k.L2, cs, sx)); e.y1 = pos_from_double((double)(float)fma(k.L2, sn, sy));
+    e.x2 = pos_from_double((double)(float)sx); e.y2 = pos_from_double((double)(float)sy);
     begin_episode(k, e, sx, sy, gx, gy, gyaw, obs);
 }
 
@@ -393,11 +422,12 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
     for (int m = 0; m < 6; m++) if (m != 1) accb = fma(TTM_K(K_B + m), u[m], accb);
     const double dpsi2 = k.h * accb;
     // goal offset of the trailer BEFORE the move (for the distance decrement below)
-    const float dxp = (float)((double)e.gx - e.x2), dyp = (float)((double)e.gy - e.y2);
-    const float ix2 = k.hv * ax2, iy2 = k.hv * ay2;
+    const float dxp = (float)(e.gx - e.x2) * k.pos_inv, dyp = (float)(e.gy - e.y2) * k.pos_inv;
+    const int32_t ix2i = f2i_rn(k.hv_fix * ax2), iy2i = f2i_rn(k.hv_fix * ay2);
+    const float ix2 = (float)ix2i * k.pos_inv, iy2 = (float)iy2i * k.pos_inv;      // the increment actually applied
     e.psi1 += hw; e.psi2 += dpsi2;                           // simv2.py:516-517
-    e.x1 += (double)(k.hv * ax1); e.y1 += (double)(k.hv * ay1);
-    e.x2 += (double)ix2; e.y2 += (double)iy2;
+    e.x1 += f2i_rn(k.hv_fix * ax1); e.y1 += f2i_rn(k.hv_fix * ay1);
+    e.x2 += ix2i; e.y2 += iy2i;
 
     // ---- trig of the new state (for the observation) ----
     double sdn, cdn;
@@ -451,11 +481,11 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
     const double th = fabs(e.psi1 - e.psi2);
     if (th > k.jk_major) { saf += -500.0f; viol = 1u; }
     else if (th > k.jk_minor) { saf += -50.0f; viol = 2u; }
-    const double mn = fmin(fmin(e.x1, e.y1), fmin(e.x2, e.y2)), mx = fmax(fmax(e.x1, e.y1), fmax(e.x2, e.y2));
-    const bool oom = mn < k.map_min || mx > k.map_max;
-    if (mn < k.map_min - 2.0 || mx > k.map_max + 2.0) { saf += -500.0f; viol = 3u; }
+    const int32_t mn = min(min(e.x1, e.y1), min(e.x2, e.y2)), mx = max(max(e.x1, e.y1), max(e.x2, e.y2));
+    const bool oom = mn < k.map_min_fix || mx > k.map_max_fix;
+    if (mn < k.maj_lo_fix || mx > k.maj_hi_fix) { saf += -500.0f; viol = 3u; }
     else if (oom) { saf += -50.0f; viol = 4u; }
-    const bool passed = (double)e.gy > e.y2;
+    const bool passed = e.gy > e.y2;
     if (passed) { saf += -500.0f; viol = 5u; }
     if (steps >= rmax) { saf += -500.0f; viol = 6u; }
     const bool exb = d > e.closest + 6.0f;                   // :120-124

@@ -14,13 +14,15 @@ int hm_replay(const double *state0, const double *start, const double *goal, con
     tt_env_cfg cfg; tt_fill_default_cfg(&cfg);
     ttm::StepConsts k = tt_make_consts(cfg);
     ttm::EnvRegs e;
-    e.psi1 = state0[0]; e.psi2 = state0[1]; e.x1 = state0[2]; e.y1 = state0[3]; e.x2 = state0[4]; e.y2 = state0[5];
+    e.psi1 = state0[0]; e.psi2 = state0[1];
+    e.x1 = ttm::pos_from_double(state0[2]); e.y1 = ttm::pos_from_double(state0[3]);
+    e.x2 = ttm::pos_from_double(state0[4]); e.y2 = ttm::pos_from_double(state0[5]);
     ttm::begin_episode(k, e, start[0], start[1], goal[0], goal[1], goal[2], obs0);
     int n = 0;
     for (int t = 0; t < T; t++) {
         ttm::StepOut o;
         ttm::env_step<true>(k, e, actions[t], o);
-        double s[6] = {e.psi1, e.psi2, e.x1, e.y1, e.x2, e.y2};
+        double s[6] = {e.psi1, e.psi2, ttm::pos_to_double(e.x1), ttm::pos_to_double(e.y1), ttm::pos_to_double(e.x2), ttm::pos_to_double(e.y2)};
         memcpy(state + 6 * t, s, sizeof s);
         memcpy(obs + 23 * t, o.obs, sizeof o.obs);
         comps[11 * t] = o.reward;
@@ -44,7 +46,7 @@ void hm_reset_pose(double sx, double sy, double syaw, double *state, float *obs)
     ttm::StepConsts k = tt_make_consts(cfg);
     ttm::EnvRegs e;
     ttm::reset_from_pose(k, e, sx, sy, syaw, cfg.goal_x, cfg.goal_y, cfg.goal_yaw, obs);
-    double s[6] = {e.psi1, e.psi2, e.x1, e.y1, e.x2, e.y2};
+    double s[6] = {e.psi1, e.psi2, ttm::pos_to_double(e.x1), ttm::pos_to_double(e.y1), ttm::pos_to_double(e.x2), ttm::pos_to_double(e.y2)};
     memcpy(state, s, sizeof s);
 }
 

@@ -103,7 +103,7 @@ def test_against_oracle_random_batch(N, T):
     for i in (0, 1, N // 2, N - 1):
         assert tuple(start[i]) == orc.rng_pose(77, i, 0x80000000)
         e = orc.OracleEnv(); e.reset_pose(*start[i])
-        assert np.array_equal(e.state, state0[i])
+        assert np.array_equal(e.state[:2], state0[i][:2]) and np.abs(e.state[2:] - state0[i][2:]).max() <= 2.0 ** -26   # fixed-point positions
     acts = np.zeros((N, T), np.float32)
     acts[: N // 2] = rng.uniform(-np.pi / 4, np.pi / 4, (N // 2, T))
     walk = np.cumsum(rng.normal(0, 0.08, (N - N // 2, T)), 1)
