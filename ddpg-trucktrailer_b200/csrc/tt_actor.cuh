@@ -18,6 +18,7 @@ struct tt_actor_dev {
     int k1p, h1p, h2p, kb1;
     float *w1t, *w2t, *b1, *g1, *be1, *b2, *g2, *be2, *w3, *b3;
     void *w1_f16, *w2_f16, *w1_bf16, *w2_bf16;     // UMMA operand images (tt_actor_tc.cu)
+    float *gram_f16, *gram_bf16;                    // [25][24]: Gram matrix of fc1 (+bias column) and its column sums
 };
 
 struct tt_actor {
@@ -35,12 +36,14 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
     const size_t o_w3 = take(sizeof(float) * h2p), o_b3 = take(sizeof(float));
     const size_t n1 = (h1 + 15) / 16 * 16, n2 = (h2 + 15) / 16 * 16, kb2 = (h1 + 1 + 31) / 32;
     const size_t o_w1h = take(2 * n1 * 64), o_w2h = take(kb2 * n2 * 64), o_w1b = take(2 * n1 * 64), o_w2b = take(kb2 * n2 * 64);
+    const size_t o_gh = take(sizeof(float) * 25 * 24), o_gb = take(sizeof(float) * 25 * 24);
     if (d) {
         d->in_dim = in_dim; d->h1 = h1; d->h2 = h2; d->k1p = k1p; d->h1p = h1p; d->h2p = h2p; d->kb1 = kb1;
         auto f = [&](size_t o) { return reinterpret_cast<float *>(base + o); };
         d->w1t = f(o_w1t); d->w2t = f(o_w2t); d->b1 = f(o_b1); d->g1 = f(o_g1); d->be1 = f(o_be1);
         d->b2 = f(o_b2); d->g2 = f(o_g2); d->be2 = f(o_be2); d->w3 = f(o_w3); d->b3 = f(o_b3);
         d->w1_f16 = base + o_w1h; d->w2_f16 = base + o_w2h; d->w1_bf16 = base + o_w1b; d->w2_bf16 = base + o_w2b;
+        d->gram_f16 = f(o_gh); d->gram_bf16 = f(o_gb);
     }
     return off;
 }

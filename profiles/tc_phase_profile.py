@@ -8,7 +8,7 @@ actor = tt.agent.CudaActor(); actor.load_state_dict(tt.init_actor_state_dict(see
 obs = torch.empty(N,23,device='cuda').uniform_(-1,1)
 dbg = torch.zeros(16, dtype=torch.int64, device='cuda')
 L.tt_debug_set_tc_profile.argtypes=[C.c_void_p]
-for prec in ('f16','bf16'):
+for prec in ("f16", "bf16"):
     for _ in range(3): actor.forward(obs, precision=prec)
     L.tt_debug_set_tc_profile(dbg.data_ptr())
     torch.cuda.synchronize()
@@ -18,4 +18,5 @@ for prec in ('f16','bf16'):
     print(prec, 'ms', e0.elapsed_time(e1), 'tiles/blk', nt)
     print('  MMA thread waits per tile: x+tmemfree %.0f  a2 %.0f  w2 %.0f' % (d[0]/nt, d[1]/nt, d[2]/nt))
     print('  epilogue per tile: xstage %.0f  wait_h1 %.0f  epi1 %.0f  wait_h2 %.0f  epi2 %.0f  total %.0f' % tuple(x/nt for x in d[4:10]))
+    print('  v3 detail: stage %.0f  bar %.0f  gram %.0f' % tuple(x/nt for x in d[10:13]))
     L.tt_debug_set_tc_profile(None)
