@@ -82,7 +82,11 @@ __global__ void pack_tc_kernel(char *__restrict__ w1, char *__restrict__ w2, con
 // Gram matrix of the (operand-rounded) first layer incl. its bias column: G[i][j] = sum_c W[c][i] W[c][j], wbar[i] =
 // sum_c W[c][i] (i, j < 24).  With them the LayerNorm statistics of H1 = W x follow from x alone:
 // sum_c h_c = wbar . x,  sum_c h_c^2 = x^T G x  -- so epilogue 1 needs ONE pass over TMEM instead of two.
-// layout: G row-major [24][24], then wbar[24].   kRound: round W to the operand type first (plain bf16 mode).
+// Stored as the upper-triangular form U (U_ii = G_ii, U_ij = 2 G_ij for j > i, 0 below) so that x^T G x = sum_i x_i
+// sum_{j>=i} U_ij x_j needs half the multiply-adds.  layout: U row-major [24][24], then wbar[24].
+// kRound: round W to the operand type first (plain bf16 mode).
+// (Keeping these per-column parameters in __constant__ memory instead of shared memory was tried and measured 30 %
+// SLOWER: the 12 KB working set thrashes the small constant cache.)
 template <typename OpT, bool kRound>
 __global__ void pack_gram_kernel(float *__restrict__ gram, const float *__restrict__ fc1_w, const float *__restrict__ fc1_b) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,7 +97,10 @@ __global__ void pack_gram_kernel(float *__restrict__ gram, const float *__restri
         return (double)(kRound ? op_to_float(to_op<OpT>(x)) : x);
     };
     double acc = 0.0;
-    if (i < 24) { for (int c = 0; c < H1; c++) acc += w(c, i) * w(c, j); gram[i * 24 + j] = (float)acc; }
+    if (i < 24) {
+        if (j >= i) for (int c = 0; c < H1; c++) acc += w(c, i) * w(c, j);
+        gram[i * 24 + j] = (float)(j > i ? 2.0 * acc : acc);
+    }
     else { for (int c = 0; c < H1; c++) acc += w(c, j); gram[24 * 24 + j] = (float)acc; }
 }
 
@@ -757,17 +764,17 @@ __global__ void __launch_bounds__(608, 1) actor_tc3_kernel(const char *__restric
             float ms = 0.f, qs = 0.f;
 #pragma unroll
             for (int ii = 0; ii < 6; ii++) {
-                const int i = grp + 4 * ii;
-                float inner = 0.f;
+                const int i = grp + 4 * ii;                               // rows grp, grp+4, ...: entries j >= 4*ii suffice (U is upper)
+                float2 in2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 24; j += 4) {
-                    const float4 g = *reinterpret_cast<const float4 *>(pgram + i * 24 + j);
-                    inner = fmaf(g.x, xr[j], inner); inner = fmaf(g.y, xr[j + 1], inner);
-                    inner = fmaf(g.z, xr[j + 2], inner); inner = fmaf(g.w, xr[j + 3], inner);
+                for (int c = ii; c < 6; c++) {
+                    const float4 g = *reinterpret_cast<const float4 *>(pgram + i * 24 + 4 * c);
+                    in2 = __ffma2_rn(make_float2(g.x, g.y), make_float2(xr[4 * c], xr[4 * c + 1]), in2);
+                    in2 = __ffma2_rn(make_float2(g.z, g.w), make_float2(xr[4 * c + 2], xr[4 * c + 3]), in2);
                 }
-                // x_i for this thread's rows of G: grp is warp-uniform, so this is a uniform 4-way select
+                // x_i for this thread's rows of U: grp is warp-uniform, so this is a uniform 4-way select
                 const float xi = grp == 0 ? xr[4 * ii] : grp == 1 ? xr[4 * ii + 1] : grp == 2 ? xr[4 * ii + 2] : xr[4 * ii + 3];
-                qs = fmaf(xi, inner, qs);
+                qs = fmaf(xi, in2.x + in2.y, qs);
                 ms = fmaf(pgram[24 * 24 + i], xi, ms);
             }
             red1[grp * kTileM + r] = make_float2(ms, qs);
