@@ -89,7 +89,7 @@ __global__ void pack_tc_kernel(char *__restrict__ w1, char *__restrict__ w2, con
 // SLOWER: the 12 KB working set thrashes the small constant cache.)
 template <typename OpT, bool kRound>
 __global__ void pack_gram_kernel(float *__restrict__ gram, const float *__restrict__ fc1_w, const float *__restrict__ fc1_b) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;     // one warp per output element
     if (t >= 25 * 24) return;
     const int i = t / 24, j = t - i * 24;
     auto w = [&](int c, int k) {
@@ -97,11 +97,11 @@ __global__ void pack_gram_kernel(float *__restrict__ gram, const float *__restri
         return (double)(kRound ? op_to_float(to_op<OpT>(x)) : x);
     };
     double acc = 0.0;
-    if (i < 24) {
-        if (j >= i) for (int c = 0; c < H1; c++) acc += w(c, i) * w(c, j);
-        gram[i * 24 + j] = (float)(j > i ? 2.0 * acc : acc);
-    }
-    else { for (int c = 0; c < H1; c++) acc += w(c, j); gram[24 * 24 + j] = (float)acc; }
+    if (i < 24) { if (j >= i) for (int c = lane; c < H1; c += 32) acc += w(c, i) * w(c, j); }
+    else for (int c = lane; c < H1; c += 32) acc += w(c, j);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) gram[t] = (float)((i < 24 && j > i) ? 2.0 * acc : acc);
 }
 
 // ---- PTX wrappers ----
@@ -969,9 +969,9 @@ int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, cons
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     pack_tc_kernel<__nv_bfloat16><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w1_bf16), reinterpret_cast<char *>(A.w2_bf16), fc1_w, fc1_b, fc2_w, fc2_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    pack_gram_kernel<__half, false><<<5, 128, 0, s>>>(A.gram_f16, fc1_w, fc1_b);
+    pack_gram_kernel<__half, false><<<75, 256, 0, s>>>(A.gram_f16, fc1_w, fc1_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    pack_gram_kernel<__nv_bfloat16, true><<<5, 128, 0, s>>>(A.gram_bf16, fc1_w, fc1_b);
+    pack_gram_kernel<__nv_bfloat16, true><<<75, 256, 0, s>>>(A.gram_bf16, fc1_w, fc1_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }

@@ -88,7 +88,7 @@ def _oracle_batch(orc, state0, start, actions):
     return out
 
 
-@pytest.mark.parametrize("N,T", [(4096, 120)])
+@pytest.mark.parametrize("N,T", [(4096, 120), (65536, 100)])
 def test_against_oracle_random_batch(N, T):
     """BASELINE.json configs[1] shape (fixed action replay vs reference trajectories) at a size the oracle
     finishes in seconds: Philox start poses, half uniform / half smooth steering, K steps in ONE launch."""
@@ -198,3 +198,39 @@ def test_n1_reference_contract(golden_dir):
     env.state = g["states"][0]
     o, r, d, i = env.step(g["actions"][:1])
     assert abs(r - g["comps"][0, 0]) < 1e-3 and np.abs(env.state - g["states"][1]).max() < 1e-5
+
+
+def test_full_size_properties():
+    """BASELINE.json's full size (2^22 envs on one GPU): size-independent properties instead of an oracle replay.
+    (1) K steps in one launch == K single launches, bit for bit, incl. auto-reset; (2) the device statistics equal
+    the per-step outputs; (3) every env that reports done was reset (episode_steps == 0) and only those;
+    (4) a shard with a global offset reproduces the corresponding slice."""
+    tt = _tt()
+    N, K = 1 << 22, 6
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    acts = torch.empty(K, N, device="cuda").uniform_(-0.785, 0.785, generator=g)
+    a = tt.VecTruckTrailerEnv(N, seed=9); a.reset()
+    b = tt.VecTruckTrailerEnv(N, seed=9); b.reset()
+    # warm both populations so that episodes end inside the window
+    warm = torch.empty(60, N, device="cuda").uniform_(-0.785, 0.785, generator=g)
+    a.step_k(warm, auto_reset=True, want_reward=False, want_done=False); b.step_k(warm, auto_reset=True, want_reward=False, want_done=False)
+    a.read_stats(); b.read_stats()
+    _, rk, dk, _ = a.step_k(acts, auto_reset=True)
+    rsum, dsum = 0.0, 0
+    for t in range(K):
+        _, r, d, _ = b.step(acts[t])
+        assert torch.equal(r, rk[t]) and torch.equal(d, dk[t].bool())
+        rsum += float(r.double().sum()); dsum += int(d.sum())
+        steps_before = b.get_state()["episode_steps"]
+        b.reset(options={"mask": d}); b.tick()
+        steps_after = b.get_state()["episode_steps"]
+        assert (steps_after[d] == 0).all() and torch.equal(steps_after[~d], steps_before[~d])
+    assert torch.equal(a.state, b.state)
+    sa, sb = a.read_stats(), b.read_stats()
+    assert sa == sb and sa["steps"] == N * K and sa["episodes"] == dsum and dsum > N // 100
+    assert abs(sa["reward_sum"] - rsum) <= 1e-6 * abs(rsum) + 1.0
+    assert sum(sa["term_" + f] for f in tt.FLAG_NAMES) >= sa["episodes"]
+    c = tt.VecTruckTrailerEnv(4096, seed=9, global_env_offset=N - 4096); c.reset()
+    c.step_k(warm[:, N - 4096:].contiguous(), auto_reset=True, want_reward=False, want_done=False)
+    _, rc, _, _ = c.step_k(acts[:, N - 4096:].contiguous(), auto_reset=True)
+    assert torch.equal(rc, rk[:, N - 4096:])
