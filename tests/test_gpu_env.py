@@ -227,7 +227,12 @@ def test_full_size_properties():
         assert (steps_after[d] == 0).all() and torch.equal(steps_after[~d], steps_before[~d])
     assert torch.equal(a.state, b.state)
     sa, sb = a.read_stats(), b.read_stats()
-    assert sa == sb and sa["steps"] == N * K and sa["episodes"] == dsum and dsum > N // 100
+    for k in sa:      # counts are exact; float sums depend on the (atomic) summation order
+        if k in ("return_sum", "return_sq_sum", "reward_sum"):
+            assert abs(sa[k] - sb[k]) <= 1e-5 * abs(sb[k]) + 1.0, k
+        else:
+            assert sa[k] == sb[k], k
+    assert sa["steps"] == N * K and sa["episodes"] == dsum and dsum > N // 100
     assert abs(sa["reward_sum"] - rsum) <= 1e-6 * abs(rsum) + 1.0
     assert sum(sa["term_" + f] for f in tt.FLAG_NAMES) >= sa["episodes"]
     c = tt.VecTruckTrailerEnv(4096, seed=9, global_env_offset=N - 4096); c.reset()
