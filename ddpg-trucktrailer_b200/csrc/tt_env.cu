@@ -71,6 +71,38 @@ __device__ __forceinline__ void load_raw(const EnvPtrs &p, int64_t i, const floa
     r.action = __ldcs(&actions[i]);
 }
 
+// --- shared-memory prefetch ring (cp.async): each thread stages ITS OWN env's words and later reads only those back,
+// so completion is per thread (cp.async.wait_group) and needs no barrier.  Frees the ~22 registers of a register
+// double buffer and allows a prefetch distance of kStages - 1 tiles.
+struct __align__(16) RawSlab {
+    double2 psi[kBlock];
+    int4 pos[kBlock];
+    float4 a[kBlock], b[kBlock];
+    int4 goal[kBlock];
+    uint32_t packed[kBlock];
+    float action[kBlock];
+};
+
+__device__ __forceinline__ void cp_async_16(void *smem, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *smem, const void *g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+
+template <bool kGoal>
+__device__ __forceinline__ void stage_raw(const EnvPtrs &p, int64_t i, const float *__restrict__ actions, RawSlab &sl, int t) {
+    cp_async_16(&sl.psi[t], &p.psi[i]); cp_async_16(&sl.pos[t], &p.pos[i]);
+    cp_async_16(&sl.a[t], &p.rsA[i]); cp_async_16(&sl.b[t], &p.rsB[i]);
+    if (kGoal) cp_async_16(&sl.goal[t], &p.goal[i]);
+    cp_async_4(&sl.packed[t], &p.packed[i]); cp_async_4(&sl.action[t], &actions[i]);
+}
+
+__device__ __forceinline__ void read_slab(const RawSlab &sl, int t, EnvRaw &r, bool goal) {
+    r.psi = sl.psi[t]; r.pos = sl.pos[t]; r.a = sl.a[t]; r.b = sl.b[t]; r.packed = sl.packed[t]; r.action = sl.action[t];
+    if (goal) r.goal = sl.goal[t];
+}
+
 template <bool kGoal>
 __device__ __forceinline__ void unpack(const StepConsts &k, const EnvRaw &r, EnvRegs &e) {
     e.psi1 = r.psi.x; e.psi2 = r.psi.y;
@@ -125,7 +157,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // K env steps per launch; state stays in registers across the K steps; persistent over 128-env tiles.
 // kMinBlocks == 7 is a memory-traffic-only probe (no arithmetic) used for roofline analysis.
-template <bool kInfo, bool kGoal, int kMinBlocks>
+template <bool kInfo, bool kGoal, int kMinBlocks, int kStages>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p, StepConsts k, const float *__restrict__ actions,
                                                                       int K, int auto_reset, float *__restrict__ obs, int64_t ld,
                                                                       float *__restrict__ reward, uint8_t *__restrict__ done,
@@ -143,20 +175,42 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
 #pragma unroll
     for (int f = 0; f < 6; f++) sa.fl[f] = 0.f;
 
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    RawSlab *slabs = reinterpret_cast<RawSlab *>(dyn_smem);       // kStages slabs (kStages == 0: unused)
     EnvRaw nxt;
-    {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    if (kStages == 0) {
         const int64_t i0 = (int64_t)blockIdx.x * kBlock + threadIdx.x;
         if (i0 < N) load_raw<kGoal>(p, i0, actions, nxt);
+    } else {
+#pragma unroll
+        for (int st = 0; st < (kStages > 0 ? kStages - 1 : 0); st++) {    // prologue: kStages - 1 tiles in flight
+            const int64_t ip = (int64_t)blockIdx.x * kBlock + threadIdx.x + st * stride;
+            if (ip < N) stage_raw<kGoal>(p, ip, actions, slabs[st], threadIdx.x);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
     }
+    int ring = 0;
     for (int64_t tileidx = blockIdx.x; tileidx < ntiles; tileidx += gridDim.x) {
         const int64_t row0 = tileidx * kBlock;
         const int64_t i = row0 + threadIdx.x;
         const bool active = i < N;
         const int rows = (int)((N - row0) < kBlock ? (N - row0) : kBlock);
-        const EnvRaw cur = nxt;
-        {   // prefetch the next tile of this CTA: in flight during the whole computation below
-            const int64_t in = i + (int64_t)gridDim.x * kBlock;
+        EnvRaw cur;
+        if (kStages == 0) {
+            cur = nxt;
+            // prefetch the next tile of this CTA: in flight during the whole computation below
+            const int64_t in = i + stride;
             if (in < N) load_raw<kGoal>(p, in, actions, nxt);
+        } else {
+            // issue the tile kStages - 1 ahead into the slab that was consumed in the previous iteration
+            const int64_t ip = i + (int64_t)(kStages - 1) * stride;
+            int slot = ring + kStages - 1; if (slot >= kStages) slot -= kStages;
+            if (ip < N) stage_raw<kGoal>(p, ip, actions, slabs[slot], threadIdx.x);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kStages > 0 ? kStages - 1 : 0) : "memory");   // this tile's group landed
+            if (active) read_slab(slabs[ring], threadIdx.x, cur, kGoal);
+            if (++ring == kStages) ring = 0;
         }
         EnvRegs e;
         if (active) unpack<kGoal>(k, cur, e);
@@ -425,27 +479,39 @@ int tt_env_step_k(tt_env *env, const float *d_actions, int32_t K, int32_t auto_r
     tt_step_info inf;
     memset(&inf, 0, sizeof inf);
     const bool want = info && (info->d_comps || info->d_violation || info->d_flags || info->d_success);
-    // occupancy knob (registers per thread): TT_ENV_MINBLOCKS = 4 (128 regs) | 5 (96) | 6 (80) | 7 (traffic-only probe)
+    // tuning knob TT_ENV_MINBLOCKS = <CTAs per SM><prefetch stages>: default 42 = 4 CTAs/SM (<=128 regs) with a 2-stage
+    // cp.async shared-memory prefetch; 43/52/53/62 = other combinations; 40/5/6 = register double buffer; 7 = traffic-only probe.
+    // Measured at N = 2^22 (profiles/env_kernel_bench.py): 42: 208 us (70.4 % of the HBM roofline), 43: 210, 52/53: 218,
+    // 40: 264, 62: 276.
     static const int variant = [] { const char *e = getenv("TT_ENV_MINBLOCKS"); return e ? atoi(e) : TT_ENV_MINBLOCKS_DEFAULT; }();
     const int64_t ntiles = grid_for(env->p.N);
-#define TT_LAUNCH_STEP(INFO, GOAL, MB)                                                                                          \
+#define TT_LAUNCH_STEP(INFO, GOAL, MB, ST)                                                                                      \
     do {                                                                                                                        \
-        auto kern = env_step_kernel<INFO, GOAL, MB>;                                                                            \
+        auto kern = env_step_kernel<INFO, GOAL, MB, ST>;                                                                        \
+        const size_t dsm = (size_t)(ST) * sizeof(RawSlab);                                                                      \
         static int per_sm = 0;                                                                                                  \
-        if (per_sm == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0) != cudaSuccess) per_sm = 4;  \
+        if (per_sm == 0) {                                                                                                      \
+            if (dsm > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);                     \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, dsm) != cudaSuccess) per_sm = 4;           \
+        }                                                                                                                       \
         const int64_t cap = (int64_t)tt::sm_count() * (per_sm > 0 ? per_sm : 4);                                                \
-        kern<<<(unsigned)(ntiles < cap ? ntiles : cap), kBlock, 0, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs, ld_obs, \
-                                                                      d_reward, d_done, inf, env->seed, env->gid0);            \
+        kern<<<(unsigned)(ntiles < cap ? ntiles : cap), kBlock, dsm, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs,       \
+                                                                         ld_obs, d_reward, d_done, inf, env->seed, env->gid0); \
     } while (0)
     const bool goal = env->per_env_goal;
     if (want) {
         inf = *info;
-        if (goal) TT_LAUNCH_STEP(true, true, 4); else TT_LAUNCH_STEP(true, false, 4);
-    } else if (goal) TT_LAUNCH_STEP(false, true, 4);
-    else if (variant == 5) TT_LAUNCH_STEP(false, false, 5);
-    else if (variant == 6) TT_LAUNCH_STEP(false, false, 6);
-    else if (variant == 7) TT_LAUNCH_STEP(false, false, 7);
-    else TT_LAUNCH_STEP(false, false, 4);
+        if (goal) TT_LAUNCH_STEP(true, true, 4, 2); else TT_LAUNCH_STEP(true, false, 4, 2);
+    } else if (goal) TT_LAUNCH_STEP(false, true, 4, 2);
+    else if (variant == 5) TT_LAUNCH_STEP(false, false, 5, 0);
+    else if (variant == 6) TT_LAUNCH_STEP(false, false, 6, 0);
+    else if (variant == 7) TT_LAUNCH_STEP(false, false, 7, 0);
+    else if (variant == 40) TT_LAUNCH_STEP(false, false, 4, 0);      /* register double buffer instead of cp.async */
+    else if (variant == 43) TT_LAUNCH_STEP(false, false, 4, 3);
+    else if (variant == 52) TT_LAUNCH_STEP(false, false, 5, 2);
+    else if (variant == 53) TT_LAUNCH_STEP(false, false, 5, 3);
+    else if (variant == 62) TT_LAUNCH_STEP(false, false, 6, 2);
+    else TT_LAUNCH_STEP(false, false, 4, 2);                        /* default: 4 CTAs/SM, 2-stage cp.async prefetch */
 #undef TT_LAUNCH_STEP
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     if (auto_reset) { tick_kernel<<<1, 1, 0, s>>>(env->p.iter, (uint32_t)K); TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK(); }
