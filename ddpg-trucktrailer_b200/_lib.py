@@ -34,6 +34,11 @@ class StepInfo(C.Structure):
     _fields_ = [("d_comps", C.c_void_p), ("d_violation", C.c_void_p), ("d_flags", C.c_void_p), ("d_success", C.c_void_p)]
 
 
+class ReplayRing(C.Structure):
+    _fields_ = [("d_state_mem", C.c_void_p), ("d_action_mem", C.c_void_p), ("d_reward_mem", C.c_void_p),
+                ("d_new_state_mem", C.c_void_p), ("d_terminal_mem", C.c_void_p), ("mem_size", C.c_int64), ("mem_cntr", C.c_int64)]
+
+
 class RolloutBufs(C.Structure):
     _fields_ = [("d_obs_cur", C.c_void_p), ("d_obs_next", C.c_void_p), ("ld_obs", C.c_int64), ("d_ou_x", C.c_void_p),
                 ("d_action", C.c_void_p), ("d_scaled", C.c_void_p), ("d_reward", C.c_void_p), ("d_done", C.c_void_p),
@@ -75,6 +80,9 @@ SYMBOLS = {
     "tt_scale_action": (C.c_int, [_P, _P, _I64, _P]),
     "tt_replay_store": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P]),
     "tt_replay_gather": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "tt_actor_forward_store": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, C.POINTER(ReplayRing), _P]),
+    "tt_ou_step_store": (C.c_int, [_P, _P, _P, _I64, _U64, _U64, _P, _I32, C.POINTER(ReplayRing), _P]),
+    "tt_env_step_store": (C.c_int, [_P, _P, _P, _I64, _P, _P, C.POINTER(ReplayRing), _P]),
     "tt_rollout_step": (C.c_int, [_P, _P, C.POINTER(RolloutBufs), _I32, _I32, _P]),
 }
 

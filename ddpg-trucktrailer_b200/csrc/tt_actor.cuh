@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include "tt_common.cuh"
 
 struct tt_actor_dev {
     int in_dim, h1, h2;
@@ -49,10 +50,12 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
 }
 
 namespace tt {
-int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, cudaStream_t s);
-int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, cudaStream_t s);
+// `ring` (may be NULL): also store the observation rows as the `state` part of the replay transitions (fused store)
+int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, const TTRingS *ring, cudaStream_t s);
+int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring, cudaStream_t s);
+bool actor_tc_fuses_ring();
 int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *fc2_w, const float *fc2_b, cudaStream_t s);
 int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
-                 uint64_t gid0, const uint32_t *d_iter, int evaluate, cudaStream_t s);
+                 uint64_t gid0, const uint32_t *d_iter, int evaluate, const TTRingA *ring, cudaStream_t s);
 int launch_ou_zero(float *d_x, const uint8_t *d_mask, int64_t n, cudaStream_t s);
 }  // namespace tt

@@ -566,7 +566,8 @@ template <typename OpT, bool kSplit>
 __global__ void __launch_bounds__(608, 1) actor_tc3_kernel(const char *__restrict__ w1img, const char *__restrict__ w2img,
                                                            const float *__restrict__ gram, tt_actor_dev A,
                                                            const float *__restrict__ obs, int64_t ld, int64_t n,
-                                                           float *__restrict__ out, unsigned long long *__restrict__ dbg) {
+                                                           float *__restrict__ out, TTRingS ring,
+                                                           unsigned long long *__restrict__ dbg) {
     using P = Plan3<kSplit>;
     constexpr int kGroups = 4, kEpiThreads = 512, kThreads = 608;
     constexpr int kM2Warp = 16, kProdWarp = 17, kM1Warp = 18;
@@ -733,6 +734,8 @@ __global__ void __launch_bounds__(608, 1) actor_tc3_kernel(const char *__restric
                     const float x = xreg[i];
                     const OpT hi = to_op<OpT>(x);
                     *reinterpret_cast<OpT *>(sm + P::x + sw64_off(rr, k)) = hi;
+                    // fused replay store of s (DRAM is idle in this kernel): same coalesced element order as the load
+                    if (ring.S && row0 + rr < n && row0 + rr >= ring.m.first) ring.S[ring.m.row(row0 + rr) * IN + k] = x;
                     if (kSplit) *reinterpret_cast<OpT *>(sm + P::x + kTileM * kRowB + sw64_off(rr, k)) = to_op<OpT>(x - op_to_float(hi));
                 }
             }
@@ -920,7 +923,9 @@ __global__ void __launch_bounds__(608, 1) actor_tc3_kernel(const char *__restric
 
 template <typename OpT, bool kSplit>
 int launch_tc3(const char *w1img, const char *w2img, const float *gram, const tt_actor_dev &A, const float *d_obs, int64_t ld, int64_t n,
-               float *d_mu, cudaStream_t st) {
+               float *d_mu, const TTRingS *ring, cudaStream_t st) {
+    TTRingS rs;
+    if (ring) rs = *ring; else { rs.S = nullptr; rs.m = tt_make_ring_map(1, 0, 0); }
     using P = Plan3<kSplit>;
     static_assert(P::total <= 232448u, "shared-memory plan exceeds 227 KB");
     auto kern = actor_tc3_kernel<OpT, kSplit>;
@@ -931,7 +936,7 @@ int launch_tc3(const char *w1img, const char *w2img, const float *gram, const tt
     }
     const int64_t ntiles = (n + kTileM - 1) / kTileM;
     const int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
-    kern<<<grid, 608, P::total, st>>>(w1img, w2img, gram, A, d_obs, ld, n, d_mu, g_tc_dbg);
+    kern<<<grid, 608, P::total, st>>>(w1img, w2img, gram, A, d_obs, ld, n, d_mu, rs, g_tc_dbg);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
@@ -976,17 +981,25 @@ int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, cons
     return TT_OK;
 }
 
-int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, cudaStream_t st) {
+static int tc_variant() {
+    static const int variant = [] { const char *e = getenv("TT_TC_VARIANT"); return e ? atoi(e) : TT_TC_VARIANT_DEFAULT; }();
+    return variant;
+}
+bool actor_tc_fuses_ring() { return tc_variant() == 3; }
+
+int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring,
+                     cudaStream_t st) {
     const tt_actor_dev &A = a->dev;
     if (!actor_tc_supported(A)) {
         set_error("tensor-core actor is specialised to layer sizes 23-400-300 (got %d-%d-%d); use TT_PREC_FP32", A.in_dim, A.h1, A.h2);
         return TT_ERR_INVALID;
     }
-    static const int variant = [] { const char *e = getenv("TT_TC_VARIANT"); return e ? atoi(e) : TT_TC_VARIANT_DEFAULT; }();
+    const int variant = tc_variant();
+    if (ring && variant != 3) { set_error("fused replay store needs the pipelined tensor-core kernel"); return TT_ERR_INVALID; }
     if (variant == 3) {
         if (precision == TT_PREC_BF16)
-            return launch_tc3<__nv_bfloat16, false>(reinterpret_cast<const char *>(A.w1_bf16), reinterpret_cast<const char *>(A.w2_bf16), A.gram_bf16, A, d_obs, ld, n, d_mu, st);
-        return launch_tc3<__half, true>(reinterpret_cast<const char *>(A.w1_f16), reinterpret_cast<const char *>(A.w2_f16), A.gram_f16, A, d_obs, ld, n, d_mu, st);
+            return launch_tc3<__nv_bfloat16, false>(reinterpret_cast<const char *>(A.w1_bf16), reinterpret_cast<const char *>(A.w2_bf16), A.gram_bf16, A, d_obs, ld, n, d_mu, ring, st);
+        return launch_tc3<__half, true>(reinterpret_cast<const char *>(A.w1_f16), reinterpret_cast<const char *>(A.w2_f16), A.gram_f16, A, d_obs, ld, n, d_mu, ring, st);
     }
     if (precision == TT_PREC_BF16)
         return launch_tc<__nv_bfloat16, false, TT_TC_GROUPS>(reinterpret_cast<const char *>(A.w1_bf16), reinterpret_cast<const char *>(A.w2_bf16), A, d_obs, ld, n, d_mu, st);

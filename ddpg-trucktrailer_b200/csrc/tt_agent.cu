@@ -19,7 +19,7 @@ constexpr float kPiOver4F = 0.78539819f;       // float32(pi/4) == env.action_sp
 __global__ void __launch_bounds__(kThreads) ou_kernel(float *__restrict__ x, float *__restrict__ action,
                                                       float *__restrict__ scaled, const uint8_t *__restrict__ reset_mask,
                                                       int64_t n, uint64_t seed, uint64_t gid0,
-                                                      const uint32_t *__restrict__ iter, int evaluate) {
+                                                      const uint32_t *__restrict__ iter, int evaluate, TTRingA ring) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     float a = action ? action[i] : 0.0f;
@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kThreads) ou_kernel(float *__restrict__ x, flo
         if (action) action[i] = a;
     }
     if (scaled) scaled[i] = fminf(fmaxf(a, -1.0f), 1.0f) * kPiOver4F;
+    if (ring.A && i >= ring.m.first) ring.A[ring.m.row(i)] = a;          // agent.remember stores the UNCLIPPED action (trainv2.py:525)
 }
 
 __global__ void __launch_bounds__(kThreads) ou_zero_kernel(float *__restrict__ x, const uint8_t *__restrict__ mask, int64_t n) {
@@ -160,7 +161,7 @@ __device__ __forceinline__ void bias_ln_relu(float (&acc)[8][CJ], const float *_
 
 template <int CJ1, int CJ2, bool kGuard>
 __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A, const float *__restrict__ obs, int64_t ld,
-                                                                int64_t n, float *__restrict__ out) {
+                                                                int64_t n, float *__restrict__ out, TTRingS ring) {
     extern __shared__ __align__(16) float smem[];
     float *xs = smem;                                   // [k1p][RS]
     float *hs = xs + A.k1p * RS;                        // [h1p][RS]
@@ -173,17 +174,11 @@ __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A,
         // ---- observation tile -> xs[k][r] (zero-padded) ----
         for (int v = threadIdx.x; v < A.k1p * RS; v += kThreads) xs[v] = 0.f;
         __syncthreads();
-        if (ld == A.in_dim) {
-            const float *src = obs + row0 * ld;
-            for (int v = threadIdx.x; v < rows * A.in_dim; v += kThreads) {
-                const int r = v / A.in_dim, k = v - r * A.in_dim;
-                xs[k * RS + r] = __ldcs(src + v);
-            }
-        } else {
-            for (int v = threadIdx.x; v < rows * A.in_dim; v += kThreads) {
-                const int r = v / A.in_dim, k = v - r * A.in_dim;
-                xs[k * RS + r] = __ldcs(obs + (row0 + r) * ld + k);
-            }
+        for (int v = threadIdx.x; v < rows * A.in_dim; v += kThreads) {
+            const int r = v / A.in_dim, k = v - r * A.in_dim;
+            const float x = __ldcs(obs + (row0 + r) * ld + k);
+            xs[k * RS + r] = x;
+            if (ring.S && row0 + r >= ring.m.first) ring.S[ring.m.row(row0 + r) * A.in_dim + k] = x;     // fused replay store of s
         }
         __syncthreads();
         // ---- layer 1: fc1 -> LN -> ReLU (networks.py:139-141) ----
@@ -242,7 +237,9 @@ size_t actor_fp32_smem(const tt_actor_dev &A) {
 
 namespace tt {
 
-int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, cudaStream_t s) {
+int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, const TTRingS *ring, cudaStream_t s) {
+    TTRingS rs;
+    if (ring) rs = *ring; else { rs.S = nullptr; rs.m = tt_make_ring_map(1, 0, 0); }
     const tt_actor_dev &A = a->dev;
     const size_t smem = actor_fp32_smem(A);
     const int64_t ntiles = (n + TM - 1) / TM;
@@ -251,11 +248,11 @@ int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_
     if (cj1 == 13 && cj2 == 10) {
         auto kern = actor_fp32_kernel<13, 10, false>;
         TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu);
+        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs);
     } else if (cj1 <= 16 && cj2 <= 16) {
         auto kern = actor_fp32_kernel<16, 16, true>;
         TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu);
+        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs);
     } else {
         set_error("actor: hidden sizes above 512 are not supported (h1=%d h2=%d)", A.h1, A.h2);
         return TT_ERR_INVALID;
@@ -265,9 +262,11 @@ int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_
 }
 
 int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
-                 uint64_t gid0, const uint32_t *d_iter, int evaluate, cudaStream_t s) {
+                 uint64_t gid0, const uint32_t *d_iter, int evaluate, const TTRingA *ring, cudaStream_t s) {
+    TTRingA ra;
+    if (ring) ra = *ring; else { ra.A = nullptr; ra.m = tt_make_ring_map(1, 0, 0); }
     ou_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(d_x, d_action, d_scaled, d_reset_mask, n, seed,
-                                                                            gid0, d_iter, evaluate);
+                                                                            gid0, d_iter, evaluate, ra);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
@@ -285,7 +284,15 @@ extern "C" {
 int tt_ou_step(float *d_x, float *d_action, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
                uint64_t global_env_offset, const uint32_t *d_iter, tt_stream_t stream) {
     TT_REQUIRE(d_x && d_iter && n > 0, "bad argument");
-    return tt::launch_noise(d_x, d_action, nullptr, d_reset_mask, n, seed, global_env_offset, d_iter, 0, tt::as_stream(stream));
+    return tt::launch_noise(d_x, d_action, nullptr, d_reset_mask, n, seed, global_env_offset, d_iter, 0, nullptr, tt::as_stream(stream));
+}
+
+int tt_ou_step_store(float *d_x, float *d_action, float *d_scaled, int64_t n, uint64_t seed, uint64_t global_env_offset,
+                     const uint32_t *d_iter, int32_t evaluate, const tt_replay_ring *ring, tt_stream_t stream) {
+    TT_REQUIRE(d_action && d_iter && n > 0 && (evaluate || d_x), "bad argument");
+    TT_REQUIRE(ring && ring->d_action_mem && ring->mem_size > 0 && ring->mem_cntr >= 0, "bad ring");
+    const TTRingA ra = {ring->d_action_mem, tt_make_ring_map(ring->mem_size, ring->mem_cntr, n)};
+    return tt::launch_noise(d_x, d_action, d_scaled, nullptr, n, seed, global_env_offset, d_iter, evaluate, &ra, tt::as_stream(stream));
 }
 
 int tt_scale_action(const float *d_action, float *d_scaled, int64_t n, tt_stream_t stream) {
@@ -338,9 +345,22 @@ int tt_actor_forward(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n,
     TT_REQUIRE(a && d_obs && d_mu, "NULL argument");
     TT_REQUIRE(a->loaded, "tt_actor_load has not been called");
     TT_REQUIRE(n > 0 && ld_obs >= a->dev.in_dim, "bad n / ld_obs");
-    if (precision == TT_PREC_FP32) return tt::actor_forward_fp32(a, d_obs, ld_obs, n, d_mu, tt::as_stream(stream));
-    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, tt::as_stream(stream));
+    if (precision == TT_PREC_FP32) return tt::actor_forward_fp32(a, d_obs, ld_obs, n, d_mu, nullptr, tt::as_stream(stream));
+    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, nullptr, tt::as_stream(stream));
     tt::set_error("tt_actor_forward: unknown precision %d", precision);
+    return TT_ERR_INVALID;
+}
+
+int tt_actor_forward_store(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n, float *d_mu, int32_t precision,
+                           const tt_replay_ring *ring, tt_stream_t stream) {
+    TT_REQUIRE(a && d_obs && d_mu, "NULL argument");
+    TT_REQUIRE(a->loaded, "tt_actor_load has not been called");
+    TT_REQUIRE(n > 0 && ld_obs >= a->dev.in_dim, "bad n / ld_obs");
+    TT_REQUIRE(ring && ring->d_state_mem && ring->mem_size > 0 && ring->mem_cntr >= 0, "bad ring");
+    const TTRingS rs = {ring->d_state_mem, tt_make_ring_map(ring->mem_size, ring->mem_cntr, n)};
+    if (precision == TT_PREC_FP32) return tt::actor_forward_fp32(a, d_obs, ld_obs, n, d_mu, &rs, tt::as_stream(stream));
+    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, &rs, tt::as_stream(stream));
+    tt::set_error("tt_actor_forward_store: unknown precision %d", precision);
     return TT_ERR_INVALID;
 }
 

@@ -5,6 +5,29 @@
 #include <stdio.h>
 #include "../../include/tt_b200.h"
 
+// Where transition i of the current batch lands in the replay ring (ReplayBuffer.store_transition semantics,
+// DDPG/replay_buffer.py:13-21: row (mem_cntr + i) % mem_size, last writer wins).  Used by the kernels that write
+// their part of the transition straight into the ring (fused store) and by the stand-alone scatter kernel.
+struct TTRingMap {
+    int64_t cap;      // mem_size
+    int64_t base;     // mem_cntr % mem_size
+    int64_t first;    // max(0, n - cap): earlier transitions of this batch are overwritten by later ones -> skipped
+    int many;         // n > cap: (base + i) may exceed 2 * cap, use a real modulo
+    __host__ __device__ __forceinline__ int64_t row(int64_t i) const {
+        int64_t r = base + i;
+        if (many) r %= cap; else if (r >= cap) r -= cap;
+        return r;
+    }
+};
+static inline TTRingMap tt_make_ring_map(int64_t cap, int64_t cntr, int64_t n) {
+    TTRingMap m;
+    m.cap = cap; m.base = cntr % cap; m.first = n > cap ? n - cap : 0; m.many = n > cap ? 1 : 0;
+    return m;
+}
+struct TTRingS { float *S; TTRingMap m; };                                   // s  rows   (written by the actor kernel)
+struct TTRingA { float *A; TTRingMap m; };                                   // a         (written by the noise kernel)
+struct TTRingOut { float *S2; float *R; uint8_t *D; TTRingMap m; };          // s', r, d  (written by the env kernel)
+
 namespace tt {
 
 void set_error(const char *fmt, ...);

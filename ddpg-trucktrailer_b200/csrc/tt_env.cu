@@ -161,7 +161,7 @@ template <bool kInfo, bool kGoal, int kMinBlocks, int kStages>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p, StepConsts k, const float *__restrict__ actions,
                                                                       int K, int auto_reset, float *__restrict__ obs, int64_t ld,
                                                                       float *__restrict__ reward, uint8_t *__restrict__ done,
-                                                                      tt_step_info info, uint64_t seed, uint64_t gid0) {
+                                                                      tt_step_info info, uint64_t seed, uint64_t gid0, TTRingOut rpl) {
     // observation tiles: double buffered; full tiles leave through the bulk-copy engine (cp.async.bulk shared ->
     // global), which drains them while the CTA already computes its next tile
     __shared__ __align__(128) float tiles[2][kBlock * TT_OBS_DIM];
@@ -248,6 +248,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                 const int64_t oi = (int64_t)j * N + i;
                 if (reward) __stcs(&reward[oi], o.reward);
                 if (done) done[oi] = o.done ? 1 : 0;
+                if (rpl.S2 && i >= rpl.m.first) {                       // fused replay store of (r, done): replay_buffer.py:13-21
+                    const int64_t rr = rpl.m.row(i);
+                    __stcs(&rpl.R[rr], o.reward); rpl.D[rr] = o.done ? 1 : 0;
+                }
                 if (kInfo) {
                     if (info.d_comps) {
 #pragma unroll
@@ -274,6 +278,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                     for (int c = 0; c < TT_OBS_DIM; c++) tile[threadIdx.x * TT_OBS_DIM + c] = o.obs[c];
                 }
                 float *dst = obs + (int64_t)j * N * ld;
+                // fused replay store of s': the tile goes to the ring's new_state rows as a second bulk copy when those
+                // rows are one aligned contiguous run, else element-wise from the same shared-memory tile
+                const int64_t rrow0 = rpl.S2 ? rpl.m.row(row0) : 0;
+                const bool ring_bulk = rpl.S2 && rows == kBlock && !rpl.m.many && row0 >= rpl.m.first && rrow0 + kBlock <= rpl.m.cap &&
+                                       (rrow0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(rpl.S2) & 15) == 0);
                 if (bulk_ok && rows == kBlock) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncthreads();
@@ -281,12 +290,21 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                         const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile);
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                      ::"l"(dst + row0 * TT_OBS_DIM), "r"(src), "r"((uint32_t)(kBlock * TT_OBS_DIM * sizeof(float))) : "memory");
+                        if (ring_bulk)
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                         ::"l"(rpl.S2 + rrow0 * TT_OBS_DIM), "r"(src), "r"((uint32_t)(kBlock * TT_OBS_DIM * sizeof(float))) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the OTHER buffer is free again
                     }
                 } else {
                     __syncthreads();
                     store_obs_tile(tile, dst, ld, row0, rows);
+                }
+                if (rpl.S2 && !(ring_bulk && bulk_ok)) {                 // (the tile stays valid: it is overwritten two tiles later)
+                    for (int v = threadIdx.x; v < rows * TT_OBS_DIM; v += kBlock) {
+                        const int r = v / TT_OBS_DIM, c = v - r * TT_OBS_DIM;
+                        if (row0 + r >= rpl.m.first) rpl.S2[rpl.m.row(row0 + r) * TT_OBS_DIM + c] = tile[v];
+                    }
                 }
                 tbuf ^= 1u;
             }
@@ -470,9 +488,12 @@ int tt_env_reset(tt_env *env, const uint8_t *d_mask, float *d_obs, int64_t ld_ob
     return TT_OK;
 }
 
-int tt_env_step_k(tt_env *env, const float *d_actions, int32_t K, int32_t auto_reset, float *d_obs, int64_t ld_obs,
-                  float *d_reward, uint8_t *d_done, const tt_step_info *info, tt_stream_t stream) {
+static int env_step_impl(tt_env *env, const float *d_actions, int32_t K, int32_t auto_reset, float *d_obs, int64_t ld_obs,
+                         float *d_reward, uint8_t *d_done, const tt_step_info *info, const TTRingOut *ring, tt_stream_t stream) {
     TT_REQUIRE(env && d_actions, "NULL argument");
+    TT_REQUIRE(!ring || (K == 1 && d_obs), "fused replay store needs K == 1 and an observation buffer");
+    TTRingOut ro;
+    if (ring) ro = *ring; else { ro.S2 = nullptr; ro.R = nullptr; ro.D = nullptr; ro.m = tt_make_ring_map(1, 0, 0); }
     TT_REQUIRE(K >= 1, "K < 1");
     TT_REQUIRE(!d_obs || ld_obs >= TT_OBS_DIM, "ld_obs < 23");
     cudaStream_t s = tt::as_stream(stream);
@@ -496,7 +517,8 @@ int tt_env_step_k(tt_env *env, const float *d_actions, int32_t K, int32_t auto_r
         }                                                                                                                       \
         const int64_t cap = (int64_t)tt::sm_count() * (per_sm > 0 ? per_sm : 4);                                                \
         kern<<<(unsigned)(ntiles < cap ? ntiles : cap), kBlock, dsm, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs,       \
-                                                                         ld_obs, d_reward, d_done, inf, env->seed, env->gid0); \
+                                                                         ld_obs, d_reward, d_done, inf, env->seed, env->gid0,  \
+                                                                         ro);                                                  \
     } while (0)
     const bool goal = env->per_env_goal;
     if (want) {
@@ -518,9 +540,23 @@ int tt_env_step_k(tt_env *env, const float *d_actions, int32_t K, int32_t auto_r
     return TT_OK;
 }
 
+int tt_env_step_k(tt_env *env, const float *d_actions, int32_t K, int32_t auto_reset, float *d_obs, int64_t ld_obs,
+                  float *d_reward, uint8_t *d_done, const tt_step_info *info, tt_stream_t stream) {
+    return env_step_impl(env, d_actions, K, auto_reset, d_obs, ld_obs, d_reward, d_done, info, nullptr, stream);
+}
+
 int tt_env_step(tt_env *env, const float *d_action, float *d_obs, int64_t ld_obs, float *d_reward, uint8_t *d_done,
                 const tt_step_info *info, tt_stream_t stream) {
-    return tt_env_step_k(env, d_action, 1, 0, d_obs, ld_obs, d_reward, d_done, info, stream);
+    return env_step_impl(env, d_action, 1, 0, d_obs, ld_obs, d_reward, d_done, info, nullptr, stream);
+}
+
+int tt_env_step_store(tt_env *env, const float *d_action, float *d_obs, int64_t ld_obs, float *d_reward, uint8_t *d_done,
+                      const tt_replay_ring *ring, tt_stream_t stream) {
+    TT_REQUIRE(env && ring && ring->d_new_state_mem && ring->d_reward_mem && ring->d_terminal_mem && ring->mem_size > 0 &&
+               ring->mem_cntr >= 0, "bad ring");
+    const TTRingOut ro = {ring->d_new_state_mem, ring->d_reward_mem, ring->d_terminal_mem,
+                          tt_make_ring_map(ring->mem_size, ring->mem_cntr, env->p.N)};
+    return env_step_impl(env, d_action, 1, 0, d_obs, ld_obs, d_reward, d_done, nullptr, &ro, stream);
 }
 
 int tt_env_tick(tt_env *env, uint32_t by, tt_stream_t stream) {

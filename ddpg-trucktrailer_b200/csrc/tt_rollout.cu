@@ -1,9 +1,13 @@
 // tt_rollout.cu -- one whole rollout iteration (DDPG/trainv2.py:511-531 without learn()) as ONE launch
-// sequence on the caller's stream:  actor -> OU noise + scaling -> env step -> replay store -> reset of
-// finished envs (+ OU reset, trainv2.py:489-492) -> iteration tick.
+// sequence on the caller's stream:  actor -> OU noise + scaling -> env step -> reset of finished envs (+ OU
+// reset, trainv2.py:489-492) -> iteration tick.  The replay store (agent.remember) is FUSED into the producers:
+// the actor kernel writes s while it reads the observations (its DRAM pipe is idle), the noise kernel writes the
+// raw action, the env kernel writes s', r and done -- 193 B written per transition and nothing re-read, instead of
+// a separate scatter kernel that reads and writes 386 B.  (TT_ROLLOUT_UNFUSED=1 selects the separate kernel.)
 #include "tt_actor.cuh"
 #include "tt_common.cuh"
 
+#include <stdlib.h>
 extern "C" {
 int tt_env_tick(tt_env *env, uint32_t by, tt_stream_t stream);
 const uint32_t *tt_env_iter_ptr(tt_env *env);
@@ -24,15 +28,28 @@ extern "C" int tt_rollout_step(tt_env *env, tt_actor *actor, const tt_rollout_bu
     const int64_t n = tt_env_num_envs(env);
     cudaStream_t s = tt::as_stream(stream);
     int rc;
-    // DDPG_agent.py:36-49 choose_action
-    if ((rc = tt_actor_forward(actor, b->d_obs_cur, b->ld_obs, n, b->d_action, precision, stream)) != TT_OK) return rc;
+    const bool store = b->d_state_mem != nullptr;
+    if (store) TT_REQUIRE(b->d_action_mem && b->d_reward_mem && b->d_new_state_mem && b->d_terminal_mem && b->mem_size > 0, "bad ring");
+    static const bool unfused_env = [] { const char *e = getenv("TT_ROLLOUT_UNFUSED"); return e && atoi(e) != 0; }();
+    const bool tc = precision == TT_PREC_BF16 || precision == TT_PREC_F16;
+    const bool fused = store && !unfused_env && (!tc || tt::actor_tc_fuses_ring());
+    const TTRingMap m = tt_make_ring_map(store ? b->mem_size : 1, store ? b->mem_cntr : 0, store ? n : 0);
+    const TTRingS rs = {b->d_state_mem, m};
+    const TTRingA ra = {b->d_action_mem, m};
+    const tt_replay_ring ring = {b->d_state_mem, b->d_action_mem, b->d_reward_mem, b->d_new_state_mem, b->d_terminal_mem, b->mem_size, b->mem_cntr};
+    // DDPG_agent.py:36-49 choose_action (+ DDPG_agent.py:51-52 remember, fused)
+    TT_REQUIRE(actor->loaded, "tt_actor_load has not been called");
+    if (tc) rc = tt::actor_forward_tc(actor, b->d_obs_cur, b->ld_obs, n, b->d_action, precision, fused ? &rs : nullptr, s);
+    else if (precision == TT_PREC_FP32) rc = tt::actor_forward_fp32(actor, b->d_obs_cur, b->ld_obs, n, b->d_action, fused ? &rs : nullptr, s);
+    else { tt::set_error("tt_rollout_step: unknown precision %d", precision); rc = TT_ERR_INVALID; }
+    if (rc != TT_OK) return rc;
     if ((rc = tt::launch_noise(b->d_ou_x, b->d_action, b->d_scaled, nullptr, n, tt_env_seed_value(env), tt_env_global_offset(env),
-                               tt_env_iter_ptr(env), evaluate, s)) != TT_OK) return rc;
+                               tt_env_iter_ptr(env), evaluate, fused ? &ra : nullptr, s)) != TT_OK) return rc;
     // simv2.py:499-545 env.step(scaled_action)
-    if ((rc = tt_env_step(env, b->d_scaled, b->d_obs_next, b->ld_obs, b->d_reward, b->d_done, nullptr, stream)) != TT_OK) return rc;
-    // DDPG_agent.py:51-52 remember(observation, action, reward, observation_, done)
-    if (b->d_state_mem) {
-        TT_REQUIRE(b->d_action_mem && b->d_reward_mem && b->d_new_state_mem && b->d_terminal_mem && b->mem_size > 0, "bad ring");
+    if (fused) rc = tt_env_step_store(env, b->d_scaled, b->d_obs_next, b->ld_obs, b->d_reward, b->d_done, &ring, stream);
+    else rc = tt_env_step(env, b->d_scaled, b->d_obs_next, b->ld_obs, b->d_reward, b->d_done, nullptr, stream);
+    if (rc != TT_OK) return rc;
+    if (store && !fused) {
         if ((rc = tt::replay_store(b->d_state_mem, b->d_action_mem, b->d_reward_mem, b->d_new_state_mem, b->d_terminal_mem,
                                    b->mem_size, b->mem_cntr, b->d_obs_cur, b->ld_obs, b->d_action, b->d_reward, b->d_obs_next,
                                    b->ld_obs, b->d_done, n, s)) != TT_OK) return rc;

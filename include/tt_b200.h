@@ -179,6 +179,23 @@ int tt_replay_gather(const float *d_state_mem, const float *d_action_mem, const 
                      int64_t batch, float *d_s, float *d_a, float *d_r, float *d_s2, uint8_t *d_done,
                      tt_stream_t stream);
 
+/* ---- fused store: the producers write their part of the transition straight into the ring ---- */
+/* A batch of n transitions goes to rows (mem_cntr + i) % mem_size exactly as tt_replay_store would put it.  The three
+ * calls below are the producers of tt_rollout_step with the store fused in (193 B written per transition, nothing
+ * re-read): the actor writes `state` while it reads the observations, the noise kernel writes the raw `action`, the
+ * env kernel writes `new_state`, `reward` and `terminal`.  Members that a call does not write may be NULL. */
+typedef struct tt_replay_ring {
+    float   *d_state_mem, *d_action_mem, *d_reward_mem, *d_new_state_mem;
+    uint8_t *d_terminal_mem;
+    int64_t  mem_size, mem_cntr;
+} tt_replay_ring;
+int tt_actor_forward_store(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n, float *d_mu, int32_t precision,
+                           const tt_replay_ring *ring, tt_stream_t stream);
+int tt_ou_step_store(float *d_x, float *d_action, float *d_scaled, int64_t n, uint64_t seed, uint64_t global_env_offset,
+                     const uint32_t *d_iter, int32_t evaluate, const tt_replay_ring *ring, tt_stream_t stream);
+int tt_env_step_store(tt_env *env, const float *d_action, float *d_obs, int64_t ld_obs, float *d_reward,
+                      uint8_t *d_done, const tt_replay_ring *ring, tt_stream_t stream);
+
 /* ---- one whole rollout iteration (trainv2.py:511-531 without learn()) as one launch sequence ---- */
 typedef struct tt_rollout_bufs {
     float   *d_obs_cur;      /* [n, ld_obs] in: s   */
@@ -194,8 +211,8 @@ typedef struct tt_rollout_bufs {
     uint8_t *d_terminal_mem;
     int64_t  mem_size, mem_cntr;
 } tt_rollout_bufs;
-/* actor -> OU noise (unless evaluate) -> scale -> env step -> replay store -> reset finished envs.
- * Advances the env's iteration counter. */
+/* actor -> OU noise (unless evaluate) -> scale -> env step -> reset finished envs, with the replay store fused into
+ * the producers (see above).  Advances the env's iteration counter. */
 int tt_rollout_step(tt_env *env, tt_actor *actor, const tt_rollout_bufs *b, int32_t precision,
                     int32_t evaluate, tt_stream_t stream);
 

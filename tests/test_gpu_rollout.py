@@ -74,3 +74,33 @@ def test_rollout_vs_oracle_small():
         if not alive.any():
             break
     assert (~alive).sum() > 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+@pytest.mark.parametrize("N,cap,cntr0", [(1000, 4096, 0), (3000, 10000, 9000), (5000, 2048, 77), (4096, 4096, 4096 * 3 + 4), (777, 1 << 16, 5)])
+def test_fused_store_equals_scatter_kernel(precision, N, cap, cntr0):
+    """The producers' fused ring writes (actor: s, noise kernel: a, env kernel: s', r, done) put exactly the bytes
+    where the stand-alone scatter kernel / ReplayBuffer.store_transition semantics put them: wrap-around, batches
+    larger than the ring (last writer wins), unaligned ring positions, ragged tiles."""
+    import ctypes as C
+    import ddpg_trucktrailer_b200 as tt
+    from ddpg_trucktrailer_b200 import _lib
+    L = tt.load(); s = _lib.stream_ptr()
+    env = tt.VecTruckTrailerEnv(N, seed=4); ag = tt.VecAgent(1e-4, 1e-3, (23,), 1e-3, 1, num_envs=N, max_size=cap, actor_seed=1, precision=precision)
+    ag.noise.bind_env(env)
+    obs, _ = env.reset()
+    obs = obs.clone()
+    ref = tt.DeviceReplayBuffer(cap); ref.mem_cntr = cntr0
+    fused = tt.DeviceReplayBuffer(cap)
+    for mem in (ref, fused):                                  # sentinel so that untouched rows are compared too
+        mem.state_memory.fill_(-7.0); mem.new_state_memory.fill_(-7.0); mem.action_memory.fill_(-7.0); mem.reward_memory.fill_(-7.0); mem.terminal_memory.fill_(9)
+    ring = _lib.ReplayRing(fused.state_memory.data_ptr(), fused.action_memory.data_ptr(), fused.reward_memory.data_ptr(),
+                           fused.new_state_memory.data_ptr(), fused.terminal_memory.data_ptr(), cap, cntr0)
+    mu = torch.empty(N, device="cuda"); scaled = torch.empty(N, device="cuda"); x = torch.zeros(N, device="cuda")
+    obs2 = torch.empty(N, 23, device="cuda"); rew = torch.empty(N, device="cuda"); done = torch.empty(N, dtype=torch.uint8, device="cuda")
+    _lib.check(L.tt_actor_forward_store(ag.actor._h, obs.data_ptr(), 23, N, mu.data_ptr(), _lib.PRECISIONS[precision], C.byref(ring), s))
+    _lib.check(L.tt_ou_step_store(x.data_ptr(), mu.data_ptr(), scaled.data_ptr(), N, 4, 0, ag.noise.iter_ptr, 0, C.byref(ring), s))
+    _lib.check(L.tt_env_step_store(env._h, scaled.data_ptr(), obs2.data_ptr(), 23, rew.data_ptr(), done.data_ptr(), C.byref(ring), s))
+    ref.store_transition(obs, mu, rew, obs2, done)
+    for f in ("state_memory", "new_state_memory", "action_memory", "reward_memory", "terminal_memory"):
+        assert torch.equal(getattr(fused, f), getattr(ref, f)), f
