@@ -563,14 +563,14 @@ constexpr int kN1A = 192, kN1B = N1 - kN1A;                    // layer-1 column
 constexpr int kChA = kN1A / 32;                                // 6 chunks in half a; half b = chunks 6..12
 
 template <typename OpT, bool kSplit>
-__global__ void __launch_bounds__(608, 1) actor_tc3_kernel(const char *__restrict__ w1img, const char *__restrict__ w2img,
+__global__ void __launch_bounds__(640, 1) actor_tc3_kernel(const char *__restrict__ w1img, const char *__restrict__ w2img,
                                                            const float *__restrict__ gram, tt_actor_dev A,
                                                            const float *__restrict__ obs, int64_t ld, int64_t n,
                                                            float *__restrict__ out, TTRingS ring,
                                                            unsigned long long *__restrict__ dbg) {
     using P = Plan3<kSplit>;
-    constexpr int kGroups = 4, kEpiThreads = 512, kThreads = 608;
-    constexpr int kM2Warp = 16, kProdWarp = 17, kM1Warp = 18;
+    constexpr int kGroups = 4, kEpiThreads = 512, kThreads = 640;
+    constexpr int kM2Warp = 16, kProdWarp = 17, kM1Warp = 18, kCopyWarp = 19;
     constexpr uint32_t kFmt = std::is_same<OpT, __nv_bfloat16>::value ? 1u : 0u;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -632,6 +632,33 @@ __global__ void __launch_bounds__(608, 1) actor_tc3_kernel(const char *__restric
                     mbar_wait(bar(C_W2EMPTY + slot), ph ^ 1u);
                     mbar_expect_tx(bar(C_W2FULL + slot), (uint32_t)N2 * kRowB);
                     bulk_g2s(sW2 + slot * P::kW2Slot, w2img + (size_t)kb * N2 * kRowB, (uint32_t)N2 * kRowB, bar(C_W2FULL + slot));
+                }
+            }
+        }
+    } else if (warp == kCopyWarp) {
+        // ================= fused replay store of s: observation rows -> ring `state` rows =================
+        // A dedicated warp, so the copy stays off the epilogue's critical path; DRAM is idle in this kernel (2.5 %).
+        if (ring.S) {
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int64_t row0 = tile * kTileM;
+                const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
+                const int64_t rrow0 = ring.m.row(row0);
+                const float *src = obs + row0 * ld;
+                float *dst = ring.S + rrow0 * IN;
+                const bool flat = ld == IN && rows == kTileM && !ring.m.many && row0 >= ring.m.first && rrow0 + kTileM <= ring.m.cap;
+                if (flat && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+                    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+                    float4 *d4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll 4
+                    for (int v = lane; v < kTileM * IN / 4; v += 32) __stcs(&d4[v], __ldcs(&s4[v]));
+                } else if (flat) {
+#pragma unroll 4
+                    for (int v = lane; v < kTileM * IN; v += 32) __stcs(&dst[v], __ldcs(&src[v]));
+                } else {
+                    for (int v = lane; v < rows * IN; v += 32) {
+                        const int rr = v / IN, k = v - rr * IN;
+                        if (row0 + rr >= ring.m.first) ring.S[ring.m.row(row0 + rr) * IN + k] = __ldcs(obs + (row0 + rr) * ld + k);
+                    }
                 }
             }
         }
@@ -734,8 +761,7 @@ __global__ void __launch_bounds__(608, 1) actor_tc3_kernel(const char *__restric
                     const float x = xreg[i];
                     const OpT hi = to_op<OpT>(x);
                     *reinterpret_cast<OpT *>(sm + P::x + sw64_off(rr, k)) = hi;
-                    // fused replay store of s (DRAM is idle in this kernel): same coalesced element order as the load
-                    if (ring.S && row0 + rr < n && row0 + rr >= ring.m.first) ring.S[ring.m.row(row0 + rr) * IN + k] = x;
+
                     if (kSplit) *reinterpret_cast<OpT *>(sm + P::x + kTileM * kRowB + sw64_off(rr, k)) = to_op<OpT>(x - op_to_float(hi));
                 }
             }
@@ -936,7 +962,7 @@ int launch_tc3(const char *w1img, const char *w2img, const float *gram, const tt
     }
     const int64_t ntiles = (n + kTileM - 1) / kTileM;
     const int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
-    kern<<<grid, 608, P::total, st>>>(w1img, w2img, gram, A, d_obs, ld, n, d_mu, rs, g_tc_dbg);
+    kern<<<grid, 640, P::total, st>>>(w1img, w2img, gram, A, d_obs, ld, n, d_mu, rs, g_tc_dbg);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }

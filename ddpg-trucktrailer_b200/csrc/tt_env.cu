@@ -336,10 +336,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
 // here (that is tt_ou_step's reset mask, trainv2.py:492).
 __global__ void __launch_bounds__(kBlock) env_reset_kernel(EnvPtrs p, StepConsts k, const uint8_t *__restrict__ mask,
                                                            float *__restrict__ obs, int64_t ld, uint64_t seed,
-                                                           uint64_t gid0, uint32_t t_salt) {
+                                                           uint64_t gid0, uint32_t t_salt, float *__restrict__ ou_x) {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= p.N) return;
     if (mask && !mask[i]) return;
+    if (ou_x) ou_x[i] = 0.0f;                                 // agent.noise.reset() for the new episode (trainv2.py:492)
     EnvRegs e;
     double sx, sy, syaw;
     rng_pose(k, seed, (uint32_t)(gid0 + i), *p.iter + t_salt, sx, sy, syaw);
@@ -475,17 +476,26 @@ int tt_env_seed(tt_env *env, uint64_t seed, tt_stream_t stream) {
     return TT_OK;
 }
 
-int tt_env_reset(tt_env *env, const uint8_t *d_mask, float *d_obs, int64_t ld_obs, tt_stream_t stream) {
+static int env_reset_impl(tt_env *env, const uint8_t *d_mask, float *d_obs, int64_t ld_obs, float *d_ou_x, tt_stream_t stream) {
     TT_REQUIRE(env, "env is NULL");
     TT_REQUIRE(!d_obs || ld_obs >= TT_OBS_DIM, "ld_obs < 23");
     cudaStream_t s = tt::as_stream(stream);
     // a masked reset shares the iteration of the step that finished the episode; a full reset uses the
     // salted counter so it never collides with it, then advances the iteration.
     env_reset_kernel<<<(unsigned)grid_for(env->p.N), kBlock, 0, s>>>(env->p, env->k, d_mask, d_obs, ld_obs, env->seed,
-                                                                    env->gid0, d_mask ? 0u : 0x80000000u);
+                                                                    env->gid0, d_mask ? 0u : 0x80000000u, d_ou_x);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     if (!d_mask) { tick_kernel<<<1, 1, 0, s>>>(env->p.iter, 1u); TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK(); }
     return TT_OK;
+}
+
+int tt_env_reset(tt_env *env, const uint8_t *d_mask, float *d_obs, int64_t ld_obs, tt_stream_t stream) {
+    return env_reset_impl(env, d_mask, d_obs, ld_obs, nullptr, stream);
+}
+
+// internal (tt_rollout.cu): masked reset that also zeroes the OU state of the reset envs (one launch instead of two)
+int tt_env_reset_ou(tt_env *env, const uint8_t *d_mask, float *d_obs, int64_t ld_obs, float *d_ou_x, tt_stream_t stream) {
+    return env_reset_impl(env, d_mask, d_obs, ld_obs, d_ou_x, stream);
 }
 
 static int env_step_impl(tt_env *env, const float *d_actions, int32_t K, int32_t auto_reset, float *d_obs, int64_t ld_obs,

@@ -9,6 +9,7 @@
 
 #include <stdlib.h>
 extern "C" {
+int tt_env_reset_ou(tt_env *env, const uint8_t *d_mask, float *d_obs, int64_t ld_obs, float *d_ou_x, tt_stream_t stream);
 int tt_env_tick(tt_env *env, uint32_t by, tt_stream_t stream);
 const uint32_t *tt_env_iter_ptr(tt_env *env);
 uint64_t tt_env_seed_value(tt_env *env);
@@ -55,7 +56,6 @@ extern "C" int tt_rollout_step(tt_env *env, tt_actor *actor, const tt_rollout_bu
                                    b->ld_obs, b->d_done, n, s)) != TT_OK) return rc;
     }
     // trainv2.py:489-492: env.reset() + agent.noise.reset() for finished episodes
-    if ((rc = tt_env_reset(env, b->d_done, b->d_obs_next, b->ld_obs, stream)) != TT_OK) return rc;
-    if (!evaluate && (rc = tt::launch_ou_zero(b->d_ou_x, b->d_done, n, s)) != TT_OK) return rc;
+    if ((rc = tt_env_reset_ou(env, b->d_done, b->d_obs_next, b->ld_obs, evaluate ? nullptr : b->d_ou_x, stream)) != TT_OK) return rc;
     return tt_env_tick(env, 1u, stream);
 }
