@@ -19,6 +19,8 @@ struct tt_actor_dev {
     int k1p, h1p, h2p, kb1;
     float *w1t, *w2t, *b1, *g1, *be1, *b2, *g2, *be2, *w3, *b3;
     void *w1_f16, *w2_f16, *w1_bf16, *w2_bf16;     // UMMA operand images (tt_actor_tc.cu)
+    void *w2s_f16, *w2s_bf16;                       // v4 layer-2 images: k-blocks grouped by output-column sweep
+    void *w1c_f16, *w1c_bf16;                       // v4 layer-1 images: centred, LayerNorm-scaled rows + statistic rows (tt_actor_tc4.cu)
     float *gram_f16, *gram_bf16;                    // [25][24]: Gram matrix of fc1 (+bias column) and its column sums
 };
 
@@ -37,6 +39,8 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
     const size_t o_w3 = take(sizeof(float) * h2p), o_b3 = take(sizeof(float));
     const size_t n1 = (h1 + 15) / 16 * 16, n2 = (h2 + 15) / 16 * 16, kb2 = (h1 + 1 + 31) / 32;
     const size_t o_w1h = take(2 * n1 * 64), o_w2h = take(kb2 * n2 * 64), o_w1b = take(2 * n1 * 64), o_w2b = take(kb2 * n2 * 64);
+    const size_t o_w2sh = take(kb2 * n2 * 64), o_w2sb = take(kb2 * n2 * 64);
+    const size_t o_w1ch = take(2 * (n1 + 32) * 64), o_w1cb = take(2 * (n1 + 32) * 64);
     const size_t o_gh = take(sizeof(float) * 25 * 24), o_gb = take(sizeof(float) * 25 * 24);
     if (d) {
         d->in_dim = in_dim; d->h1 = h1; d->h2 = h2; d->k1p = k1p; d->h1p = h1p; d->h2p = h2p; d->kb1 = kb1;
@@ -44,6 +48,8 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
         d->w1t = f(o_w1t); d->w2t = f(o_w2t); d->b1 = f(o_b1); d->g1 = f(o_g1); d->be1 = f(o_be1);
         d->b2 = f(o_b2); d->g2 = f(o_g2); d->be2 = f(o_be2); d->w3 = f(o_w3); d->b3 = f(o_b3);
         d->w1_f16 = base + o_w1h; d->w2_f16 = base + o_w2h; d->w1_bf16 = base + o_w1b; d->w2_bf16 = base + o_w2b;
+        d->w2s_f16 = base + o_w2sh; d->w2s_bf16 = base + o_w2sb;
+        d->w1c_f16 = base + o_w1ch; d->w1c_bf16 = base + o_w1cb;
         d->gram_f16 = f(o_gh); d->gram_bf16 = f(o_gb);
     }
     return off;
@@ -54,6 +60,9 @@ namespace tt {
 int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, const TTRingS *ring, cudaStream_t s);
 int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring, cudaStream_t s);
 bool actor_tc_fuses_ring();
+int actor_pack_tc4(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *g1, const float *fc2_w, const float *fc2_b, cudaStream_t s);
+int actor_forward_tc4(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring,
+                      unsigned long long *dbg, cudaStream_t s);
 int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *fc2_w, const float *fc2_b, cudaStream_t s);
 int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
                  uint64_t gid0, const uint32_t *d_iter, int evaluate, const TTRingA *ring, cudaStream_t s);

@@ -1,0 +1,606 @@
+// tt_actor_tc4.cu -- kernel (c), tensor-core path, 4th version ("v4") of the batched actor forward
+// (ActorNetwork.forward, DDPG/networks.py:138-147) on tcgen05 / TMEM.
+//
+// What changed against v3 (tt_actor_tc.cu) and why.  Measured on v3 (profiles/): a tile took 14 300 cycles of which the
+// tensor pipe was busy 5 000; the rest was the CUDA-core side running strictly after / before the MMAs, and every
+// tcgen05.mma with N <= 64 costs 52 cycles whatever N (profiles/mma_probe.cu), N = 256 + 48 therefore 185 per k-step.
+//  * LayerNorm 1 is folded into the operands.  W1' = diag(g1) (W1 - 1 m^T) with m = column mean of [fc1.weight | fc1.bias]
+//    makes the tensor core emit t' = g1 * (h - mean(h)) directly, so epilogue 1 is ONE packed FMA per column pair
+//    (y = relu(t' * rstd + be1)).
+//  * The LayerNorm variance comes from the tensor core too: var(h) = x^T Gc x / 400 with Gc the Gram matrix of the
+//    centred weights; with the Cholesky factor Gc = L L^T, x^T Gc x = |L^T x|^2, and L^T x is 24 extra output columns
+//    of the layer-1 GEMM (32 TMEM columns in front of part 0).  Every epilogue thread reads them and squares them: no
+//    Gram-matrix phase on the CUDA cores (2 600 cycles per tile in v3), no cross-warp reduction, no barrier.
+//  * Layer 1 = 3 parts (N = 128 | 160 | 144: statistics + 96, 160, 144 columns) through one 160-column TMEM window; an
+//    epilogue thread pulls its 8 columns of every 32-column A2 block of the part into registers at once and frees the
+//    window before it does the math, so the next part's MMAs run under it.
+//  * Layer 2 is split by OUTPUT columns into two K-sweeps (N = 160, then N = 144; 84 + 76 cycles per k-step instead of
+//    185), with separate full/free barriers: the statistics pass over half A runs under sweep B, and sweep A of the next
+//    tile starts as soon as pass 2 has read half A -- epilogue 2 is no longer serial with the layer-2 MMAs.  W2 is
+//    streamed per sweep in half-size k-blocks (4 ring slots instead of 2 in the same shared memory).
+//  * X staging: one thread = 6 consecutive inputs of one row (three 32-bit stores per operand block, no divisions), one
+//    tile ahead.  Epilogue 2: contiguous balanced column ranges (40 + 36 columns per thread).
+//
+// TMEM columns: [0,160) H2 half A | [160,304) H2 half B | [304,464) layer-1 window (part 0: 32 statistic columns first).
+// Warp roles (640 threads): warps 0-15 epilogue (warp w: TMEM lanes 32 (w % 4), column group w / 4), warp 16 lane 0
+// layer-2 MMA issuer, warp 17 lane 0 bulk-copy producer (W2 k-blocks streamed from L2), warp 18 lane 0 layer-1 MMA
+// issuer, warp 19 fused replay-ring store of the observation rows.
+#include <stdlib.h>
+#include "tt_actor.cuh"
+#include "tt_common.cuh"
+#include "tt_tc_ptx.cuh"
+
+namespace {
+
+constexpr int kStatRows = 32;                 // statistic rows appended to the layer-1 B image (24 used)
+constexpr int N1I = N1 + kStatRows;           // rows per hi / lo block of the v4 layer-1 image (432)
+constexpr int kParts = 3;                     // layer-1 parts: [32 statistics + 96] | 160 | 144 columns
+constexpr int kWin0 = 304;                    // first TMEM column of the layer-1 window (160 columns)
+constexpr int kNA = 160, kNB = N2 - kNA;      // layer-2 output halves (sweep A / sweep B)
+constexpr uint32_t kW2SlotB = kNA * kRowB;    // ring slot: one half k-block (10 240 B; sweep B uses 9 216 of it)
+constexpr size_t kW2SweepB = (size_t)KB2 * kNA * kRowB;   // byte offset of sweep B inside the v4 W2 image
+
+__device__ __forceinline__ void tmem_ld4_async(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+template <int NR>
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[NR]) {      // 8 columns into r[0..7], rest zero
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 8; i < NR; i++) r[i] = 0u;
+}
+
+// ---- v4 layer-1 image, built at tt_actor_load time (one block of 576 threads) ----
+// rows 0..23   : L[k][j] (row j): lower Cholesky factor of Gc = sum_c (Wf[c] - m)(Wf[c] - m)^T, so that
+//                sum_j (row_j . x)^2 = x^T Gc x = sum_c (h_c - mean(h))^2;   rows 24..31: 0
+// rows 32..431 : g1[c] * (Wf[c][k] - m[k]),  Wf = [fc1.weight | fc1.bias], m = column means
+// Written as [hi | lo] f16 blocks (lo = rounding residual) and as one bf16 block.
+__global__ void __launch_bounds__(576) pack_l1c_kernel(char *__restrict__ img_f16, char *__restrict__ img_bf16,
+                                                        const float *__restrict__ fc1_w, const float *__restrict__ fc1_b,
+                                                        const float *__restrict__ g1) {
+    __shared__ double m[24], G[24][25], Lf[24][25];
+    __shared__ double gmax;
+    const int t = threadIdx.x, i = t / 24, j = t - i * 24;
+    auto wf = [&](int c, int k) { return (double)(k < IN ? fc1_w[c * IN + k] : fc1_b[c]); };
+    {
+        double si = 0.0, sj = 0.0, sij = 0.0;
+        for (int c = 0; c < H1; c++) { const double a = wf(c, i), b = wf(c, j); si += a; sj += b; sij += a * b; }
+        G[i][j] = sij - si * sj / H1;
+        Lf[i][j] = 0.0;
+        if (j == 0) m[i] = si / H1;
+    }
+    __syncthreads();
+    if (t == 0) { double d = 0.0; for (int k = 0; k < 24; k++) d = fmax(d, G[k][k]); gmax = d; }
+    __syncthreads();
+    for (int k = 0; k < 24; k++) {                 // right-looking Cholesky, column k; tiny pivots -> zero column
+        const double d = G[k][k];
+        const bool ok = d > 1e-13 * gmax && d > 0.0;
+        const double piv = ok ? sqrt(d) : 0.0;
+        if (j == k && i >= k) Lf[i][k] = ok ? (i == k ? piv : G[i][k] / piv) : 0.0;
+        __syncthreads();
+        if (i > k && j > k) G[i][j] -= Lf[i][k] * Lf[j][k];
+        __syncthreads();
+    }
+    auto put = [&](int row, int k, double x) {
+        const float xf = (float)x;
+        const __half hi = __float2half_rn(xf);
+        *reinterpret_cast<__half *>(img_f16 + sw64_off(row, k)) = hi;
+        *reinterpret_cast<__half *>(img_f16 + N1I * kRowB + sw64_off(row, k)) = __float2half_rn(xf - __half2float(hi));
+        *reinterpret_cast<__nv_bfloat16 *>(img_bf16 + sw64_off(row, k)) = __float2bfloat16_rn(xf);
+    };
+    for (int v = t; v < N1I * 32; v += blockDim.x) {
+        const int row = v >> 5, k = v & 31;
+        double x = 0.0;
+        if (k < 24) {
+            if (row >= kStatRows) x = (double)g1[row - kStatRows] * (wf(row - kStatRows, k) - m[k]);
+            else if (row < 24) x = Lf[k][row];                      // row j of the statistic block = column j of L
+        }
+        put(row, k, x);
+    }
+}
+
+// ---- v4 layer-2 image: [sweep A: kb 0..12, 160 rows x 64 B][sweep B: kb 0..12, 144 rows x 64 B] ----
+// row n of sweep A = output column n, of sweep B = output column 160 + n (k < H1: fc2.weight, k == H1: fc2.bias, else 0)
+template <typename OpT>
+__global__ void pack_w2s_kernel(char *__restrict__ img, const float *__restrict__ fc2_w, const float *__restrict__ fc2_b) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int v = tid; v < KB2 * N2 * 32; v += nth) {
+        const int kb = v / (N2 * 32), rem = v - kb * N2 * 32, col = rem / 32, kk = rem - col * 32, k = kb * 32 + kk;
+        float x = 0.f;
+        if (col < H2) x = k < H1 ? fc2_w[col * H1 + k] : (k == H1 ? fc2_b[col] : 0.f);
+        const size_t off = col < kNA ? (size_t)kb * kNA * kRowB + sw64_off(col, kk)
+                                     : kW2SweepB + (size_t)kb * kNB * kRowB + sw64_off(col - kNA, kk);
+        *reinterpret_cast<OpT *>(img + off) = to_op<OpT>(x);
+    }
+}
+
+template <bool kSplit>
+struct Plan4 {
+    static constexpr int kXBlocks = kSplit ? 2 : 1;
+    static constexpr int kSlots = kSplit ? 4 : 6;
+    static constexpr uint32_t kW2Slot = kW2SlotB;
+    static constexpr uint32_t x = 0;
+    static constexpr uint32_t w1 = x + kXBlocks * kTileM * kRowB;
+    static constexpr uint32_t a2 = w1 + kXBlocks * N1I * kRowB;
+    static constexpr uint32_t w2 = a2 + KB2 * kTileM * kRowB;
+    static constexpr uint32_t par = w2 + kSlots * kW2Slot;
+    static constexpr uint32_t npar = K2P + 3 * H2P;                               // be1 | g2 be2 w3
+    static constexpr uint32_t red = par + npar * 4;
+    static constexpr uint32_t bars = red + 4 * kTileM * 8 + 4 * kTileM * 4;
+    static constexpr uint32_t nbars = 40;
+    static constexpr uint32_t tmem_slot = bars + nbars * 8;
+    static constexpr uint32_t total = tmem_slot + 16 + 1024;
+};
+
+enum { D_W1 = 0, D_XFULL, D_WFULL, D_WFREE, D_A2FULL, D_H2AFULL, D_H2BFULL, D_H2AFREE, D_H2BFREE,
+       D_W2FULL, D_W2EMPTY = D_W2FULL + 6, D_A2FREE = D_W2EMPTY + 6, D_COUNT = D_A2FREE + KB2 };
+static_assert(D_COUNT <= 40, "barrier table");
+
+template <typename OpT, bool kSplit>
+__global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restrict__ w1img, const char *__restrict__ w2img,
+                                                           tt_actor_dev A, const float *__restrict__ obs, int64_t ld, int64_t n,
+                                                           float *__restrict__ out, TTRingS ring,
+                                                           unsigned long long *__restrict__ dbg) {
+    using P = Plan4<kSplit>;
+    constexpr int kGroups = 4, kEpiThreads = 512, kThreads = 640;
+    constexpr int kM2Warp = 16, kProdWarp = 17, kM1Warp = 18, kCopyWarp = 19;
+    constexpr uint32_t kFmt = std::is_same<OpT, __nv_bfloat16>::value ? 1u : 0u;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (base - raw);
+    const uint32_t sX = base + P::x, sW1 = base + P::w1, sA2 = base + P::a2, sW2 = base + P::w2, sBar = base + P::bars;
+    float *par = reinterpret_cast<float *>(sm + P::par);
+    float *pbe1 = par, *pg2 = par + K2P, *pbe2 = pg2 + H2P, *pw3 = pbe2 + H2P;
+    float2 *red1 = reinterpret_cast<float2 *>(sm + P::red);
+    float *red3 = reinterpret_cast<float *>(red1 + 4 * kTileM);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sm + P::tmem_slot);
+    auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (n + kTileM - 1) / kTileM;
+
+    // ---------------- one-time setup ----------------
+    if (threadIdx.x == 0) {
+        mbar_init(bar(D_W1), 1);
+        mbar_init(bar(D_XFULL), kEpiThreads); mbar_init(bar(D_WFULL), 1); mbar_init(bar(D_WFREE), kEpiThreads);
+        mbar_init(bar(D_A2FULL), kEpiThreads);
+        mbar_init(bar(D_H2AFULL), 1); mbar_init(bar(D_H2BFULL), 1); mbar_init(bar(D_H2AFREE), kEpiThreads); mbar_init(bar(D_H2BFREE), kEpiThreads);
+        for (int i = 0; i < P::kSlots; i++) { mbar_init(bar(D_W2FULL + i), 1); mbar_init(bar(D_W2EMPTY + i), 1); }
+        for (int i = 0; i < KB2; i++) mbar_init(bar(D_A2FREE + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kM2Warp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + P::tmem_slot), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int c = threadIdx.x; c < K2P; c += kThreads) pbe1[c] = c < H1 ? A.be1[c] : 0.f;
+    for (int c = threadIdx.x; c < H2P; c += kThreads) {
+        const bool in = c < H2;
+        pg2[c] = in ? A.g2[c] : 0.f; pbe2[c] = in ? A.be2[c] : 0.f; pw3[c] = in ? A.w3[c] : 0.f;
+    }
+    // X blocks: zero once (k = 24..31 stay zero).  A2 block 12, columns 400..415: constant (1, 0, ..., 0) -- column 400
+    // carries the fc2 bias -- written once; the epilogue only ever rewrites columns 384..399 of that block.
+    for (int v = threadIdx.x; v < P::kXBlocks * kTileM * kRowB / 4; v += kThreads) reinterpret_cast<uint32_t *>(sm + P::x)[v] = 0u;
+    if (threadIdx.x < kTileM) {
+        const int r = threadIdx.x;
+        const uint32_t xsw = ((uint32_t)r >> 1) & 3u;
+        uint8_t *blk = sm + P::a2 + (size_t)12 * kTileM * kRowB + (size_t)r * kRowB;
+        uint4 one = make_uint4(0u, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+        const OpT o = to_op<OpT>(1.0f);
+        one.x = (uint32_t)(*reinterpret_cast<const uint16_t *>(&o));
+        *reinterpret_cast<uint4 *>(blk + ((2u ^ xsw) << 4)) = one;
+        *reinterpret_cast<uint4 *>(blk + ((3u ^ xsw) << 4)) = zero;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const float b3 = A.b3[0];
+
+    if (warp == kProdWarp) {
+        // ================= bulk-copy producer: W1 once, then per tile 13 half k-blocks of sweep A and 13 of sweep B =================
+        // (warp-uniform control flow; one elected lane issues the copies)
+        constexpr uint32_t w1bytes = (uint32_t)P::kXBlocks * N1I * kRowB;
+        if (elect_one()) {
+            mbar_expect_tx(bar(D_W1), w1bytes);
+            bulk_g2s(sW1, w1img, w1bytes, bar(D_W1));
+        }
+        __syncwarp();
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll 1
+            for (int sweep = 0; sweep < 2; sweep++) {
+                const uint32_t bytes = (uint32_t)(sweep ? kNB : kNA) * kRowB;
+                const char *src = w2img + (sweep ? kW2SweepB : 0);
+#pragma unroll 1
+                for (int kb = 0; kb < KB2; kb++, it++) {
+                    const uint32_t slot = it % P::kSlots, ph = (it / P::kSlots) & 1u;
+                    mbar_wait(bar(D_W2EMPTY + slot), ph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar(D_W2FULL + slot), bytes);
+                        bulk_g2s(sW2 + slot * P::kW2Slot, src + (size_t)kb * bytes, bytes, bar(D_W2FULL + slot));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == kCopyWarp) {
+        // ================= fused replay store of s: observation rows -> ring `state` rows =================
+        if (ring.S) {
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int64_t row0 = tile * kTileM;
+                const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
+                const int64_t rrow0 = ring.m.row(row0);
+                const float *src = obs + row0 * ld;
+                float *dst = ring.S + rrow0 * IN;
+                const bool flat = ld == IN && rows == kTileM && !ring.m.many && row0 >= ring.m.first && rrow0 + kTileM <= ring.m.cap;
+                if (flat && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+                    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+                    float4 *d4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll 4
+                    for (int v = lane; v < kTileM * IN / 4; v += 32) __stcs(&d4[v], __ldcs(&s4[v]));
+                } else if (flat) {
+#pragma unroll 4
+                    for (int v = lane; v < kTileM * IN; v += 32) __stcs(&dst[v], __ldcs(&src[v]));
+                } else {
+                    for (int v = lane; v < rows * IN; v += 32) {
+                        const int rr = v / IN, k = v - rr * IN;
+                        if (row0 + rr >= ring.m.first) ring.S[ring.m.row(row0 + rr) * IN + k] = __ldcs(obs + (row0 + rr) * ld + k);
+                    }
+                }
+            }
+        }
+    } else if (warp == kM1Warp) {
+        // ================= layer-1 MMA issuer: 3 parts through the window =================
+        {
+            const uint32_t idp[kParts] = {make_idesc(128, kFmt), make_idesc(160, kFmt), make_idesc(144, kFmt)};
+            constexpr uint32_t rowp[kParts] = {0u, 128u, 288u};            // first image row of each part
+            constexpr int npairs = kSplit ? 3 : 1;
+            const uint64_t dX = make_desc(sX), dW1 = make_desc(sW1);      // descriptor address field is in 16 B units
+            uint32_t c1 = 0, use = 0;
+            mbar_wait(bar(D_W1), 0);
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, c1++) {
+                mbar_wait(bar(D_XFULL), c1 & 1u);
+#pragma unroll
+                for (int p = 0; p < kParts; p++, use++) {
+                    mbar_wait(bar(D_WFREE), (use & 1u) ^ 1u);              // the epilogue has pulled the previous part out of the window
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int pr = 0; pr < npairs; pr++) {
+                            const uint64_t xb = dX + (uint64_t)(pr == 1 ? kTileM * kRowB / 16 : 0);
+                            const uint64_t wb = dW1 + (uint64_t)((pr == 2 ? N1I * kRowB : 0) + rowp[p] * kRowB) / 16;
+                            umma(tmem + kWin0, xb, wb, idp[p], pr ? 1u : 0u);
+                            umma(tmem + kWin0, xb + 2, wb + 2, idp[p], 1u);
+                        }
+                        umma_commit(bar(D_WFULL));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == kM2Warp) {
+        // ================= layer-2 MMA issuer: sweep A (columns 0..159), then sweep B (160..303) =================
+        {
+            const uint32_t idA = make_idesc(kNA, kFmt), idB = make_idesc(kNB, kFmt);
+            const uint64_t dA2 = make_desc(sA2), dW2 = make_desc(sW2);    // descriptor address field is in 16 B units
+            const bool prof = dbg != nullptr;
+            uint32_t it = 0, c2 = 0;
+            long long t_a2 = 0, t_w2 = 0, t_h2 = 0, t0 = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, c2++) {
+                const uint32_t ph = c2 & 1u;
+                if (prof) t0 = clock64();
+                mbar_wait(bar(D_A2FULL), ph);
+                if (prof) t_a2 += clock64() - t0;
+#pragma unroll 1
+                for (int sweep = 0; sweep < 2; sweep++) {
+                    if (prof) t0 = clock64();
+                    mbar_wait(bar(sweep ? D_H2BFREE : D_H2AFREE), ph ^ 1u);   // pass 2 of the previous tile has read this half
+                    if (prof) t_h2 += clock64() - t0;
+                    tc_fence_after();
+                    const uint32_t d = tmem + (sweep ? kNA : 0), id = sweep ? idB : idA;
+#pragma unroll 1
+                    for (int kb = 0; kb < KB2; kb++, it++) {
+                        const uint32_t slot = it % P::kSlots, wph = (it / P::kSlots) & 1u;
+                        if (prof) t0 = clock64();
+                        mbar_wait(bar(D_W2FULL + slot), wph);
+                        if (prof) t_w2 += clock64() - t0;
+                        tc_fence_after();
+                        const uint64_t a = dA2 + (uint64_t)(kb * (kTileM * kRowB / 16)), b = dW2 + (uint64_t)(slot * (P::kW2Slot / 16));
+                        if (elect_one()) {
+                            umma(d, a, b, id, kb ? 1u : 0u);
+                            umma(d, a + 2, b + 2, id, 1u);
+                            umma_commit(bar(D_W2EMPTY + slot));
+                            if (sweep) umma_commit(bar(D_A2FREE + kb));     // A2 block kb may be overwritten for the next tile
+                        }
+                        __syncwarp();
+                    }
+                    if (elect_one()) umma_commit(bar(sweep ? D_H2BFULL : D_H2AFULL));
+                    __syncwarp();
+                }
+            }
+            if (prof && blockIdx.x == 0 && lane == 0) { dbg[0] = t_h2; dbg[1] = t_a2; dbg[2] = t_w2; dbg[3] = c2; }
+        }
+    } else {
+        // ================= epilogue warps: thread = (row, column group) =================
+        const int grp = warp >> 2;
+        const int r = (warp & 3) * 32 + lane;
+        const int et = threadIdx.x;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t xsw = (((uint32_t)r >> 1) & 3u);
+        // X staging role: row et / 4, inputs k0 .. k0 + 5 with k0 = 6 (et % 4); k = 23 is the constant-1 bias column
+        const int srow = et >> 2, k0 = 6 * (et & 3);
+        const uint32_t ssw = (((uint32_t)srow >> 1) & 3u);
+        float xreg[6];
+        auto load_x = [&](int64_t t) {
+            const int64_t gr = t * kTileM + srow;
+            const bool ok = gr < n;
+            const float *p = obs + gr * ld + k0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) xreg[i] = (k0 + i < IN) ? (ok ? __ldg(p + i) : 0.f) : 1.0f;
+        };
+        const bool prof = dbg != nullptr;
+        long long e_st = 0, e_1 = 0, e_wa = 0, e_pa = 0, e_wb = 0, e_2 = 0, t0 = 0, t1 = 0;
+        const long long t_begin = clock64();
+        uint32_t wuse = 0;
+
+        // stage the observation tile held in xreg as the layer-1 A operand (hi [+ lo residual]) and release it
+        auto stage = [&]() {
+            if (prof) t0 = clock64();
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float a = xreg[2 * i], b = xreg[2 * i + 1];
+                const OpT ah = to_op<OpT>(a), bh = to_op<OpT>(b);
+                const uint32_t byte = 12u * (uint32_t)(et & 3) + 4u * (uint32_t)i;
+                const uint32_t off = (uint32_t)srow * kRowB + ((((byte >> 4) ^ ssw)) << 4) + (byte & 15u);
+                const uint32_t hi = (uint32_t)(*reinterpret_cast<const uint16_t *>(&ah)) | ((uint32_t)(*reinterpret_cast<const uint16_t *>(&bh)) << 16);
+                *reinterpret_cast<uint32_t *>(sm + P::x + off) = hi;
+                if (kSplit) *reinterpret_cast<uint32_t *>(sm + P::x + kTileM * kRowB + off) = pack2<OpT>(a - op_to_float(ah), b - op_to_float(bh));
+            }
+            fence_proxy_async();
+            mbar_arrive(bar(D_XFULL));
+            if (prof) { t1 = clock64(); e_st += t1 - t0; }
+        };
+
+        // layer-1 side of one tile: statistics -> rstd, then the 3 parts -> A2.  c1 = layer-1 tile counter
+        auto layer1 = [&](uint32_t c1) {
+            const uint32_t ph = c1 & 1u;
+            if (prof) t0 = clock64();
+            float2 rstd2 = make_float2(0.f, 0.f);
+            auto emit = [&](const uint32_t (&v)[8], int ch) {              // 8 columns of A2 block ch: relu(t' rstd + be1)
+                mbar_wait(bar(D_A2FREE + ch), ph ^ 1u);                    // sweep B of the previous tile has read this block
+                const float4 e0 = *reinterpret_cast<const float4 *>(pbe1 + ch * 32 + grp * 8), e1 = *reinterpret_cast<const float4 *>(pbe1 + ch * 32 + grp * 8 + 4);
+                const float2 ee[4] = {make_float2(e0.x, e0.y), make_float2(e0.z, e0.w), make_float2(e1.x, e1.y), make_float2(e1.z, e1.w)};
+                uint32_t pk4[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    const float2 y = __ffma2_rn(x, rstd2, ee[j]);
+                    pk4[j] = pack2_relu<OpT>(y.x, y.y);
+                }
+                uint4 pk;
+                pk.x = pk4[0]; pk.y = pk4[1]; pk.z = pk4[2]; pk.w = pk4[3];
+                *reinterpret_cast<uint4 *>(sm + P::a2 + (size_t)ch * kTileM * kRowB + (size_t)r * kRowB + (((uint32_t)grp ^ xsw) << 4)) = pk;
+            };
+            const uint32_t wcol = trow + (uint32_t)(kWin0 + grp * 8);
+            uint32_t v[5][8];
+            {   // part 0: 32 statistic columns, then A2 blocks 0..2
+                mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
+                tc_fence_after();
+                uint32_t sv[32];
+                tmem_ld32_async(trow + kWin0, sv);
+#pragma unroll
+                for (int c = 0; c < 3; c++) tmem_ld8_async(wcol + 32 + 32 * c, v[c]);
+                tmem_wait();
+                tc_fence_before();
+                mbar_arrive(bar(D_WFREE));                                 // values are in registers: the window may be refilled
+                float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 12; j++) {                             // columns 24..31 are zero rows of the image
+                    const float2 x = make_float2(__uint_as_float(sv[2 * j]), __uint_as_float(sv[2 * j + 1]));
+                    q2 = __ffma2_rn(x, x, q2);
+                }
+                const float rstd = rsqrtf((q2.x + q2.y) * (1.0f / H1) + 1e-5f);
+                rstd2 = make_float2(rstd, rstd);
+#pragma unroll
+                for (int c = 0; c < 3; c++) emit(v[c], c);
+            }
+            {   // part 1: A2 blocks 3..7
+                mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 5; c++) tmem_ld8_async(wcol + 32 * c, v[c]);
+                tmem_wait();
+                tc_fence_before();
+                mbar_arrive(bar(D_WFREE));
+#pragma unroll
+                for (int c = 0; c < 5; c++) emit(v[c], 3 + c);
+            }
+            {   // part 2: A2 blocks 8..11 and the 16 real columns of block 12 (groups 0, 1)
+                mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; c++) tmem_ld8_async(wcol + 32 * c, v[c]);
+                if (grp < 2) tmem_ld8_async(wcol + 128, v[4]);
+                tmem_wait();
+                tc_fence_before();
+                mbar_arrive(bar(D_WFREE));
+#pragma unroll
+                for (int c = 0; c < 4; c++) emit(v[c], 8 + c);
+                if (grp < 2) emit(v[4], 12);
+            }
+            fence_proxy_async();
+            mbar_arrive(bar(D_A2FULL));
+            if (prof) { t1 = clock64(); e_1 += t1 - t0; t0 = t1; }
+        };
+
+        // layer-2 side of one tile: LayerNorm + ReLU over H2, dot with mu.weight, tanh.  Column group g owns columns
+        // [40 g, 40 g + 40) of half A and [160 + 36 g, 160 + 36 g + 36) of half B.
+        const int ca = 40 * grp, cbb = kNA + 36 * grp;
+        float2 s2, q2;
+        auto acc = [&](const uint32_t *v, int cnt) {
+#pragma unroll
+            for (int j = 0; j < cnt / 2; j++) {
+                const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                s2 = __fadd2_rn(s2, x); q2 = __ffma2_rn(x, x, q2);
+            }
+        };
+        auto pass1a = [&](uint32_t c2) {                                   // statistics of half A (runs under sweep B)
+            if (prof) t0 = clock64();
+            mbar_wait(bar(D_H2AFULL), c2 & 1u);
+            if (prof) { t1 = clock64(); e_wa += t1 - t0; t0 = t1; }
+            tc_fence_after();
+            uint32_t va[32], vt[8];
+            tmem_ld32_async(trow + (uint32_t)ca, va);
+            tmem_ld8_async(trow + (uint32_t)(ca + 32), vt);
+            tmem_wait();
+            s2 = make_float2(0.f, 0.f); q2 = make_float2(0.f, 0.f);
+            acc(va, 32); acc(vt, 8);
+            if (prof) { t1 = clock64(); e_pa += t1 - t0; t0 = t1; }
+        };
+        auto layer2 = [&](int64_t tile, uint32_t c2) {
+            const uint32_t ph = c2 & 1u;
+            const int64_t row0 = tile * kTileM;
+            const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
+            if (prof) t0 = clock64();
+            mbar_wait(bar(D_H2BFULL), ph);
+            if (prof) { t1 = clock64(); e_wb += t1 - t0; t0 = t1; }
+            tc_fence_after();
+            uint32_t va[32], vt[8], vq[4];
+            tmem_ld32_async(trow + (uint32_t)cbb, va);
+            tmem_ld4_async(trow + (uint32_t)(cbb + 32), vq);
+            tmem_wait();
+            acc(va, 32); acc(vq, 4);
+            red1[grp * kTileM + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
+            // pass 2 re-reads the accumulators; half A's loads fly while the statistics are exchanged
+            tmem_ld32_async(trow + (uint32_t)ca, va);
+            tmem_ld8_async(trow + (uint32_t)(ca + 32), vt);
+            named_bar_sync(1, kEpiThreads);
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int g = 0; g < kGroups; g++) { const float2 t = red1[g * kTileM + r]; sum += t.x; sq += t.y; }
+            const float mean = sum * (1.0f / H2);
+            const float rstd = rsqrtf(fmaxf(sq * (1.0f / H2) - mean * mean, 0.f) + 1e-5f);
+            const float nmr = -mean * rstd;
+            const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
+            float2 dot2 = make_float2(0.f, 0.f);
+            auto fin = [&](const uint32_t *v, int c0, int cnt) {           // columns c0 .. c0 + cnt - 1 (cnt % 4 == 0; pad parameters are 0)
+#pragma unroll
+                for (int q = 0; q < cnt / 4; q++) {
+                    const float4 g0 = *reinterpret_cast<const float4 *>(pg2 + c0 + q * 4), e0 = *reinterpret_cast<const float4 *>(pbe2 + c0 + q * 4),
+                                 w0 = *reinterpret_cast<const float4 *>(pw3 + c0 + q * 4);
+                    const float2 xa = make_float2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]));
+                    const float2 xb = make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                    float2 ya = __ffma2_rn(__ffma2_rn(xa, rstd2, nmr2), make_float2(g0.x, g0.y), make_float2(e0.x, e0.y));
+                    float2 yb = __ffma2_rn(__ffma2_rn(xb, rstd2, nmr2), make_float2(g0.z, g0.w), make_float2(e0.z, e0.w));
+                    ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
+                    dot2 = __ffma2_rn(ya, make_float2(w0.x, w0.y), dot2);
+                    dot2 = __ffma2_rn(yb, make_float2(w0.z, w0.w), dot2);
+                }
+            };
+            tmem_wait();
+            tc_fence_before();
+            mbar_arrive(bar(D_H2AFREE));                                   // half A is in registers: sweep A of the next tile may start
+            fin(va, ca, 32); fin(vt, ca + 32, 8);
+            tmem_ld32_async(trow + (uint32_t)cbb, va);
+            tmem_ld4_async(trow + (uint32_t)(cbb + 32), vq);
+            tmem_wait();
+            tc_fence_before();
+            mbar_arrive(bar(D_H2BFREE));
+            fin(va, cbb, 32); fin(vq, cbb + 32, 4);
+            red3[grp * kTileM + r] = dot2.x + dot2.y;
+            named_bar_sync(1, kEpiThreads);
+            if (grp == 0 && r < rows) {
+                float d = b3;
+#pragma unroll
+                for (int g = 0; g < kGroups; g++) d += red3[g * kTileM + r];
+                out[row0 + r] = tanhf(d);
+            }
+            if (prof) { t1 = clock64(); e_2 += t1 - t0; t0 = t1; }
+        };
+
+        const int64_t first = blockIdx.x, G = gridDim.x;
+        uint32_t c1 = 0, c2 = 0;
+        if (first < ntiles) {
+            load_x(first);
+            stage(); load_x(first + G);                                    // X(0); registers <- tile 1
+            layer1(c1++);
+            if (first + G < ntiles) { stage(); load_x(first + 2 * G); }    // X(1)
+            int64_t prev = first;
+            for (;;) {
+                const int64_t next = prev + G;
+                const bool has_next = next < ntiles;
+                pass1a(c2);                                                // half A of `prev`, under its sweep B
+                if (has_next) {
+                    layer1(c1++);                                          // trails sweep B of `prev`
+                    if (next + G < ntiles) { stage(); load_x(next + 2 * G); }   // X of the tile after: ready long before it is needed
+                }
+                layer2(prev, c2++);
+                if (!has_next) break;
+                prev = next;
+            }
+        }
+        if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
+            dbg[4] = e_wa; dbg[5] = e_pa; dbg[6] = e_1; dbg[7] = e_wb; dbg[8] = e_2; dbg[9] = clock64() - t_begin;
+            dbg[10] = e_st; dbg[11] = 0; dbg[12] = 0;
+        }
+    }
+    // ---------------- teardown ----------------
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kM2Warp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <typename OpT, bool kSplit>
+int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, const float *d_obs, int64_t ld, int64_t n, float *d_mu,
+               const TTRingS *ring, unsigned long long *dbg, cudaStream_t st) {
+    TTRingS rs;
+    if (ring) rs = *ring; else { rs.S = nullptr; rs.m = tt_make_ring_map(1, 0, 0); }
+    using P = Plan4<kSplit>;
+    static_assert(P::total <= 232448u, "shared-memory plan exceeds 227 KB");
+    auto kern = actor_tc4_kernel<OpT, kSplit>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
+        attr_set = true;
+    }
+    const int64_t ntiles = (n + kTileM - 1) / kTileM;
+    const int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
+    kern<<<grid, 640, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, rs, dbg);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
+}
+
+}  // namespace
+
+namespace tt {
+
+int actor_pack_tc4(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *g1, const float *fc2_w, const float *fc2_b, cudaStream_t s) {
+    const tt_actor_dev &A = a->dev;
+    pack_l1c_kernel<<<1, 576, 0, s>>>(reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), fc1_w, fc1_b, g1);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    pack_w2s_kernel<__half><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_f16), fc2_w, fc2_b);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    pack_w2s_kernel<__nv_bfloat16><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_bf16), fc2_w, fc2_b);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
+}
+
+int actor_forward_tc4(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring,
+                      unsigned long long *dbg, cudaStream_t st) {
+    const tt_actor_dev &A = a->dev;
+    if (precision == TT_PREC_BF16)
+        return launch_tc4<__nv_bfloat16, false>(reinterpret_cast<const char *>(A.w1c_bf16), reinterpret_cast<const char *>(A.w2s_bf16), A, d_obs, ld, n, d_mu, ring, dbg, st);
+    return launch_tc4<__half, true>(reinterpret_cast<const char *>(A.w1c_f16), reinterpret_cast<const char *>(A.w2s_f16), A, d_obs, ld, n, d_mu, ring, dbg, st);
+}
+
+}  // namespace tt

@@ -16,7 +16,6 @@ for prec in ("f16", "bf16"):
     e0.record(); actor.forward(obs, precision=prec); e1.record(); torch.cuda.synchronize()
     d = dbg.cpu().tolist(); nt = d[3]
     print(prec, 'ms', e0.elapsed_time(e1), 'tiles/blk', nt)
-    print('  MMA thread waits per tile: x+tmemfree %.0f  a2 %.0f  w2 %.0f' % (d[0]/nt, d[1]/nt, d[2]/nt))
-    print('  epilogue per tile: xstage %.0f  wait_h1 %.0f  epi1 %.0f  wait_h2 %.0f  epi2 %.0f  total %.0f' % tuple(x/nt for x in d[4:10]))
-    print('  v3 detail: stage %.0f  bar %.0f  gram %.0f' % tuple(x/nt for x in d[10:13]))
+    print('  layer-2 MMA thread waits per tile: h2free %.0f  a2full %.0f  w2full %.0f' % (d[0]/nt, d[1]/nt, d[2]/nt))
+    print('  epilogue per tile (v4): wait_h2a %.0f  pass1a %.0f  epi1(+waits) %.0f  wait_h2b %.0f  epi2 %.0f  total %.0f  stage %.0f' % tuple(x/nt for x in d[4:11]))
     L.tt_debug_set_tc_profile(None)
