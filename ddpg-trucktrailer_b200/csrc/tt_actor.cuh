@@ -14,6 +14,12 @@
 #include <stdint.h>
 #include "tt_common.cuh"
 
+// The v4 kernel streams W2 from L2 in every tile on every SM; TT_W2_REPLICAS identical copies of the image (SM i reads
+// copy i % TT_W2_REPLICAS) spread that traffic over more L2 lines / slices.
+#ifndef TT_W2_REPLICAS
+#define TT_W2_REPLICAS 1
+#endif
+
 struct tt_actor_dev {
     int in_dim, h1, h2;
     int k1p, h1p, h2p, kb1;
@@ -39,7 +45,7 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
     const size_t o_w3 = take(sizeof(float) * h2p), o_b3 = take(sizeof(float));
     const size_t n1 = (h1 + 15) / 16 * 16, n2 = (h2 + 15) / 16 * 16, kb2 = (h1 + 1 + 31) / 32;
     const size_t o_w1h = take(2 * n1 * 64), o_w2h = take(kb2 * n2 * 64), o_w1b = take(2 * n1 * 64), o_w2b = take(kb2 * n2 * 64);
-    const size_t o_w2sh = take(kb2 * n2 * 64), o_w2sb = take(kb2 * n2 * 64);
+    const size_t o_w2sh = take(TT_W2_REPLICAS * kb2 * n2 * 64), o_w2sb = take(TT_W2_REPLICAS * kb2 * n2 * 64);
     const size_t o_w1ch = take(2 * (n1 + 32) * 64), o_w1cb = take(2 * (n1 + 32) * 64);
     const size_t o_gh = take(sizeof(float) * 25 * 24), o_gb = take(sizeof(float) * 25 * 24);
     if (d) {

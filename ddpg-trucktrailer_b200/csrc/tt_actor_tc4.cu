@@ -39,6 +39,7 @@ constexpr int kWin0 = 304;                    // first TMEM column of the layer-
 constexpr int kNA = 160, kNB = N2 - kNA;      // layer-2 output halves (sweep A / sweep B)
 constexpr uint32_t kW2SlotB = kNA * kRowB;    // ring slot: one half k-block (10 240 B; sweep B uses 9 216 of it)
 constexpr size_t kW2SweepB = (size_t)KB2 * kNA * kRowB;   // byte offset of sweep B inside the v4 W2 image
+constexpr size_t kW2ImageB = (size_t)KB2 * N2 * kRowB;     // one replica of the image
 
 __device__ __forceinline__ void tmem_ld4_async(uint32_t taddr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -113,8 +114,21 @@ __global__ void pack_w2s_kernel(char *__restrict__ img, const float *__restrict_
         if (col < H2) x = k < H1 ? fc2_w[col * H1 + k] : (k == H1 ? fc2_b[col] : 0.f);
         const size_t off = col < kNA ? (size_t)kb * kNA * kRowB + sw64_off(col, kk)
                                      : kW2SweepB + (size_t)kb * kNB * kRowB + sw64_off(col - kNA, kk);
-        *reinterpret_cast<OpT *>(img + off) = to_op<OpT>(x);
+        const OpT o = to_op<OpT>(x);
+#pragma unroll
+        for (int rep = 0; rep < TT_W2_REPLICAS; rep++) *reinterpret_cast<OpT *>(img + (size_t)rep * kW2ImageB + off) = o;
     }
+}
+
+// W2 ring schedule: one tile = 26 steps (sweep A: k-blocks 0..12, sweep B: 0..12); step -> slot is a fixed compile-time
+// pattern (round-robin, the last 26 % kSlots steps reuse slots 0, 1, ...) so that the fully unrolled issue loops carry no
+// address or phase arithmetic.  A slot is used kSteps / kSlots (+ 1 for the first 26 % kSlots slots) times per tile.
+constexpr int kSteps = 2 * KB2;
+__host__ __device__ constexpr int w2_slot(int step, int nslots) { return step < (kSteps / nslots) * nslots ? step % nslots : step - (kSteps / nslots) * nslots; }
+__host__ __device__ constexpr int w2_uses_per_tile(int slot, int nslots) { return kSteps / nslots + (slot < kSteps % nslots ? 1 : 0); }
+// phase parity of the `step`-th ring use of tile number `tile_parity` (0/1)
+__device__ __forceinline__ uint32_t w2_parity(int step, int nslots, uint32_t tile_parity) {
+    return ((w2_uses_per_tile(w2_slot(step, nslots), nslots) & 1) ? tile_parity : 0u) ^ (uint32_t)((step / nslots) & 1);
 }
 
 template <bool kSplit>
@@ -139,7 +153,9 @@ enum { D_W1 = 0, D_XFULL, D_WFULL, D_WFREE, D_A2FULL, D_H2AFULL, D_H2BFULL, D_H2
        D_W2FULL, D_W2EMPTY = D_W2FULL + 6, D_A2FREE = D_W2EMPTY + 6, D_COUNT = D_A2FREE + KB2 };
 static_assert(D_COUNT <= 40, "barrier table");
 
-template <typename OpT, bool kSplit>
+// kProf: per-phase cycle counters of block 0 (profiles/tc_phase_profile.py); compiled out of the production instantiation
+// (they cost ~25 registers per thread).
+template <typename OpT, bool kSplit, bool kProf>
 __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restrict__ w1img, const char *__restrict__ w2img,
                                                            tt_actor_dev A, const float *__restrict__ obs, int64_t ld, int64_t n,
                                                            float *__restrict__ out, TTRingS ring,
@@ -211,22 +227,19 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             bulk_g2s(sW1, w1img, w1bytes, bar(D_W1));
         }
         __syncwarp();
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-#pragma unroll 1
-            for (int sweep = 0; sweep < 2; sweep++) {
+        const char *w2rep = w2img + (size_t)(blockIdx.x % TT_W2_REPLICAS) * kW2ImageB;     // this SM's replica
+        uint32_t tp = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tp ^= 1u) {
+#pragma unroll
+            for (int step = 0; step < kSteps; step++) {
+                const int sweep = step / KB2, kb = step % KB2, slot = w2_slot(step, P::kSlots);
                 const uint32_t bytes = (uint32_t)(sweep ? kNB : kNA) * kRowB;
-                const char *src = w2img + (sweep ? kW2SweepB : 0);
-#pragma unroll 1
-                for (int kb = 0; kb < KB2; kb++, it++) {
-                    const uint32_t slot = it % P::kSlots, ph = (it / P::kSlots) & 1u;
-                    mbar_wait(bar(D_W2EMPTY + slot), ph ^ 1u);
-                    if (elect_one()) {
-                        mbar_expect_tx(bar(D_W2FULL + slot), bytes);
-                        bulk_g2s(sW2 + slot * P::kW2Slot, src + (size_t)kb * bytes, bytes, bar(D_W2FULL + slot));
-                    }
-                    __syncwarp();
+                mbar_wait(bar(D_W2EMPTY + slot), w2_parity(step, P::kSlots, tp) ^ 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(bar(D_W2FULL + slot), bytes);
+                    bulk_g2s(sW2 + slot * P::kW2Slot, w2rep + (sweep ? kW2SweepB : 0) + (size_t)kb * bytes, bytes, bar(D_W2FULL + slot));
                 }
+                __syncwarp();
             }
         }
     } else if (warp == kCopyWarp) {
@@ -289,38 +302,35 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         {
             const uint32_t idA = make_idesc(kNA, kFmt), idB = make_idesc(kNB, kFmt);
             const uint64_t dA2 = make_desc(sA2), dW2 = make_desc(sW2);    // descriptor address field is in 16 B units
-            const bool prof = dbg != nullptr;
-            uint32_t it = 0, c2 = 0;
+            constexpr bool prof = kProf;
+            uint32_t c2 = 0;
             long long t_a2 = 0, t_w2 = 0, t_h2 = 0, t0 = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, c2++) {
                 const uint32_t ph = c2 & 1u;
                 if (prof) t0 = clock64();
                 mbar_wait(bar(D_A2FULL), ph);
                 if (prof) t_a2 += clock64() - t0;
-#pragma unroll 1
-                for (int sweep = 0; sweep < 2; sweep++) {
-                    if (prof) t0 = clock64();
-                    mbar_wait(bar(sweep ? D_H2BFREE : D_H2AFREE), ph ^ 1u);   // pass 2 of the previous tile has read this half
-                    if (prof) t_h2 += clock64() - t0;
-                    tc_fence_after();
-                    const uint32_t d = tmem + (sweep ? kNA : 0), id = sweep ? idB : idA;
-#pragma unroll 1
-                    for (int kb = 0; kb < KB2; kb++, it++) {
-                        const uint32_t slot = it % P::kSlots, wph = (it / P::kSlots) & 1u;
+#pragma unroll
+                for (int step = 0; step < kSteps; step++) {
+                    const int sweep = step / KB2, kb = step % KB2, slot = w2_slot(step, P::kSlots);
+                    if (kb == 0) {
                         if (prof) t0 = clock64();
-                        mbar_wait(bar(D_W2FULL + slot), wph);
-                        if (prof) t_w2 += clock64() - t0;
-                        tc_fence_after();
-                        const uint64_t a = dA2 + (uint64_t)(kb * (kTileM * kRowB / 16)), b = dW2 + (uint64_t)(slot * (P::kW2Slot / 16));
-                        if (elect_one()) {
-                            umma(d, a, b, id, kb ? 1u : 0u);
-                            umma(d, a + 2, b + 2, id, 1u);
-                            umma_commit(bar(D_W2EMPTY + slot));
-                            if (sweep) umma_commit(bar(D_A2FREE + kb));     // A2 block kb may be overwritten for the next tile
-                        }
-                        __syncwarp();
+                        mbar_wait(bar(sweep ? D_H2BFREE : D_H2AFREE), ph ^ 1u);   // pass 2 of the previous tile has read this half
+                        if (prof) t_h2 += clock64() - t0;
                     }
-                    if (elect_one()) umma_commit(bar(sweep ? D_H2BFULL : D_H2AFULL));
+                    if (prof) t0 = clock64();
+                    mbar_wait(bar(D_W2FULL + slot), w2_parity(step, P::kSlots, ph));
+                    if (prof) t_w2 += clock64() - t0;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t a = dA2 + (uint64_t)(kb * (kTileM * kRowB / 16)), b = dW2 + (uint64_t)(slot * (P::kW2Slot / 16));
+                        const uint32_t d = tmem + (sweep ? kNA : 0);
+                        umma(d, a, b, sweep ? idB : idA, kb ? 1u : 0u);
+                        umma(d, a + 2, b + 2, sweep ? idB : idA, 1u);
+                        umma_commit(bar(D_W2EMPTY + slot));
+                        if (sweep) umma_commit(bar(D_A2FREE + kb));         // A2 block kb may be overwritten for the next tile
+                        if (kb == KB2 - 1) umma_commit(bar(sweep ? D_H2BFULL : D_H2AFULL));
+                    }
                     __syncwarp();
                 }
             }
@@ -344,8 +354,8 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
 #pragma unroll
             for (int i = 0; i < 6; i++) xreg[i] = (k0 + i < IN) ? (ok ? __ldg(p + i) : 0.f) : 1.0f;
         };
-        const bool prof = dbg != nullptr;
-        long long e_st = 0, e_1 = 0, e_wa = 0, e_pa = 0, e_wb = 0, e_2 = 0, t0 = 0, t1 = 0;
+        constexpr bool prof = kProf;
+        long long e_st = 0, e_1 = 0, e_wa = 0, e_pa = 0, e_wb = 0, e_2 = 0, e_2a = 0, e_2b = 0, e_2c = 0, e_2d = 0, t0 = 0, t1 = 0, t2 = 0;
         const long long t_begin = clock64();
         uint32_t wuse = 0;
 
@@ -367,8 +377,34 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             if (prof) { t1 = clock64(); e_st += t1 - t0; }
         };
 
+        // layer-2 side of one tile: LayerNorm + ReLU over H2, dot with mu.weight, tanh.  Column group g owns columns
+        // [40 g, 40 g + 40) of half A and [160 + 36 g, 160 + 36 g + 36) of half B.
+        const int ca = 40 * grp, cbb = kNA + 36 * grp;
+        float2 s2, q2;
+        auto acc = [&](const uint32_t *v, int cnt) {
+#pragma unroll
+            for (int j = 0; j < cnt / 2; j++) {
+                const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                s2 = __fadd2_rn(s2, x); q2 = __ffma2_rn(x, x, q2);
+            }
+        };
+        auto pass1a = [&](uint32_t c2) {                                   // statistics of half A (runs under sweep B)
+            if (prof) t0 = clock64();
+            mbar_wait(bar(D_H2AFULL), c2 & 1u);
+            if (prof) { t1 = clock64(); e_wa += t1 - t0; t0 = t1; }
+            tc_fence_after();
+            uint32_t va[32], vt[8];
+            tmem_ld32_async(trow + (uint32_t)ca, va);
+            tmem_ld8_async(trow + (uint32_t)(ca + 32), vt);
+            tmem_wait();
+            s2 = make_float2(0.f, 0.f); q2 = make_float2(0.f, 0.f);
+            acc(va, 32); acc(vt, 8);
+            if (prof) { t1 = clock64(); e_pa += t1 - t0; t0 = t1; }
+        };
         // layer-1 side of one tile: statistics -> rstd, then the 3 parts -> A2.  c1 = layer-1 tile counter
-        auto layer1 = [&](uint32_t c1) {
+        // `with_p1a`: run the statistics pass over half A of the layer-2 tile c2 between part 0 and part 1 -- it fills the
+        // wait for the layer-1 MMAs of part 1, which queue behind the sweep-B MMAs.
+        auto layer1 = [&](uint32_t c1, bool with_p1a, uint32_t c2) {
             const uint32_t ph = c1 & 1u;
             if (prof) t0 = clock64();
             float2 rstd2 = make_float2(0.f, 0.f);
@@ -410,6 +446,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
 #pragma unroll
                 for (int c = 0; c < 3; c++) emit(v[c], c);
             }
+            if (with_p1a) { if (prof) { t1 = clock64(); e_1 += t1 - t0; } pass1a(c2); }
             {   // part 1: A2 blocks 3..7
                 mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
                 tc_fence_after();
@@ -439,30 +476,6 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             if (prof) { t1 = clock64(); e_1 += t1 - t0; t0 = t1; }
         };
 
-        // layer-2 side of one tile: LayerNorm + ReLU over H2, dot with mu.weight, tanh.  Column group g owns columns
-        // [40 g, 40 g + 40) of half A and [160 + 36 g, 160 + 36 g + 36) of half B.
-        const int ca = 40 * grp, cbb = kNA + 36 * grp;
-        float2 s2, q2;
-        auto acc = [&](const uint32_t *v, int cnt) {
-#pragma unroll
-            for (int j = 0; j < cnt / 2; j++) {
-                const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                s2 = __fadd2_rn(s2, x); q2 = __ffma2_rn(x, x, q2);
-            }
-        };
-        auto pass1a = [&](uint32_t c2) {                                   // statistics of half A (runs under sweep B)
-            if (prof) t0 = clock64();
-            mbar_wait(bar(D_H2AFULL), c2 & 1u);
-            if (prof) { t1 = clock64(); e_wa += t1 - t0; t0 = t1; }
-            tc_fence_after();
-            uint32_t va[32], vt[8];
-            tmem_ld32_async(trow + (uint32_t)ca, va);
-            tmem_ld8_async(trow + (uint32_t)(ca + 32), vt);
-            tmem_wait();
-            s2 = make_float2(0.f, 0.f); q2 = make_float2(0.f, 0.f);
-            acc(va, 32); acc(vt, 8);
-            if (prof) { t1 = clock64(); e_pa += t1 - t0; t0 = t1; }
-        };
         auto layer2 = [&](int64_t tile, uint32_t c2) {
             const uint32_t ph = c2 & 1u;
             const int64_t row0 = tile * kTileM;
@@ -476,6 +489,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             tmem_ld4_async(trow + (uint32_t)(cbb + 32), vq);
             tmem_wait();
             acc(va, 32); acc(vq, 4);
+            if (prof) { t2 = clock64(); e_2a += t2 - t0; }
             red1[grp * kTileM + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
             // pass 2 re-reads the accumulators; half A's loads fly while the statistics are exchanged
             tmem_ld32_async(trow + (uint32_t)ca, va);
@@ -489,30 +503,52 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             const float nmr = -mean * rstd;
             const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
             float2 dot2 = make_float2(0.f, 0.f);
-            auto fin = [&](const uint32_t *v, int c0, int cnt) {           // columns c0 .. c0 + cnt - 1 (cnt % 4 == 0; pad parameters are 0)
-#pragma unroll
-                for (int q = 0; q < cnt / 4; q++) {
-                    const float4 g0 = *reinterpret_cast<const float4 *>(pg2 + c0 + q * 4), e0 = *reinterpret_cast<const float4 *>(pbe2 + c0 + q * 4),
-                                 w0 = *reinterpret_cast<const float4 *>(pw3 + c0 + q * 4);
-                    const float2 xa = make_float2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]));
-                    const float2 xb = make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
-                    float2 ya = __ffma2_rn(__ffma2_rn(xa, rstd2, nmr2), make_float2(g0.x, g0.y), make_float2(e0.x, e0.y));
-                    float2 yb = __ffma2_rn(__ffma2_rn(xb, rstd2, nmr2), make_float2(g0.z, g0.w), make_float2(e0.z, e0.w));
-                    ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
-                    dot2 = __ffma2_rn(ya, make_float2(w0.x, w0.y), dot2);
-                    dot2 = __ffma2_rn(yb, make_float2(w0.z, w0.w), dot2);
-                }
+            // Pass 2 over this thread's 19 column quads (10 of half A, 9 of half B).  Parameters are fetched two quads ahead
+            // (lds128_early) into a 2-slot register ring; half B's TMEM load is issued as soon as va is dead and flies under
+            // the last two quads of half A.
+            constexpr int kQA = 10, kQ = 19;
+            float4 G[2], E[2], W[2];
+            auto qcol = [&](int qi) { return qi < kQA ? ca + 4 * qi : cbb + 4 * (qi - kQA); };
+            auto loadp = [&](int slot, int qi) {
+                const int c = qcol(qi);
+                G[slot] = lds128_early(pg2 + c); E[slot] = lds128_early(pbe2 + c); W[slot] = lds128_early(pw3 + c);
             };
+            auto quad = [&](int slot, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
+                const float2 xa = make_float2(__uint_as_float(x0), __uint_as_float(x1)), xb = make_float2(__uint_as_float(x2), __uint_as_float(x3));
+                float2 ya = __ffma2_rn(__ffma2_rn(xa, rstd2, nmr2), make_float2(G[slot].x, G[slot].y), make_float2(E[slot].x, E[slot].y));
+                float2 yb = __ffma2_rn(__ffma2_rn(xb, rstd2, nmr2), make_float2(G[slot].z, G[slot].w), make_float2(E[slot].z, E[slot].w));
+                ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
+                dot2 = __ffma2_rn(ya, make_float2(W[slot].x, W[slot].y), dot2);
+                dot2 = __ffma2_rn(yb, make_float2(W[slot].z, W[slot].w), dot2);
+            };
+            loadp(0, 0); loadp(1, 1);
             tmem_wait();
+            if (prof) { t1 = clock64(); e_2b += t1 - t2; t2 = t1; }
             tc_fence_before();
             mbar_arrive(bar(D_H2AFREE));                                   // half A is in registers: sweep A of the next tile may start
-            fin(va, ca, 32); fin(vt, ca + 32, 8);
-            tmem_ld32_async(trow + (uint32_t)cbb, va);
+#pragma unroll
+            for (int qi = 0; qi < 8; qi++) {                               // half A, columns ca .. ca + 31
+                quad(qi & 1, va[4 * qi], va[4 * qi + 1], va[4 * qi + 2], va[4 * qi + 3]);
+                loadp(qi & 1, qi + 2);
+            }
+            tmem_ld32_async(trow + (uint32_t)cbb, va);                     // half B flies under the last two quads of half A
             tmem_ld4_async(trow + (uint32_t)(cbb + 32), vq);
+#pragma unroll
+            for (int qi = 8; qi < kQA; qi++) {                             // half A, columns ca + 32 .. ca + 39
+                quad(qi & 1, vt[4 * (qi - 8)], vt[4 * (qi - 8) + 1], vt[4 * (qi - 8) + 2], vt[4 * (qi - 8) + 3]);
+                loadp(qi & 1, qi + 2);
+            }
             tmem_wait();
             tc_fence_before();
             mbar_arrive(bar(D_H2BFREE));
-            fin(va, cbb, 32); fin(vq, cbb + 32, 4);
+            if (prof) { t1 = clock64(); e_2c += t1 - t2; t2 = t1; }
+#pragma unroll
+            for (int qi = kQA; qi < kQ - 1; qi++) {                        // half B, columns cbb .. cbb + 31
+                quad(qi & 1, va[4 * (qi - kQA)], va[4 * (qi - kQA) + 1], va[4 * (qi - kQA) + 2], va[4 * (qi - kQA) + 3]);
+                if (qi + 2 < kQ) loadp(qi & 1, qi + 2);
+            }
+            quad((kQ - 1) & 1, vq[0], vq[1], vq[2], vq[3]);                // columns cbb + 32 .. cbb + 35
+            if (prof) { t1 = clock64(); e_2d += t1 - t2; t2 = t1; }
             red3[grp * kTileM + r] = dot2.x + dot2.y;
             named_bar_sync(1, kEpiThreads);
             if (grp == 0 && r < rows) {
@@ -529,17 +565,16 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         if (first < ntiles) {
             load_x(first);
             stage(); load_x(first + G);                                    // X(0); registers <- tile 1
-            layer1(c1++);
+            layer1(c1++, false, 0u);
             if (first + G < ntiles) { stage(); load_x(first + 2 * G); }    // X(1)
             int64_t prev = first;
             for (;;) {
                 const int64_t next = prev + G;
                 const bool has_next = next < ntiles;
-                pass1a(c2);                                                // half A of `prev`, under its sweep B
                 if (has_next) {
-                    layer1(c1++);                                          // trails sweep B of `prev`
+                    layer1(c1++, true, c2);                                // trails sweep B of `prev`; includes pass 1 over half A of `prev`
                     if (next + G < ntiles) { stage(); load_x(next + 2 * G); }   // X of the tile after: ready long before it is needed
-                }
+                } else pass1a(c2);
                 layer2(prev, c2++);
                 if (!has_next) break;
                 prev = next;
@@ -547,7 +582,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         }
         if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
             dbg[4] = e_wa; dbg[5] = e_pa; dbg[6] = e_1; dbg[7] = e_wb; dbg[8] = e_2; dbg[9] = clock64() - t_begin;
-            dbg[10] = e_st; dbg[11] = 0; dbg[12] = 0;
+            dbg[10] = e_st; dbg[11] = e_2a; dbg[12] = e_2b; dbg[13] = e_2c; dbg[14] = e_2d;
         }
     }
     // ---------------- teardown ----------------
@@ -567,10 +602,11 @@ int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, cons
     if (ring) rs = *ring; else { rs.S = nullptr; rs.m = tt_make_ring_map(1, 0, 0); }
     using P = Plan4<kSplit>;
     static_assert(P::total <= 232448u, "shared-memory plan exceeds 227 KB");
-    auto kern = actor_tc4_kernel<OpT, kSplit>;
+    auto kern = dbg ? actor_tc4_kernel<OpT, kSplit, true> : actor_tc4_kernel<OpT, kSplit, false>;
     static bool attr_set = false;
     if (!attr_set) {
-        TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
+        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
+        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
         attr_set = true;
     }
     const int64_t ntiles = (n + kTileM - 1) / kTileM;

@@ -29,41 +29,44 @@ __global__ void __launch_bounds__(640, 1) probe(int nmma, int N, int reps, int m
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = slot;
-    if (warp == 16) {
-        if (lane == 0) {
-            const uint32_t id = make_idesc(N, 0u);
-            const uint32_t sA = base, sB = base + 13 * 8192;       // A: 128 rows x 64 B (2 ks), B: up to 256 rows x 64 B
-            uint32_t ph = 0;
-            long long best = 1ll << 60;
-            for (int rep = 0; rep < reps; rep++) {
-                const long long t0 = clock64();
-                if (commit_every == 0) {
-                    for (int i = 0; i < nmma; i++) umma(tmem, make_desc(sA + (i & 1) * 32), make_desc(sB + (i & 1) * 32), id, 1u);
-                } else if (commit_every > 0) {       // a commit (nobody waits on it) after every `commit_every` (power of two) MMAs
-                    for (int i = 0; i < nmma; i++) {
-                        umma(tmem, make_desc(sA + (i & 1) * 32), make_desc(sB + (i & 1) * 32), id, 1u);
-                        if ((i & (commit_every - 1)) == commit_every - 1) umma_commit(smem_u32(&bars[1]));
+    if (warp == 16) {      // warp-uniform issue loop, one elected lane issues (see tt_tc_ptx.cuh: elect_one)
+        const uint32_t id = make_idesc(N, 0u);
+        const uint32_t sA = base, sB = base + 13 * 8192;       // A: 13 blocks of 128 rows x 64 B, B: slots of 10 KB
+        const uint64_t dA = make_desc(sA), dB = make_desc(sB);
+        uint32_t ph = 0;
+        long long best = 1ll << 60;
+        for (int rep = 0; rep < reps; rep++) {
+            const long long t0 = clock64();
+            if (commit_every >= 0) {                 // a commit (nobody waits on it) after every `commit_every` (power of two) MMAs
+                for (int i = 0; i < nmma; i++) {
+                    if (elect_one()) {
+                        umma(tmem, dA + (uint64_t)((i & 1) * 2), dB + (uint64_t)((i & 1) * 2), id, 1u);
+                        if (commit_every && (i & (commit_every - 1)) == commit_every - 1) umma_commit(smem_u32(&bars[1]));
                     }
-                } else {                              // the actor kernel's k-block step: wait on a (complete) barrier, fence, 2 MMAs on
-                    const uint64_t dA = make_desc(sA), dB = make_desc(sB);                 // moving operand addresses, 1 or 2 commits
-                    for (int i = 0; i < nmma; i += 2) {
-                        mbar_wait(smem_u32(&bars[2]), 1u);                                 // fresh barrier, parity 1: passes at once
-                        tc_fence_after();
-                        const uint64_t a = dA + (uint64_t)(((i >> 1) % 13) * 512), b = dB + (uint64_t)(((i >> 1) & 3) * 640);
+                    __syncwarp();
+                }
+            } else {                                  // the actor kernel's k-block step: wait on a (complete) barrier, fence, 2 MMAs on
+                for (int i = 0; i < nmma; i += 2) {   // moving operand addresses, 1 or 2 commits
+                    mbar_wait(smem_u32(&bars[2]), 1u);                                 // fresh barrier, parity 1: passes at once
+                    tc_fence_after();
+                    const uint64_t a = dA + (uint64_t)(((i >> 1) % 13) * 512), b = dB + (uint64_t)(((i >> 1) & 3) * 640);
+                    if (elect_one()) {
                         umma(tmem, a, b, id, 1u);
                         umma(tmem, a + 2, b + 2, id, 1u);
                         umma_commit(smem_u32(&bars[1]));
                         if (commit_every == -2) umma_commit(smem_u32(&bars[3]));
                     }
+                    __syncwarp();
                 }
-                umma_commit(smem_u32(&bars[0]));
-                mbar_wait(smem_u32(&bars[0]), ph); ph ^= 1u;
-                const long long t1 = clock64();
-                if (t1 - t0 < best) best = t1 - t0;
             }
-            if (blockIdx.x == 0) out[0] = (unsigned long long)best;
-            stop = 1;
+            if (elect_one()) umma_commit(smem_u32(&bars[0]));
+            __syncwarp();
+            mbar_wait(smem_u32(&bars[0]), ph); ph ^= 1u;
+            const long long t1 = clock64();
+            if (t1 - t0 < best) best = t1 - t0;
         }
+        if (blockIdx.x == 0 && lane == 0) out[0] = (unsigned long long)best;
+        if (lane == 0) stop = 1;
     } else if (warp < 16 && mode != 0) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 *p = reinterpret_cast<const float4 *>(sm + 160 * 1024);
@@ -103,7 +106,7 @@ int main() {
             }
         }
     }
-    for (int ce : {0, 1, 2, 4, -1, -2}) {      // cost of a tcgen05.commit after every `ce` MMAs (N = 160, 64 MMAs)
+    for (int ce : {0, 1, 2, 4, 8, -1, -2}) {      // cost of a tcgen05.commit after every `ce` MMAs (N = 160, 64 MMAs)
         probe<<<148, 640, 200 * 1024>>>(64, 160, 20, 0, ce, d_out);
         cudaDeviceSynchronize();
         unsigned long long cyc = 0;

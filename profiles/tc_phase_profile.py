@@ -18,4 +18,5 @@ for prec in ("f16", "bf16"):
     print(prec, 'ms', e0.elapsed_time(e1), 'tiles/blk', nt)
     print('  layer-2 MMA thread waits per tile: h2free %.0f  a2full %.0f  w2full %.0f' % (d[0]/nt, d[1]/nt, d[2]/nt))
     print('  epilogue per tile (v4): wait_h2a %.0f  pass1a %.0f  epi1(+waits) %.0f  wait_h2b %.0f  epi2 %.0f  total %.0f  stage %.0f' % tuple(x/nt for x in d[4:11]))
+    print('  epi2 detail: pass1b %.0f  exchange+reloadA %.0f  pass2A(+reload B) %.0f  pass2B %.0f' % tuple(x/nt for x in d[11:15]))
     L.tt_debug_set_tc_profile(None)
