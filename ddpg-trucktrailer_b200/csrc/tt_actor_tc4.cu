@@ -253,10 +253,20 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                 float *dst = ring.S + rrow0 * IN;
                 const bool flat = ld == IN && rows == kTileM && !ring.m.many && row0 >= ring.m.first && rrow0 + kTileM <= ring.m.cap;
                 if (flat && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+                    // the tile (128 x 23 floats = 23 x 32 float4) in two rounds of 12 / 11 loads in flight per lane: two memory round trips.
+                    // (4 loads in flight per lane made this warp latency-bound at ~17 k cycles per tile -- slower than
+                    // the GEMMs it is supposed to hide under.)
                     const float4 *s4 = reinterpret_cast<const float4 *>(src);
                     float4 *d4 = reinterpret_cast<float4 *>(dst);
-#pragma unroll 4
-                    for (int v = lane; v < kTileM * IN / 4; v += 32) __stcs(&d4[v], __ldcs(&s4[v]));
+                    constexpr int kV = kTileM * IN / 4 / 32, kHalf = (kV + 1) / 2;      // 23 float4 per lane, in two rounds of 12 + 11
+                    float4 buf[kHalf];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+#pragma unroll
+                        for (int i = 0; i < kHalf; i++) if (h * kHalf + i < kV) buf[i] = __ldcs(&s4[lane + 32 * (h * kHalf + i)]);
+#pragma unroll
+                        for (int i = 0; i < kHalf; i++) if (h * kHalf + i < kV) __stcs(&d4[lane + 32 * (h * kHalf + i)], buf[i]);
+                    }
                 } else if (flat) {
 #pragma unroll 4
                     for (int v = lane; v < kTileM * IN; v += 32) __stcs(&dst[v], __ldcs(&src[v]));
