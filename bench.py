@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--ring", type=int, default=1 << 24, help="replay ring capacity per GPU (transitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--preroll", type=int, default=256, help="untimed rollout iterations before the warm-up, so that episodes "
+                    "terminate and reset at their steady-state rate inside the timed region")
     return ap.parse_args()
 
 
@@ -178,6 +180,9 @@ def run_b200(args):
         return float(ms)
 
     W, K = max(args.warmup, 3), args.steps
+    for _ in range(args.preroll):          # population reaches its stationary mix of episode ages (max episode ~ 250 steps)
+        eng.step()
+    env.stats_tensor(clear=True)
     for _ in range(W):
         eng.step()
     torch.cuda.synchronize()
@@ -330,7 +335,7 @@ def run_b200(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "bf16": "bf16", "f16": "f16"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": f"full rollout: actor(23-400-300-1,{args.precision})+OU+simv2 step(f64/f32 DP5)+reward_functionv1+"
-                                       f"replay store (fused into the producers)+auto-reset, {N} envs/GPU", "envs_per_gpu": N, "ring_capacity": args.ring,
+                                       f"replay store (fused into the producers)+auto-reset, {N} envs/GPU", "envs_per_gpu": N, "ring_capacity": args.ring, "preroll_iterations": args.preroll,
                            "l2": "working set per step (>1.2 GB/GPU) far exceeds the 126 MB L2; no flush needed",
                            "sharding": "global env id ranges, no data-path collective; NCCL only for actor broadcast + stats all-reduce"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
