@@ -12,6 +12,7 @@ from .env import VecTruckTrailerEnv, Truck_trailer_Env_2, EnvConfig  # noqa: F40
 from .replay import DeviceReplayBuffer, ReplayBuffer  # noqa: F401
 from .agent import VecAgent, Agent, OUNoiseState, init_actor_state_dict, ACTOR_KEYS  # noqa: F401
 from .rollout import RolloutEngine  # noqa: F401
+from . import checkpoint, recording, evaluate  # noqa: F401
 
 __all__ = ["VecTruckTrailerEnv", "Truck_trailer_Env_2", "EnvConfig", "DeviceReplayBuffer", "ReplayBuffer", "VecAgent",
            "Agent", "OUNoiseState", "RolloutEngine", "init_actor_state_dict", "TTError", "load", "lib_path"]

@@ -174,6 +174,48 @@ class VecAgent:
     def load_actor_state_dict(self, sd):
         self.actor.load_state_dict(sd)
 
+    # ---- checkpoint interop with the reference (DDPG_agent.py:54-70, networks.py:69-95,149-169) ----
+    chkpt_dir = "tmp/ddpg"
+
+    def _state_dicts(self):
+        sds = {"actor": self.actor.state_dict()}
+        if self._learner is not None:
+            ln = self._learner
+            sds.update(target_actor=ln.target_actor.state_dict(), critic=ln.critic.state_dict(), target_critic=ln.target_critic.state_dict())
+        else:
+            sds["target_actor"] = self.actor.state_dict()        # update_network_parameters(tau=1), DDPG_agent.py:34
+        return sds
+
+    def save_models(self):
+        """``Agent.save_models``: <chkpt_dir>/{actor,target_actor,critic,target_critic}_ddpg in the reference's format
+        (the critics exist once ``learn()`` has run)."""
+        from . import checkpoint
+        return checkpoint.save_models(self._state_dicts(), self.chkpt_dir)
+
+    def save_models_progress(self, success):
+        from . import checkpoint
+        return checkpoint.save_models(self._state_dicts(), self.chkpt_dir, progress=success)
+
+    def load_models(self):
+        """``Agent.load_models``: loads whatever of the four reference checkpoints exists; the actor goes to the CUDA
+        kernels' weight layouts (fp32 + tensor-core images), the others to the learner."""
+        from . import checkpoint
+        sds = checkpoint.load_models(self.chkpt_dir)
+        if "actor" not in sds:
+            raise FileNotFoundError(checkpoint.checkpoint_path(self.chkpt_dir, "actor"))
+        checkpoint.check_actor_state_dict(sds["actor"], *self.actor.dims)
+        self.actor.load_state_dict(sds["actor"])
+        if len(sds) > 1:
+            from .learner import TorchLearner
+            if self._learner is None:
+                self._learner = TorchLearner(self)
+            ln = self._learner
+            ln.actor.load_state_dict(sds["actor"])
+            for name, net in (("target_actor", ln.target_actor), ("critic", ln.critic), ("target_critic", ln.target_critic)):
+                if name in sds:
+                    net.load_state_dict(sds[name])
+        return sorted(sds)
+
     def learn(self):
         """Learner step (DDPG_agent.py:72-106), not part of the B200 hot path: plain torch on the device ring."""
         from .learner import TorchLearner

@@ -10,6 +10,7 @@
 //   rsB[N]  float4   g1 g2 g3 d0                (g = per-step distance decrements)
 //   packed[N] u32    steps | emax | rmax-emax | stage bits | finished
 //   goal[N] int4     gx gy (fixed point) sin/cos(gyaw) bits -- only READ when per-env goals were injected
+//   l2v[N]  double2  trailer length L2 and v1x / L2 -- only READ by the step kernel after a per-env injection
 //   pose[4][N] f64   startx starty startyaw goalyaw (written on reset only; host-visible attributes)
 //   stats[16] f64, iter u32
 // One thread owns one environment.  The step kernel is persistent: a CTA walks over 128-env tiles and issues
@@ -32,6 +33,7 @@ struct EnvPtrs {
     float4 *rsA, *rsB;
     uint32_t *packed;
     int4 *goal;
+    double2 *l2v;        // (L2, v1x / L2) per env (heatmap.py:89 varies the trailer length per trial)
     double *pose;        // [4][N]
     double *stats;       // [16]
     uint32_t *iter;
@@ -44,7 +46,7 @@ struct tt_env {
     EnvPtrs p;
     uint64_t seed;
     uint64_t gid0;
-    bool per_env_goal;
+    bool per_env_goal;   // per-env goals and/or trailer lengths were injected: the step kernel reads goal[] and l2v[]
 };
 
 namespace {
@@ -60,6 +62,7 @@ struct EnvRaw {
     int4 pos;
     float4 a, b;
     int4 goal;
+    double2 l2v;
     uint32_t packed;
     float action;
 };
@@ -67,7 +70,7 @@ struct EnvRaw {
 template <bool kGoal>
 __device__ __forceinline__ void load_raw(const EnvPtrs &p, int64_t i, const float *__restrict__ actions, EnvRaw &r) {
     r.psi = p.psi[i]; r.pos = p.pos[i]; r.a = p.rsA[i]; r.b = p.rsB[i]; r.packed = p.packed[i];
-    if (kGoal) r.goal = __ldg(&p.goal[i]);
+    if (kGoal) { r.goal = __ldg(&p.goal[i]); r.l2v = __ldg(&p.l2v[i]); }
     r.action = __ldcs(&actions[i]);
 }
 
@@ -79,6 +82,7 @@ struct __align__(16) RawSlab {
     int4 pos[kBlock];
     float4 a[kBlock], b[kBlock];
     int4 goal[kBlock];
+    double2 l2v[kBlock];
     uint32_t packed[kBlock];
     float action[kBlock];
 };
@@ -94,13 +98,13 @@ template <bool kGoal>
 __device__ __forceinline__ void stage_raw(const EnvPtrs &p, int64_t i, const float *__restrict__ actions, RawSlab &sl, int t) {
     cp_async_16(&sl.psi[t], &p.psi[i]); cp_async_16(&sl.pos[t], &p.pos[i]);
     cp_async_16(&sl.a[t], &p.rsA[i]); cp_async_16(&sl.b[t], &p.rsB[i]);
-    if (kGoal) cp_async_16(&sl.goal[t], &p.goal[i]);
+    if (kGoal) { cp_async_16(&sl.goal[t], &p.goal[i]); cp_async_16(&sl.l2v[t], &p.l2v[i]); }
     cp_async_4(&sl.packed[t], &p.packed[i]); cp_async_4(&sl.action[t], &actions[i]);
 }
 
 __device__ __forceinline__ void read_slab(const RawSlab &sl, int t, EnvRaw &r, bool goal) {
     r.psi = sl.psi[t]; r.pos = sl.pos[t]; r.a = sl.a[t]; r.b = sl.b[t]; r.packed = sl.packed[t]; r.action = sl.action[t];
-    if (goal) r.goal = sl.goal[t];
+    if (goal) { r.goal = sl.goal[t]; r.l2v = sl.l2v[t]; }
 }
 
 template <bool kGoal>
@@ -110,8 +114,8 @@ __device__ __forceinline__ void unpack(const StepConsts &k, const EnvRaw &r, Env
     e.closest = r.a.x; e.cum = r.a.y; e.first_steer = r.a.z; e.ep_ret = r.a.w;
     e.g1 = r.b.x; e.g2 = r.b.y; e.g3 = r.b.z; e.d0 = r.b.w;
     e.packed = r.packed;
-    if (kGoal) { e.gx = r.goal.x; e.gy = r.goal.y; e.sgy = __int_as_float(r.goal.z); e.cgy = __int_as_float(r.goal.w); }
-    else { e.gx = k.gx_fix; e.gy = k.gy_fix; e.sgy = k.sgy0; e.cgy = k.cgy0; }
+    if (kGoal) { e.gx = r.goal.x; e.gy = r.goal.y; e.sgy = __int_as_float(r.goal.z); e.cgy = __int_as_float(r.goal.w); e.L2 = r.l2v.x; e.vL2 = r.l2v.y; }
+    else { e.gx = k.gx_fix; e.gy = k.gy_fix; e.sgy = k.sgy0; e.cgy = k.cgy0; use_default_l2(k, e); }
 }
 
 __device__ __forceinline__ void store_dyn(const EnvPtrs &p, int64_t i, const EnvRegs &e) {
@@ -342,6 +346,7 @@ __global__ void __launch_bounds__(kBlock) env_reset_kernel(EnvPtrs p, StepConsts
     if (mask && !mask[i]) return;
     if (ou_x) ou_x[i] = 0.0f;                                 // agent.noise.reset() for the new episode (trainv2.py:492)
     EnvRegs e;
+    { const double2 l = p.l2v[i]; e.L2 = l.x; e.vL2 = l.y; }
     double sx, sy, syaw;
     rng_pose(k, seed, (uint32_t)(gid0 + i), *p.iter + t_salt, sx, sy, syaw);
     float o[TT_OBS_DIM];
@@ -364,6 +369,7 @@ __global__ void __launch_bounds__(kBlock) env_set_state_kernel(EnvPtrs p, StepCo
     const int64_t i = idx ? idx[j] : j;
     if (i < 0 || i >= p.N) return;
     EnvRegs e;
+    { const double2 l = p.l2v[i]; e.L2 = l.x; e.vL2 = l.y; }
     e.psi1 = state[6 * j]; e.psi2 = state[6 * j + 1];
     e.x1 = pos_from_double(state[6 * j + 2]); e.y1 = pos_from_double(state[6 * j + 3]);
     e.x2 = pos_from_double(state[6 * j + 4]); e.y2 = pos_from_double(state[6 * j + 5]);
@@ -401,7 +407,26 @@ __global__ void tick_kernel(uint32_t *iter, uint32_t by) { *iter += by; }
 
 __global__ void __launch_bounds__(kBlock) env_init_goal_kernel(EnvPtrs p, StepConsts k) {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i < p.N) p.goal[i] = make_int4(k.gx_fix, k.gy_fix, __float_as_int(k.sgy0), __float_as_int(k.cgy0));
+    if (i < p.N) {
+        p.goal[i] = make_int4(k.gx_fix, k.gy_fix, __float_as_int(k.sgy0), __float_as_int(k.cgy0));
+        p.l2v[i] = make_double2(k.L2, k.vL2);
+        p.pose[3 * p.N + i] = k.gyaw;          // env.goalyaw is valid before the first reset (simv2.py:61-63)
+    }
+}
+
+// env.L2 = value (heatmap.py:89): per-env trailer length.  Takes effect for the dynamics at once and for the truck
+// position of the next reset / set_state.
+__global__ void __launch_bounds__(kBlock) env_set_l2_kernel(EnvPtrs p, double v1x, const int64_t *__restrict__ idx, int64_t n,
+                                                            const double *__restrict__ l2) {
+    const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (j >= n) return;
+    const int64_t i = idx ? idx[j] : j;
+    if (i < 0 || i >= p.N) return;
+    p.l2v[i] = make_double2(l2[j], v1x / l2[j]);
+}
+__global__ void __launch_bounds__(kBlock) env_get_l2_kernel(EnvPtrs p, double *__restrict__ l2) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < p.N) l2[i] = p.l2v[i].x;
 }
 
 __global__ void stats_read_kernel(double *stats, double *out, int clear) {
@@ -429,12 +454,12 @@ static size_t env_layout(int64_t n, EnvPtrs *p, char *base) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = tt::align_up(off + bytes, 256); return o; };
     const size_t o_psi = take(sizeof(double2) * n), o_pos = take(sizeof(int4) * n), o_a = take(sizeof(float4) * n),
-                 o_b = take(sizeof(float4) * n), o_pk = take(sizeof(uint32_t) * n), o_goal = take(sizeof(int4) * n),
+                 o_b = take(sizeof(float4) * n), o_pk = take(sizeof(uint32_t) * n), o_goal = take(sizeof(int4) * n), o_l2v = take(sizeof(double2) * n),
                  o_pose = take(sizeof(double) * 4 * n), o_stats = take(sizeof(double) * TT_NSTATS), o_iter = take(256);
     if (p) {
         p->psi = reinterpret_cast<double2 *>(base + o_psi); p->pos = reinterpret_cast<int4 *>(base + o_pos);
         p->rsA = reinterpret_cast<float4 *>(base + o_a); p->rsB = reinterpret_cast<float4 *>(base + o_b);
-        p->packed = reinterpret_cast<uint32_t *>(base + o_pk); p->goal = reinterpret_cast<int4 *>(base + o_goal);
+        p->packed = reinterpret_cast<uint32_t *>(base + o_pk); p->goal = reinterpret_cast<int4 *>(base + o_goal); p->l2v = reinterpret_cast<double2 *>(base + o_l2v);
         p->pose = reinterpret_cast<double *>(base + o_pose); p->stats = reinterpret_cast<double *>(base + o_stats);
         p->iter = reinterpret_cast<uint32_t *>(base + o_iter); p->N = n;
     }
@@ -593,6 +618,22 @@ int tt_env_get_state(tt_env *env, double *d_state, double *d_start, double *d_go
     TT_REQUIRE(env, "env is NULL");
     env_get_state_kernel<<<(unsigned)grid_for(env->p.N), kBlock, 0, tt::as_stream(stream)>>>(env->p, d_state, d_start,
                                                                                             d_goal, d_steps, d_max_steps);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
+}
+
+int tt_env_set_l2(tt_env *env, const int64_t *d_idx, int64_t n, const double *d_l2, tt_stream_t stream) {
+    TT_REQUIRE(env && d_l2, "NULL argument");
+    TT_REQUIRE(n > 0 && n <= env->p.N, "bad n");
+    env_set_l2_kernel<<<(unsigned)grid_for(n), kBlock, 0, tt::as_stream(stream)>>>(env->p, env->cfg.v1x, d_idx, n, d_l2);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    env->per_env_goal = true;      // the step kernel must read l2v[] (and goal[]) from now on
+    return TT_OK;
+}
+
+int tt_env_get_l2(tt_env *env, double *d_l2, tt_stream_t stream) {
+    TT_REQUIRE(env && d_l2, "NULL argument");
+    env_get_l2_kernel<<<(unsigned)grid_for(env->p.N), kBlock, 0, tt::as_stream(stream)>>>(env->p, d_l2);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }

@@ -124,7 +124,12 @@ struct EnvRegs {
     float  g1, g2, g3;
     float  ep_ret;                             // running episode return (trainv2.py:529 `score`)
     uint32_t packed;
+    // trailer length of THIS env and v1x / L2 (heatmap.py:89 assigns env.L2 per trial).  Filled from StepConsts unless
+    // per-env values were injected (tt_env_set_l2); they are episode-independent and survive reset_from_pose.
+    double L2, vL2;
 };
+
+TT_HD void use_default_l2(const StepConsts &k, EnvRegs &e) { e.L2 = k.L2; e.vL2 = k.vL2; }
 
 struct StepOut {
     float obs[23];
@@ -310,7 +315,7 @@ TT_HD void reset_from_pose(const StepConsts &k, EnvRegs &e, double sx, double sy
     double sn, cs;
     sincos_f64(syaw, sn, cs);
     e.psi1 = e.psi2 = (double)(float)syaw;
-    e.x1 = pos_from_double((double)(float)fma(k.L2, cs, sx)); e.y1 = pos_from_double((double)(float)fma(k.L2, sn, sy));
+    e.x1 = pos_from_double((double)(float)fma(e.L2, cs, sx)); e.y1 = pos_from_double((double)(float)fma(e.L2, sn, sy));
     e.x2 = pos_from_double((double)(float)sx); e.y2 = pos_from_double((double)(float)sy);
     begin_episode(k, e, sx, sy, gx, gy, gyaw, obs);
 }
@@ -382,7 +387,7 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
 
     // ---- Dormand-Prince 5 (scipy rk.py:541-550 tableau, TTM_K), theta/psi2 in float64, positions in float32 ----
     double u[6];                                             // psi2' at the stages = (v/L2) sin(theta_j)
-    u[0] = k.vL2 * S0;
+    u[0] = e.vL2 * S0;
     float ax1, ay1, ax2, ay2;                                // sum_j b_j * (unit velocity components)
     {
         const float s1b = fmaf(S0f, c2b, C0f * s2b), c1b = fmaf(C0f, c2b, -S0f * s2b);
@@ -403,7 +408,7 @@ TT_HD void env_step(const StepConsts &k, EnvRegs &e, float action, StepOut &out)
         double sd, cd;
         sincos_small_f64(dth, sd, cd);
         const double sth = fma(S0, cd, C0 * sd);
-        u[j] = k.vL2 * sth;
+        u[j] = e.vL2 * sth;
         if (j != 1) {                                        // b2 = 0: stage 2 does not enter the position quadrature
             const float cthf = (float)fma(C0, cd, -S0 * sd), sthf = (float)sth;
             float sp, cp;

@@ -79,6 +79,7 @@ class VecTruckTrailerEnv:
                                        self._ws_ptr, nbytes))
             self._h = h
             self._obs = [torch.zeros(N, self.ld_obs, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._per_env_l2 = False
             self._cur = 0
             self._reward = torch.zeros(N, dtype=torch.float32, device=self.device)
             self._done = torch.zeros(N, dtype=torch.uint8, device=self.device)
@@ -108,7 +109,30 @@ class VecTruckTrailerEnv:
 
     @property
     def L2(self):
-        return self.cfg.L2
+        """Trailer length: the configured scalar, or the per-env float64[N] tensor once ``set_l2`` was used."""
+        return self.get_l2() if self._per_env_l2 else self.cfg.L2
+
+    def set_l2(self, l2, idx=None):
+        """``env.L2 = value`` per environment (heatmap.py:89 draws the trailer length per trial).  ``l2``: scalar or [n]
+        float64; ``idx``: env indices (default 0..n-1).  Affects the dynamics from the next step on and the truck pose of
+        the next ``reset`` / ``set_state``."""
+        with torch.cuda.device(self.device):
+            ix = None if idx is None else torch.as_tensor(idx, dtype=torch.int64, device=self.device).reshape(-1).contiguous()
+            n = self.num_envs if ix is None else ix.numel()
+            v = torch.as_tensor(l2, dtype=torch.float64, device=self.device).reshape(-1)
+            if v.numel() == 1:
+                v = v.expand(n)
+            v = v.contiguous()
+            if v.numel() != n or bool((v <= 0).any()):
+                raise ValueError("set_l2: need one positive length per selected env")
+            check(self.L.tt_env_set_l2(self._h, ptr(ix), n, v.data_ptr(), stream_ptr()))
+            self._per_env_l2 = True
+
+    def get_l2(self):
+        with torch.cuda.device(self.device):
+            out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+            check(self.L.tt_env_get_l2(self._h, out.data_ptr(), stream_ptr()))
+        return out
 
     def _obs_view(self, t):
         return t[:, :TT_OBS_DIM] if self.ld_obs != TT_OBS_DIM else t
@@ -271,7 +295,7 @@ class Truck_trailer_Env_2:
         self.observation_dim = TT_OBS_DIM
         self.position_threshold, self.orientation_threshold = v.position_threshold, v.orientation_threshold
         self.min_map_x, self.min_map_y, self.max_map_x, self.max_map_y = v.min_map_x, v.min_map_y, v.max_map_x, v.max_map_y
-        self.L1, self.L2, self.v1x, self.dt = v.L1, v.L2, v.v1x, v.dt
+        self.L1, self._L2, self.v1x, self.dt = v.L1, float(v.cfg.L2), v.v1x, v.dt
         self.path_x = self.path_y = self.path_yaw = []       # read by DDPG/train.py:362-364 (simv1 legacy)
         self.jackknife = self.out_of_map = self.max_steps_reached = self.goal_passed = self.goal_reached = False
         self._episode = 0
@@ -285,6 +309,16 @@ class Truck_trailer_Env_2:
         self.goalx, self.goaly, self.goalyaw = float(gl[0]), float(gl[1]), float(gl[2])
         self.episode_steps = int(s["episode_steps"][0])
         self.max_episode_steps = int(s["max_episode_steps"][0])
+
+    @property
+    def L2(self):
+        return self._L2
+
+    @L2.setter
+    def L2(self, value):
+        # heatmap.py:89: `env.L2 = np.random.uniform(5, 7)` before the start state of the trial is assigned
+        self._L2 = float(value)
+        self.vec.set_l2(self._L2)
 
     @property
     def state(self):
@@ -326,7 +360,17 @@ class Truck_trailer_Env_2:
         return obs[0].cpu().numpy().copy(), out["total_reward"], bool(done[0]), out
 
     def compute_observation(self, state, steering_angle):
-        raise NotImplementedError("observations are produced by the CUDA kernel; use reset()/step()")
+        """simv2.py:103-181 for an arbitrary state (heatmap.py:122 calls it on the state it has just assigned): computed by
+        the state-injection kernel of a scratch env with the current start / goal / L2; the steering angle only enters the
+        observation as sin/cos at indices 10, 11."""
+        if getattr(self, "_scratch", None) is None:
+            self._scratch = VecTruckTrailerEnv(1, seed=0, device=self.vec.device)
+        sc = self._scratch
+        sc.set_l2(self._L2)
+        obs = sc.set_state(np.asarray(state, np.float64)[None], [[self.startx, self.starty, self.startyaw]],
+                           [[self.goalx, self.goaly, self.goalyaw]])[0].cpu().numpy().copy()
+        obs[10], obs[11] = np.float32(math.sin(steering_angle)), np.float32(math.cos(steering_angle))
+        return obs
 
     def render(self, mode="human"):
         return None

@@ -119,6 +119,13 @@ int tt_env_set_state(tt_env *env, const int64_t *d_idx, int64_t n, const double 
 int tt_env_get_state(tt_env *env, double *d_state, double *d_start, double *d_goal, int32_t *d_steps,
                      int32_t *d_max_steps, tt_stream_t stream);
 
+/* env.L2 = value per environment (heatmap.py:89 draws the trailer length per trial: `env.L2 = np.random.uniform(5,7)`).
+ * d_idx NULL = envs 0..n-1; d_l2 [n] float64 > 0.  The dynamics (simv2.py:291) use the new length from the next step on,
+ * reset / set_state place the truck L2 ahead of the trailer (simv2.py:483-484, heatmap.py:116-117).  Does not restart
+ * the episode.  tt_env_get_l2 writes all n_envs lengths. */
+int tt_env_set_l2(tt_env *env, const int64_t *d_idx, int64_t n, const double *d_l2, tt_stream_t stream);
+int tt_env_get_l2(tt_env *env, double *d_l2, tt_stream_t stream);
+
 /* Iteration counter of the Philox streams (device-resident so that launch sequences stay graph-capturable).
  * tt_env_step does not advance it; a driver that steps and resets by hand calls tt_env_tick once per
  * iteration (tt_rollout_step, tt_env_step_k with auto_reset and a full tt_env_reset do it themselves). */

@@ -14,6 +14,7 @@ int hm_replay(const double *state0, const double *start, const double *goal, con
     tt_env_cfg cfg; tt_fill_default_cfg(&cfg);
     ttm::StepConsts k = tt_make_consts(cfg);
     ttm::EnvRegs e;
+    ttm::use_default_l2(k, e);
     e.psi1 = state0[0]; e.psi2 = state0[1];
     e.x1 = ttm::pos_from_double(state0[2]); e.y1 = ttm::pos_from_double(state0[3]);
     e.x2 = ttm::pos_from_double(state0[4]); e.y2 = ttm::pos_from_double(state0[5]);
@@ -45,6 +46,7 @@ void hm_reset_pose(double sx, double sy, double syaw, double *state, float *obs)
     tt_env_cfg cfg; tt_fill_default_cfg(&cfg);
     ttm::StepConsts k = tt_make_consts(cfg);
     ttm::EnvRegs e;
+    ttm::use_default_l2(k, e);
     ttm::reset_from_pose(k, e, sx, sy, syaw, cfg.goal_x, cfg.goal_y, cfg.goal_yaw, obs);
     double s[6] = {e.psi1, e.psi2, ttm::pos_to_double(e.x1), ttm::pos_to_double(e.y1), ttm::pos_to_double(e.x2), ttm::pos_to_double(e.y2)};
     memcpy(state, s, sizeof s);
