@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     float2 *red1 = reinterpret_cast<float2 *>(sm + P::red);
     float *red3 = reinterpret_cast<float *>(red1 + 4 * kTileM);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sm + P::tmem_slot);
+    volatile uint32_t *staged = tmem_slot + 2;           // number of observation tiles the epilogue has staged so far
     auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
 
     // ---------------- one-time setup ----------------
     if (threadIdx.x == 0) {
+        *staged = 0u;
         mbar_init(bar(D_W1), 1);
         mbar_init(bar(D_XFULL), kEpiThreads); mbar_init(bar(D_WFULL), 1); mbar_init(bar(D_WFREE), kEpiThreads);
         mbar_init(bar(D_A2FULL), kEpiThreads);
@@ -244,8 +246,13 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         }
     } else if (warp == kCopyWarp) {
         // ================= fused replay store of s: observation rows -> ring `state` rows =================
+        // It follows the epilogue's staging counter, so its reads of a tile come right after the epilogue's own prefetch of
+        // the same rows and hit L2 (unsynchronised, this warp ran far ahead and every observation row was fetched from
+        // DRAM twice: 743 MB instead of 386 MB per launch at N = 2^22).
         if (ring.S) {
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            uint32_t j = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, j++) {
+                while (*staged <= j) __nanosleep(200);
                 const int64_t row0 = tile * kTileM;
                 const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
                 const int64_t rrow0 = ring.m.row(row0);
@@ -384,6 +391,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             }
             fence_proxy_async();
             mbar_arrive(bar(D_XFULL));
+            if (et == 0) *staged = *staged + 1u;                           // progress signal for the replay-store warp
             if (prof) { t1 = clock64(); e_st += t1 - t0; }
         };
 
