@@ -155,7 +155,11 @@ static_assert(D_COUNT <= 40, "barrier table");
 
 // kProf: per-phase cycle counters of block 0 (profiles/tc_phase_profile.py); compiled out of the production instantiation
 // (they cost ~25 registers per thread).
-template <typename OpT, bool kSplit, bool kProf>
+// kCluster: CTAs per cluster (1 or 2).  With 2, the two CTAs of a pair work on different row tiles but share the W2 stream:
+// each fetches half of every k-block and multicasts it into both shared memories (half the L2 -> SM traffic, which bounds the
+// sweeps); a ring slot is recycled when BOTH CTAs' MMAs have read it (multicast tcgen05.commit, mbarrier count 2).  The pair
+// runs the same number of ring iterations; a CTA whose last tile does not exist streams and releases without computing.
+template <typename OpT, bool kSplit, bool kProf, int kCluster>
 __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restrict__ w1img, const char *__restrict__ w2img,
                                                            tt_actor_dev A, const float *__restrict__ obs, int64_t ld, int64_t n,
                                                            float *__restrict__ out, TTRingS ring,
@@ -179,6 +183,10 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = (n + kTileM - 1) / kTileM;
+    // ring iterations of this CTA (pair): the lower-ranked CTA of a pair never has fewer tiles than the other
+    const int64_t pair_first = kCluster > 1 ? (int64_t)(blockIdx.x - cluster_ctarank()) : (int64_t)blockIdx.x;
+    const int64_t niter = pair_first < ntiles ? (ntiles - pair_first + gridDim.x - 1) / gridDim.x : 0;
+    constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1u);
 
     // ---------------- one-time setup ----------------
     if (threadIdx.x == 0) {
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         mbar_init(bar(D_XFULL), kEpiThreads); mbar_init(bar(D_WFULL), 1); mbar_init(bar(D_WFREE), kEpiThreads);
         mbar_init(bar(D_A2FULL), kEpiThreads);
         mbar_init(bar(D_H2AFULL), 1); mbar_init(bar(D_H2BFULL), 1); mbar_init(bar(D_H2AFREE), kEpiThreads); mbar_init(bar(D_H2BFREE), kEpiThreads);
-        for (int i = 0; i < P::kSlots; i++) { mbar_init(bar(D_W2FULL + i), 1); mbar_init(bar(D_W2EMPTY + i), 1); }
+        for (int i = 0; i < P::kSlots; i++) { mbar_init(bar(D_W2FULL + i), 1); mbar_init(bar(D_W2EMPTY + i), kCluster); }
         for (int i = 0; i < KB2; i++) mbar_init(bar(D_A2FREE + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -216,6 +224,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (kCluster > 1) cluster_sync_all();            // the partner's mbarriers are initialised before anything multicasts into them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const float b3 = A.b3[0];
@@ -230,16 +239,22 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         }
         __syncwarp();
         const char *w2rep = w2img + (size_t)(blockIdx.x % TT_W2_REPLICAS) * kW2ImageB;     // this SM's replica
+        const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
         uint32_t tp = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tp ^= 1u) {
+        for (int64_t itn = 0; itn < niter; itn++, tp ^= 1u) {
 #pragma unroll
             for (int step = 0; step < kSteps; step++) {
                 const int sweep = step / KB2, kb = step % KB2, slot = w2_slot(step, P::kSlots);
                 const uint32_t bytes = (uint32_t)(sweep ? kNB : kNA) * kRowB;
-                mbar_wait(bar(D_W2EMPTY + slot), w2_parity(step, P::kSlots, tp) ^ 1u);
+                mbar_wait(bar(D_W2EMPTY + slot), w2_parity(step, P::kSlots, tp) ^ 1u);     // every CTA of the cluster has read the slot
                 if (elect_one()) {
                     mbar_expect_tx(bar(D_W2FULL + slot), bytes);
-                    bulk_g2s(sW2 + slot * P::kW2Slot, w2rep + (sweep ? kW2SweepB : 0) + (size_t)kb * bytes, bytes, bar(D_W2FULL + slot));
+                    const char *src = w2rep + (sweep ? kW2SweepB : 0) + (size_t)kb * bytes;
+                    if (kCluster == 1) bulk_g2s(sW2 + slot * P::kW2Slot, src, bytes, bar(D_W2FULL + slot));
+                    else {                                                                  // my share of the block, to every CTA
+                        const uint32_t part = bytes / kCluster, off = crank * part;
+                        bulk_g2s_mc(sW2 + slot * P::kW2Slot + off, src + off, part, bar(D_W2FULL + slot), kMask);
+                    }
                 }
                 __syncwarp();
             }
@@ -322,8 +337,19 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             constexpr bool prof = kProf;
             uint32_t c2 = 0;
             long long t_a2 = 0, t_w2 = 0, t_h2 = 0, t0 = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, c2++) {
+            for (int64_t itn = 0; itn < niter; itn++, c2++) {
                 const uint32_t ph = c2 & 1u;
+                if (kCluster > 1 && (int64_t)blockIdx.x + itn * gridDim.x >= ntiles) {
+                    // no tile of its own in the pair's last iteration: keep the shared W2 ring moving
+#pragma unroll
+                    for (int step = 0; step < kSteps; step++) {
+                        const int slot = w2_slot(step, P::kSlots);
+                        mbar_wait(bar(D_W2FULL + slot), w2_parity(step, P::kSlots, ph));
+                        if (elect_one()) umma_commit_mc(bar(D_W2EMPTY + slot), kMask);
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 if (prof) t0 = clock64();
                 mbar_wait(bar(D_A2FULL), ph);
                 if (prof) t_a2 += clock64() - t0;
@@ -344,7 +370,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                         const uint32_t d = tmem + (sweep ? kNA : 0);
                         umma(d, a, b, sweep ? idB : idA, kb ? 1u : 0u);
                         umma(d, a + 2, b + 2, sweep ? idB : idA, 1u);
-                        umma_commit(bar(D_W2EMPTY + slot));
+                        if (kCluster == 1) umma_commit(bar(D_W2EMPTY + slot)); else umma_commit_mc(bar(D_W2EMPTY + slot), kMask);
                         if (sweep) umma_commit(bar(D_A2FREE + kb));         // A2 block kb may be overwritten for the next tile
                         if (kb == KB2 - 1) umma_commit(bar(sweep ? D_H2BFULL : D_H2AFULL));
                     }
@@ -607,6 +633,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     __syncwarp();
     tc_fence_before();
     __syncthreads();
+    if (kCluster > 1) cluster_sync_all();            // nobody leaves while the partner may still multicast into / arrive on this CTA
     if (warp == kM2Warp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
@@ -620,16 +647,44 @@ int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, cons
     if (ring) rs = *ring; else { rs.S = nullptr; rs.m = tt_make_ring_map(1, 0, 0); }
     using P = Plan4<kSplit>;
     static_assert(P::total <= 232448u, "shared-memory plan exceeds 227 KB");
-    auto kern = dbg ? actor_tc4_kernel<OpT, kSplit, true> : actor_tc4_kernel<OpT, kSplit, false>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
-        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
-        attr_set = true;
+    static int cluster = -1;      // 2 = CTA pairs with multicast W2 loads (default when 74 pairs are co-resident), 1 = single CTAs
+    if (cluster < 0) {
+        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
+        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
+        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
+        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
+        const char *e = getenv("TT_TC_CLUSTER");
+        int want = e ? atoi(e) : 2;
+        if (want == 2) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3((unsigned)(tt::sm_count() & ~1)); q.blockDim = dim3(640); q.dynamicSmemBytes = P::total;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, actor_tc4_kernel<OpT, kSplit, false, 2>, &q) != cudaSuccess || 2 * nclusters < (tt::sm_count() & ~1)) {
+                (void)cudaGetLastError();
+                want = 1;
+            }
+        }
+        cluster = want == 2 ? 2 : 1;
     }
     const int64_t ntiles = (n + kTileM - 1) / kTileM;
-    const int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
-    kern<<<grid, 640, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, rs, dbg);
+    int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
+    if (cluster == 2) {
+        grid = (grid + 1) & ~1;                                  // whole pairs; a CTA without tiles only serves the pair's W2 ring
+        if (grid > (tt::sm_count() & ~1)) grid = tt::sm_count() & ~1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(640); cfg.dynamicSmemBytes = P::total; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (dbg) TT_CUDA(cudaLaunchKernelEx(&cfg, actor_tc4_kernel<OpT, kSplit, true, 2>, w1img, w2img, A, d_obs, ld, n, d_mu, rs, dbg));
+        else TT_CUDA(cudaLaunchKernelEx(&cfg, actor_tc4_kernel<OpT, kSplit, false, 2>, w1img, w2img, A, d_obs, ld, n, d_mu, rs, dbg));
+    } else {
+        auto kern = dbg ? actor_tc4_kernel<OpT, kSplit, true, 1> : actor_tc4_kernel<OpT, kSplit, false, 1>;
+        kern<<<grid, 640, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, rs, dbg);
+    }
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
