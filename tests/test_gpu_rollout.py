@@ -104,3 +104,32 @@ def test_fused_store_equals_scatter_kernel(precision, N, cap, cntr0):
     ref.store_transition(obs, mu, rew, obs2, done)
     for f in ("state_memory", "new_state_memory", "action_memory", "reward_memory", "terminal_memory"):
         assert torch.equal(getattr(fused, f), getattr(ref, f)), f
+
+
+def test_cuda_graph_of_k_iterations_equals_eager_steps():
+    """RolloutEngine.capture(): K iterations as ONE CUDA graph replay == the same K iterations launched one by one
+    (trajectories, ring contents, statistics) -- the launch sequences of the C ABI are capturable as they are."""
+    import ddpg_trucktrailer_b200 as tt
+    N, cap = 2048, 8192
+
+    def make():
+        env = tt.VecTruckTrailerEnv(N, seed=5)
+        ag = tt.VecAgent(1e-4, 1e-3, (23,), 1e-3, 1, num_envs=N, max_size=cap, actor_seed=1, precision="f16")
+        eng = tt.RolloutEngine(env, ag)
+        eng.reset(seed=5)
+        return env, ag, eng
+
+    e0, a0, g0 = make()
+    e1, a1, g1 = make()
+    k = g1.capture()                      # smallest K with K * N % cap == 0 and K even -> 4; runs 2 warm-up steps first
+    assert k == 4
+    for _ in range(2 + 3 * k):
+        obs0, r0, d0 = g0.step()
+    for _ in range(3):
+        obs1, r1, d1 = g1.step_graph()
+    assert g0.iterations == g1.iterations and a0.memory.mem_cntr == a1.memory.mem_cntr
+    assert torch.equal(obs0, obs1) and torch.equal(r0, r1) and torch.equal(d0, d1)
+    for name in ("state_memory", "action_memory", "reward_memory", "new_state_memory", "terminal_memory"):
+        assert torch.equal(getattr(a0.memory, name), getattr(a1.memory, name)), name
+    assert torch.equal(e0.get_state()["state"], e1.get_state()["state"])
+    assert e0.read_stats() == e1.read_stats()
