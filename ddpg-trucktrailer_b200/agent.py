@@ -82,7 +82,7 @@ class CudaActor:
         self._sd = dev
 
     def state_dict(self):
-        return {k: v.clone() for k, v in self._sd.items()}
+        return {k: v.detach().clone() for k, v in self._sd.items()}
 
     def forward(self, obs, out=None, precision="fp32"):
         """tanh(mu(relu(LN(fc2(relu(LN(fc1(obs)))))))) -> [n] float32 (networks.py:138-147).
@@ -216,11 +216,13 @@ class VecAgent:
                     net.load_state_dict(sds[name])
         return sorted(sds)
 
+    learner_graph = False          # True: capture the learner step into one CUDA graph (learner.py)
+
     def learn(self):
         """Learner step (DDPG_agent.py:72-106), not part of the B200 hot path: plain torch on the device ring."""
         from .learner import TorchLearner
         if self._learner is None:
-            self._learner = TorchLearner(self)
+            self._learner = TorchLearner(self, graph=self.learner_graph)
         return self._learner.learn()
 
 
