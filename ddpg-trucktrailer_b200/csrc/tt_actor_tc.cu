@@ -866,9 +866,13 @@ void set_tc_profile_buffer(unsigned long long *d) { g_tc_dbg = d; }
 
 bool actor_tc_supported(const tt_actor_dev &A) { return A.in_dim == IN && A.h1 == H1 && A.h2 == H2; }
 
+static int tc_variant();
+
 int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *fc2_w, const float *fc2_b, cudaStream_t s) {
     const tt_actor_dev &A = a->dev;
     if (!actor_tc_supported(A)) return TT_OK;       // tensor-core path is specialised to 23-400-300; forward() will refuse
+    // only the images of the kernel variant in use (the policy is re-packed after every learner step)
+    if (tc_variant() >= 4) return actor_pack_tc4(a, fc1_w, fc1_b, A.g1, fc2_w, fc2_b, s);
     pack_tc_kernel<__half><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w1_f16), reinterpret_cast<char *>(A.w2_f16), fc1_w, fc1_b, fc2_w, fc2_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     pack_tc_kernel<__nv_bfloat16><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w1_bf16), reinterpret_cast<char *>(A.w2_bf16), fc1_w, fc1_b, fc2_w, fc2_b);
@@ -877,7 +881,7 @@ int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, cons
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     pack_gram_kernel<__nv_bfloat16, true><<<75, 256, 0, s>>>(A.gram_bf16, fc1_w, fc1_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    return actor_pack_tc4(a, fc1_w, fc1_b, A.g1, fc2_w, fc2_b, s);
+    return TT_OK;
 }
 
 static int tc_variant() {

@@ -54,26 +54,40 @@ __device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[NR]
     for (int i = 8; i < NR; i++) r[i] = 0u;
 }
 
-// ---- v4 layer-1 image, built at tt_actor_load time (one block of 576 threads) ----
+// ---- v4 layer-1 image, built at tt_actor_load time ----
 // rows 0..23   : L[k][j] (row j): lower Cholesky factor of Gc = sum_c (Wf[c] - m)(Wf[c] - m)^T, so that
 //                sum_j (row_j . x)^2 = x^T Gc x = sum_c (h_c - mean(h))^2;   rows 24..31: 0
 // rows 32..431 : g1[c] * (Wf[c][k] - m[k]),  Wf = [fc1.weight | fc1.bias], m = column means
 // Written as [hi | lo] f16 blocks (lo = rounding residual) and as one bf16 block.
-__global__ void __launch_bounds__(576) pack_l1c_kernel(char *__restrict__ img_f16, char *__restrict__ img_bf16,
-                                                        const float *__restrict__ fc1_w, const float *__restrict__ fc1_b,
-                                                        const float *__restrict__ g1) {
-    __shared__ double m[24], G[24][25], Lf[24][25];
+// Three small kernels (the policy is re-packed after every learner step, so this is on the end-to-end path):
+//   1. partial sums  S_ij = sum_c Wf[c][i] Wf[c][j],  s_i = sum_c Wf[c][i]  over a slice of c per block  -> float64 atomics
+//   2. one block: Gc = S - s s^T / 400, Cholesky, column means                                          -> scratch
+//   3. all blocks: the image rows
+constexpr int kGramBlocks = 16;
+__device__ __forceinline__ double wfull(const float *__restrict__ fc1_w, const float *__restrict__ fc1_b, int c, int k) {
+    return (double)(k < IN ? fc1_w[c * IN + k] : fc1_b[c]);
+}
+__global__ void __launch_bounds__(576) pack_l1c_gram_kernel(double *__restrict__ acc, const float *__restrict__ fc1_w, const float *__restrict__ fc1_b) {
+    const int t = threadIdx.x, i = t / 24, j = t - i * 24;
+    const int c0 = blockIdx.x * (H1 / kGramBlocks), c1 = c0 + H1 / kGramBlocks;
+    double si = 0.0, sij = 0.0;
+#pragma unroll 5
+    for (int c = c0; c < c1; c++) { const double a = wfull(fc1_w, fc1_b, c, i), b = wfull(fc1_w, fc1_b, c, j); si += a; sij += a * b; }
+    atomicAdd(&acc[t], sij);
+    if (j == 0) atomicAdd(&acc[576 + i], si);
+}
+static_assert(H1 % kGramBlocks == 0, "gram slices");
+
+__global__ void __launch_bounds__(576) pack_l1c_chol_kernel(double *__restrict__ acc, double *__restrict__ out /* m[24], L[24][24] */) {
+    __shared__ double G[24][25], Lf[24][25];
     __shared__ double gmax;
     const int t = threadIdx.x, i = t / 24, j = t - i * 24;
-    auto wf = [&](int c, int k) { return (double)(k < IN ? fc1_w[c * IN + k] : fc1_b[c]); };
-    {
-        double si = 0.0, sj = 0.0, sij = 0.0;
-        for (int c = 0; c < H1; c++) { const double a = wf(c, i), b = wf(c, j); si += a; sj += b; sij += a * b; }
-        G[i][j] = sij - si * sj / H1;
-        Lf[i][j] = 0.0;
-        if (j == 0) m[i] = si / H1;
-    }
+    G[i][j] = acc[t] - acc[576 + i] * acc[576 + j] / H1;
+    Lf[i][j] = 0.0;
+    if (j == 0) out[i] = acc[576 + i] / H1;
     __syncthreads();
+    acc[t] = 0.0;                                  // accumulators are clean for the next pack
+    if (t < 24) acc[576 + t] = 0.0;
     if (t == 0) { double d = 0.0; for (int k = 0; k < 24; k++) d = fmax(d, G[k][k]); gmax = d; }
     __syncthreads();
     for (int k = 0; k < 24; k++) {                 // right-looking Cholesky, column k; tiny pivots -> zero column
@@ -85,21 +99,24 @@ __global__ void __launch_bounds__(576) pack_l1c_kernel(char *__restrict__ img_f1
         if (i > k && j > k) G[i][j] -= Lf[i][k] * Lf[j][k];
         __syncthreads();
     }
-    auto put = [&](int row, int k, double x) {
+    out[24 + t] = Lf[i][j];
+}
+
+__global__ void __launch_bounds__(256) pack_l1c_image_kernel(char *__restrict__ img_f16, char *__restrict__ img_bf16, const double *__restrict__ ml,
+                                                             const float *__restrict__ fc1_w, const float *__restrict__ fc1_b,
+                                                             const float *__restrict__ g1) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < N1I * 32; v += gridDim.x * blockDim.x) {
+        const int row = v >> 5, k = v & 31;
+        double x = 0.0;
+        if (k < 24) {
+            if (row >= kStatRows) x = (double)g1[row - kStatRows] * (wfull(fc1_w, fc1_b, row - kStatRows, k) - ml[k]);
+            else if (row < 24) x = ml[24 + k * 24 + row];           // row j of the statistic block = column j of L
+        }
         const float xf = (float)x;
         const __half hi = __float2half_rn(xf);
         *reinterpret_cast<__half *>(img_f16 + sw64_off(row, k)) = hi;
         *reinterpret_cast<__half *>(img_f16 + N1I * kRowB + sw64_off(row, k)) = __float2half_rn(xf - __half2float(hi));
         *reinterpret_cast<__nv_bfloat16 *>(img_bf16 + sw64_off(row, k)) = __float2bfloat16_rn(xf);
-    };
-    for (int v = t; v < N1I * 32; v += blockDim.x) {
-        const int row = v >> 5, k = v & 31;
-        double x = 0.0;
-        if (k < 24) {
-            if (row >= kStatRows) x = (double)g1[row - kStatRows] * (wf(row - kStatRows, k) - m[k]);
-            else if (row < 24) x = Lf[k][row];                      // row j of the statistic block = column j of L
-        }
-        put(row, k, x);
     }
 }
 
@@ -695,7 +712,12 @@ namespace tt {
 
 int actor_pack_tc4(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *g1, const float *fc2_w, const float *fc2_b, cudaStream_t s) {
     const tt_actor_dev &A = a->dev;
-    pack_l1c_kernel<<<1, 576, 0, s>>>(reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), fc1_w, fc1_b, g1);
+    if (!a->scratch_clean) { TT_CUDA(cudaMemsetAsync(A.l1c_scratch, 0, sizeof(double) * 600, s)); a->scratch_clean = true; }
+    pack_l1c_gram_kernel<<<kGramBlocks, 576, 0, s>>>(A.l1c_scratch, fc1_w, fc1_b);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    pack_l1c_chol_kernel<<<1, 576, 0, s>>>(A.l1c_scratch, A.l1c_scratch + 600);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    pack_l1c_image_kernel<<<54, 256, 0, s>>>(reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + 600, fc1_w, fc1_b, g1);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     pack_w2s_kernel<__half><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_f16), fc2_w, fc2_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
