@@ -29,30 +29,9 @@
 #include "tt_actor.cuh"
 #include "tt_common.cuh"
 #include "tt_tc_ptx.cuh"
+#include "tt_tc4_layout.cuh"
 
 namespace {
-
-constexpr int kStatRows = 32;                 // statistic rows appended to the layer-1 B image (24 used)
-constexpr int N1I = N1 + kStatRows;           // rows per hi / lo block of the v4 layer-1 image (432)
-constexpr int kParts = 3;                     // layer-1 parts: [32 statistics + 96] | 160 | 144 columns
-constexpr int kWin0 = 304;                    // first TMEM column of the layer-1 window (160 columns)
-constexpr int kNA = 160, kNB = N2 - kNA;      // layer-2 output halves (sweep A / sweep B)
-constexpr uint32_t kW2SlotB = kNA * kRowB;    // ring slot: one half k-block (10 240 B; sweep B uses 9 216 of it)
-constexpr size_t kW2SweepB = (size_t)KB2 * kNA * kRowB;   // byte offset of sweep B inside the v4 W2 image
-constexpr size_t kW2ImageB = (size_t)KB2 * N2 * kRowB;     // one replica of the image
-
-__device__ __forceinline__ void tmem_ld4_async(uint32_t taddr, uint32_t (&r)[4]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
-}
-template <int NR>
-__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[NR]) {      // 8 columns into r[0..7], rest zero
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-#pragma unroll
-    for (int i = 8; i < NR; i++) r[i] = 0u;
-}
 
 // ---- v4 layer-1 image, built at tt_actor_load time ----
 // rows 0..23   : L[k][j] (row j): lower Cholesky factor of Gc = sum_c (Wf[c] - m)(Wf[c] - m)^T, so that
@@ -135,17 +114,6 @@ __global__ void pack_w2s_kernel(char *__restrict__ img, const float *__restrict_
 #pragma unroll
         for (int rep = 0; rep < TT_W2_REPLICAS; rep++) *reinterpret_cast<OpT *>(img + (size_t)rep * kW2ImageB + off) = o;
     }
-}
-
-// W2 ring schedule: one tile = 26 steps (sweep A: k-blocks 0..12, sweep B: 0..12); step -> slot is a fixed compile-time
-// pattern (round-robin, the last 26 % kSlots steps reuse slots 0, 1, ...) so that the fully unrolled issue loops carry no
-// address or phase arithmetic.  A slot is used kSteps / kSlots (+ 1 for the first 26 % kSlots slots) times per tile.
-constexpr int kSteps = 2 * KB2;
-__host__ __device__ constexpr int w2_slot(int step, int nslots) { return step < (kSteps / nslots) * nslots ? step % nslots : step - (kSteps / nslots) * nslots; }
-__host__ __device__ constexpr int w2_uses_per_tile(int slot, int nslots) { return kSteps / nslots + (slot < kSteps % nslots ? 1 : 0); }
-// phase parity of the `step`-th ring use of tile number `tile_parity` (0/1)
-__device__ __forceinline__ uint32_t w2_parity(int step, int nslots, uint32_t tile_parity) {
-    return ((w2_uses_per_tile(w2_slot(step, nslots), nslots) & 1) ? tile_parity : 0u) ^ (uint32_t)((step / nslots) & 1);
 }
 
 template <bool kSplit>
