@@ -1,31 +1,25 @@
-// tt_actor_tc.cu -- kernel (c), tensor-core path: the batched actor forward (ActorNetwork.forward,
-// DDPG/networks.py:138-147) on the 5th-generation tensor cores of sm_100a: tcgen05.mma with bf16 operands
-// staged in shared memory, fp32 accumulators in TMEM, tcgen05.ld for the LayerNorm/ReLU/tanh epilogues.
+// tt_actor_tc.cu -- kernel (c), tensor-core path of the batched actor forward (ActorNetwork.forward,
+// DDPG/networks.py:138-147): dispatch between the kernel generations and the PREVIOUS generation ("v3": pipelined, LayerNorm-1
+// statistics from the Gram matrix of W1 on the CUDA cores, layer 2 as one N = 256 + 48 sweep).  The default kernel ("v4") lives
+// in tt_actor_tc4.cu; v3 stays selectable with TT_TC_VARIANT=3 as a cross-check.
 //
-// One persistent CTA per SM; one tile = 128 observation rows (TMEM lane = row).
-//
-//   X[128 x 32] bf16  (23 obs + a constant-1 column that carries the fc1 bias)       shared, SWIZZLE_64B
-//   H1 = X . W1^T       tcgen05.mma kind::f16, N = 400 as 256 + 144, K = 32           TMEM cols [0, 400)
-//   A2 = relu(LN(H1))   tcgen05.ld -> registers -> bf16 -> shared (13 k-blocks of 32; column 400 = 1 carries
+//   X[128 x 32] 16-bit (23 obs + a constant-1 column that carries the fc1 bias)       shared, SWIZZLE_64B
+//   H1 = X . W1^T       tcgen05.mma kind::f16, N = 400 in two halves through a 208-column TMEM window, K = 32
+//   A2 = relu(LN(H1))   tcgen05.ld -> registers -> 16-bit -> shared (13 k-blocks of 32; column 400 = 1 carries
 //                       the fc2 bias), written directly in the UMMA K-major SWIZZLE_64B image
 //   H2 = A2 . W2^T      N = 304 (300 padded) as 256 + 48, K = 416; W2 is streamed per tile from L2 in 13
-//                       k-blocks of 19 KB by cp.async.bulk into a 3-slot ring           TMEM cols [0, 304)
+//                       k-blocks of 19 KB by cp.async.bulk into a ring                   TMEM cols [0, 304)
 //   mu = tanh(w3 . relu(LN(H2)) + b3)                                                 tcgen05.ld epilogue
 //
-// Warp roles (192 threads): warps 0-3 epilogue (warp w owns TMEM lanes 32w..32w+31 = rows), warp 4 lane 0
-// issues every tcgen05.mma / commit, warp 5 lane 0 is the bulk-copy producer.  All hand-offs are mbarriers.
-// The weight images are pre-swizzled once at tt_actor_load time so a k-block is one contiguous bulk copy.
+// The weight images are pre-swizzled at tt_actor_load time so a k-block is one contiguous bulk copy.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <type_traits>
 #include "tt_actor.cuh"
 #include "tt_common.cuh"
 
-#ifndef TT_TC_GROUPS
-#define TT_TC_GROUPS 4      // 16 epilogue warps
-#endif
 #ifndef TT_TC_VARIANT_DEFAULT
-#define TT_TC_VARIANT_DEFAULT 4   // 4 = v4 (tt_actor_tc4.cu, default), 3 = v3 pipelined, 2 = serial phases (TT_TC_VARIANT overrides)
+#define TT_TC_VARIANT_DEFAULT 4   // 4 = v4 (tt_actor_tc4.cu, default), 3 = v3 (this file; TT_TC_VARIANT overrides)
 #endif
 
 #include "tt_tc_ptx.cuh"
@@ -79,324 +73,6 @@ __global__ void pack_gram_kernel(float *__restrict__ gram, const float *__restri
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) gram[t] = (float)((i < 24 && j > i) ? 2.0 * acc : acc);
-}
-
-template <bool kSplit>
-struct Plan {
-    static constexpr int kXBlocks = kSplit ? 2 : 1;
-    static constexpr int kSlots = kSplit ? 2 : 3;                               // W2 ring depth (shared-memory budget)
-    static constexpr uint32_t kW2Slot = ((uint32_t)N2 * kRowB + 1023u) / 1024u * 1024u;
-    static constexpr uint32_t x = 0;
-    static constexpr uint32_t w1 = x + kXBlocks * kTileM * kRowB;               // 8 KB per X block
-    static constexpr uint32_t a2 = w1 + kXBlocks * N1 * kRowB;                   // 25 KB per W1 block
-    static constexpr uint32_t w2 = a2 + KB2 * kTileM * kRowB;                    // 104 KB
-    static constexpr uint32_t par = w2 + kSlots * kW2Slot;
-    static constexpr uint32_t npar = 2 * K2P + 3 * H2P;
-    static constexpr uint32_t red = par + npar * 4;                              // cross-group reductions
-    static constexpr uint32_t bars = red + 4 * kTileM * 8 + 4 * kTileM * 4;
-    static constexpr uint32_t tmem_slot = bars + 16 * 8;
-    static constexpr uint32_t total = tmem_slot + 16 + 1024;                     // + slack for manual 1024 B alignment
-};
-
-enum { B_W1 = 0, B_XFULL, B_H1FULL, B_A2FULL, B_H2FULL, B_TMEMFREE, B_W2FULL, B_W2EMPTY = B_W2FULL + 3, B_COUNT = B_W2EMPTY + 3 };
-
-// OpT: operand type (__half or __nv_bfloat16); kSplit: layer 1 as X_hi.W_hi + X_lo.W_hi + X_hi.W_lo (fp32-accurate);
-// kGroups: column groups of the epilogue (4 * kGroups epilogue warps; warp w reads TMEM lanes 32 * (w % 4))
-template <typename OpT, bool kSplit, int kGroups>
-__global__ void __launch_bounds__(128 * kGroups + 64, 1) actor_tc_kernel(const char *__restrict__ w1img, const char *__restrict__ w2img,
-                                                                         tt_actor_dev A, const float *__restrict__ obs, int64_t ld,
-                                                                         int64_t n, float *__restrict__ out,
-                                                                         unsigned long long *__restrict__ dbg) {
-    using P = Plan<kSplit>;
-    constexpr int kEpiThreads = 128 * kGroups, kThreads = kEpiThreads + 64;
-    constexpr int kMmaWarp = 4 * kGroups, kProdWarp = kMmaWarp + 1;
-    constexpr uint32_t kFmt = sizeof(OpT) == 2 && std::is_same<OpT, __nv_bfloat16>::value ? 1u : 0u;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t *sm = smem_raw + (base - raw);
-    const uint32_t sX = base + P::x, sW1 = base + P::w1, sA2 = base + P::a2, sW2 = base + P::w2, sBar = base + P::bars;
-    float *par = reinterpret_cast<float *>(sm + P::par);
-    float *pg1 = par, *pbe1 = par + K2P, *pg2 = par + 2 * K2P, *pbe2 = pg2 + H2P, *pw3 = pbe2 + H2P;
-    // cross-group reductions: (sum, sumsq) [4][128] shared by both layers (the A2FULL -> H2FULL hand-off orders the
-    // reuse), dot partials [4][128]
-    float2 *red1 = reinterpret_cast<float2 *>(sm + P::red);
-    float2 *red2 = red1;
-    float *red3 = reinterpret_cast<float *>(red1 + 4 * kTileM);
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sm + P::tmem_slot);
-    auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t ntiles = (n + kTileM - 1) / kTileM;
-
-    // ---------------- one-time setup ----------------
-    if (threadIdx.x == 0) {
-        mbar_init(bar(B_W1), 1);
-        mbar_init(bar(B_XFULL), kEpiThreads); mbar_init(bar(B_H1FULL), 1); mbar_init(bar(B_A2FULL), kEpiThreads);
-        mbar_init(bar(B_H2FULL), 1); mbar_init(bar(B_TMEMFREE), kEpiThreads);
-        for (int i = 0; i < P::kSlots; i++) { mbar_init(bar(B_W2FULL + i), 1); mbar_init(bar(B_W2EMPTY + i), 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == kMmaWarp) {     // TMEM allocation (whole warp), 512 columns: one CTA per SM
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + P::tmem_slot), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // per-column epilogue parameters -> shared (g = 0 / be = 1 at column H1 makes A2[:, H1] == 1: the fc2-bias column)
-    for (int c = threadIdx.x; c < K2P; c += kThreads) {
-        pg1[c] = c < H1 ? A.g1[c] : 0.f;
-        pbe1[c] = c < H1 ? A.be1[c] : (c == H1 ? 1.f : 0.f);
-    }
-    for (int c = threadIdx.x; c < H2P; c += kThreads) {
-        const bool in = c < H2;
-        pg2[c] = in ? A.g2[c] : 0.f; pbe2[c] = in ? A.be2[c] : 0.f; pw3[c] = in ? A.w3[c] : 0.f;
-    }
-    // X blocks: zero once; constant-1 bias column at k = IN of the hi block (never overwritten afterwards)
-    for (int v = threadIdx.x; v < P::kXBlocks * kTileM * kRowB / 4; v += kThreads) reinterpret_cast<uint32_t *>(sm + P::x)[v] = 0u;
-    __syncthreads();
-    if (threadIdx.x < kTileM) *reinterpret_cast<OpT *>(sm + P::x + sw64_off(threadIdx.x, IN)) = to_op<OpT>(1.0f);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const float b3 = A.b3[0];
-
-    if (warp == kProdWarp) {
-        // ================= bulk-copy producer =================
-        if (lane == 0) {
-            constexpr uint32_t w1bytes = (uint32_t)P::kXBlocks * N1 * kRowB;
-            mbar_expect_tx(bar(B_W1), w1bytes);
-            bulk_g2s(sW1, w1img, w1bytes, bar(B_W1));
-            uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int kb = 0; kb < KB2; kb++, it++) {
-                    const uint32_t slot = it % P::kSlots, ph = (it / P::kSlots) & 1u;
-                    mbar_wait(bar(B_W2EMPTY + slot), ph ^ 1u);          // first pass through the ring passes immediately
-                    mbar_expect_tx(bar(B_W2FULL + slot), (uint32_t)N2 * kRowB);
-                    bulk_g2s(sW2 + slot * P::kW2Slot, w2img + (size_t)kb * N2 * kRowB, (uint32_t)N2 * kRowB, bar(B_W2FULL + slot));
-                }
-            }
-        }
-    } else if (warp == kMmaWarp) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
-            constexpr int nA = 256, nB = N1 - 256, mA = 256, mB = N2 - 256;
-            const uint32_t id1a = make_idesc(nA, kFmt), id1b = make_idesc(nB, kFmt), id2a = make_idesc(mA, kFmt), id2b = make_idesc(mB, kFmt);
-            uint32_t it = 0, tcount = 0;
-            long long t_x = 0, t_a2 = 0, t_w2 = 0, t0;
-            mbar_wait(bar(B_W1), 0);
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
-                const uint32_t ph = tcount & 1u;
-                t0 = clock64();
-                mbar_wait(bar(B_XFULL), ph);
-                mbar_wait(bar(B_TMEMFREE), ph ^ 1u);                      // previous tile's accumulators drained
-                t_x += clock64() - t0;
-                tc_fence_after();
-                // layer 1: (X_hi, W_hi) [+ (X_lo, W_hi) + (X_hi, W_lo)], each K = 32 = 2 x UMMA_K
-                constexpr int npairs = kSplit ? 3 : 1;
-#pragma unroll
-                for (int pr = 0; pr < npairs; pr++) {
-                    const uint32_t xb = sX + (pr == 1 ? kTileM * kRowB : 0), wb = sW1 + (pr == 2 ? N1 * kRowB : 0);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ks++) {
-                        const uint64_t a = make_desc(xb + ks * 32);
-                        const uint32_t acc = (pr | ks) ? 1u : 0u;
-                        umma(tmem, a, make_desc(wb + ks * 32), id1a, acc);
-                        umma(tmem + 256, a, make_desc(wb + 256 * kRowB + ks * 32), id1b, acc);
-                    }
-                }
-                umma_commit(bar(B_H1FULL));
-                t0 = clock64();
-                mbar_wait(bar(B_A2FULL), ph);
-                t_a2 += clock64() - t0;
-                tc_fence_after();
-                for (int kb = 0; kb < KB2; kb++, it++) {
-                    const uint32_t slot = it % P::kSlots, wph = (it / P::kSlots) & 1u;
-                    t0 = clock64();
-                    mbar_wait(bar(B_W2FULL + slot), wph);
-                    t_w2 += clock64() - t0;
-                    tc_fence_after();
-                    const uint32_t wb = sW2 + slot * P::kW2Slot, ab = sA2 + (uint32_t)kb * kTileM * kRowB;
-#pragma unroll
-                    for (int ks = 0; ks < 2; ks++) {
-                        const uint64_t a = make_desc(ab + ks * 32);
-                        const uint32_t acc = (kb | ks) ? 1u : 0u;
-                        umma(tmem, a, make_desc(wb + ks * 32), id2a, acc);
-                        umma(tmem + 256, a, make_desc(wb + 256 * kRowB + ks * 32), id2b, acc);
-                    }
-                    umma_commit(bar(B_W2EMPTY + slot));                   // frees the W2 slot once these MMAs retire
-                }
-                umma_commit(bar(B_H2FULL));
-            }
-            if (dbg && blockIdx.x == 0) { dbg[0] = t_x; dbg[1] = t_a2; dbg[2] = t_w2; dbg[3] = tcount; }
-        }
-    } else {
-        // ================= epilogue warps: thread = (row, column group) =================
-        const int grp = warp >> 2;                                        // column group
-        const int r = (warp & 3) * 32 + lane;                             // row = TMEM lane
-        const int et = threadIdx.x;                                       // 0 .. kEpiThreads-1
-        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t xsw = (((uint32_t)r >> 1) & 3u);
-        constexpr int kXPer = (kTileM * IN + kEpiThreads - 1) / kEpiThreads;
-        float xreg[kXPer];
-        auto load_x = [&](int64_t t) {
-            const int64_t r0 = t * kTileM;
-#pragma unroll
-            for (int i = 0; i < kXPer; i++) {
-                const int v = et + i * kEpiThreads;
-                const int rr = v / IN, k = v - rr * IN;
-                xreg[i] = (v < kTileM * IN && r0 + rr < n) ? __ldcs(obs + (r0 + rr) * ld + k) : 0.f;
-            }
-        };
-        load_x(blockIdx.x);
-        uint32_t tcount = 0;
-        long long e_x = 0, e_w1 = 0, e_1 = 0, e_w2 = 0, e_2 = 0, t0 = clock64(), t1;
-        const long long t_begin = t0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
-            const uint32_t ph = tcount & 1u;
-            const int64_t row0 = tile * kTileM;
-            const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
-            // ---- observation tile (prefetched into registers one tile ahead) -> 16-bit hi [+ lo residual], swizzled.
-            //      X may be overwritten here: the layer-1 MMAs of the previous tile completed before its H1FULL, which
-            //      every epilogue thread has waited on. ----
-#pragma unroll
-            for (int i = 0; i < kXPer; i++) {
-                const int v = et + i * kEpiThreads;
-                if (v < kTileM * IN) {
-                    const int rr = v / IN, k = v - rr * IN;
-                    const float x = xreg[i];
-                    const OpT hi = to_op<OpT>(x);
-                    *reinterpret_cast<OpT *>(sm + P::x + sw64_off(rr, k)) = hi;
-                    if (kSplit) *reinterpret_cast<OpT *>(sm + P::x + kTileM * kRowB + sw64_off(rr, k)) = to_op<OpT>(x - op_to_float(hi));
-                }
-            }
-            fence_proxy_async();
-            mbar_arrive(bar(B_XFULL));
-            load_x(tile + gridDim.x);                                     // in flight during this tile's epilogues
-            t1 = clock64(); e_x += t1 - t0; t0 = t1;
-            // ---- epilogue 1: LayerNorm + ReLU over H1 columns -> A2 (16-bit, UMMA image) ----
-            mbar_wait(bar(B_H1FULL), ph);
-            t1 = clock64(); e_w1 += t1 - t0; t0 = t1;
-            tc_fence_after();
-            uint32_t v[32];
-            float sum, sq;
-            float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int ch = 0; ch < NCH1; ch++) {
-                if (ch % kGroups != grp) continue;
-                tmem_ld_chunk<N1>(trow, ch, v);
-                tmem_wait();
-#pragma unroll
-                for (int j = 0; j < 16; j++) {                             // packed fp32x2 (FADD2 / FFMA2); columns >= N1 read as 0
-                    const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                    s2 = __fadd2_rn(s2, x); q2 = __ffma2_rn(x, x, q2);
-                }
-            }
-            red1[grp * kTileM + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
-            named_bar_sync(1, kEpiThreads);
-            sum = 0.f; sq = 0.f;
-#pragma unroll
-            for (int g = 0; g < kGroups; g++) { const float2 t = red1[g * kTileM + r]; sum += t.x; sq += t.y; }
-            float mean = sum * (1.0f / H1);
-            float rstd = rsqrtf(fmaxf(sq * (1.0f / H1) - mean * mean, 0.f) + 1e-5f);
-            float nmr = -mean * rstd;
-            float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
-#pragma unroll
-            for (int ch = 0; ch < NCH1; ch++) {
-                if (ch % kGroups != grp) continue;
-                tmem_ld_chunk<N1>(trow, ch, v);
-                tmem_wait();
-                uint8_t *blk = sm + P::a2 + (size_t)ch * kTileM * kRowB + (size_t)r * kRowB;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {                             // 4 chunks of 8 columns = 16 B each
-                    const float4 g0 = *reinterpret_cast<const float4 *>(pg1 + ch * 32 + q * 8), g1 = *reinterpret_cast<const float4 *>(pg1 + ch * 32 + q * 8 + 4);
-                    const float4 e0 = *reinterpret_cast<const float4 *>(pbe1 + ch * 32 + q * 8), e1 = *reinterpret_cast<const float4 *>(pbe1 + ch * 32 + q * 8 + 4);
-                    const float2 gg[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
-                    const float2 ee[4] = {make_float2(e0.x, e0.y), make_float2(e0.z, e0.w), make_float2(e1.x, e1.y), make_float2(e1.z, e1.w)};
-                    uint32_t pk4[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {                          // y = relu(((x - mean) rstd) g + be): 2 x FFMA2, pack, packed max
-                        const float2 x = make_float2(__uint_as_float(v[q * 8 + 2 * j]), __uint_as_float(v[q * 8 + 2 * j + 1]));
-                        const float2 y = __ffma2_rn(__ffma2_rn(x, rstd2, nmr2), gg[j], ee[j]);
-                        pk4[j] = pack2_relu<OpT>(y.x, y.y);
-                    }
-                    uint4 pk;
-                    pk.x = pk4[0]; pk.y = pk4[1]; pk.z = pk4[2]; pk.w = pk4[3];
-                    *reinterpret_cast<uint4 *>(blk + (((uint32_t)q ^ xsw) << 4)) = pk;
-                }
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(bar(B_A2FULL));
-            t1 = clock64(); e_1 += t1 - t0; t0 = t1;
-            // ---- epilogue 2: LayerNorm + ReLU over H2 columns, dot with mu.weight, tanh ----
-            mbar_wait(bar(B_H2FULL), ph);
-            t1 = clock64(); e_w2 += t1 - t0; t0 = t1;
-            tc_fence_after();
-            s2 = make_float2(0.f, 0.f); q2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int ch = 0; ch < NCH2; ch++) {
-                if (ch % kGroups != grp) continue;
-                tmem_ld_chunk<N2>(trow, ch, v);
-                tmem_wait();
-#pragma unroll
-                for (int j = 0; j < 16; j++) {                             // pad columns are exactly 0
-                    const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                    s2 = __fadd2_rn(s2, x); q2 = __ffma2_rn(x, x, q2);
-                }
-            }
-            red2[grp * kTileM + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
-            named_bar_sync(1, kEpiThreads);
-            sum = 0.f; sq = 0.f;
-#pragma unroll
-            for (int g = 0; g < kGroups; g++) { const float2 t = red2[g * kTileM + r]; sum += t.x; sq += t.y; }
-            mean = sum * (1.0f / H2);
-            rstd = rsqrtf(fmaxf(sq * (1.0f / H2) - mean * mean, 0.f) + 1e-5f);
-            nmr = -mean * rstd;
-            rstd2 = make_float2(rstd, rstd); nmr2 = make_float2(nmr, nmr);
-            float2 dot2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int ch = 0; ch < NCH2; ch++) {
-                if (ch % kGroups != grp) continue;
-                tmem_ld_chunk<N2>(trow, ch, v);
-                tmem_wait();
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const float4 g0 = *reinterpret_cast<const float4 *>(pg2 + ch * 32 + q * 4), e0 = *reinterpret_cast<const float4 *>(pbe2 + ch * 32 + q * 4),
-                                 w0 = *reinterpret_cast<const float4 *>(pw3 + ch * 32 + q * 4);
-                    const float2 xa = make_float2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]));
-                    const float2 xb = make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
-                    float2 ya = __ffma2_rn(__ffma2_rn(xa, rstd2, nmr2), make_float2(g0.x, g0.y), make_float2(e0.x, e0.y));
-                    float2 yb = __ffma2_rn(__ffma2_rn(xb, rstd2, nmr2), make_float2(g0.z, g0.w), make_float2(e0.z, e0.w));
-                    ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
-                    dot2 = __ffma2_rn(ya, make_float2(w0.x, w0.y), dot2);
-                    dot2 = __ffma2_rn(yb, make_float2(w0.z, w0.w), dot2);
-                }
-            }
-            const float dot = dot2.x + dot2.y;
-            tc_fence_before();
-            mbar_arrive(bar(B_TMEMFREE));
-            red3[grp * kTileM + r] = dot;
-            named_bar_sync(1, kEpiThreads);
-            if (grp == 0 && r < rows) {
-                float d = b3;
-#pragma unroll
-                for (int g = 0; g < kGroups; g++) d += red3[g * kTileM + r];
-                out[row0 + r] = tanhf(d);
-            }
-            t1 = clock64(); e_2 += t1 - t0; t0 = t1;
-        }
-        if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
-            dbg[4] = e_x; dbg[5] = e_w1; dbg[6] = e_1; dbg[7] = e_w2; dbg[8] = e_2; dbg[9] = clock64() - t_begin;
-        }
-    }
-    // ---------------- teardown ----------------
-    __syncwarp();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == kMmaWarp) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
-    }
 }
 
 unsigned long long *g_tc_dbg = nullptr;      // optional device buffer for the per-phase cycle counters (tt_debug_set_tc_profile)
@@ -840,24 +516,6 @@ int launch_tc3(const char *w1img, const char *w2img, const float *gram, const tt
     return TT_OK;
 }
 
-template <typename OpT, bool kSplit, int kGroups>
-int launch_tc(const char *w1img, const char *w2img, const tt_actor_dev &A, const float *d_obs, int64_t ld, int64_t n, float *d_mu,
-              cudaStream_t st) {
-    using P = Plan<kSplit>;
-    static_assert(P::total <= 232448u, "shared-memory plan exceeds 227 KB");
-    auto kern = actor_tc_kernel<OpT, kSplit, kGroups>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
-        attr_set = true;
-    }
-    const int64_t ntiles = (n + kTileM - 1) / kTileM;
-    const int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
-    kern<<<grid, 128 * kGroups + 64, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, g_tc_dbg);
-    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    return TT_OK;
-}
-
 }  // namespace
 
 namespace tt {
@@ -898,16 +556,14 @@ int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t 
         return TT_ERR_INVALID;
     }
     const int variant = tc_variant();
-    if (ring && variant < 3) { set_error("fused replay store needs the pipelined tensor-core kernel"); return TT_ERR_INVALID; }
     if (variant >= 4) return actor_forward_tc4(a, d_obs, ld, n, d_mu, precision, ring, g_tc_dbg, st);
     if (variant == 3) {
         if (precision == TT_PREC_BF16)
             return launch_tc3<__nv_bfloat16, false>(reinterpret_cast<const char *>(A.w1_bf16), reinterpret_cast<const char *>(A.w2_bf16), A.gram_bf16, A, d_obs, ld, n, d_mu, ring, st);
         return launch_tc3<__half, true>(reinterpret_cast<const char *>(A.w1_f16), reinterpret_cast<const char *>(A.w2_f16), A.gram_f16, A, d_obs, ld, n, d_mu, ring, st);
     }
-    if (precision == TT_PREC_BF16)
-        return launch_tc<__nv_bfloat16, false, TT_TC_GROUPS>(reinterpret_cast<const char *>(A.w1_bf16), reinterpret_cast<const char *>(A.w2_bf16), A, d_obs, ld, n, d_mu, st);
-    return launch_tc<__half, true, TT_TC_GROUPS>(reinterpret_cast<const char *>(A.w1_f16), reinterpret_cast<const char *>(A.w2_f16), A, d_obs, ld, n, d_mu, st);
+    set_error("unknown tensor-core kernel variant %d (TT_TC_VARIANT: 4 = default, 3 = previous pipelined kernel)", variant);
+    return TT_ERR_INVALID;
 }
 
 }  // namespace tt
