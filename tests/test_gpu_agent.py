@@ -162,3 +162,26 @@ def test_actor_tc_refuses_other_layer_sizes():
     actor = tt.agent.CudaActor(23, 256, 128); actor.load_state_dict(tt.init_actor_state_dict(23, 256, 128, 1, seed=3))
     with pytest.raises(tt.TTError):
         actor.forward(torch.zeros(4, 23, device="cuda"), precision="f16")
+
+
+def test_actor_tc_previous_kernel_generation_agrees(golden_dir, tmp_path):
+    """TT_TC_VARIANT=3 (the previous tensor-core kernel, kept as a cross-check) and the default kernel implement the same
+    forward with different factorizations (Gram-matrix statistics on the CUDA cores vs Cholesky columns on the tensor core):
+    both within the 1e-3 bar of the reference torch outputs, and within 2e-4 of each other in f16 mode."""
+    import subprocess
+    import sys
+    import ddpg_trucktrailer_b200 as tt
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "v3.npy")
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests');"
+            "import ddpg_trucktrailer_b200 as tt; from test_gpu_agent import _sets;"
+            "g = np.load(%r); a = tt.agent.CudaActor(); a.load_state_dict(_sets(g)[1]);"
+            "np.save(%r, a.forward(torch.from_numpy(g['obs']).cuda(), precision='f16').cpu().numpy())"
+            % (root, root, os.path.join(golden_dir, "ref_actor.npz"), out))
+    subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, TT_TC_VARIANT="3"), timeout=300)
+    g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
+    actor = tt.agent.CudaActor(); actor.load_state_dict(_sets(g)[1])
+    v4 = actor.forward(torch.from_numpy(g["obs"]).cuda(), precision="f16").cpu().numpy()
+    v3 = np.load(out)
+    assert np.abs(v3 - g["out1"]).max() < 1e-3 and np.abs(v4 - g["out1"]).max() < 1e-3
+    assert np.abs(v3 - v4).max() < 2e-4
