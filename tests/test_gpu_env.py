@@ -239,3 +239,34 @@ def test_full_size_properties():
     c.step_k(warm[:, N - 4096:].contiguous(), auto_reset=True, want_reward=False, want_done=False)
     _, rc, _, _ = c.step_k(acts[:, N - 4096:].contiguous(), auto_reset=True)
     assert torch.equal(rc, rk[:, N - 4096:])
+
+
+def test_sparse_masked_reset_equals_per_env_reset():
+    """The persistent mask-scanning reset kernel (N >= 2^16 with a 16 B aligned mask: warp-level compaction of the finished
+    envs, one env per lane) resets exactly the masked envs and produces the same episodes / observations as the
+    one-thread-per-env kernel (unaligned mask -> fallback), for sparse and for dense masks."""
+    tt = _tt()
+    N = (1 << 16) + 5                                   # ragged last group of 16
+    for density in (0.02, 0.7):
+        envs = [tt.VecTruckTrailerEnv(N, seed=31) for _ in range(2)]
+        for e in envs:
+            e.reset()
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        mask = (torch.rand(N, device="cuda", generator=g) < density).to(torch.uint8)
+        mask[-1] = 1; mask[0] = 1
+        raw = torch.zeros(N + 16, dtype=torch.uint8, device="cuda")
+        unaligned = raw[1:N + 1]; unaligned.copy_(mask)
+        assert unaligned.data_ptr() % 16 != 0 and mask.data_ptr() % 16 == 0
+        before = envs[0].get_state()["state"].clone()
+        a = torch.zeros(N, device="cuda")
+        for e in envs:
+            e.step(a)
+        o0, _ = envs[0].reset(options={"mask": mask})
+        o1, _ = envs[1].reset(options={"mask": unaligned})
+        s0, s1 = envs[0].get_state(), envs[1].get_state()
+        for k in ("state", "start", "goal", "episode_steps", "max_episode_steps"):
+            assert torch.equal(s0[k], s1[k]), k
+        assert torch.equal(o0, o1)
+        m = mask.bool()
+        assert (s0["episode_steps"][m] == 0).all() and (s0["episode_steps"][~m] == 1).all()
+        assert not torch.equal(s0["state"][m], before[m])
