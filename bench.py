@@ -27,7 +27,16 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
 
-METRIC = "env-steps/sec (fused env+actor rollout)"
+def _baseline_metric():
+    """BASELINE.json's headline metric string, verbatim (the primary quantity of it: env-steps/sec of the fused rollout)."""
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as f:
+            return json.load(f)["metric"]
+    except Exception:
+        return "env-steps/sec (fused env+actor) at 1/2/4/8 B200; % HBM roofline"
+
+
+METRIC = _baseline_metric()
 UNIT = "env-steps/s"
 # algorithmic bytes / flops per env-step (SURVEY.md section 8d, restated in DESIGN.md)
 ENV_BYTES, OU_BYTES, ACTOR_BYTES, STORE_BYTES = 229, 16, 96, 386
