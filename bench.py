@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--ring", type=int, default=1 << 24, help="replay ring capacity per GPU (transitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--config4", action="store_true", help="also time BASELINE.json configs[3]: rollout + replay store + one DDPG "
+                    "critic/actor update (batch 64) per iteration + stats all-reduce + actor broadcast (extra key `config4`)")
     ap.add_argument("--preroll", type=int, default=256, help="untimed rollout iterations before the warm-up, so that episodes "
                     "terminate and reset at their steady-state rate inside the timed region")
     return ap.parse_args()
@@ -331,6 +333,29 @@ def run_b200(args):
                 "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": pk["src"],
                 "share_of_step": kms[dom] / sum(kms[k] for k in in_step)}
 
+    # ---- optional: BASELINE.json configs[3] = the rollout iteration + one learner update (batch 64) per iteration ----
+    config4 = None
+    if args.config4:
+        agent.learner_graph = True                   # learner.py: the whole DDPG update as one CUDA graph, samples rank-local ring
+        for _ in range(3):
+            agent.learn()
+        torch.cuda.synchronize()
+        stats_dev = torch.zeros(16, dtype=torch.float64, device=dev)
+
+        def c4_step():
+            eng.step()
+            agent.learn()                                              # replays the graph (incl. the actor re-pack) on the same stream
+            if world > 1:                                              # section 8e: the only collectives of the path
+                stats_dev.copy_(env.stats_tensor(clear=True)); dist.all_reduce(stats_dev)
+                flat = ttd.flatten_actor(agent.actor.state_dict(), device=dev); dist.broadcast(flat, src=0)
+                agent.load_actor_state_dict(ttd.unflatten_actor(flat, sd))
+        for _ in range(3):
+            c4_step()
+        ms4 = timed(c4_step, K)
+        config4 = {"value": world * N * K / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / K,
+                   "note": "configs[3]: rollout + fused replay store + one DDPG update (batch 64, learner step as one CUDA graph, "
+                           "sequential on the rollout stream)" + (" + stats all-reduce + actor broadcast (NCCL)" if world > 1 else "")}
+
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -352,6 +377,8 @@ def run_b200(args):
                            "sharding": "global env id ranges, no data-path collective; NCCL only for actor broadcast + stats all-reduce"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
                 "cpu_baseline": cpu, "rollout_stats": ttd.summarize(stats)}
+        if config4 is not None:
+            line["config4"] = config4
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
