@@ -23,9 +23,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line: NCCL's own messages (the "NCCL version ..." banner is printed from NCCL_DEBUG=VERSION
+# upwards, and the image sets it) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":          # the banner itself ignores NCCL_DEBUG_FILE
+    del os.environ["NCCL_DEBUG"]
 
 def _baseline_metric():
     """BASELINE.json's headline metric string, verbatim (the primary quantity of it: env-steps/sec of the fused rollout)."""
