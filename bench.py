@@ -220,8 +220,21 @@ def run_b200(args):
     #      H2D of the step's external input (the current actor parameters from pinned host memory, re-packed on the
     #      device) and D2H of the step's results the reference driver reads (reward and done of every env + stats)
     flat_host = ttd.flatten_actor(sd).cpu().pin_memory()
-    flat_dev = torch.empty_like(flat_host, device=dev)
-    views = ttd.unflatten_actor(flat_dev, sd)
+    # the policy of step t + 1 is uploaded and re-packed on a side stream WHILE step t runs (two packed actors, used
+    # alternately): what an asynchronous learner hands over; every byte still moves, every step, inside the timed region
+    flat_dev = [torch.empty_like(flat_host, device=dev) for _ in range(2)]
+    views = [ttd.unflatten_actor(f, sd) for f in flat_dev]
+    actors = [agent.actor, tt.agent.CudaActor(*agent.actor.dims, device=dev)]
+    up_stream = torch.cuda.Stream(device=dev)
+    packed = [torch.cuda.Event() for _ in range(2)]
+    step_done = torch.cuda.Event()
+
+    def upload(slot):                                                  # H2D + device re-pack of one policy, on up_stream
+        with torch.cuda.stream(up_stream):
+            up_stream.wait_event(step_done)                            # the previous user of this slot's images has finished
+            flat_dev[slot].copy_(flat_host, non_blocking=True)
+            actors[slot].load_state_dict(views[slot])
+            packed[slot].record(up_stream)
     # results are read back one iteration behind on a copy stream (double-buffered staging), so the PCIe transfer of
     # step t overlaps the kernels of step t+1; every byte still moves inside the timed region
     rew_host = [torch.empty(N, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -241,8 +254,10 @@ def run_b200(args):
         b = e2e_it[0] & 1
         e2e_it[0] += 1
         main = torch.cuda.current_stream()
-        flat_dev.copy_(flat_host, non_blocking=True)                 # H2D: this step's actor parameters
-        agent.actor.load_state_dict(views)                           # device re-pack (fp32 + tensor-core images)
+        main.wait_event(packed[b])                                   # this step's policy: uploaded + re-packed during the previous step
+        agent.actor = actors[b]
+        step_done.record(main)                                       # (everything before this step, incl. the last user of slot b ^ 1)
+        upload(b ^ 1)                                                # H2D + re-pack of the NEXT step's policy, overlapped with this step
         _, r, d = eng.step()
         main.wait_event(drained[b])                                  # staging buffer b was read out two steps ago
         rew_stage[b].copy_(r); done_stage[b].copy_(d); stats_stage[b].copy_(env.stats_tensor(clear=True))
@@ -257,7 +272,10 @@ def run_b200(args):
     def e2e_run(iters):
         for _ in range(iters):
             e2e_step()
-        copy_stream.synchronize()
+        copy_stream.synchronize(); up_stream.synchronize()
+
+    step_done.record()
+    upload(0)                                                          # the first step's policy
 
     e2e_run(2)
     torch.cuda.synchronize()
@@ -266,15 +284,17 @@ def run_b200(args):
     ev0.record()
     e2e_run(K)
     torch.cuda.current_stream().wait_stream(copy_stream)
+    torch.cuda.current_stream().wait_stream(up_stream)               # every upload issued inside the region also ends inside it
     ev1.record()
     torch.cuda.synchronize(); barrier()
     t_e2e = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = float(t_e2e)
+    agent.actor = actors[0]
     e2e = {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": flat_host.numel() * 4,
            "d2h_bytes_per_step": N * 5 + 128, "ms_per_step": ms_e2e / K,
-           "note": "host buffers: actor parameters H2D + re-pack every step; reward/done/stats D2H every step (copy stream, one step behind)"}
+           "note": "host buffers: actor parameters H2D + re-pack every step (side stream, one step ahead, two packed actors); reward/done/stats D2H every step (copy stream, one step behind)"}
 
     # ---- per-kernel timing (CUDA events on the launching stream) -> roofline of the dominant kernel ----
     s = _lib.stream_ptr()
