@@ -5,8 +5,8 @@ hands updated actor weights back to the CUDA actor.
 
 ``TorchLearner(agent, graph=True)`` captures the whole step -- index sampling, the ring gather kernel (tt_replay_gather),
 both forward / backward passes, Adam, the soft target update and the re-pack of the new actor weights into the CUDA
-actor's fp32 / tensor-core layouts (tt_actor_load) -- into ONE CUDA graph: the step is ~200 tiny launches, i.e. pure
-launch latency in eager mode."""
+actor's fp32 / tensor-core layouts (tt_actor_load) -- into ONE CUDA graph (fused Adam, multi-tensor soft update): the step is
+~200 tiny launches, i.e. pure launch latency in eager mode (3.0 ms eager, 0.51 ms as a graph on a B200)."""
 from __future__ import annotations
 
 import numpy as np
@@ -57,13 +57,18 @@ class TorchLearner:
         self.actor.load_state_dict(agent.actor.state_dict())
         self.target_actor.load_state_dict(self.actor.state_dict())
         self.target_critic.load_state_dict(self.critic.state_dict())
-        cap = dict(capturable=True) if self.use_graph else {}
+        cap = dict(capturable=True, fused=True) if self.use_graph else {}      # one kernel per optimizer step inside the graph
         self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=agent.alpha, **cap)
         self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=agent.beta, weight_decay=0.01, **cap)
 
     @torch.no_grad()
     def _soft_update(self, net, target, tau):
-        for p, tp in zip(net.parameters(), target.parameters()):
+        ps, tps = list(net.parameters()), list(target.parameters())
+        if self.use_graph:                                       # two multi-tensor kernels instead of two per parameter
+            torch._foreach_mul_(tps, 1 - tau)
+            torch._foreach_add_(tps, ps, alpha=tau)
+            return
+        for p, tp in zip(ps, tps):
             tp.mul_(1 - tau).add_(p, alpha=tau)
 
     def learn(self):
