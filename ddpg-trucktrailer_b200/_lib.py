@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 TT_OBS_DIM = 23
 TT_NCOMP = 10
 TT_NSTATS = 16
-TT_PREC_FP32, TT_PREC_BF16, TT_PREC_F16 = 0, 1, 2
-PRECISIONS = {"fp32": 0, "bf16": 1, "f16": 2, "fp16": 2, 0: 0, 1: 1, 2: 2}
+TT_PREC_FP32, TT_PREC_BF16, TT_PREC_F16, TT_PREC_F16_PLAIN = 0, 1, 2, 3
+PRECISIONS = {"fp32": 0, "bf16": 1, "f16": 2, "fp16": 2, "f16_plain": 3, 0: 0, 1: 1, 2: 2, 3: 3}
 
 COMP_NAMES = ("distance_reward", "progress_reward", "heading_reward", "orientation_reward", "staged_success",
               "safety_penalty", "exploration_bonus", "final_success_bonus", "backward_penalty", "smoothness_penalty")

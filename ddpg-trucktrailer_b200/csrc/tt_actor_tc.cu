@@ -556,6 +556,7 @@ int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t 
         return TT_ERR_INVALID;
     }
     const int variant = tc_variant();
+    if (variant < 4 && precision == TT_PREC_F16_PLAIN) precision = TT_PREC_F16;      // the previous kernel has no plain-fp16 mode
     if (variant >= 4) return actor_forward_tc4(a, d_obs, ld, n, d_mu, precision, ring, g_tc_dbg, st);
     if (variant == 3) {
         if (precision == TT_PREC_BF16)

@@ -699,6 +699,8 @@ int actor_forward_tc4(const tt_actor *a, const float *d_obs, int64_t ld, int64_t
     const tt_actor_dev &A = a->dev;
     if (precision == TT_PREC_BF16)
         return launch_tc4<__nv_bfloat16, false>(reinterpret_cast<const char *>(A.w1c_bf16), reinterpret_cast<const char *>(A.w2s_bf16), A, d_obs, ld, n, d_mu, ring, dbg, st);
+    if (precision == TT_PREC_F16_PLAIN)          // plain fp16 first layer: only the hi block of the image is loaded
+        return launch_tc4<__half, false>(reinterpret_cast<const char *>(A.w1c_f16), reinterpret_cast<const char *>(A.w2s_f16), A, d_obs, ld, n, d_mu, ring, dbg, st);
     return launch_tc4<__half, true>(reinterpret_cast<const char *>(A.w1c_f16), reinterpret_cast<const char *>(A.w2s_f16), A, d_obs, ld, n, d_mu, ring, dbg, st);
 }
 

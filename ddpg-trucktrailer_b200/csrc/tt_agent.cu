@@ -347,7 +347,7 @@ int tt_actor_forward(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n,
     TT_REQUIRE(a->loaded, "tt_actor_load has not been called");
     TT_REQUIRE(n > 0 && ld_obs >= a->dev.in_dim, "bad n / ld_obs");
     if (precision == TT_PREC_FP32) return tt::actor_forward_fp32(a, d_obs, ld_obs, n, d_mu, nullptr, tt::as_stream(stream));
-    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, nullptr, tt::as_stream(stream));
+    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16 || precision == TT_PREC_F16_PLAIN) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, nullptr, tt::as_stream(stream));
     tt::set_error("tt_actor_forward: unknown precision %d", precision);
     return TT_ERR_INVALID;
 }
@@ -360,7 +360,7 @@ int tt_actor_forward_store(tt_actor *a, const float *d_obs, int64_t ld_obs, int6
     TT_REQUIRE(ring && ring->d_state_mem && ring->mem_size > 0 && ring->mem_cntr >= 0, "bad ring");
     const TTRingS rs = {ring->d_state_mem, tt_make_ring_map(ring->mem_size, ring->mem_cntr, n)};
     if (precision == TT_PREC_FP32) return tt::actor_forward_fp32(a, d_obs, ld_obs, n, d_mu, &rs, tt::as_stream(stream));
-    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, &rs, tt::as_stream(stream));
+    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16 || precision == TT_PREC_F16_PLAIN) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, &rs, tt::as_stream(stream));
     tt::set_error("tt_actor_forward_store: unknown precision %d", precision);
     return TT_ERR_INVALID;
 }

@@ -32,7 +32,7 @@ extern "C" int tt_rollout_step(tt_env *env, tt_actor *actor, const tt_rollout_bu
     const bool store = b->d_state_mem != nullptr;
     if (store) TT_REQUIRE(b->d_action_mem && b->d_reward_mem && b->d_new_state_mem && b->d_terminal_mem && b->mem_size > 0, "bad ring");
     static const bool unfused_env = [] { const char *e = getenv("TT_ROLLOUT_UNFUSED"); return e && atoi(e) != 0; }();
-    const bool tc = precision == TT_PREC_BF16 || precision == TT_PREC_F16;
+    const bool tc = precision == TT_PREC_BF16 || precision == TT_PREC_F16 || precision == TT_PREC_F16_PLAIN;
     const bool fused = store && !unfused_env && (!tc || tt::actor_tc_fuses_ring());
     const TTRingMap m = tt_make_ring_map(store ? b->mem_size : 1, store ? b->mem_cntr : 0, store ? n : 0);
     const TTRingS rs = {b->d_state_mem, m};

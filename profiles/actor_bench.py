@@ -20,7 +20,7 @@ if store:
 else:
     def fwd(prec):
         actor.forward(obs, out=out, precision=prec)
-for prec in ("f16", "bf16") + (("fp32",) if "--fp32" in sys.argv else ()):
+for prec in ("f16", "f16_plain", "bf16") + (("fp32",) if "--fp32" in sys.argv else ()):
     for _ in range(3): fwd(prec)
     torch.cuda.synchronize()
     ts = []

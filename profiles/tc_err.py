@@ -10,6 +10,6 @@ obs = torch.from_numpy(g["obs"]).cuda()
 actor = tt.agent.CudaActor()
 for name, w, ref in zip(("init", "amplified"), _sets(g), (g["out0"], g["out1"])):
     actor.load_state_dict(w)
-    for prec in ("fp32", "f16", "bf16"):
+    for prec in ("fp32", "f16", "f16_plain", "bf16"):
         out = actor.forward(obs, precision=prec).cpu().numpy()
         print(f"{name:10s} {prec:5s} max|err| = {np.abs(out - ref).max():.3e}")

@@ -124,12 +124,12 @@ def test_choose_action_and_scaling():
 # ------------------------------------------------------------------------------------------------------------
 # tcgen05 tensor-core actor: north_star bar 1e-3 against the reference torch forward
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision,tol0,tol1", [("f16", 1e-4, 1e-3), ("bf16", 1e-3, 2e-2)])
+@pytest.mark.parametrize("precision,tol0,tol1", [("f16", 1e-4, 1e-3), ("f16_plain", 1e-4, 2e-3), ("bf16", 1e-3, 2e-2)])
 def test_actor_tc_matches_reference_torch(golden_dir, precision, tol0, tol1):
     """Set 0 = the reference's own initialisation (torch.manual_seed(0)); set 1 = deliberately amplified
     "trained-like" weights (mu.weight x60, fc2 x2, random LayerNorm affine).  The default tensor-core mode
-    ("f16": fp16 operands, exact split first layer) holds 1e-3 on both; plain bf16 operands hold it on the
-    reference-scale weights only (its error on set 1 is pure operand rounding, reproduced by a CPU emulation)."""
+    ("f16": fp16 operands, exact split first layer) holds 1e-3 on both; plain fp16 ("f16_plain", 10 % faster) and plain
+    bf16 operands hold it on the reference-scale weights only (their error on set 1 is pure operand rounding)."""
     import ddpg_trucktrailer_b200 as tt
     g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
     obs = torch.from_numpy(g["obs"]).cuda()
@@ -141,7 +141,7 @@ def test_actor_tc_matches_reference_torch(golden_dir, precision, tol0, tol1):
         assert err < tol, (precision, err)
 
 
-@pytest.mark.parametrize("precision", ["f16", "bf16"])
+@pytest.mark.parametrize("precision", ["f16", "f16_plain", "bf16"])
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 5000, 148 * 128 * 3 + 17])
 def test_actor_tc_ragged_sizes_vs_fp32_kernel(golden_dir, n, precision):
     import ddpg_trucktrailer_b200 as tt
@@ -151,7 +151,7 @@ def test_actor_tc_ragged_sizes_vs_fp32_kernel(golden_dir, n, precision):
     obs = torch.empty(n, 24, device="cuda").uniform_(-1, 1)[:, :23]          # ld_obs = 24
     a = actor.forward(obs, precision=precision).clone()
     b = actor.forward(obs, precision="fp32")
-    assert (a - b).abs().max() < (1e-4 if precision == "f16" else 1e-3)
+    assert (a - b).abs().max() < (1e-3 if precision == "bf16" else 1e-4)
     a2 = actor.forward(obs, precision=precision)
     assert torch.equal(a, a2)                                                # deterministic
 
