@@ -65,6 +65,7 @@ SYMBOLS = {
     "tt_env_step_k": (C.c_int, [_P, _P, _I32, _I32, _P, _I64, _P, _P, C.POINTER(StepInfo), _P]),
     "tt_env_set_state": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _I64, _P]),
     "tt_env_get_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "tt_env_get_reward_state": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "tt_env_set_l2": (C.c_int, [_P, _P, _I64, _P, _P]),
     "tt_env_get_l2": (C.c_int, [_P, _P, _P]),
     "tt_env_tick": (C.c_int, [_P, _U32, _P]),

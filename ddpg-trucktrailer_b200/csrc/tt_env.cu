@@ -449,6 +449,18 @@ __global__ void __launch_bounds__(kBlock) env_get_state_kernel(EnvPtrs p, double
     if (max_steps) max_steps[i] = (int32_t)((pk >> PK_EMAX_SHIFT) & PK_EMAX_MASK);
 }
 
+// persistent reward state (reward_functionv1.py:99-109) as float32 arrays; any pointer may be NULL
+__global__ void __launch_bounds__(kBlock) env_get_reward_state_kernel(EnvPtrs p, float *__restrict__ closest, float *__restrict__ cum,
+                                                                      float *__restrict__ first_steer, float *__restrict__ ep_ret) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= p.N) return;
+    const float4 a = p.rsA[i];
+    if (closest) closest[i] = a.x;
+    if (cum) cum[i] = a.y;
+    if (first_steer) first_steer[i] = a.z;
+    if (ep_ret) ep_ret[i] = a.w;
+}
+
 __global__ void tick_kernel(uint32_t *iter, uint32_t by) { *iter += by; }
 
 __global__ void __launch_bounds__(kBlock) env_init_goal_kernel(EnvPtrs p, StepConsts k) {
@@ -686,6 +698,15 @@ int tt_env_set_l2(tt_env *env, const int64_t *d_idx, int64_t n, const double *d_
 int tt_env_get_l2(tt_env *env, double *d_l2, tt_stream_t stream) {
     TT_REQUIRE(env && d_l2, "NULL argument");
     env_get_l2_kernel<<<(unsigned)grid_for(env->p.N), kBlock, 0, tt::as_stream(stream)>>>(env->p, d_l2);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
+}
+
+int tt_env_get_reward_state(tt_env *env, float *d_closest, float *d_cum_backward, float *d_first_steer, float *d_episode_return,
+                            tt_stream_t stream) {
+    TT_REQUIRE(env, "env is NULL");
+    env_get_reward_state_kernel<<<(unsigned)grid_for(env->p.N), kBlock, 0, tt::as_stream(stream)>>>(env->p, d_closest, d_cum_backward,
+                                                                                                   d_first_steer, d_episode_return);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }

@@ -252,6 +252,14 @@ class VecTruckTrailerEnv:
                                           stream_ptr()))
         return dict(state=st, start=sp, goal=gl, episode_steps=steps, max_episode_steps=ms)
 
+    def get_reward_state(self):
+        """The reward function's persistent per-episode state (reward_functionv1.py:99-109) as float32 [N] tensors:
+        closest_distance_to_goal, cumulative_backward_movement, previous_steering (frozen first steering), episode_return."""
+        with torch.cuda.device(self.device):
+            out = [torch.empty(self.num_envs, dtype=torch.float32, device=self.device) for _ in range(4)]
+            check(self.L.tt_env_get_reward_state(self._h, *[t.data_ptr() for t in out], stream_ptr()))
+        return dict(zip(("closest_distance_to_goal", "cumulative_backward_movement", "previous_steering", "episode_return"), out))
+
     @property
     def state(self):
         return self.get_state()["state"]
@@ -357,6 +365,11 @@ class Truck_trailer_Env_2:
         s = self.vec.get_state()
         self._state = s["state"][0].cpu().numpy()
         self.episode_steps = int(s["episode_steps"][0])
+        # reward_functionv1.py:250-283 `penalty_info` (the 14th key of the reference's info dict)
+        cum = float(self.vec.get_reward_state()["cumulative_backward_movement"][0])
+        budget = 5.0 * min(1.0, self.episode_steps / 50)
+        out["backward_movement_info"] = {"cumulative_backward": cum, "movement_budget": budget,
+                                         "excess_movement": max(0.0, cum - budget), "penalty": out["backward_penalty"]}
         return obs[0].cpu().numpy().copy(), out["total_reward"], bool(done[0]), out
 
     def compute_observation(self, state, steering_angle):

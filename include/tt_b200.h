@@ -119,6 +119,12 @@ int tt_env_set_state(tt_env *env, const int64_t *d_idx, int64_t n, const double 
 int tt_env_get_state(tt_env *env, double *d_state, double *d_start, double *d_goal, int32_t *d_steps,
                      int32_t *d_max_steps, tt_stream_t stream);
 
+/* The reward function's persistent per-episode state (reward_functionv1.py:99-109, threaded through simv2.py:347-373):
+ * closest_distance_to_goal, cumulative_backward_movement, the frozen first steering angle (previous_steering), and the
+ * running episode return (trainv2.py:529 `score`).  float32 [n_envs]; any pointer may be NULL. */
+int tt_env_get_reward_state(tt_env *env, float *d_closest, float *d_cum_backward, float *d_first_steer, float *d_episode_return,
+                            tt_stream_t stream);
+
 /* env.L2 = value per environment (heatmap.py:89 draws the trailer length per trial: `env.L2 = np.random.uniform(5,7)`).
  * d_idx NULL = envs 0..n-1; d_l2 [n] float64 > 0.  The dynamics (simv2.py:291) use the new length from the next step on,
  * reset / set_state place the truck L2 ahead of the trailer (simv2.py:483-484, heatmap.py:116-117).  Does not restart

@@ -198,6 +198,14 @@ def test_n1_reference_contract(golden_dir):
     env.state = g["states"][0]
     o, r, d, i = env.step(g["actions"][:1])
     assert abs(r - g["comps"][0, 0]) < 1e-3 and np.abs(env.state - g["states"][1]).max() < 1e-5
+    # all 14 keys of the reference's info dict (reward_functionv1.py:488-504), incl. the backward-movement diagnostics
+    want = {"total_reward", "distance_reward", "progress_reward", "heading_reward", "orientation_reward", "staged_success", "safety_penalty",
+            "exploration_bonus", "final_success_bonus", "violation_type", "backward_penalty", "smoothness_penalty", "backward_movement_info", "success"}
+    assert want <= set(i)
+    for t in range(1, 60):
+        o, r, d, i = env.step(g["actions"][t:t + 1])
+        assert abs(i["backward_movement_info"]["cumulative_backward"] - g["cumulative_backward"][t]) < 1e-4, t
+        assert i["backward_movement_info"]["movement_budget"] == pytest.approx(5.0 * min(1.0, (t + 1) / 50))
 
 
 def test_full_size_properties():
