@@ -18,7 +18,7 @@ constexpr float kPiOver4F = 0.78539819f;       // float32(pi/4) == env.action_sp
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) ou_kernel(float *__restrict__ x, float *__restrict__ action,
                                                       float *__restrict__ scaled, const uint8_t *__restrict__ reset_mask,
-                                                      int64_t n, uint64_t seed, uint64_t gid0,
+                                                      int64_t n, ttm::PhiloxKeys keys, uint64_t gid0,
                                                       const uint32_t *__restrict__ iter, int evaluate, TTRingA ring) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(kThreads) ou_kernel(float *__restrict__ x, flo
     if (!evaluate) {
         float xp = x[i];
         if (reset_mask && reset_mask[i]) xp = 0.0f;                      // trainv2.py:492 agent.noise.reset()
-        const float nrm = ttm::rng_normal(seed, (uint32_t)(gid0 + i), *iter);
+        const float nrm = ttm::rng_normal_ks(keys, (uint32_t)(gid0 + i), *iter);
         const float xn = xp + 0.2f * (0.0f - xp) * 0.01f + 0.15f * 0.1f * nrm;
         x[i] = xn;
         a += xn;
@@ -265,8 +265,8 @@ int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_
                  uint64_t gid0, const uint32_t *d_iter, int evaluate, const TTRingA *ring, cudaStream_t s) {
     TTRingA ra;
     if (ring) ra = *ring; else { ra.A = nullptr; ra.m = tt_make_ring_map(1, 0, 0); }
-    ou_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(d_x, d_action, d_scaled, d_reset_mask, n, seed,
-                                                                            gid0, d_iter, evaluate, ra);
+    ou_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(d_x, d_action, d_scaled, d_reset_mask, n,
+                                                                            ttm::philox_expand_key(seed), gid0, d_iter, evaluate, ra);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }

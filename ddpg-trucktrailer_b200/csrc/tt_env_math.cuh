@@ -349,6 +349,33 @@ TT_HD void rng_pose(const StepConsts &k, uint64_t seed, uint32_t gid, uint32_t t
     sx = fma(k.sx_w, u0, k.sx_lo); sy = fma(k.sy_w, u1, k.sy_lo); syaw = fma(k.syaw_w, u2, k.syaw_lo);
 }
 
+// The same generator with the 10 round keys (k + r * Weyl constant) expanded once on the host: passed by value as a kernel
+// parameter they are constant-bank operands of the round's XOR, which saves 20 integer adds per call (OU noise kernel).
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };
+inline PhiloxKeys philox_expand_key(uint64_t seed) {
+    PhiloxKeys ks;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { ks.k0[r] = a; ks.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    return ks;
+}
+TT_HD float rng_normal_ks(const PhiloxKeys &ks, uint32_t gid, uint32_t t) {
+    uint32_t c0 = gid, c1 = t, c2 = 1u, c3 = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ ks.k0[r]; c1 = l1; c2 = h0 ^ c3 ^ ks.k1[r]; c3 = l0;
+    }
+    const float u1 = (float)((c0 >> 8) + 1u) * (1.0f / 16777216.0f), u2 = (float)(c1 >> 8) * (1.0f / 16777216.0f);
+#if defined(__CUDA_ARCH__)
+    return sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2);
+#else
+    return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+#endif
+}
+
 TT_HD float rng_normal(uint64_t seed, uint32_t gid, uint32_t t) {
     uint32_t w[4];
     philox4x32_10(gid, t, 1u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
