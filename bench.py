@@ -93,12 +93,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self, t0, t1):
+    def stop(self, t0, t1, load0=None, load1=None):
+        """Clocks inside the timed region [t0, t1] (the region lasts tens of ms, nvidia-smi samples every 20 ms); if no
+        sample fell into it, the samples taken under the same load right around it (pre-roll .. end of the e2e run)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        rows = [r for t, r in self.rows if t0 - 0.02 <= t <= t1 + 0.02]
+        if not rows and load0 is not None:
+            rows = [r for t, r in self.rows if load0 <= t <= load1]
+        rows = rows or [r for _, r in self.rows[-3:]]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm = sorted(float(r[0]) for r in rows)
@@ -196,6 +201,10 @@ def run_b200(args):
         return float(ms)
 
     W, K = max(args.warmup, 3), args.steps
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t_load0 = time.time()
     for _ in range(args.preroll):          # population reaches its stationary mix of episode ages (max episode ~ 250 steps)
         eng.step()
     env.stats_tensor(clear=True)
@@ -204,15 +213,11 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     # ---- headline: K rollout iterations, everything resident in HBM ----
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start(); time.sleep(0.3)
     launches0 = L.tt_launch_count()
     t_wall0 = time.time()
     ms = timed(eng.step, K)
     t_wall1 = time.time()
     launches = L.tt_launch_count() - launches0
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     value = world * N * K / (ms * 1e-3)
     stats = ttd.all_reduce_stats(env.stats_tensor(clear=True).clone())
 
@@ -292,6 +297,7 @@ def run_b200(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = float(t_e2e)
     agent.actor = actors[0]
+    clocks = sampler.stop(t_wall0, t_wall1, t_load0, time.time()) if sampler else None     # sampled from the pre-roll to the end of e2e
     e2e = {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": flat_host.numel() * 4,
            "d2h_bytes_per_step": N * 5 + 128, "ms_per_step": ms_e2e / K,
            "note": "host buffers: actor parameters H2D + re-pack every step (side stream, one step ahead, two packed actors); reward/done/stats D2H every step (copy stream, one step behind)"}

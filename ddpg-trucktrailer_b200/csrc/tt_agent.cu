@@ -16,6 +16,8 @@ constexpr float kPiOver4F = 0.78539819f;       // float32(pi/4) == env.action_sp
 // (b) OU noise, DDPG/noise.py:12-17 with theta=0.2, sigma=0.15, dt=1e-2, mu=0; optional fused
 //     "mu + noise" (DDPG_agent.py:41-43) and "clip(a,-1,1) * pi/4" (trainv2.py:516)
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ou_advance(float xp, float nrm) { return xp + 0.2f * (0.0f - xp) * 0.01f + 0.15f * 0.1f * nrm; }
+
 __global__ void __launch_bounds__(kThreads) ou_kernel(float *__restrict__ x, float *__restrict__ action,
                                                       float *__restrict__ scaled, const uint8_t *__restrict__ reset_mask,
                                                       int64_t n, ttm::PhiloxKeys keys, uint64_t gid0,
@@ -26,14 +28,43 @@ __global__ void __launch_bounds__(kThreads) ou_kernel(float *__restrict__ x, flo
     if (!evaluate) {
         float xp = x[i];
         if (reset_mask && reset_mask[i]) xp = 0.0f;                      // trainv2.py:492 agent.noise.reset()
-        const float nrm = ttm::rng_normal_ks(keys, (uint32_t)(gid0 + i), *iter);
-        const float xn = xp + 0.2f * (0.0f - xp) * 0.01f + 0.15f * 0.1f * nrm;
+        const float xn = ou_advance(xp, ttm::rng_normal_ks(keys, (uint32_t)(gid0 + i), *iter));
         x[i] = xn;
         a += xn;
         if (action) action[i] = a;
     }
     if (scaled) scaled[i] = fminf(fmaxf(a, -1.0f), 1.0f) * kPiOver4F;
     if (ring.A && i >= ring.m.first) ring.A[ring.m.row(i)] = a;          // agent.remember stores the UNCLIPPED action (trainv2.py:525)
+}
+
+// The rollout's form of the same kernel: four consecutive envs per thread, 16 B loads / stores (x, action, scaled and the
+// ring's action rows), no reset mask (tt_rollout_step zeroes the OU state in the reset kernel).  Needs n % 4 == 0, 16 B
+// aligned arrays and a ring position that keeps every group of four rows contiguous and aligned.
+__global__ void __launch_bounds__(kThreads) ou_kernel_x4(float4 *__restrict__ x, float4 *__restrict__ action, float4 *__restrict__ scaled,
+                                                         int64_t n4, ttm::PhiloxKeys keys, uint32_t gid0, const uint32_t *__restrict__ iter,
+                                                         int evaluate, float4 *__restrict__ ring_a, int64_t ring_base4, int64_t ring_cap4) {
+    const uint32_t t = *iter;
+    for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n4; v += (int64_t)gridDim.x * kThreads) {
+        float4 a = __ldcs(&action[v]);
+        if (!evaluate) {
+            float4 xp = x[v];
+            const uint32_t g = gid0 + (uint32_t)(4 * v);
+            xp.x = ou_advance(xp.x, ttm::rng_normal_ks(keys, g, t));     xp.y = ou_advance(xp.y, ttm::rng_normal_ks(keys, g + 1u, t));
+            xp.z = ou_advance(xp.z, ttm::rng_normal_ks(keys, g + 2u, t)); xp.w = ou_advance(xp.w, ttm::rng_normal_ks(keys, g + 3u, t));
+            x[v] = xp;
+            a.x += xp.x; a.y += xp.y; a.z += xp.z; a.w += xp.w;
+            action[v] = a;
+        }
+        float4 sc;
+        sc.x = fminf(fmaxf(a.x, -1.0f), 1.0f) * kPiOver4F; sc.y = fminf(fmaxf(a.y, -1.0f), 1.0f) * kPiOver4F;
+        sc.z = fminf(fmaxf(a.z, -1.0f), 1.0f) * kPiOver4F; sc.w = fminf(fmaxf(a.w, -1.0f), 1.0f) * kPiOver4F;
+        __stcs(&scaled[v], sc);
+        if (ring_a) {                                                    // rows (base + 4 v .. + 3) % cap, wrapping between groups only
+            int64_t r4 = ring_base4 + v;
+            if (r4 >= ring_cap4) r4 -= ring_cap4;
+            __stcs(&ring_a[r4], a);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) ou_zero_kernel(float *__restrict__ x, const uint8_t *__restrict__ mask, int64_t n) {
@@ -265,8 +296,17 @@ int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_
                  uint64_t gid0, const uint32_t *d_iter, int evaluate, const TTRingA *ring, cudaStream_t s) {
     TTRingA ra;
     if (ring) ra = *ring; else { ra.A = nullptr; ra.m = tt_make_ring_map(1, 0, 0); }
-    ou_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(d_x, d_action, d_scaled, d_reset_mask, n,
-                                                                            ttm::philox_expand_key(seed), gid0, d_iter, evaluate, ra);
+    const ttm::PhiloxKeys keys = ttm::philox_expand_key(seed);
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool ring_ok = !ra.A || (!ra.m.many && ra.m.first == 0 && ra.m.base % 4 == 0 && ra.m.cap % 4 == 0 && al16(ra.A));
+    if (!d_reset_mask && d_action && d_scaled && d_x && n % 4 == 0 && n >= 4096 && al16(d_x) && al16(d_action) && al16(d_scaled) && ring_ok) {
+        const int64_t n4 = n / 4, want = (n4 + kThreads - 1) / kThreads, cap = (int64_t)sm_count() * 16;
+        ou_kernel_x4<<<(unsigned)(want < cap ? want : cap), kThreads, 0, s>>>(
+            reinterpret_cast<float4 *>(d_x), reinterpret_cast<float4 *>(d_action), reinterpret_cast<float4 *>(d_scaled), n4, keys, (uint32_t)gid0, d_iter,
+            evaluate, reinterpret_cast<float4 *>(ra.A), ra.m.base / 4, ra.m.cap / 4);
+    } else
+        ou_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(d_x, d_action, d_scaled, d_reset_mask, n, keys, gid0, d_iter,
+                                                                                evaluate, ra);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
