@@ -21,12 +21,23 @@ else:
     def fwd(prec):
         actor.forward(obs, out=out, precision=prec)
 for prec in ("f16", "f16_plain", "bf16") + (("fp32",) if "--fp32" in sys.argv else ()):
-    for _ in range(3): fwd(prec)
-    torch.cuda.synchronize()
+    sustained = "--sustained" in sys.argv     # 300 launches first: the GPU reaches its power cap (what a long rollout sees)
+    for _ in range(300 if sustained else 3): fwd(prec)
+    if not sustained: torch.cuda.synchronize()
     ts = []
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fwd(prec); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+    if sustained:
+        evs = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10): fwd(prec)
+            e1.record(); evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) / 10 for a, b in evs]
+    else:
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fwd(prec); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
     ms = sorted(ts)[2]
-    print(f"store={store} TT_TC_VARIANT={os.environ.get('TT_TC_VARIANT','default')} {prec}: {ms:.3f} ms  {N/ms/1e6:.2f} Grows/s  {N*259000/ms/1e9:.0f} TFLOP/s  all={['%.3f'%t for t in ts]}")
+    print(f"sustained={sustained} store={store} TT_TC_VARIANT={os.environ.get('TT_TC_VARIANT','default')} {prec}: {ms:.3f} ms  {N/ms/1e6:.2f} Grows/s  {N*259000/ms/1e9:.0f} TFLOP/s  all={['%.3f'%t for t in ts]}")
