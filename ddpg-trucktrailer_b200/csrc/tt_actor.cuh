@@ -27,7 +27,7 @@ struct tt_actor_dev {
     void *w1_f16, *w2_f16, *w1_bf16, *w2_bf16;     // UMMA operand images (tt_actor_tc.cu)
     void *w2s_f16, *w2s_bf16;                       // v4 layer-2 images: k-blocks grouped by output-column sweep
     void *w1c_f16, *w1c_bf16;                       // v4 layer-1 images: centred, LayerNorm-scaled rows + statistic rows (tt_actor_tc4.cu)
-    double *l1c_scratch;                            // [1200]: Gram accumulators (600) + column means / Cholesky factor (600) of the v4 pack
+    double *l1c_scratch;                            // [2048]: v4 pack: Gram accumulators (600) + column means / Cholesky factor (600) of layer 1, column means / linear column of layer 2 (2 x 416)
     float *gram_f16, *gram_bf16;                    // [25][24]: Gram matrix of fc1 (+bias column) and its column sums
 };
 
@@ -49,7 +49,7 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
     const size_t o_w1h = take(2 * n1 * 64), o_w2h = take(kb2 * n2 * 64), o_w1b = take(2 * n1 * 64), o_w2b = take(kb2 * n2 * 64);
     const size_t o_w2sh = take(TT_W2_REPLICAS * kb2 * n2 * 64), o_w2sb = take(TT_W2_REPLICAS * kb2 * n2 * 64);
     const size_t o_w1ch = take(2 * (n1 + 32) * 64), o_w1cb = take(2 * (n1 + 32) * 64);
-    const size_t o_l1s = take(sizeof(double) * 1200);
+    const size_t o_l1s = take(sizeof(double) * 2048);
     const size_t o_gh = take(sizeof(float) * 25 * 24), o_gb = take(sizeof(float) * 25 * 24);
     if (d) {
         d->in_dim = in_dim; d->h1 = h1; d->h2 = h2; d->k1p = k1p; d->h1p = h1p; d->h2p = h2p; d->kb1 = kb1;

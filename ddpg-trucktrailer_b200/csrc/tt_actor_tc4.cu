@@ -100,14 +100,43 @@ __global__ void __launch_bounds__(256) pack_l1c_image_kernel(char *__restrict__ 
 }
 
 // ---- v4 layer-2 image: [sweep A: kb 0..12, 160 rows x 64 B][sweep B: kb 0..12, 144 rows x 64 B] ----
-// row n of sweep A = output column n, of sweep B = output column 160 + n (k < H1: fc2.weight, k == H1: fc2.bias, else 0)
+// row n of sweep A = output column n, of sweep B = output column 160 + n.  With Wf2 = [fc2.weight | fc2.bias] (k == H1: bias):
+//   columns 0..299 : Wf2[n][k] - m2[k], m2 = mean over the 300 outputs: the GEMM delivers h - mean(h), i.e. LayerNorm 2's
+//                    centring costs nothing and its variance is a plain sum of squares;
+//   columns 300,301: hi / lo halves of l2[k] = 1/2 sum_n (Wf2[n][k] - m2[k]) g2[n] w3[n].  relu(y) = (y + |y|) / 2, and
+//                    sum_n w3[n] y[n] / 2 is linear in the layer-2 input: rstd * (a2 . l2) + 1/2 sum be2 w3 -- the tensor core
+//                    computes it in two of the four padding columns and the epilogue only accumulates |y[n]| w3[n] / 2.
+__device__ __forceinline__ float wf2(const float *__restrict__ fc2_w, const float *__restrict__ fc2_b, int n, int k) {
+    return k < H1 ? fc2_w[n * H1 + k] : (k == H1 ? fc2_b[n] : 0.f);
+}
+__global__ void __launch_bounds__(256) pack_w2_colstats_kernel(double *__restrict__ out /* m2[K2P], l2[K2P] */, const float *__restrict__ fc2_w,
+                                                               const float *__restrict__ fc2_b, const float *__restrict__ g2, const float *__restrict__ w3) {
+    __shared__ double r1[8][33], r2[8][33], rg[8][33];
+    const int kk = threadIdx.x & 31, sl = threadIdx.x >> 5, k = blockIdx.x * 32 + kk;
+    double s1 = 0.0, s2 = 0.0, sg = 0.0;
+    for (int n = sl; n < H2; n += 8) {
+        const double w = (double)wf2(fc2_w, fc2_b, n, k), gw = (double)g2[n] * (double)w3[n];
+        s1 += w; s2 += w * gw; sg += gw;
+    }
+    r1[sl][kk] = s1; r2[sl][kk] = s2; rg[sl][kk] = sg;
+    __syncthreads();
+    if (sl == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; i++) { s1 += r1[i][kk]; s2 += r2[i][kk]; sg += rg[i][kk]; }
+        const double m = s1 / H2;
+        out[k] = m;
+        out[K2P + k] = 0.5 * (s2 - m * sg);
+    }
+}
 template <typename OpT>
-__global__ void pack_w2s_kernel(char *__restrict__ img, const float *__restrict__ fc2_w, const float *__restrict__ fc2_b) {
+__global__ void pack_w2s_kernel(char *__restrict__ img, const double *__restrict__ st, const float *__restrict__ fc2_w, const float *__restrict__ fc2_b) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int v = tid; v < KB2 * N2 * 32; v += nth) {
         const int kb = v / (N2 * 32), rem = v - kb * N2 * 32, col = rem / 32, kk = rem - col * 32, k = kb * 32 + kk;
         float x = 0.f;
-        if (col < H2) x = k < H1 ? fc2_w[col * H1 + k] : (k == H1 ? fc2_b[col] : 0.f);
+        if (col < H2) x = (float)((double)wf2(fc2_w, fc2_b, col, k) - st[k]);
+        else if (col == H2) x = (float)st[K2P + k];
+        else if (col == H2 + 1) { const float l = (float)st[K2P + k]; x = l - op_to_float(to_op<OpT>(l)); }
         const size_t off = col < kNA ? (size_t)kb * kNA * kRowB + sw64_off(col, kk)
                                      : kW2SweepB + (size_t)kb * kNB * kRowB + sw64_off(col - kNA, kk);
         const OpT o = to_op<OpT>(x);
@@ -126,9 +155,9 @@ struct Plan4 {
     static constexpr uint32_t a2 = w1 + kXBlocks * N1I * kRowB;
     static constexpr uint32_t w2 = a2 + KB2 * kTileM * kRowB;
     static constexpr uint32_t par = w2 + kSlots * kW2Slot;
-    static constexpr uint32_t npar = K2P + 3 * H2P;                               // be1 | g2 be2 w3
+    static constexpr uint32_t npar = K2P + 2 * H2P;                               // be1 | be2 / g2, w3 |g2| / 2
     static constexpr uint32_t red = par + npar * 4;
-    static constexpr uint32_t bars = red + 4 * kTileM * 8 + 4 * kTileM * 4;
+    static constexpr uint32_t bars = red + 2 * 4 * kTileM * 4;
     static constexpr uint32_t nbars = 40;
     static constexpr uint32_t tmem_slot = bars + nbars * 8;
     static constexpr uint32_t total = tmem_slot + 16 + 1024;
@@ -159,9 +188,9 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     uint8_t *sm = smem_raw + (base - raw);
     const uint32_t sX = base + P::x, sW1 = base + P::w1, sA2 = base + P::a2, sW2 = base + P::w2, sBar = base + P::bars;
     float *par = reinterpret_cast<float *>(sm + P::par);
-    float *pbe1 = par, *pg2 = par + K2P, *pbe2 = pg2 + H2P, *pw3 = pbe2 + H2P;
-    float2 *red1 = reinterpret_cast<float2 *>(sm + P::red);
-    float *red3 = reinterpret_cast<float *>(red1 + 4 * kTileM);
+    float *pbe1 = par, *pbe2 = par + K2P, *pw3 = pbe2 + H2P;
+    float *red1 = reinterpret_cast<float *>(sm + P::red);          // per (column group, row): sum of squares | output dot
+    float *red3 = red1 + 4 * kTileM;
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(sm + P::tmem_slot);
     volatile uint32_t *staged = tmem_slot + 2;           // number of observation tiles the epilogue has staged so far
     auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
@@ -190,8 +219,11 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     }
     for (int c = threadIdx.x; c < K2P; c += kThreads) pbe1[c] = c < H1 ? A.be1[c] : 0.f;
     for (int c = threadIdx.x; c < H2P; c += kThreads) {
-        const bool in = c < H2;
-        pg2[c] = in ? A.g2[c] : 0.f; pbe2[c] = in ? A.be2[c] : 0.f; pw3[c] = in ? A.w3[c] : 0.f;
+        // LayerNorm 2 + ReLU + mu:  w3 relu(g z + be), z = (h - mean) rstd.  relu(y) = (y + |y|) / 2; the y / 2 half is linear in
+        // the layer-2 input and comes out of the GEMM (see the pack); |g z + be| w3 / 2 = |z + be / g| (w3 |g| / 2).  A column
+        // with g == 0 is the constant relu(be) w3: part of b3 below.
+        const bool in = c < H2 && fabsf(A.g2[c]) > 1e-30f;
+        pbe2[c] = in ? A.be2[c] / A.g2[c] : 0.f; pw3[c] = in ? 0.5f * A.w3[c] * fabsf(A.g2[c]) : 0.f;
     }
     // X blocks: zero once (k = 24..31 stay zero).  A2 block 12, columns 400..415: constant (1, 0, ..., 0) -- column 400
     // carries the fc2 bias -- written once; the epilogue only ever rewrites columns 384..399 of that block.
@@ -212,7 +244,15 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     if (kCluster > 1) cluster_sync_all();            // the partner's mbarriers are initialised before anything multicasts into them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const float b3 = A.b3[0];
+    // constant part of the output: mu.bias + 1/2 sum be2 w3 (every warp computes it: 30 loads per lane, once)
+    float b3 = 0.f;
+    for (int c = lane; c < H2; c += 32) {
+        const float be = A.be2[c], w = A.w3[c];
+        b3 = fmaf(fabsf(A.g2[c]) > 1e-30f ? 0.5f * be : fmaxf(be, 0.f), w, b3);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) b3 += __shfl_xor_sync(0xffffffffu, b3, o);
+    b3 += A.b3[0];
 
     if (warp == kProdWarp) {
         // ================= bulk-copy producer: W1 once, then per tile 13 half k-blocks of sweep A and 13 of sweep B =================
@@ -229,7 +269,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         for (int64_t itn = 0; itn < niter; itn++, tp ^= 1u) {
 #pragma unroll
             for (int step = 0; step < kSteps; step++) {
-                const int sweep = step / KB2, kb = step % KB2, slot = w2_slot(step, P::kSlots);
+                const int sweep = w2_step_sweep(step), kb = w2_step_kb(step), slot = w2_slot(step, P::kSlots);
                 const uint32_t bytes = (uint32_t)(sweep ? kNB : kNA) * kRowB;
                 mbar_wait(bar(D_W2EMPTY + slot), w2_parity(step, P::kSlots, tp) ^ 1u);     // every CTA of the cluster has read the slot
                 if (elect_one()) {
@@ -340,7 +380,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                 if (prof) t_a2 += clock64() - t0;
 #pragma unroll
                 for (int step = 0; step < kSteps; step++) {
-                    const int sweep = step / KB2, kb = step % KB2, slot = w2_slot(step, P::kSlots);
+                    const int sweep = w2_step_sweep(step), kb = w2_step_kb(step), slot = w2_slot(step, P::kSlots);
                     if (kb == 0) {
                         if (prof) t0 = clock64();
                         mbar_wait(bar(sweep ? D_H2BFREE : D_H2AFREE), ph ^ 1u);   // pass 2 of the previous tile has read this half
@@ -356,7 +396,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                         umma(d, a, b, sweep ? idB : idA, kb ? 1u : 0u);
                         umma(d, a + 2, b + 2, sweep ? idB : idA, 1u);
                         if (kCluster == 1) umma_commit(bar(D_W2EMPTY + slot)); else umma_commit_mc(bar(D_W2EMPTY + slot), kMask);
-                        if (sweep) umma_commit(bar(D_A2FREE + kb));         // A2 block kb may be overwritten for the next tile
+                        if (sweep && (kb == 2 || kb == 7 || kb == 10 || kb == 12)) umma_commit(bar(D_A2FREE + kb));   // A2 blocks <= kb may be overwritten (epilogue 1: a2wait)
                         if (kb == KB2 - 1) umma_commit(bar(sweep ? D_H2BFULL : D_H2AFULL));
                     }
                     __syncwarp();
@@ -383,7 +423,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             for (int i = 0; i < 6; i++) xreg[i] = (k0 + i < IN) ? (ok ? __ldg(p + i) : 0.f) : 1.0f;
         };
         constexpr bool prof = kProf;
-        long long e_st = 0, e_1 = 0, e_wa = 0, e_pa = 0, e_wb = 0, e_2 = 0, e_2a = 0, e_2b = 0, e_2c = 0, e_2d = 0, t0 = 0, t1 = 0, t2 = 0;
+        long long e_wf = 0, e_af = 0, e_b1 = 0, e_b2 = 0, tw = 0, e_st = 0, e_1 = 0, e_wa = 0, e_pa = 0, e_wb = 0, e_2 = 0, e_2a = 0, e_2b = 0, e_2c = 0, e_2d = 0, t0 = 0, t1 = 0, t2 = 0;
         const long long t_begin = clock64();
         uint32_t wuse = 0;
 
@@ -409,12 +449,12 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         // layer-2 side of one tile: LayerNorm + ReLU over H2, dot with mu.weight, tanh.  Column group g owns columns
         // [40 g, 40 g + 40) of half A and [160 + 36 g, 160 + 36 g + 36) of half B.
         const int ca = 40 * grp, cbb = kNA + 36 * grp;
-        float2 s2, q2;
+        float2 q2;                                                         // the accumulators are centred (see the pack): variance = sum of squares
         auto acc = [&](const uint32_t *v, int cnt) {
 #pragma unroll
             for (int j = 0; j < cnt / 2; j++) {
                 const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                s2 = __fadd2_rn(s2, x); q2 = __ffma2_rn(x, x, q2);
+                q2 = __ffma2_rn(x, x, q2);
             }
         };
         auto pass1a = [&](uint32_t c2) {                                   // statistics of half A (runs under sweep B)
@@ -426,7 +466,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             tmem_ld32_async(trow + (uint32_t)ca, va);
             tmem_ld8_async(trow + (uint32_t)(ca + 32), vt);
             tmem_wait();
-            s2 = make_float2(0.f, 0.f); q2 = make_float2(0.f, 0.f);
+            q2 = make_float2(0.f, 0.f);
             acc(va, 32); acc(vt, 8);
             if (prof) { t1 = clock64(); e_pa += t1 - t0; t0 = t1; }
         };
@@ -437,9 +477,19 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             const uint32_t ph = c1 & 1u;
             if (prof) t0 = clock64();
             float2 rstd2 = make_float2(0.f, 0.f);
-            auto emit = [&](const uint32_t (&v)[8], int ch) {              // 8 columns of A2 block ch: relu(t' rstd + be1)
-                mbar_wait(bar(D_A2FREE + ch), ph ^ 1u);                    // sweep B of the previous tile has read this block
-                const float4 e0 = *reinterpret_cast<const float4 *>(pbe1 + ch * 32 + grp * 8), e1 = *reinterpret_cast<const float4 *>(pbe1 + ch * 32 + grp * 8 + 4);
+            // A2 blocks are released in order (sweep B's commits), and an mbarrier wait costs ~90 cycles even when the phase is
+            // already complete: wait once per run of blocks (kA2Waits), on the last block of the run.
+            auto a2wait = [&](int ch) {
+                if (prof) tw = clock64();
+                mbar_wait(bar(D_A2FREE + ch), ph ^ 1u);                    // sweep B of the previous tile has read blocks <= ch
+                if (prof) e_af += clock64() - tw;
+            };
+            float4 E0[2], E1[2];                                           // be1 of the next chunk, fetched one chunk ahead
+            auto lde = [&](int slot, int ch) {
+                E0[slot] = lds128_early(pbe1 + ch * 32 + grp * 8); E1[slot] = lds128_early(pbe1 + ch * 32 + grp * 8 + 4);
+            };
+            auto emit = [&](const uint32_t (&v)[8], int ch, int slot) {    // 8 columns of A2 block ch: relu(t' rstd + be1)
+                const float4 e0 = E0[slot], e1 = E1[slot];
                 const float2 ee[4] = {make_float2(e0.x, e0.y), make_float2(e0.z, e0.w), make_float2(e1.x, e1.y), make_float2(e1.z, e1.w)};
                 uint32_t pk4[4];
 #pragma unroll
@@ -455,12 +505,15 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             const uint32_t wcol = trow + (uint32_t)(kWin0 + grp * 8);
             uint32_t v[5][8];
             {   // part 0: 32 statistic columns, then A2 blocks 0..2
+                if (prof) tw = clock64();
                 mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
+                if (prof) e_wf += clock64() - tw;
                 tc_fence_after();
                 uint32_t sv[32];
                 tmem_ld32_async(trow + kWin0, sv);
 #pragma unroll
                 for (int c = 0; c < 3; c++) tmem_ld8_async(wcol + 32 + 32 * c, v[c]);
+                lde(0, 0);
                 tmem_wait();
                 tc_fence_before();
                 mbar_arrive(bar(D_WFREE));                                 // values are in registers: the window may be refilled
@@ -472,33 +525,45 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                 }
                 const float rstd = rsqrtf((q2.x + q2.y) * (1.0f / H1) + 1e-5f);
                 rstd2 = make_float2(rstd, rstd);
+                a2wait(2);
 #pragma unroll
-                for (int c = 0; c < 3; c++) emit(v[c], c);
+                for (int c = 0; c < 3; c++) { if (c < 2) lde((c + 1) & 1, c + 1); emit(v[c], c, c & 1); }
             }
             if (with_p1a) { if (prof) { t1 = clock64(); e_1 += t1 - t0; } pass1a(c2); }
             {   // part 1: A2 blocks 3..7
+                if (prof) tw = clock64();
                 mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
+                if (prof) e_wf += clock64() - tw;
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < 5; c++) tmem_ld8_async(wcol + 32 * c, v[c]);
+                lde(0, 3);
                 tmem_wait();
                 tc_fence_before();
                 mbar_arrive(bar(D_WFREE));
+                a2wait(7);
 #pragma unroll
-                for (int c = 0; c < 5; c++) emit(v[c], 3 + c);
+                for (int c = 0; c < 5; c++) { if (c < 4) lde((c + 1) & 1, 4 + c); emit(v[c], 3 + c, c & 1); }
             }
             {   // part 2: A2 blocks 8..11 and the 16 real columns of block 12 (groups 0, 1)
+                if (prof) tw = clock64();
                 mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
+                if (prof) e_wf += clock64() - tw;
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < 4; c++) tmem_ld8_async(wcol + 32 * c, v[c]);
                 if (grp < 2) tmem_ld8_async(wcol + 128, v[4]);
+                lde(0, 8);
                 tmem_wait();
                 tc_fence_before();
                 mbar_arrive(bar(D_WFREE));
+                a2wait(10);
 #pragma unroll
-                for (int c = 0; c < 4; c++) emit(v[c], 8 + c);
-                if (grp < 2) emit(v[4], 12);
+                for (int c = 0; c < 3; c++) { lde((c + 1) & 1, 9 + c); emit(v[c], 8 + c, c & 1); }
+                if (grp < 2) lde(0, 12);
+                a2wait(12);
+                emit(v[3], 11, 1);
+                if (grp < 2) emit(v[4], 12, 0);
             }
             fence_proxy_async();
             mbar_arrive(bar(D_A2FULL));
@@ -517,38 +582,40 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             tmem_ld32_async(trow + (uint32_t)cbb, va);
             tmem_ld4_async(trow + (uint32_t)(cbb + 32), vq);
             tmem_wait();
+            float lin = 0.f;                                               // columns 300, 301: the linear half of the output dot (hi + lo)
+            if (grp == kGroups - 1) { lin = __uint_as_float(vq[0]) + __uint_as_float(vq[1]); vq[0] = 0u; vq[1] = 0u; }
             acc(va, 32); acc(vq, 4);
             if (prof) { t2 = clock64(); e_2a += t2 - t0; }
-            red1[grp * kTileM + r] = make_float2(s2.x + s2.y, q2.x + q2.y);
+            red1[grp * kTileM + r] = q2.x + q2.y;
             // pass 2 re-reads the accumulators; half A's loads fly while the statistics are exchanged
             tmem_ld32_async(trow + (uint32_t)ca, va);
             tmem_ld8_async(trow + (uint32_t)(ca + 32), vt);
+            if (prof) tw = clock64();
             named_bar_sync(1, kEpiThreads);
-            float sum = 0.f, sq = 0.f;
+            if (prof) e_b1 += clock64() - tw;
+            float sq = 0.f;
 #pragma unroll
-            for (int g = 0; g < kGroups; g++) { const float2 t = red1[g * kTileM + r]; sum += t.x; sq += t.y; }
-            const float mean = sum * (1.0f / H2);
-            const float rstd = rsqrtf(fmaxf(sq * (1.0f / H2) - mean * mean, 0.f) + 1e-5f);
-            const float nmr = -mean * rstd;
-            const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
-            float2 dot2 = make_float2(0.f, 0.f);
+            for (int g = 0; g < kGroups; g++) sq += red1[g * kTileM + r];
+            const float rstd = rsqrtf(sq * (1.0f / H2) + 1e-5f);
+            const float2 rstd2 = make_float2(rstd, rstd);
+            float2 dot2 = make_float2(rstd * lin, 0.f);
             // Pass 2 over this thread's 19 column quads (10 of half A, 9 of half B).  Parameters are fetched two quads ahead
             // (lds128_early) into a 2-slot register ring; half B's TMEM load is issued as soon as va is dead and flies under
             // the last two quads of half A.
             constexpr int kQA = 10, kQ = 19;
-            float4 G[2], E[2], W[2];
+            float4 E[2], W[2];
             auto qcol = [&](int qi) { return qi < kQA ? ca + 4 * qi : cbb + 4 * (qi - kQA); };
             auto loadp = [&](int slot, int qi) {
                 const int c = qcol(qi);
-                G[slot] = lds128_early(pg2 + c); E[slot] = lds128_early(pbe2 + c); W[slot] = lds128_early(pw3 + c);
+                E[slot] = lds128_early(pbe2 + c); W[slot] = lds128_early(pw3 + c);
             };
             auto quad = [&](int slot, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
                 const float2 xa = make_float2(__uint_as_float(x0), __uint_as_float(x1)), xb = make_float2(__uint_as_float(x2), __uint_as_float(x3));
-                float2 ya = __ffma2_rn(__ffma2_rn(xa, rstd2, nmr2), make_float2(G[slot].x, G[slot].y), make_float2(E[slot].x, E[slot].y));
-                float2 yb = __ffma2_rn(__ffma2_rn(xb, rstd2, nmr2), make_float2(G[slot].z, G[slot].w), make_float2(E[slot].z, E[slot].w));
-                ya.x = fmaxf(ya.x, 0.f); ya.y = fmaxf(ya.y, 0.f); yb.x = fmaxf(yb.x, 0.f); yb.y = fmaxf(yb.y, 0.f);
-                dot2 = __ffma2_rn(ya, make_float2(W[slot].x, W[slot].y), dot2);
-                dot2 = __ffma2_rn(yb, make_float2(W[slot].z, W[slot].w), dot2);
+                // |x rstd + be / g| (w3 |g| / 2): two FFMA2 per column pair, the second with an |.| source modifier
+                const float2 ya = __ffma2_rn(xa, rstd2, make_float2(E[slot].x, E[slot].y));
+                const float2 yb = __ffma2_rn(xb, rstd2, make_float2(E[slot].z, E[slot].w));
+                dot2 = __ffma2_rn(make_float2(fabsf(ya.x), fabsf(ya.y)), make_float2(W[slot].x, W[slot].y), dot2);
+                dot2 = __ffma2_rn(make_float2(fabsf(yb.x), fabsf(yb.y)), make_float2(W[slot].z, W[slot].w), dot2);
             };
             loadp(0, 0); loadp(1, 1);
             tmem_wait();
@@ -579,7 +646,9 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             quad((kQ - 1) & 1, vq[0], vq[1], vq[2], vq[3]);                // columns cbb + 32 .. cbb + 35
             if (prof) { t1 = clock64(); e_2d += t1 - t2; t2 = t1; }
             red3[grp * kTileM + r] = dot2.x + dot2.y;
+            if (prof) tw = clock64();
             named_bar_sync(1, kEpiThreads);
+            if (prof) e_b2 += clock64() - tw;
             if (grp == 0 && r < rows) {
                 float d = b3;
 #pragma unroll
@@ -601,8 +670,11 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                 const int64_t next = prev + G;
                 const bool has_next = next < ntiles;
                 if (has_next) {
-                    layer1(c1++, true, c2);                                // trails sweep B of `prev`; includes pass 1 over half A of `prev`
+                    // runs under the layer-2 MMAs of `prev`, block by block as they release A2.  Back-to-back sweeps
+                    // (kLead == KB2): half A of `prev` is complete early, its statistics pass goes between parts 0 and 1.
+                    layer1(c1++, kLead == KB2, c2);
                     if (next + G < ntiles) { stage(); load_x(next + 2 * G); }   // X of the tile after: ready long before it is needed
+                    if (kLead != KB2) pass1a(c2);                          // interleaved sweeps: half A completes kLead steps before half B
                 } else pass1a(c2);
                 layer2(prev, c2++);
                 if (!has_next) break;
@@ -612,6 +684,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
             dbg[4] = e_wa; dbg[5] = e_pa; dbg[6] = e_1; dbg[7] = e_wb; dbg[8] = e_2; dbg[9] = clock64() - t_begin;
             dbg[10] = e_st; dbg[11] = e_2a; dbg[12] = e_2b; dbg[13] = e_2c; dbg[14] = e_2d;
+            dbg[15] = e_wf; dbg[16] = e_af; dbg[17] = e_b1; dbg[18] = e_b2;
         }
     }
     // ---------------- teardown ----------------
@@ -687,9 +760,12 @@ int actor_pack_tc4(tt_actor *a, const float *fc1_w, const float *fc1_b, const fl
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     pack_l1c_image_kernel<<<54, 256, 0, s>>>(reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + 600, fc1_w, fc1_b, g1);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    pack_w2s_kernel<__half><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_f16), fc2_w, fc2_b);
+    double *st2 = A.l1c_scratch + 1200;
+    pack_w2_colstats_kernel<<<KB2, 256, 0, s>>>(st2, fc2_w, fc2_b, A.g2, A.w3);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    pack_w2s_kernel<__nv_bfloat16><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_bf16), fc2_w, fc2_b);
+    pack_w2s_kernel<__half><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_f16), st2, fc2_w, fc2_b);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    pack_w2s_kernel<__nv_bfloat16><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_bf16), st2, fc2_w, fc2_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }

@@ -27,10 +27,27 @@ __device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[NR]
     for (int i = 8; i < NR; i++) r[i] = 0u;
 }
 
-// W2 ring schedule: one tile = 26 steps (sweep A: k-blocks 0..12, sweep B: 0..12); step -> slot is a fixed compile-time
+// W2 ring schedule: one tile = 26 steps (13 k-blocks of half A, 13 of half B, order below); step -> slot is a fixed compile-time
 // pattern (round-robin, the last 26 % kSlots steps reuse slots 0, 1, ...) so that the fully unrolled issue loops carry no
 // address or phase arithmetic.  A slot is used kSteps / kSlots (+ 1 for the first 26 % kSlots slots) times per tile.
 constexpr int kSteps = 2 * KB2;
+// Step order within a tile.  The two output halves are separate accumulators (so that the statistics of half A can be taken
+// while half B is still being computed), but their k-blocks are INTERLEAVED: sweep A leads by kLead k-blocks, then the steps
+// alternate B(j), A(j + kLead), and sweep B finishes alone.  A2 block j is free for the next tile's epilogue 1 after B(j),
+// i.e. from step kLead + 2 j + 1 on -- not only in the second half of the tile as with two back-to-back sweeps
+// (kLead = 13), where epilogue 1 of the next tile could not start before sweep A had ended and the tensor pipe then waited
+// for it.  Half A is complete at step 26 - kLead: late enough to matter only for pass 1 A, which needs ~4 steps.
+#ifndef TT_TC4_LEAD
+#define TT_TC4_LEAD 4
+#endif
+constexpr int kLead = TT_TC4_LEAD;
+static_assert(kLead >= 1 && kLead <= KB2, "sweep A leads by 1..13 k-blocks");
+__host__ __device__ constexpr int w2_step_sweep(int step) {
+    return step < kLead ? 0 : step >= kSteps - kLead ? 1 : ((step - kLead) & 1) ? 0 : 1;
+}
+__host__ __device__ constexpr int w2_step_kb(int step) {
+    return step < kLead ? step : step >= kSteps - kLead ? step - KB2 : ((step - kLead) & 1) ? kLead + (step - kLead) / 2 : (step - kLead) / 2;
+}
 __host__ __device__ constexpr int w2_slot(int step, int nslots) { return step < (kSteps / nslots) * nslots ? step % nslots : step - (kSteps / nslots) * nslots; }
 __host__ __device__ constexpr int w2_uses_per_tile(int slot, int nslots) { return kSteps / nslots + (slot < kSteps % nslots ? 1 : 0); }
 // phase parity of the `step`-th ring use of tile number `tile_parity` (0/1)

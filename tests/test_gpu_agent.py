@@ -164,10 +164,34 @@ def test_actor_tc_refuses_other_layer_sizes():
         actor.forward(torch.zeros(4, 23, device="cuda"), precision="f16")
 
 
+@pytest.mark.parametrize("precision,tol", [("f16", 1e-3), ("f16_plain", 1.5e-3)])
+def test_actor_tc_zero_and_negative_layernorm2_weights(golden_dir, precision, tol):
+    """The tensor-core epilogue rewrites w3 relu(g z + be) as |z + be / g| (w3 |g| / 2) plus a linear GEMM column: columns with
+    g == 0 (constant relu(be) w3), g < 0 and tiny |g| must still match the oracle."""
+    import ddpg_trucktrailer_b200 as tt
+    from oracle import oracle as orc
+    g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
+    _, w1 = _sets(g)
+    w1 = {k: v.copy() for k, v in w1.items()}
+    rng = np.random.default_rng(5)
+    gw = w1["bn2.weight"]
+    gw[rng.choice(300, 40, replace=False)] *= -1
+    gw[rng.choice(300, 25, replace=False)] = 0.0
+    gw[rng.choice(300, 10, replace=False)] = 1e-35
+    gw[7] = 3e-6
+    w1["bn2.bias"] = rng.uniform(-0.3, 0.3, 300).astype(np.float32)
+    obs = rng.uniform(-1, 1, (4099, 23)).astype(np.float32)
+    actor = tt.agent.CudaActor(); actor.load_state_dict(w1)
+    ref = orc.OracleActor(w1).forward(obs)
+    assert np.abs(actor.forward(torch.from_numpy(obs).cuda()).cpu().numpy() - ref).max() < 1e-5
+    assert np.abs(actor.forward(torch.from_numpy(obs).cuda(), precision=precision).cpu().numpy() - ref).max() < tol
+
+
 def test_actor_tc_previous_kernel_generation_agrees(golden_dir, tmp_path):
     """TT_TC_VARIANT=3 (the previous tensor-core kernel, kept as a cross-check) and the default kernel implement the same
     forward with different factorizations (Gram-matrix statistics on the CUDA cores vs Cholesky columns on the tensor core):
-    both within the 1e-3 bar of the reference torch outputs, and within 2e-4 of each other in f16 mode."""
+    and of layer 2 (LayerNorm 2 centring and half of the ReLU folded into the GEMM in the default kernel): both within the 1e-3
+    bar of the reference torch outputs, hence within 2e-3 of each other -- 1e-3 in practice -- in f16 mode."""
     import subprocess
     import sys
     import ddpg_trucktrailer_b200 as tt
@@ -184,4 +208,4 @@ def test_actor_tc_previous_kernel_generation_agrees(golden_dir, tmp_path):
     v4 = actor.forward(torch.from_numpy(g["obs"]).cuda(), precision="f16").cpu().numpy()
     v3 = np.load(out)
     assert np.abs(v3 - g["out1"]).max() < 1e-3 and np.abs(v4 - g["out1"]).max() < 1e-3
-    assert np.abs(v3 - v4).max() < 2e-4
+    assert np.abs(v3 - v4).max() < 1e-3
