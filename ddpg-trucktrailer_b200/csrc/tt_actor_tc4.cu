@@ -14,14 +14,24 @@
 //  * Layer 1 = 3 parts (N = 128 | 160 | 144: statistics + 96, 160, 144 columns) through one 160-column TMEM window; an
 //    epilogue thread pulls its 8 columns of every 32-column A2 block of the part into registers at once and frees the
 //    window before it does the math, so the next part's MMAs run under it.
-//  * Layer 2 is split by OUTPUT columns into two K-sweeps (N = 160, then N = 144; 84 + 76 cycles per k-step instead of
-//    185), with separate full/free barriers: the statistics pass over half A runs under sweep B, and sweep A of the next
-//    tile starts as soon as pass 2 has read half A -- epilogue 2 is no longer serial with the layer-2 MMAs.  W2 is
-//    streamed per sweep in half-size k-blocks (4 ring slots instead of 2 in the same shared memory).
-//  * X staging: one thread = 6 consecutive inputs of one row (three 32-bit stores per operand block, no divisions), one
-//    tile ahead.  Epilogue 2: contiguous balanced column ranges (40 + 36 columns per thread).
+//  * Layer 2 is split by OUTPUT columns into two accumulator halves (N = 160 and N = 144; 84 + 76 cycles per k-step instead of
+//    185) with separate full/free barriers, their k-blocks interleaved (half A leads by kLead blocks, tt_tc4_layout.cuh): the
+//    statistics pass over half A runs under the tail of half B, the next tile's half A starts as soon as pass 2 has read
+//    half A, and the A2 blocks are released to the next tile's epilogue 1 from step kLead + 1 on.  W2 is streamed in
+//    half-size k-blocks through a 6-slot ring (5 KB multicast halves per CTA of a pair).
+//  * LayerNorm 2 and the output layer are folded into the GEMM as far as they are linear (see the pack kernels): W2 is
+//    centred over its 300 outputs, so the accumulators are h - mean(h) and the variance is a plain sum of squares; and with
+//    relu(y) = (y + |y|) / 2 the y / 2 half of the final dot product is two extra output columns (hi / lo) in the padding.
+//    Epilogue 2 is then ONE FFMA2 per column pair in pass 1 and TWO in pass 2 (|x rstd + be / g| (w3 |g| / 2), the |.| is a
+//    source modifier), with two parameter vectors instead of three.
+//  * The observation tile (layer 1's A operand) lives in tensor memory: every epilogue thread converts 8 inputs of its own
+//    row and writes them with one tcgen05.st (two in split mode); the 16 KB of shared memory this frees are two more ring
+//    slots.  Epilogue 2: contiguous balanced column ranges (40 + 36 columns per thread).
+//  * An mbarrier wait costs ~90 cycles even when the phase is already complete: epilogue 1 waits for A2 blocks 4 times per
+//    tile (they are released in order), not 13 times, and fetches its be1 vectors one chunk ahead of the wait.
 //
-// TMEM columns: [0,160) H2 half A | [160,304) H2 half B | [304,464) layer-1 window (part 0: 32 statistic columns first).
+// TMEM columns: [0,160) H2 half A | [160,304) H2 half B | [304,464) layer-1 window (part 0: 32 statistic columns first) |
+// [464,496) observation tile, hi and lo halves.
 // Warp roles (640 threads): warps 0-15 epilogue (warp w: TMEM lanes 32 (w % 4), column group w / 4), warp 16 lane 0
 // layer-2 MMA issuer, warp 17 lane 0 bulk-copy producer (W2 k-blocks streamed from L2), warp 18 lane 0 layer-1 MMA
 // issuer, warp 19 fused replay-ring store of the observation rows.
@@ -30,6 +40,13 @@
 #include "tt_common.cuh"
 #include "tt_tc_ptx.cuh"
 #include "tt_tc4_layout.cuh"
+
+// Timing-only ablations (WRONG results; profiles/build_variants.sh): which stage pins the tile time?
+//   1: no W2 stream (the layer-2 MMAs read whatever the ring holds)   2: epilogue 2 without pass 2's math
+//   4: epilogue 1 without the A2 conversion / stores                 8: pass 1 without its math
+#ifndef TT_ABLATE
+#define TT_ABLATE 0
+#endif
 
 namespace {
 
@@ -147,11 +164,10 @@ __global__ void pack_w2s_kernel(char *__restrict__ img, const double *__restrict
 
 template <bool kSplit>
 struct Plan4 {
-    static constexpr int kXBlocks = kSplit ? 2 : 1;
-    static constexpr int kSlots = kSplit ? 4 : 6;
+    static constexpr int kXBlocks = kSplit ? 2 : 1;                               // operand blocks of layer 1: hi [+ lo residual]
+    static constexpr int kSlots = 6;
     static constexpr uint32_t kW2Slot = kW2SlotB;
-    static constexpr uint32_t x = 0;
-    static constexpr uint32_t w1 = x + kXBlocks * kTileM * kRowB;
+    static constexpr uint32_t w1 = 0;                                             // (the observation tile, layer 1's A operand, lives in TMEM)
     static constexpr uint32_t a2 = w1 + kXBlocks * N1I * kRowB;
     static constexpr uint32_t w2 = a2 + KB2 * kTileM * kRowB;
     static constexpr uint32_t par = w2 + kSlots * kW2Slot;
@@ -160,7 +176,7 @@ struct Plan4 {
     static constexpr uint32_t bars = red + 2 * 4 * kTileM * 4;
     static constexpr uint32_t nbars = 40;
     static constexpr uint32_t tmem_slot = bars + nbars * 8;
-    static constexpr uint32_t total = tmem_slot + 16 + 1024;
+    static constexpr uint32_t total = tmem_slot + 16;                             // the dynamic shared memory window is 1024 B aligned (checked)
 };
 
 enum { D_W1 = 0, D_XFULL, D_WFULL, D_WFREE, D_A2FULL, D_H2AFULL, D_H2BFULL, D_H2AFREE, D_H2BFREE,
@@ -183,10 +199,10 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     constexpr int kM2Warp = 16, kProdWarp = 17, kM1Warp = 18, kCopyWarp = 19;
     constexpr uint32_t kFmt = std::is_same<OpT, __nv_bfloat16>::value ? 1u : 0u;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t *sm = smem_raw + (base - raw);
-    const uint32_t sX = base + P::x, sW1 = base + P::w1, sA2 = base + P::a2, sW2 = base + P::w2, sBar = base + P::bars;
+    const uint32_t base = smem_u32(smem_raw);
+    if (base & 1023u) __trap();                      // SWIZZLE_64B operand blocks need 1024 B alignment; there is no static shared memory in front
+    uint8_t *sm = smem_raw;
+    const uint32_t sW1 = base + P::w1, sA2 = base + P::a2, sW2 = base + P::w2, sBar = base + P::bars;
     float *par = reinterpret_cast<float *>(sm + P::par);
     float *pbe1 = par, *pbe2 = par + K2P, *pw3 = pbe2 + H2P;
     float *red1 = reinterpret_cast<float *>(sm + P::red);          // per (column group, row): sum of squares | output dot
@@ -227,7 +243,6 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     }
     // X blocks: zero once (k = 24..31 stay zero).  A2 block 12, columns 400..415: constant (1, 0, ..., 0) -- column 400
     // carries the fc2 bias -- written once; the epilogue only ever rewrites columns 384..399 of that block.
-    for (int v = threadIdx.x; v < P::kXBlocks * kTileM * kRowB / 4; v += kThreads) reinterpret_cast<uint32_t *>(sm + P::x)[v] = 0u;
     if (threadIdx.x < kTileM) {
         const int r = threadIdx.x;
         const uint32_t xsw = ((uint32_t)r >> 1) & 3u;
@@ -266,7 +281,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         const char *w2rep = w2img + (size_t)(blockIdx.x % TT_W2_REPLICAS) * kW2ImageB;     // this SM's replica
         const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
         uint32_t tp = 0;
-        for (int64_t itn = 0; itn < niter; itn++, tp ^= 1u) {
+        for (int64_t itn = 0; itn < ((TT_ABLATE & 1) ? 0 : niter); itn++, tp ^= 1u) {
 #pragma unroll
             for (int step = 0; step < kSteps; step++) {
                 const int sweep = w2_step_sweep(step), kb = w2_step_kb(step), slot = w2_slot(step, P::kSlots);
@@ -331,7 +346,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             const uint32_t idp[kParts] = {make_idesc(128, kFmt), make_idesc(160, kFmt), make_idesc(144, kFmt)};
             constexpr uint32_t rowp[kParts] = {0u, 128u, 288u};            // first image row of each part
             constexpr int npairs = kSplit ? 3 : 1;
-            const uint64_t dX = make_desc(sX), dW1 = make_desc(sW1);      // descriptor address field is in 16 B units
+            const uint64_t dW1 = make_desc(sW1);                          // descriptor address field is in 16 B units
             uint32_t c1 = 0, use = 0;
             mbar_wait(bar(D_W1), 0);
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, c1++) {
@@ -343,10 +358,10 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                     if (elect_one()) {
 #pragma unroll
                         for (int pr = 0; pr < npairs; pr++) {
-                            const uint64_t xb = dX + (uint64_t)(pr == 1 ? kTileM * kRowB / 16 : 0);
+                            const uint32_t xa = tmem + kXCol0 + (pr == 1 ? 16u : 0u);                 // hi . W1hi + lo . W1hi + hi . W1lo
                             const uint64_t wb = dW1 + (uint64_t)((pr == 2 ? N1I * kRowB : 0) + rowp[p] * kRowB) / 16;
-                            umma(tmem + kWin0, xb, wb, idp[p], pr ? 1u : 0u);
-                            umma(tmem + kWin0, xb + 2, wb + 2, idp[p], 1u);
+                            umma_ts(tmem + kWin0, xa, wb, idp[p], pr ? 1u : 0u);
+                            umma_ts(tmem + kWin0, xa + 8u, wb + 2, idp[p], 1u);                      // next 16 inputs: 8 TMEM columns
                         }
                         umma_commit(bar(D_WFULL));
                     }
@@ -369,7 +384,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
 #pragma unroll
                     for (int step = 0; step < kSteps; step++) {
                         const int slot = w2_slot(step, P::kSlots);
-                        mbar_wait(bar(D_W2FULL + slot), w2_parity(step, P::kSlots, ph));
+                        if (!(TT_ABLATE & 1)) mbar_wait(bar(D_W2FULL + slot), w2_parity(step, P::kSlots, ph));
                         if (elect_one()) umma_commit_mc(bar(D_W2EMPTY + slot), kMask);
                         __syncwarp();
                     }
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                         if (prof) t_h2 += clock64() - t0;
                     }
                     if (prof) t0 = clock64();
-                    mbar_wait(bar(D_W2FULL + slot), w2_parity(step, P::kSlots, ph));
+                    if (!(TT_ABLATE & 1)) mbar_wait(bar(D_W2FULL + slot), w2_parity(step, P::kSlots, ph));
                     if (prof) t_w2 += clock64() - t0;
                     tc_fence_after();
                     if (elect_one()) {
@@ -411,16 +426,16 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         const int et = threadIdx.x;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t xsw = (((uint32_t)r >> 1) & 3u);
-        // X staging role: row et / 4, inputs k0 .. k0 + 5 with k0 = 6 (et % 4); k = 23 is the constant-1 bias column
-        const int srow = et >> 2, k0 = 6 * (et & 3);
-        const uint32_t ssw = (((uint32_t)srow >> 1) & 3u);
-        float xreg[6];
+        // X staging role: this thread's own row (its TMEM lane), inputs 8 grp .. 8 grp + 7; k = 23 is the constant-1 bias column,
+        // k = 24..31 (group 3) are zero
+        const int k0 = 8 * grp;
+        float xreg[8];
         auto load_x = [&](int64_t t) {
-            const int64_t gr = t * kTileM + srow;
-            const bool ok = gr < n;
+            const int64_t gr = t * kTileM + r;
+            const bool ok = gr < n && grp < 3;
             const float *p = obs + gr * ld + k0;
 #pragma unroll
-            for (int i = 0; i < 6; i++) xreg[i] = (k0 + i < IN) ? (ok ? __ldg(p + i) : 0.f) : 1.0f;
+            for (int i = 0; i < 8; i++) xreg[i] = (k0 + i < IN) ? (ok ? __ldg(p + i) : 0.f) : (k0 + i == IN ? 1.0f : 0.f);
         };
         constexpr bool prof = kProf;
         long long e_wf = 0, e_af = 0, e_b1 = 0, e_b2 = 0, tw = 0, e_st = 0, e_1 = 0, e_wa = 0, e_pa = 0, e_wb = 0, e_2 = 0, e_2a = 0, e_2b = 0, e_2c = 0, e_2d = 0, t0 = 0, t1 = 0, t2 = 0;
@@ -430,17 +445,18 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         // stage the observation tile held in xreg as the layer-1 A operand (hi [+ lo residual]) and release it
         auto stage = [&]() {
             if (prof) t0 = clock64();
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
+            for (int i = 0; i < 4; i++) {
                 const float a = xreg[2 * i], b = xreg[2 * i + 1];
                 const OpT ah = to_op<OpT>(a), bh = to_op<OpT>(b);
-                const uint32_t byte = 12u * (uint32_t)(et & 3) + 4u * (uint32_t)i;
-                const uint32_t off = (uint32_t)srow * kRowB + ((((byte >> 4) ^ ssw)) << 4) + (byte & 15u);
-                const uint32_t hi = (uint32_t)(*reinterpret_cast<const uint16_t *>(&ah)) | ((uint32_t)(*reinterpret_cast<const uint16_t *>(&bh)) << 16);
-                *reinterpret_cast<uint32_t *>(sm + P::x + off) = hi;
-                if (kSplit) *reinterpret_cast<uint32_t *>(sm + P::x + kTileM * kRowB + off) = pack2<OpT>(a - op_to_float(ah), b - op_to_float(bh));
+                hi[i] = (uint32_t)(*reinterpret_cast<const uint16_t *>(&ah)) | ((uint32_t)(*reinterpret_cast<const uint16_t *>(&bh)) << 16);
+                lo[i] = pack2<OpT>(a - op_to_float(ah), b - op_to_float(bh));
             }
-            fence_proxy_async();
+            tmem_st4(trow + (uint32_t)(kXCol0 + 4 * grp), hi);             // TMEM column c of the block = inputs 2 c, 2 c + 1 of this lane's row
+            if (kSplit) tmem_st4(trow + (uint32_t)(kXCol0 + 16 + 4 * grp), lo);
+            tmem_wait_st();
+            tc_fence_before();
             mbar_arrive(bar(D_XFULL));
             if (et == 0) *staged = *staged + 1u;                           // progress signal for the replay-store warp
             if (prof) { t1 = clock64(); e_st += t1 - t0; }
@@ -451,6 +467,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         const int ca = 40 * grp, cbb = kNA + 36 * grp;
         float2 q2;                                                         // the accumulators are centred (see the pack): variance = sum of squares
         auto acc = [&](const uint32_t *v, int cnt) {
+            if (TT_ABLATE & 8) return;
 #pragma unroll
             for (int j = 0; j < cnt / 2; j++) {
                 const float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
@@ -486,9 +503,11 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             };
             float4 E0[2], E1[2];                                           // be1 of the next chunk, fetched one chunk ahead
             auto lde = [&](int slot, int ch) {
+                if (TT_ABLATE & 4) return;
                 E0[slot] = lds128_early(pbe1 + ch * 32 + grp * 8); E1[slot] = lds128_early(pbe1 + ch * 32 + grp * 8 + 4);
             };
             auto emit = [&](const uint32_t (&v)[8], int ch, int slot) {    // 8 columns of A2 block ch: relu(t' rstd + be1)
+                if (TT_ABLATE & 4) return;
                 const float4 e0 = E0[slot], e1 = E1[slot];
                 const float2 ee[4] = {make_float2(e0.x, e0.y), make_float2(e0.z, e0.w), make_float2(e1.x, e1.y), make_float2(e1.z, e1.w)};
                 uint32_t pk4[4];
@@ -607,9 +626,11 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             auto qcol = [&](int qi) { return qi < kQA ? ca + 4 * qi : cbb + 4 * (qi - kQA); };
             auto loadp = [&](int slot, int qi) {
                 const int c = qcol(qi);
+                if (TT_ABLATE & 2) return;
                 E[slot] = lds128_early(pbe2 + c); W[slot] = lds128_early(pw3 + c);
             };
             auto quad = [&](int slot, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
+                if (TT_ABLATE & 2) return;
                 const float2 xa = make_float2(__uint_as_float(x0), __uint_as_float(x1)), xb = make_float2(__uint_as_float(x2), __uint_as_float(x3));
                 // |x rstd + be / g| (w3 |g| / 2): two FFMA2 per column pair, the second with an |.| source modifier
                 const float2 ya = __ffma2_rn(xa, rstd2, make_float2(E[slot].x, E[slot].y));

@@ -9,6 +9,7 @@ constexpr int kStatRows = 32;                 // statistic rows appended to the 
 constexpr int N1I = N1 + kStatRows;           // rows per hi / lo block of the v4 layer-1 image (432)
 constexpr int kParts = 3;                     // layer-1 parts: [32 statistics + 96] | 160 | 144 columns
 constexpr int kWin0 = 304;                    // first TMEM column of the layer-1 window (160 columns)
+constexpr int kXCol0 = kWin0 + 160;             // observation tile (layer-1 A operand): 16 columns hi [464, 480) + 16 columns lo [480, 496)
 constexpr int kNA = 160, kNB = N2 - kNA;      // layer-2 output halves (sweep A / sweep B)
 constexpr uint32_t kW2SlotB = kNA * kRowB;    // ring slot: one half k-block (10 240 B; sweep B uses 9 216 of it)
 constexpr size_t kW2SweepB = (size_t)KB2 * kNA * kRowB;   // byte offset of sweep B inside the v4 W2 image
@@ -17,6 +18,15 @@ constexpr size_t kW2ImageB = (size_t)KB2 * N2 * kRowB;     // one replica of the
 __device__ __forceinline__ void tmem_ld4_async(uint32_t taddr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (128 lanes x 8 columns of packed 16-bit pairs per K = 16 step) read from tensor memory
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 template <int NR>
 __device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[NR]) {      // 8 columns into r[0..7], rest zero
