@@ -44,6 +44,7 @@
 // Timing-only ablations (WRONG results; profiles/build_variants.sh): which stage pins the tile time?
 //   1: no W2 stream (the layer-2 MMAs read whatever the ring holds)   2: epilogue 2 without pass 2's math
 //   4: epilogue 1 without the A2 conversion / stores                 8: pass 1 without its math
+//  16: the layer-2 MMAs do not wait for epilogue 2 to have read the previous tile's accumulators
 #ifndef TT_ABLATE
 #define TT_ABLATE 0
 #endif
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                     const int sweep = w2_step_sweep(step), kb = w2_step_kb(step), slot = w2_slot(step, P::kSlots);
                     if (kb == 0) {
                         if (prof) t0 = clock64();
-                        mbar_wait(bar(sweep ? D_H2BFREE : D_H2AFREE), ph ^ 1u);   // pass 2 of the previous tile has read this half
+                        if (!(TT_ABLATE & 16)) mbar_wait(bar(sweep ? D_H2BFREE : D_H2AFREE), ph ^ 1u);   // pass 2 of the previous tile has read this half
                         if (prof) t_h2 += clock64() - t0;
                     }
                     if (prof) t0 = clock64();
