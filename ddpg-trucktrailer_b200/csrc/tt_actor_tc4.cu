@@ -127,20 +127,20 @@ __global__ void __launch_bounds__(256) pack_l1c_image_kernel(char *__restrict__ 
 __device__ __forceinline__ float wf2(const float *__restrict__ fc2_w, const float *__restrict__ fc2_b, int n, int k) {
     return k < H1 ? fc2_w[n * H1 + k] : (k == H1 ? fc2_b[n] : 0.f);
 }
-__global__ void __launch_bounds__(256) pack_w2_colstats_kernel(double *__restrict__ out /* m2[K2P], l2[K2P] */, const float *__restrict__ fc2_w,
+constexpr int kStatSlices = 32;
+__global__ void __launch_bounds__(32 * kStatSlices) pack_w2_colstats_kernel(double *__restrict__ out /* m2[K2P], l2[K2P] */, const float *__restrict__ fc2_w,
                                                                const float *__restrict__ fc2_b, const float *__restrict__ g2, const float *__restrict__ w3) {
-    __shared__ double r1[8][33], r2[8][33], rg[8][33];
+    __shared__ double r1[kStatSlices][33], r2[kStatSlices][33], rg[kStatSlices][33];
     const int kk = threadIdx.x & 31, sl = threadIdx.x >> 5, k = blockIdx.x * 32 + kk;
     double s1 = 0.0, s2 = 0.0, sg = 0.0;
-    for (int n = sl; n < H2; n += 8) {
+    for (int n = sl; n < H2; n += kStatSlices) {
         const double w = (double)wf2(fc2_w, fc2_b, n, k), gw = (double)g2[n] * (double)w3[n];
         s1 += w; s2 += w * gw; sg += gw;
     }
     r1[sl][kk] = s1; r2[sl][kk] = s2; rg[sl][kk] = sg;
     __syncthreads();
     if (sl == 0) {
-#pragma unroll
-        for (int i = 1; i < 8; i++) { s1 += r1[i][kk]; s2 += r2[i][kk]; sg += rg[i][kk]; }
+        for (int i = 1; i < kStatSlices; i++) { s1 += r1[i][kk]; s2 += r2[i][kk]; sg += rg[i][kk]; }
         const double m = s1 / H2;
         out[k] = m;
         out[K2P + k] = 0.5 * (s2 - m * sg);
@@ -783,7 +783,7 @@ int actor_pack_tc4(tt_actor *a, const float *fc1_w, const float *fc1_b, const fl
     pack_l1c_image_kernel<<<54, 256, 0, s>>>(reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + 600, fc1_w, fc1_b, g1);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     double *st2 = A.l1c_scratch + 1200;
-    pack_w2_colstats_kernel<<<KB2, 256, 0, s>>>(st2, fc2_w, fc2_b, A.g2, A.w3);
+    pack_w2_colstats_kernel<<<KB2, 32 * kStatSlices, 0, s>>>(st2, fc2_w, fc2_b, A.g2, A.w3);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     pack_w2s_kernel<__half><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_f16), st2, fc2_w, fc2_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
