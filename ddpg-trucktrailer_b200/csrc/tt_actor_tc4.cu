@@ -16,9 +16,10 @@
 //    window before it does the math, so the next part's MMAs run under it.
 //  * Layer 2 is split by OUTPUT columns into two accumulator halves (N = 160 and N = 144; 84 + 76 cycles per k-step instead of
 //    185) with separate full/free barriers, their k-blocks interleaved (half A leads by kLead blocks, tt_tc4_layout.cuh): the
-//    statistics pass over half A runs under the tail of half B, the next tile's half A starts as soon as pass 2 has read
-//    half A, and the A2 blocks are released to the next tile's epilogue 1 from step kLead + 1 on.  W2 is streamed in
-//    half-size k-blocks through a 6-slot ring (5 KB multicast halves per CTA of a pair).
+//    statistics pass over half A runs under the rest of half B -- placed where the epilogue would otherwise wait for the
+//    layer-1 MMAs of part 1 --, the next tile's half A starts as soon as pass 2 has read half A, and the A2 blocks are
+//    released to the next tile's epilogue 1 from step kLead + 1 on.  W2 is streamed in half-size k-blocks through a 6-slot
+//    ring (5 KB multicast halves per CTA of a pair).
 //  * LayerNorm 2 and the output layer are folded into the GEMM as far as they are linear (see the pack kernels): W2 is
 //    centred over its 300 outputs, so the accumulators are h - mean(h) and the variance is a plain sum of squares; and with
 //    relu(y) = (y + |y|) / 2 the y / 2 half of the final dot product is two extra output columns (hi / lo) in the padding.
@@ -45,11 +46,16 @@
 //   1: no W2 stream (the layer-2 MMAs read whatever the ring holds)   2: epilogue 2 without pass 2's math
 //   4: epilogue 1 without the A2 conversion / stores                 8: pass 1 without its math
 //  16: the layer-2 MMAs do not wait for epilogue 2 to have read the previous tile's accumulators
+#ifndef TT_TC4_P1A
+#define TT_TC4_P1A (TT_TC4_LEAD >= 9 ? 0 : TT_TC4_LEAD >= 6 ? 1 : 2)
+#endif
 #ifndef TT_ABLATE
 #define TT_ABLATE 0
 #endif
 
 namespace {
+
+constexpr int kP1A = TT_TC4_P1A;
 
 // ---- v4 layer-1 image, built at tt_actor_load time ----
 // rows 0..23   : L[k][j] (row j): lower Cholesky factor of Gc = sum_c (Wf[c] - m)(Wf[c] - m)^T, so that
@@ -491,7 +497,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         // layer-1 side of one tile: statistics -> rstd, then the 3 parts -> A2.  c1 = layer-1 tile counter
         // `with_p1a`: run the statistics pass over half A of the layer-2 tile c2 between part 0 and part 1 -- it fills the
         // wait for the layer-1 MMAs of part 1, which queue behind the sweep-B MMAs.
-        auto layer1 = [&](uint32_t c1, bool with_p1a, uint32_t c2) {
+        auto layer1 = [&](uint32_t c1, int p1a_pos, uint32_t c2) {
             const uint32_t ph = c1 & 1u;
             if (prof) t0 = clock64();
             float2 rstd2 = make_float2(0.f, 0.f);
@@ -549,7 +555,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
 #pragma unroll
                 for (int c = 0; c < 3; c++) { if (c < 2) lde((c + 1) & 1, c + 1); emit(v[c], c, c & 1); }
             }
-            if (with_p1a) { if (prof) { t1 = clock64(); e_1 += t1 - t0; } pass1a(c2); }
+            if (p1a_pos == 0) { if (prof) { t1 = clock64(); e_1 += t1 - t0; } pass1a(c2); }
             {   // part 1: A2 blocks 3..7
                 if (prof) tw = clock64();
                 mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
@@ -565,6 +571,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
 #pragma unroll
                 for (int c = 0; c < 5; c++) { if (c < 4) lde((c + 1) & 1, 4 + c); emit(v[c], 3 + c, c & 1); }
             }
+            if (p1a_pos == 1) { if (prof) { t1 = clock64(); e_1 += t1 - t0; } pass1a(c2); }
             {   // part 2: A2 blocks 8..11 and the 16 real columns of block 12 (groups 0, 1)
                 if (prof) tw = clock64();
                 mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
@@ -685,18 +692,19 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         if (first < ntiles) {
             load_x(first);
             stage(); load_x(first + G);                                    // X(0); registers <- tile 1
-            layer1(c1++, false, 0u);
+            layer1(c1++, -1, 0u);
             if (first + G < ntiles) { stage(); load_x(first + 2 * G); }    // X(1)
             int64_t prev = first;
             for (;;) {
                 const int64_t next = prev + G;
                 const bool has_next = next < ntiles;
                 if (has_next) {
-                    // runs under the layer-2 MMAs of `prev`, block by block as they release A2.  Back-to-back sweeps
-                    // (kLead == KB2): half A of `prev` is complete early, its statistics pass goes between parts 0 and 1.
-                    layer1(c1++, kLead == KB2, c2);
+                    // runs under the layer-2 MMAs of `prev`, block by block as they release A2.  The statistics pass over half A
+                    // of `prev` (complete at step 26 - kLead) goes where the epilogue would otherwise wait for the next
+                    // layer-1 part: after part 0 (kP1A = 0), after part 1 (1), or after the whole of epilogue 1 (2).
+                    layer1(c1++, kP1A, c2);
                     if (next + G < ntiles) { stage(); load_x(next + 2 * G); }   // X of the tile after: ready long before it is needed
-                    if (kLead != KB2) pass1a(c2);                          // interleaved sweeps: half A completes kLead steps before half B
+                    if (kP1A == 2) pass1a(c2);
                 } else pass1a(c2);
                 layer2(prev, c2++);
                 if (!has_next) break;

@@ -42,13 +42,14 @@ __device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[NR]
 // address or phase arithmetic.  A slot is used kSteps / kSlots (+ 1 for the first 26 % kSlots slots) times per tile.
 constexpr int kSteps = 2 * KB2;
 // Step order within a tile.  The two output halves are separate accumulators (so that the statistics of half A can be taken
-// while half B is still being computed), but their k-blocks are INTERLEAVED: sweep A leads by kLead k-blocks, then the steps
-// alternate B(j), A(j + kLead), and sweep B finishes alone.  A2 block j is free for the next tile's epilogue 1 after B(j),
-// i.e. from step kLead + 2 j + 1 on -- not only in the second half of the tile as with two back-to-back sweeps
-// (kLead = 13), where epilogue 1 of the next tile could not start before sweep A had ended and the tensor pipe then waited
-// for it.  Half A is complete at step 26 - kLead: late enough to matter only for pass 1 A, which needs ~4 steps.
+// while half B is still being computed), and their k-blocks are INTERLEAVED: half A leads by kLead k-blocks, then the steps
+// alternate B(j), A(j + kLead), and half B finishes alone.  A2 block j is free for the next tile's epilogue 1 after B(j),
+// i.e. from step kLead + 2 j + 1 on, and half A is complete at step 26 - kLead.  kLead trades the two: a small lead releases
+// the A2 blocks early, a large one completes half A early enough for its statistics pass to fill the epilogue's wait for the
+// layer-1 MMAs of part 1 (kP1A in tt_actor_tc4.cu).  Measured (profiles/build_variants.sh): kLead 9..13 with the pass in that
+// gap are 3 % faster than kLead 2..8 with the pass at the end; 13 = two back-to-back sweeps.
 #ifndef TT_TC4_LEAD
-#define TT_TC4_LEAD 4
+#define TT_TC4_LEAD 10
 #endif
 constexpr int kLead = TT_TC4_LEAD;
 static_assert(kLead >= 1 && kLead <= KB2, "sweep A leads by 1..13 k-blocks");

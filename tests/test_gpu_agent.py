@@ -164,6 +164,27 @@ def test_actor_tc_refuses_other_layer_sizes():
         actor.forward(torch.zeros(4, 23, device="cuda"), precision="f16")
 
 
+@pytest.mark.parametrize("precision", ["f16", "bf16"])
+def test_actor_tc_full_size_position_independence(golden_dir, precision):
+    """BASELINE size (2^22 rows): a row's output must not depend on where the row sits -- tile, TMEM lane, CTA, CTA-pair rank,
+    ring slot phase.  The batch is a 4 099-row block (not a multiple of the 128-row tile) repeated to 2^22 rows: every copy of
+    the block must be bit-identical to the first one, and the first one within the bar of the fp32 kernel."""
+    import ddpg_trucktrailer_b200 as tt
+    g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
+    _, w1 = _sets(g)
+    actor = tt.agent.CudaActor(); actor.load_state_dict(w1)
+    N, B = 1 << 22, 4099
+    block = torch.empty(B, 23, device="cuda").uniform_(-2, 2)
+    reps = (N + B - 1) // B
+    obs = block.repeat(reps, 1)[:N].contiguous()
+    out = actor.forward(obs, precision=precision)
+    ref = actor.forward(block, precision="fp32")
+    assert (out[:B] - ref).abs().max() < (2e-2 if precision == "bf16" else 1.5e-3)
+    full = out[: (N // B) * B].view(N // B, B)
+    assert torch.equal(full, full[0:1].expand_as(full))
+    assert torch.equal(out[(N // B) * B:], out[: N - (N // B) * B])
+
+
 @pytest.mark.parametrize("precision,tol", [("f16", 1e-3), ("f16_plain", 1.5e-3)])
 def test_actor_tc_zero_and_negative_layernorm2_weights(golden_dir, precision, tol):
     """The tensor-core epilogue rewrites w3 relu(g z + be) as |z + be / g| (w3 |g| / 2) plus a linear GEMM column: columns with
