@@ -49,6 +49,10 @@
 #ifndef TT_TC4_P1A
 #define TT_TC4_P1A (TT_TC4_LEAD >= 9 ? 0 : TT_TC4_LEAD >= 6 ? 1 : 2)
 #endif
+#ifndef TT_TC4_EPI2
+#define TT_TC4_EPI2 0      // epilogue 2: 0 = one row per thread (tcgen05.ld.32x32b; default), 1 = four rows x two columns per 8-column octet
+                           // (16x256b: a quarter of the parameter-load wavefronts, but two shuffle reductions -- measured 1 % slower)
+#endif
 #ifndef TT_ABLATE
 #define TT_ABLATE 0
 #endif
@@ -469,6 +473,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             if (prof) { t1 = clock64(); e_st += t1 - t0; }
         };
 
+#if TT_TC4_EPI2 == 0
         // layer-2 side of one tile: LayerNorm + ReLU over H2, dot with mu.weight, tanh.  Column group g owns columns
         // [40 g, 40 g + 40) of half A and [160 + 36 g, 160 + 36 g + 36) of half B.
         const int ca = 40 * grp, cbb = kNA + 36 * grp;
@@ -494,6 +499,56 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             acc(va, 32); acc(vt, 8);
             if (prof) { t1 = clock64(); e_pa += t1 - t0; t0 = t1; }
         };
+#else
+        // layer-2 side of one tile: LayerNorm + ReLU over H2, dot with mu.weight, tanh -- tcgen05.ld.16x256b mapping
+        // (profiles/ld_shape_probe.cu): a thread (lane quarter q = warp % 4, lane t, column group grp) owns the FOUR rows
+        // 32 q + t / 4 + 8 i (i = 0..3) and, of every 8-column octet of its group's ranges, the TWO columns 2 (t % 4), + 1.  One
+        // 8-byte parameter load then serves four rows (a quarter of the shared-memory wavefronts of the row-per-thread mapping;
+        // the four threads of a row combine their partial sums with two shuffles).
+        // Octets per group: half A 5 each (40 columns); half B 5, 5, 4, 4 (144 columns; columns 300, 301 -- group 3, t % 4 == 2 of
+        // its last octet -- are the linear half of the output dot, see the pack).
+        const int tq = lane & 3;
+        const int rw = (warp & 3) * 32 + (lane >> 2);                      // first of this thread's four rows (+ 8 i)
+        const int ca = 40 * grp, cbb = kNA + (grp < 2 ? 40 * grp : 80 + 32 * (grp - 2));
+        const bool b5 = grp < 2;                                           // half B: 5 octets (else 4)
+        const bool islin = grp == kGroups - 1 && tq == 2;
+        const uint32_t trow16 = trow + (16u << 16);
+        float q4[4];                                                       // per-row sum of squares of this thread's columns
+        // value pair of row i (0..3) in octet j (0..3) of a 4-octet load pair (lo: rows +0, +8; hi: rows +16, +24)
+#define TT_X4(lo, hi, j, i) make_float2(__uint_as_float(((i) < 2 ? lo : hi)[4 * (j) + 2 * ((i) & 1)]), __uint_as_float(((i) < 2 ? lo : hi)[4 * (j) + 2 * ((i) & 1) + 1]))
+        auto acc4 = [&](const uint32_t (&lo)[16], const uint32_t (&hi)[16], float2 (&q)[4], int noct) {
+            if (TT_ABLATE & 8) return;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) if (j < noct) { const float2 x = TT_X4(lo, hi, j, i); q[i] = __ffma2_rn(x, x, q[i]); }
+        };
+        auto acc1 = [&](const uint32_t (&lo)[4], const uint32_t (&hi)[4], float2 (&q)[4]) {
+            if (TT_ABLATE & 8) return;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t *s = i < 2 ? lo : hi;
+                const float2 x = make_float2(__uint_as_float(s[2 * (i & 1)]), __uint_as_float(s[2 * (i & 1) + 1]));
+                q[i] = __ffma2_rn(x, x, q[i]);
+            }
+        };
+        auto pass1a = [&](uint32_t c2) {                                   // statistics of half A (runs under the rest of half B)
+            if (prof) t0 = clock64();
+            mbar_wait(bar(D_H2AFULL), c2 & 1u);
+            if (prof) { t1 = clock64(); e_wa += t1 - t0; t0 = t1; }
+            tc_fence_after();
+            uint32_t alo[16], ahi[16], tlo[4], thi[4];
+            tmem_ld16x256_x4(trow + (uint32_t)ca, alo); tmem_ld16x256_x4(trow16 + (uint32_t)ca, ahi);
+            tmem_ld16x256_x1(trow + (uint32_t)(ca + 32), tlo); tmem_ld16x256_x1(trow16 + (uint32_t)(ca + 32), thi);
+            tmem_wait();
+            float2 q[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            acc4(alo, ahi, q, 4); acc1(tlo, thi, q);
+#pragma unroll
+            for (int i = 0; i < 4; i++) q4[i] = q[i].x + q[i].y;
+            if (prof) { t1 = clock64(); e_pa += t1 - t0; t0 = t1; }
+        };
+#endif
+
         // layer-1 side of one tile: statistics -> rstd, then the 3 parts -> A2.  c1 = layer-1 tile counter
         // `with_p1a`: run the statistics pass over half A of the layer-2 tile c2 between part 0 and part 1 -- it fills the
         // wait for the layer-1 MMAs of part 1, which queue behind the sweep-B MMAs.
@@ -597,6 +652,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             if (prof) { t1 = clock64(); e_1 += t1 - t0; t0 = t1; }
         };
 
+#if TT_TC4_EPI2 == 0
         auto layer2 = [&](int64_t tile, uint32_t c2) {
             const uint32_t ph = c2 & 1u;
             const int64_t row0 = tile * kTileM;
@@ -686,6 +742,121 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             }
             if (prof) { t1 = clock64(); e_2 += t1 - t0; t0 = t1; }
         };
+
+#else
+        auto layer2 = [&](int64_t tile, uint32_t c2) {
+            const uint32_t ph = c2 & 1u;
+            const int64_t row0 = tile * kTileM;
+            const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
+            if (prof) t0 = clock64();
+            mbar_wait(bar(D_H2BFULL), ph);
+            if (prof) { t1 = clock64(); e_wb += t1 - t0; t0 = t1; }
+            tc_fence_after();
+            uint32_t alo[16], ahi[16], tlo[4], thi[4];
+            tmem_ld16x256_x4(trow + (uint32_t)cbb, alo); tmem_ld16x256_x4(trow16 + (uint32_t)cbb, ahi);
+            if (b5) { tmem_ld16x256_x1(trow + (uint32_t)(cbb + 32), tlo); tmem_ld16x256_x1(trow16 + (uint32_t)(cbb + 32), thi); }
+            tmem_wait();
+            float lin[4];                                                  // columns 300, 301: the linear half of the output dot (hi + lo)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t *s = i < 2 ? alo : ahi;
+                const int k = 12 + 2 * (i & 1);                            // octet 3 of group 3's half-B range = columns 296..303
+                lin[i] = islin ? __uint_as_float(s[k]) + __uint_as_float(s[k + 1]) : 0.f;
+                if (islin) { s[k] = 0u; s[k + 1] = 0u; }
+            }
+            {
+                float2 q[4] = {make_float2(q4[0], 0.f), make_float2(q4[1], 0.f), make_float2(q4[2], 0.f), make_float2(q4[3], 0.f)};
+                acc4(alo, ahi, q, 4);
+                if (b5) acc1(tlo, thi, q);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float s = q[i].x + q[i].y;
+                    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    q4[i] = s;
+                }
+            }
+            if (prof) { t2 = clock64(); e_2a += t2 - t0; }
+            // statistics exchange between the column groups: red1[row][group]; the thread with t % 4 == i writes row i
+            red1[(rw + 8 * tq) * kGroups + grp] = tq == 0 ? q4[0] : tq == 1 ? q4[1] : tq == 2 ? q4[2] : q4[3];
+            // pass 2 re-reads the accumulators; half A's loads fly while the statistics are exchanged
+            tmem_ld16x256_x4(trow + (uint32_t)ca, alo); tmem_ld16x256_x4(trow16 + (uint32_t)ca, ahi);
+            tmem_ld16x256_x1(trow + (uint32_t)(ca + 32), tlo); tmem_ld16x256_x1(trow16 + (uint32_t)(ca + 32), thi);
+            if (prof) tw = clock64();
+            named_bar_sync(1, kEpiThreads);
+            if (prof) e_b1 += clock64() - tw;
+            float rstd[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 s = *reinterpret_cast<const float4 *>(red1 + (rw + 8 * i) * kGroups);
+                rstd[i] = rsqrtf(((s.x + s.y) + (s.z + s.w)) * (1.0f / H2) + 1e-5f);
+            }
+            float2 dot2[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) dot2[i] = make_float2(rstd[i] * lin[i], 0.f);
+            // parameters of this thread's two columns of an octet: be2 / g2 and w3 |g2| / 2 (8-byte loads, two octets ahead)
+            float2 E[2], W[2];
+            auto loadp = [&](int slot, int col) {
+                if (TT_ABLATE & 2) return;
+                E[slot] = lds64_early(pbe2 + col + 2 * tq); W[slot] = lds64_early(pw3 + col + 2 * tq);
+            };
+            auto oct = [&](int slot, float2 x0, float2 x1, float2 x2, float2 x3) {
+                if (TT_ABLATE & 2) return;
+                const float2 x[4] = {x0, x1, x2, x3};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float2 y = __ffma2_rn(x[i], make_float2(rstd[i], rstd[i]), E[slot]);
+                    dot2[i] = __ffma2_rn(make_float2(fabsf(y.x), fabsf(y.y)), W[slot], dot2[i]);
+                }
+            };
+            auto oct1 = [&](int slot, const uint32_t (&lo)[4], const uint32_t (&hi)[4]) {
+                oct(slot, make_float2(__uint_as_float(lo[0]), __uint_as_float(lo[1])), make_float2(__uint_as_float(lo[2]), __uint_as_float(lo[3])),
+                    make_float2(__uint_as_float(hi[0]), __uint_as_float(hi[1])), make_float2(__uint_as_float(hi[2]), __uint_as_float(hi[3])));
+            };
+            // octet sequence: half A 0..4, half B 0..3 (4): columns ca + 8 o | cbb + 8 o
+            loadp(0, ca); loadp(1, ca + 8);
+            tmem_wait();
+            if (prof) { t1 = clock64(); e_2b += t1 - t2; t2 = t1; }
+            tc_fence_before();
+            mbar_arrive(bar(D_H2AFREE));                                   // half A is in registers: the next tile's half A may start
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                oct(o & 1, TT_X4(alo, ahi, o, 0), TT_X4(alo, ahi, o, 1), TT_X4(alo, ahi, o, 2), TT_X4(alo, ahi, o, 3));
+                loadp(o & 1, o + 2 < 5 ? ca + 8 * (o + 2) : cbb + 8 * (o + 2 - 5));
+            }
+            tmem_ld16x256_x4(trow + (uint32_t)cbb, alo); tmem_ld16x256_x4(trow16 + (uint32_t)cbb, ahi);   // half B flies under the last octet of half A
+            oct1(0, tlo, thi);                                             // half A, octet 4
+            loadp(0, cbb + 8);
+            if (b5) { tmem_ld16x256_x1(trow + (uint32_t)(cbb + 32), tlo); tmem_ld16x256_x1(trow16 + (uint32_t)(cbb + 32), thi); }
+            tmem_wait();
+            tc_fence_before();
+            mbar_arrive(bar(D_H2BFREE));
+            if (prof) { t1 = clock64(); e_2c += t1 - t2; t2 = t1; }
+#pragma unroll
+            for (int o = 0; o < 4; o++) {                                  // half B, octets 0..3: parameter slots 1, 0, 1, 0
+                oct((o + 1) & 1, TT_X4(alo, ahi, o, 0), TT_X4(alo, ahi, o, 1), TT_X4(alo, ahi, o, 2), TT_X4(alo, ahi, o, 3));
+                if (o + 2 < 5) loadp((o + 1) & 1, cbb + 8 * (o + 2));
+            }
+            if (b5) oct1(1, tlo, thi);                                     // half B, octet 4 (groups 0, 1)
+            if (prof) { t1 = clock64(); e_2d += t1 - t2; t2 = t1; }
+            float dsel = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float s = dot2[i].x + dot2[i].y;
+                s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
+                dsel = tq == i ? s : dsel;
+            }
+            red3[(rw + 8 * tq) * kGroups + grp] = dsel;
+            if (prof) tw = clock64();
+            named_bar_sync(1, kEpiThreads);
+            if (prof) e_b2 += clock64() - tw;
+            if (grp == 0 && rw + 8 * tq < rows) {
+                const float4 s = *reinterpret_cast<const float4 *>(red3 + (rw + 8 * tq) * kGroups);
+                out[row0 + rw + 8 * tq] = tanhf(b3 + ((s.x + s.y) + (s.z + s.w)));
+            }
+            if (prof) { t1 = clock64(); e_2 += t1 - t0; t0 = t1; }
+        };
+#undef TT_X4
+#endif
 
         const int64_t first = blockIdx.x, G = gridDim.x;
         uint32_t c1 = 0, c2 = 0;
