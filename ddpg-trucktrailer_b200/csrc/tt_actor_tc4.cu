@@ -60,6 +60,15 @@
 namespace {
 
 constexpr int kP1A = TT_TC4_P1A;
+// A2 blocks the epilogue waits on (bit ch = block ch ends a run of blocks released together; bit 12 must be set): the
+// layer-2 issuer commits exactly these, epilogue 1 waits for a run's last block before it writes the run's first.
+#ifndef TT_TC4_A2WAITS
+#define TT_TC4_A2WAITS 0x1484      // blocks 2, 7, 10, 12
+#endif
+constexpr uint32_t kA2Waits = TT_TC4_A2WAITS;
+static_assert((kA2Waits >> (KB2 - 1)) == 1u, "the last A2 block must end the last run");
+__host__ __device__ constexpr bool a2_run_start(int ch) { return ch == 0 || ((kA2Waits >> (ch - 1)) & 1u); }
+__host__ __device__ constexpr int a2_run_end(int ch) { return ((kA2Waits >> ch) & 1u) ? ch : a2_run_end(ch + 1); }
 
 // ---- v4 layer-1 image, built at tt_actor_load time ----
 // rows 0..23   : L[k][j] (row j): lower Cholesky factor of Gc = sum_c (Wf[c] - m)(Wf[c] - m)^T, so that
@@ -422,7 +431,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                         umma(d, a, b, sweep ? idB : idA, kb ? 1u : 0u);
                         umma(d, a + 2, b + 2, sweep ? idB : idA, 1u);
                         if (kCluster == 1) umma_commit(bar(D_W2EMPTY + slot)); else umma_commit_mc(bar(D_W2EMPTY + slot), kMask);
-                        if (sweep && (kb == 2 || kb == 7 || kb == 10 || kb == 12)) umma_commit(bar(D_A2FREE + kb));   // A2 blocks <= kb may be overwritten (epilogue 1: a2wait)
+                        if (sweep && ((kA2Waits >> kb) & 1u)) umma_commit(bar(D_A2FREE + kb));   // A2 blocks <= kb may be overwritten (epilogue 1: a2wait)
                         if (kb == KB2 - 1) umma_commit(bar(sweep ? D_H2BFULL : D_H2AFULL));
                     }
                     __syncwarp();
@@ -606,9 +615,12 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                 }
                 const float rstd = rsqrtf((q2.x + q2.y) * (1.0f / H1) + 1e-5f);
                 rstd2 = make_float2(rstd, rstd);
-                a2wait(2);
 #pragma unroll
-                for (int c = 0; c < 3; c++) { if (c < 2) lde((c + 1) & 1, c + 1); emit(v[c], c, c & 1); }
+                for (int c = 0; c < 3; c++) {
+                    if (c < 2) lde((c + 1) & 1, c + 1);
+                    if (a2_run_start(c)) a2wait(a2_run_end(c));
+                    emit(v[c], c, c & 1);
+                }
             }
             if (p1a_pos == 0) { if (prof) { t1 = clock64(); e_1 += t1 - t0; } pass1a(c2); }
             {   // part 1: A2 blocks 3..7
@@ -622,9 +634,12 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                 tmem_wait();
                 tc_fence_before();
                 mbar_arrive(bar(D_WFREE));
-                a2wait(7);
 #pragma unroll
-                for (int c = 0; c < 5; c++) { if (c < 4) lde((c + 1) & 1, 4 + c); emit(v[c], 3 + c, c & 1); }
+                for (int c = 0; c < 5; c++) {
+                    if (c < 4) lde((c + 1) & 1, 4 + c);
+                    if (a2_run_start(3 + c)) a2wait(a2_run_end(3 + c));
+                    emit(v[c], 3 + c, c & 1);
+                }
             }
             if (p1a_pos == 1) { if (prof) { t1 = clock64(); e_1 += t1 - t0; } pass1a(c2); }
             {   // part 2: A2 blocks 8..11 and the 16 real columns of block 12 (groups 0, 1)
@@ -639,12 +654,13 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                 tmem_wait();
                 tc_fence_before();
                 mbar_arrive(bar(D_WFREE));
-                a2wait(10);
 #pragma unroll
-                for (int c = 0; c < 3; c++) { lde((c + 1) & 1, 9 + c); emit(v[c], 8 + c, c & 1); }
-                if (grp < 2) lde(0, 12);
-                a2wait(12);
-                emit(v[3], 11, 1);
+                for (int c = 0; c < 4; c++) {
+                    if (c < 3) lde((c + 1) & 1, 9 + c); else if (grp < 2) lde(0, 12);
+                    if (a2_run_start(8 + c)) a2wait(a2_run_end(8 + c));
+                    emit(v[c], 8 + c, c & 1);
+                }
+                if (a2_run_start(12)) a2wait(12);                          // (all groups wait: A2FULL below covers block 12 as well)
                 if (grp < 2) emit(v[4], 12, 0);
             }
             fence_proxy_async();
