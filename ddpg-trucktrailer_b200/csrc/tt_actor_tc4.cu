@@ -49,9 +49,6 @@
 #ifndef TT_TC4_P1A
 #define TT_TC4_P1A (TT_TC4_LEAD >= 9 ? 0 : TT_TC4_LEAD >= 6 ? 1 : 2)
 #endif
-#ifndef TT_TC4_TEAMS
-#define TT_TC4_TEAMS 0     // 1: warps 0-7 run epilogue 1, warps 8-15 epilogue 2 (two independent chains), each thread half a row
-#endif
 #ifndef TT_TC4_EPI2
 #define TT_TC4_EPI2 0      // epilogue 2: 0 = one row per thread (tcgen05.ld.32x32b; default), 1 = four rows x two columns per 8-column octet
                            // (16x256b: a quarter of the parameter-load wavefronts, but two shuffle reductions -- measured 1 % slower)
@@ -245,10 +242,9 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     if (threadIdx.x == 0) {
         *staged = 0u;
         mbar_init(bar(D_W1), 1);
-        constexpr int kTeam = TT_TC4_TEAMS ? kEpiThreads / 2 : kEpiThreads;     // threads that arrive on the epilogue-side barriers
-        mbar_init(bar(D_XFULL), kTeam); mbar_init(bar(D_WFULL), 1); mbar_init(bar(D_WFREE), kTeam);
-        mbar_init(bar(D_A2FULL), kTeam);
-        mbar_init(bar(D_H2AFULL), 1); mbar_init(bar(D_H2BFULL), 1); mbar_init(bar(D_H2AFREE), kTeam); mbar_init(bar(D_H2BFREE), kTeam);
+        mbar_init(bar(D_XFULL), kEpiThreads); mbar_init(bar(D_WFULL), 1); mbar_init(bar(D_WFREE), kEpiThreads);
+        mbar_init(bar(D_A2FULL), kEpiThreads);
+        mbar_init(bar(D_H2AFULL), 1); mbar_init(bar(D_H2BFULL), 1); mbar_init(bar(D_H2AFREE), kEpiThreads); mbar_init(bar(D_H2BFREE), kEpiThreads);
         for (int i = 0; i < P::kSlots; i++) { mbar_init(bar(D_W2FULL + i), 1); mbar_init(bar(D_W2EMPTY + i), kCluster); }
         for (int i = 0; i < KB2; i++) mbar_init(bar(D_A2FREE + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -443,7 +439,6 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             }
             if (prof && blockIdx.x == 0 && lane == 0) { dbg[0] = t_h2; dbg[1] = t_a2; dbg[2] = t_w2; dbg[3] = c2; }
         }
-#if !TT_TC4_TEAMS
     } else {
         // ================= epilogue warps: thread = (row, column group) =================
         const int grp = warp >> 2;
@@ -909,240 +904,6 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             dbg[15] = e_wf; dbg[16] = e_af; dbg[17] = e_b1; dbg[18] = e_b2;
         }
     }
-#else
-    } else {
-        // ================= epilogue warps, two teams =================
-        // warps 0-7: epilogue 1 (observation staging, layer-1 accumulators -> A2), warps 8-15: epilogue 2 (LayerNorm 2, ReLU, output).
-        // thread = (row, half h): 16 of every 32 columns.  The two chains only meet through the MMA warps' mbarriers, so the fixed
-        // hand-off latencies of one (mbarrier waits, TMEM round trips, block barriers) are covered by the work of the other.
-        const int team = warp >> 3, h = (warp >> 2) & 1;
-        const int r = (warp & 3) * 32 + lane;
-        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const int64_t first = blockIdx.x, G = gridDim.x;
-        constexpr int kTeamThreads = kEpiThreads / 2;
-        if (team == 0) {
-            const uint32_t xsw = (((uint32_t)r >> 1) & 3u);
-            const int nv = h ? IN - 16 : 16;                               // inputs 16 h .. 16 h + 15: k < 23 real, k = 23 the constant 1, rest 0
-            float xreg[16];
-            auto load_x = [&](int64_t tl) {
-                const int64_t gr = tl * kTileM + r;
-                const bool ok = gr < n;
-                const float *p = obs + gr * ld + 16 * h;
-#pragma unroll
-                for (int i = 0; i < 16; i++) xreg[i] = i < nv ? (ok ? __ldg(p + i) : 0.f) : ((h && i == nv) ? 1.0f : 0.f);
-            };
-            auto stage = [&]() {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float a = xreg[2 * i], b = xreg[2 * i + 1];
-                    const OpT ah = to_op<OpT>(a), bh = to_op<OpT>(b);
-                    hi[i] = (uint32_t)(*reinterpret_cast<const uint16_t *>(&ah)) | ((uint32_t)(*reinterpret_cast<const uint16_t *>(&bh)) << 16);
-                    lo[i] = pack2<OpT>(a - op_to_float(ah), b - op_to_float(bh));
-                }
-                tmem_st8(trow + (uint32_t)(kXCol0 + 8 * h), hi);
-                if (kSplit) tmem_st8(trow + (uint32_t)(kXCol0 + 16 + 8 * h), lo);
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(bar(D_XFULL));
-                if (threadIdx.x == 0) *staged = *staged + 1u;               // progress signal for the replay-store warp
-            };
-            uint32_t wuse = 0;
-            auto layer1 = [&](uint32_t c1) {
-                const uint32_t ph = c1 & 1u;
-                float2 rstd2 = make_float2(0.f, 0.f);
-                // 8 columns (chunk j of this thread's 16) of A2 block ch: relu(t' rstd + be1)
-                auto emit8 = [&](const uint32_t *v, int ch, int j) {
-                    const float *e = pbe1 + ch * 32 + 16 * h + 8 * j;
-                    const float4 e0 = *reinterpret_cast<const float4 *>(e), e1 = *reinterpret_cast<const float4 *>(e + 4);
-                    const float2 ee[4] = {make_float2(e0.x, e0.y), make_float2(e0.z, e0.w), make_float2(e1.x, e1.y), make_float2(e1.z, e1.w)};
-                    uint32_t pk4[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const float2 x = make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
-                        const float2 y = __ffma2_rn(x, rstd2, ee[q]);
-                        pk4[q] = pack2_relu<OpT>(y.x, y.y);
-                    }
-                    uint4 pk;
-                    pk.x = pk4[0]; pk.y = pk4[1]; pk.z = pk4[2]; pk.w = pk4[3];
-                    *reinterpret_cast<uint4 *>(sm + P::a2 + (size_t)ch * kTileM * kRowB + (size_t)r * kRowB + (((uint32_t)(2 * h + j) ^ xsw) << 4)) = pk;
-                };
-                auto emit16 = [&](const uint32_t (&v)[32], int ch) {
-                    if (a2_run_start(ch)) mbar_wait(bar(D_A2FREE + a2_run_end(ch)), ph ^ 1u);   // the previous tile's MMAs have read blocks <= run end
-                    emit8(v, ch, 0); emit8(v + 8, ch, 1);
-                };
-                const uint32_t wcol = trow + (uint32_t)(kWin0 + 16 * h);
-                uint32_t v[3][32];                                         // (tmem_ld16_async fills 16 registers and zeroes the rest: dead code)
-                {   // part 0: 32 statistic columns, then A2 blocks 0..2
-                    mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
-                    tc_fence_after();
-                    uint32_t sv[32];
-                    tmem_ld32_async(trow + kWin0, sv);
-                    tmem_wait();
-                    float2 q2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int q = 0; q < 12; q++) {
-                        const float2 x = make_float2(__uint_as_float(sv[2 * q]), __uint_as_float(sv[2 * q + 1]));
-                        q2 = __ffma2_rn(x, x, q2);
-                    }
-                    const float rstd = rsqrtf((q2.x + q2.y) * (1.0f / H1) + 1e-5f);
-                    rstd2 = make_float2(rstd, rstd);
-#pragma unroll
-                    for (int c = 0; c < 3; c++) tmem_ld16_async(wcol + 32 + 32 * c, v[c]);
-                    tmem_wait();
-                    tc_fence_before();
-                    mbar_arrive(bar(D_WFREE));
-#pragma unroll
-                    for (int c = 0; c < 3; c++) emit16(v[c], c);
-                }
-                {   // part 1: A2 blocks 3..5, then 6..7
-                    mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < 3; c++) tmem_ld16_async(wcol + 32 * c, v[c]);
-                    tmem_wait();
-#pragma unroll
-                    for (int c = 0; c < 3; c++) emit16(v[c], 3 + c);
-#pragma unroll
-                    for (int c = 0; c < 2; c++) tmem_ld16_async(wcol + 32 * (3 + c), v[c]);
-                    tmem_wait();
-                    tc_fence_before();
-                    mbar_arrive(bar(D_WFREE));
-#pragma unroll
-                    for (int c = 0; c < 2; c++) emit16(v[c], 6 + c);
-                }
-                {   // part 2: A2 blocks 8..10, then 11 and the 16 real columns of block 12 (h == 0)
-                    mbar_wait(bar(D_WFULL), wuse & 1u); wuse++;
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < 3; c++) tmem_ld16_async(wcol + 32 * c, v[c]);
-                    tmem_wait();
-#pragma unroll
-                    for (int c = 0; c < 3; c++) emit16(v[c], 8 + c);
-                    tmem_ld16_async(wcol + 96, v[0]);
-                    if (h == 0) tmem_ld16_async(wcol + 128, v[1]);
-                    tmem_wait();
-                    tc_fence_before();
-                    mbar_arrive(bar(D_WFREE));
-                    emit16(v[0], 11);
-                    if (a2_run_start(12)) mbar_wait(bar(D_A2FREE + 12), ph ^ 1u);
-                    if (h == 0) { emit8(v[1], 12, 0); emit8(v[1] + 8, 12, 1); }
-                }
-                fence_proxy_async();
-                mbar_arrive(bar(D_A2FULL));
-            };
-            if (first < ntiles) {
-                load_x(first);
-                stage(); load_x(first + G);
-                uint32_t c1 = 0;
-                for (int64_t tl = first; tl < ntiles; tl += G) {
-                    layer1(c1++);
-                    if (tl + G < ntiles) { stage(); load_x(tl + 2 * G); }
-                }
-            }
-        } else {
-            // ---------- epilogue 2: columns [80 h, 80 h + 80) of half A and [160 + 72 h, + 72) of half B, in rounds of 40 / 36 ----------
-            const int ca = 80 * h, cb = kNA + 72 * h;
-            float2 q2 = make_float2(0.f, 0.f);
-            auto acc = [&](const uint32_t *v, int cnt) {
-#pragma unroll
-                for (int q = 0; q < cnt / 2; q++) {
-                    const float2 x = make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
-                    q2 = __ffma2_rn(x, x, q2);
-                }
-            };
-            auto pass1a = [&](uint32_t c2) {
-                mbar_wait(bar(D_H2AFULL), c2 & 1u);
-                tc_fence_after();
-                q2 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int rd = 0; rd < 2; rd++) {
-                    uint32_t va[32], vt[8];
-                    tmem_ld32_async(trow + (uint32_t)(ca + 40 * rd), va);
-                    tmem_ld8_async(trow + (uint32_t)(ca + 40 * rd + 32), vt);
-                    tmem_wait();
-                    acc(va, 32); acc(vt, 8);
-                }
-            };
-            auto layer2 = [&](int64_t tile, uint32_t c2) {
-                const uint32_t ph = c2 & 1u;
-                const int64_t row0 = tile * kTileM;
-                const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
-                mbar_wait(bar(D_H2BFULL), ph);
-                tc_fence_after();
-                uint32_t va[32], vt[8], vq[4];
-                float lin = 0.f;                                           // columns 300, 301: the linear half of the output dot (hi + lo)
-#pragma unroll
-                for (int rd = 0; rd < 2; rd++) {
-                    tmem_ld32_async(trow + (uint32_t)(cb + 36 * rd), va);
-                    tmem_ld4_async(trow + (uint32_t)(cb + 36 * rd + 32), vq);
-                    tmem_wait();
-                    if (rd == 1 && h == 1) { lin = __uint_as_float(vq[0]) + __uint_as_float(vq[1]); vq[0] = 0u; vq[1] = 0u; }
-                    acc(va, 32); acc(vq, 4);
-                }
-                red1[h * kTileM + r] = q2.x + q2.y;
-                tmem_ld32_async(trow + (uint32_t)ca, va);                  // pass 2, half A round 0: in flight during the exchange
-                tmem_ld8_async(trow + (uint32_t)(ca + 32), vt);
-                named_bar_sync(1, kTeamThreads);
-                const float rstd = rsqrtf((red1[r] + red1[kTileM + r]) * (1.0f / H2) + 1e-5f);
-                const float2 rstd2 = make_float2(rstd, rstd);
-                float2 dot2 = make_float2(rstd * lin, 0.f);
-                // pass 2 over 38 column quads (20 of half A, 18 of half B), parameters two quads ahead
-                constexpr int kQA = 20, kQ = 38;
-                float4 E[2], W[2];
-                auto qcol = [&](int qi) { return qi < kQA ? ca + 4 * qi : cb + 4 * (qi - kQA); };
-                auto loadp = [&](int slot, int qi) {
-                    const int c = qcol(qi);
-                    E[slot] = lds128_early(pbe2 + c); W[slot] = lds128_early(pw3 + c);
-                };
-                auto quad = [&](int qi, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
-                    const int slot = qi & 1;
-                    const float2 xa = make_float2(__uint_as_float(x0), __uint_as_float(x1)), xb = make_float2(__uint_as_float(x2), __uint_as_float(x3));
-                    const float2 ya = __ffma2_rn(xa, rstd2, make_float2(E[slot].x, E[slot].y));
-                    const float2 yb = __ffma2_rn(xb, rstd2, make_float2(E[slot].z, E[slot].w));
-                    dot2 = __ffma2_rn(make_float2(fabsf(ya.x), fabsf(ya.y)), make_float2(W[slot].x, W[slot].y), dot2);
-                    dot2 = __ffma2_rn(make_float2(fabsf(yb.x), fabsf(yb.y)), make_float2(W[slot].z, W[slot].w), dot2);
-                    if (qi + 2 < kQ) loadp(slot, qi + 2);
-                };
-                loadp(0, 0); loadp(1, 1);
-                tmem_wait();
-                // half A, round 0 (quads 0..9); round 1's loads are issued as the registers become free
-#pragma unroll
-                for (int q = 0; q < 8; q++) quad(q, va[4 * q], va[4 * q + 1], va[4 * q + 2], va[4 * q + 3]);
-                tmem_ld32_async(trow + (uint32_t)(ca + 40), va);
-#pragma unroll
-                for (int q = 0; q < 2; q++) quad(8 + q, vt[4 * q], vt[4 * q + 1], vt[4 * q + 2], vt[4 * q + 3]);
-                tmem_ld8_async(trow + (uint32_t)(ca + 72), vt);
-                tmem_wait();
-                tc_fence_before();
-                mbar_arrive(bar(D_H2AFREE));                               // all of half A is in registers: the next tile's half A may start
-#pragma unroll
-                for (int q = 0; q < 8; q++) quad(10 + q, va[4 * q], va[4 * q + 1], va[4 * q + 2], va[4 * q + 3]);
-                tmem_ld32_async(trow + (uint32_t)cb, va);                  // half B, round 0
-#pragma unroll
-                for (int q = 0; q < 2; q++) quad(18 + q, vt[4 * q], vt[4 * q + 1], vt[4 * q + 2], vt[4 * q + 3]);
-                tmem_ld4_async(trow + (uint32_t)(cb + 32), vq);
-                tmem_wait();
-#pragma unroll
-                for (int q = 0; q < 8; q++) quad(20 + q, va[4 * q], va[4 * q + 1], va[4 * q + 2], va[4 * q + 3]);
-                tmem_ld32_async(trow + (uint32_t)(cb + 36), va);           // half B, round 1
-                quad(28, vq[0], vq[1], vq[2], vq[3]);
-                tmem_ld4_async(trow + (uint32_t)(cb + 68), vq);
-                tmem_wait();
-                tc_fence_before();
-                mbar_arrive(bar(D_H2BFREE));
-#pragma unroll
-                for (int q = 0; q < 8; q++) quad(29 + q, va[4 * q], va[4 * q + 1], va[4 * q + 2], va[4 * q + 3]);
-                quad(37, vq[0], vq[1], vq[2], vq[3]);
-                red3[h * kTileM + r] = dot2.x + dot2.y;
-                named_bar_sync(1, kTeamThreads);
-                if (h == 0 && r < rows) out[row0 + r] = tanhf(b3 + red3[r] + red3[kTileM + r]);
-            };
-            uint32_t c2 = 0;
-            for (int64_t tl = first; tl < ntiles; tl += G) { pass1a(c2); layer2(tl, c2++); }
-        }
-    }
-#endif
     // ---------------- teardown ----------------
     __syncwarp();
     tc_fence_before();
