@@ -162,15 +162,17 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, f
     return *reinterpret_cast<uint32_t *>(&p);
 }
 
-// round two floats to the operand type and apply ReLU on the packed pair (exactly relu-then-round: rounding is monotonic)
+// ReLU and round two floats to the packed operand type in ONE instruction (F2FP.RELU...PACK_AB; NaN stays NaN like torch's relu)
 template <typename OpT> __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi);
 template <> __device__ __forceinline__ uint32_t pack2_relu<__half>(float lo, float hi) {
-    __half2 p = __hmax2(__floats2half2_rn(lo, hi), __float2half2_rn(0.f));
-    return *reinterpret_cast<uint32_t *>(&p);
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 template <> __device__ __forceinline__ uint32_t pack2_relu<__nv_bfloat16>(float lo, float hi) {
-    __nv_bfloat162 p = __hmax2(__floats2bfloat162_rn(lo, hi), __float2bfloat162_rn(0.f));
-    return *reinterpret_cast<uint32_t *>(&p);
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
 }  // namespace
