@@ -307,19 +307,17 @@ def run_b200(args):
     cur, nxt = env._obs[env._cur], env._obs[env._cur ^ 1]
     m = agent.memory
     prec = _lib.PRECISIONS[args.precision]
-    mask = (torch.rand(N, device=dev) < 1.0 / 70).to(torch.uint8)
     import ctypes as C
     ring = _lib.ReplayRing(m.state_memory.data_ptr(), m.action_memory.data_ptr(), m.reward_memory.data_ptr(),
                            m.new_state_memory.data_ptr(), m.terminal_memory.data_ptr(), m.mem_size, m.mem_cntr)
     rp = C.byref(ring)
-    # the kernels of one tt_rollout_step, each timed alone: the replay store is fused into the three producers
+    # the two kernels of one tt_rollout_step, each timed alone (the replay store, the OU noise, the reset of finished envs
+    # and the iteration tick are fused into them)
     kern = {
-        "actor": lambda: _lib.check(L.tt_actor_forward_store(agent.actor._h, cur.data_ptr(), env.ld_obs, N, eng.action.data_ptr(), prec, rp, s)),
-        "ou_scale": lambda: _lib.check(L.tt_ou_step_store(agent.noise.x_prev.data_ptr(), eng.action.data_ptr(), eng.scaled.data_ptr(), N, 27, offset,
-                                                          agent.noise.iter_ptr, 0, rp, s)),
-        "env_step": lambda: _lib.check(L.tt_env_step_store(env._h, eng.scaled.data_ptr(), nxt.data_ptr(), env.ld_obs, env._reward.data_ptr(),
-                                                           env._done.data_ptr(), rp, s)),
-        "env_reset": lambda: _lib.check(L.tt_env_reset(env._h, mask.data_ptr(), nxt.data_ptr(), env.ld_obs, s)),
+        "actor": lambda: _lib.check(L.tt_actor_choose_action(agent.actor._h, cur.data_ptr(), env.ld_obs, N, agent.noise.x_prev.data_ptr(), 27, offset,
+                                                             agent.noise.iter_ptr, 0, eng.action.data_ptr(), eng.scaled.data_ptr(), prec, rp, s)),
+        "env_step": lambda: _lib.check(L.tt_env_step_reset(env._h, eng.scaled.data_ptr(), nxt.data_ptr(), env.ld_obs, env._reward.data_ptr(),
+                                                           env._done.data_ptr(), agent.noise.x_prev.data_ptr(), rp, s)),
         # for reference only (NOT part of the fused rollout): the stand-alone ring scatter kernel
         "replay_store_standalone": lambda: _lib.check(L.tt_replay_store(m.state_memory.data_ptr(), m.action_memory.data_ptr(), m.reward_memory.data_ptr(),
                                                              m.new_state_memory.data_ptr(), m.terminal_memory.data_ptr(), m.mem_size, m.mem_cntr,
@@ -341,17 +339,16 @@ def run_b200(args):
             evs.append((e0, e1))
         torch.cuda.synchronize()
         kms[name] = sum(a.elapsed_time(b) for a, b in evs) / K
-    # algorithmic work per launch: env step 229 B + its share of the fused store (s', r, done: 97 B); OU 16 B + 4 B
+    # algorithmic work per launch: env step 229 B + its share of the fused store (s', r, done: 97 B)
     algo = {"actor": ("tensor", N * ACTOR_FLOPS / 1e12), "env_step": ("hbm", N * (ENV_BYTES + 97) / 1e9),
-            "ou_scale": ("hbm", N * (OU_BYTES + 4) / 1e9), "replay_store_standalone": ("hbm", N * STORE_BYTES / 1e9)}
+            "replay_store_standalone": ("hbm", N * STORE_BYTES / 1e9)}
     kernels = {}
     for name, (bound, work) in algo.items():
         peak = pk["hbm"] if bound == "hbm" else pk["tf_sust"]     # kernels timed inside the running rollout: sustained figure
         ach = work / (kms[name] * 1e-3)
         kernels[name] = {"ms": kms[name], "bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
                          "frac": ach / peak}
-    kernels["env_reset"] = {"ms": kms["env_reset"]}
-    in_step = ["actor", "ou_scale", "env_step", "env_reset"]
+    in_step = ["actor", "env_step"]
     dom = max([k for k in algo if k in in_step], key=lambda n: kms[n])
     try:      # DRAM bytes per env from the committed `ncu --set full` capture (profiles/), scaled to this launch
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:

@@ -12,8 +12,26 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 TT_OBS_DIM = 23
 TT_NCOMP = 10
 TT_NSTATS = 16
-TT_PREC_FP32, TT_PREC_BF16, TT_PREC_F16, TT_PREC_F16_PLAIN = 0, 1, 2, 3
-PRECISIONS = {"fp32": 0, "bf16": 1, "f16": 2, "fp16": 2, "f16_plain": 3, 0: 0, 1: 1, 2: 2, 3: 3}
+TT_PREC_FP32, TT_PREC_BF16, TT_PREC_F16, TT_PREC_F16_PLAIN, TT_PREC_AUTO = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": 0, "bf16": 1, "f16": 2, "fp16": 2, "f16_plain": 3, "auto": 4, 0: 0, 1: 1, 2: 2, 3: 3, 4: 4}
+
+# Tensor-core modes whose worst-case error on strongly amplified "trained-like" weights exceeds north_star's 1e-3 bar
+# (plain 16-bit operands: 1.2e-3 f16_plain, 1e-2 bf16; tests/test_gpu_agent.py).  They are faster, and within the bar on
+# reference-scale weights, but the Python classes refuse them unless the caller passes allow_out_of_bar=True.
+OUT_OF_BAR = ("bf16", "f16_plain")
+
+
+def resolve_precision(precision, allow_out_of_bar=False):
+    """Name or code -> (name, TT_PREC_* code); raises for modes outside the accuracy bar unless explicitly allowed."""
+    names = {0: "fp32", 1: "bf16", 2: "f16", 3: "f16_plain", 4: "auto", "fp16": "f16"}
+    name = names.get(precision, precision)
+    if name not in PRECISIONS:
+        raise ValueError(f"unknown precision {precision!r}")
+    if name in OUT_OF_BAR and not allow_out_of_bar:
+        raise ValueError(f"precision {name!r} does not hold the 1e-3 actor bar on strongly amplified weights; "
+                         f"pass allow_out_of_bar=True to use it anyway, or use 'f16' / 'auto' / 'fp32'")
+    return name, PRECISIONS[name]
+
 
 COMP_NAMES = ("distance_reward", "progress_reward", "heading_reward", "orientation_reward", "staged_success",
               "safety_penalty", "exploration_bonus", "final_success_bonus", "backward_penalty", "smoothness_penalty")
@@ -80,12 +98,15 @@ SYMBOLS = {
     "tt_actor_destroy": (C.c_int, [_P]),
     "tt_actor_load": (C.c_int, [_P] + [_P] * 10 + [_P]),
     "tt_actor_forward": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, _P]),
+    "tt_actor_auto_precision": (C.c_int, [_P, _I64]),
+    "tt_actor_choose_action": (C.c_int, [_P, _P, _I64, _I64, _P, _U64, _U64, _P, _I32, _P, _P, _I32, C.POINTER(ReplayRing), _P]),
     "tt_scale_action": (C.c_int, [_P, _P, _I64, _P]),
     "tt_replay_store": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P]),
     "tt_replay_gather": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "tt_actor_forward_store": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, C.POINTER(ReplayRing), _P]),
     "tt_ou_step_store": (C.c_int, [_P, _P, _P, _I64, _U64, _U64, _P, _I32, C.POINTER(ReplayRing), _P]),
     "tt_env_step_store": (C.c_int, [_P, _P, _P, _I64, _P, _P, C.POINTER(ReplayRing), _P]),
+    "tt_env_step_reset": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, C.POINTER(ReplayRing), _P]),
     "tt_rollout_step": (C.c_int, [_P, _P, C.POINTER(RolloutBufs), _I32, _I32, _P]),
 }
 

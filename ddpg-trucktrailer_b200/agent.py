@@ -84,10 +84,16 @@ class CudaActor:
     def state_dict(self):
         return {k: v.detach().clone() for k, v in self._sd.items()}
 
-    def forward(self, obs, out=None, precision="fp32"):
+    def auto_precision(self, n):
+        """What precision="auto" resolves to for a batch of n rows: "f16" (tcgen05 tiles) once the batch is a real dense
+        contraction, "fp32" (warp-level FMA) below."""
+        return {0: "fp32", 2: "f16"}[self.L.tt_actor_auto_precision(self._h, int(n))]
+
+    def forward(self, obs, out=None, precision="fp32", allow_out_of_bar=False):
         """tanh(mu(relu(LN(fc2(relu(LN(fc1(obs)))))))) -> [n] float32 (networks.py:138-147).
-        precision: "fp32" (CUDA cores, <=1e-5), "f16" (tcgen05, fp16 operands + exact first layer, <=1e-3), "f16_plain"
-        (tcgen05, plain fp16 operands, 10 % faster) or "bf16" (tcgen05, plain bf16 operands)."""
+        precision: "fp32" (CUDA cores, <=1e-5), "f16" (tcgen05, fp16 operands + exact first layer, <=1e-3), "auto" (one of
+        those two by batch size); with ``allow_out_of_bar=True`` also "f16_plain" / "bf16" (tcgen05, plain 16-bit operands:
+        faster, but above the 1e-3 bar on strongly amplified weights)."""
         with torch.cuda.device(self.device):
             if obs.dim() == 1:
                 obs = obs.reshape(1, -1)
@@ -96,7 +102,7 @@ class CudaActor:
             n = obs.shape[0]
             if out is None:
                 out = torch.empty(n, dtype=torch.float32, device=self.device)
-            prec = PRECISIONS[precision]
+            _, prec = _lib.resolve_precision(precision, allow_out_of_bar)
             check(self.L.tt_actor_forward(self._h, obs.data_ptr(), obs.stride(0), n, out.data_ptr(), prec, stream_ptr()))
         return out
 
@@ -131,7 +137,8 @@ class VecAgent:
     """``Agent`` (DDPG/DDPG_agent.py:9-52) for ``num_envs`` environments; same constructor arguments."""
 
     def __init__(self, alpha, beta, input_dims, tau, n_actions, gamma=0.99, max_size=1000000, fc1_dims=400, fc2_dims=300,
-                 batch_size=64, num_envs=1, device=None, seed=27, global_env_offset=0, precision="fp32", actor_seed=None):
+                 batch_size=64, num_envs=1, device=None, seed=27, global_env_offset=0, precision="auto", actor_seed=None,
+                 allow_out_of_bar=False):
         _lib.require_cuda()
         self.L = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -140,7 +147,8 @@ class VecAgent:
         if n_actions != 1:
             raise ValueError("the CUDA actor is specialised to n_actions == 1 (simv2 action space)")
         self.num_envs = int(num_envs)
-        self.precision = precision
+        self.allow_out_of_bar = bool(allow_out_of_bar)
+        self.precision, _ = _lib.resolve_precision(precision, self.allow_out_of_bar)
         self.memory = DeviceReplayBuffer(max_size, (in_dim,), n_actions, device=self.device)
         self.noise = OUNoiseState(self.num_envs, self.device, seed, global_env_offset)
         self.actor = CudaActor(in_dim, fc1_dims, fc2_dims, device=self.device)
@@ -149,17 +157,26 @@ class VecAgent:
         self._learner = None
 
     def choose_action(self, observation, evaluate=False):
-        """DDPG_agent.py:36-49: mu(obs) + OU noise (unless ``evaluate``); returns the UNCLIPPED action [N,1]."""
+        """DDPG_agent.py:36-49: mu(obs) + OU noise (unless ``evaluate``); returns the UNCLIPPED action [N,1].  One launch
+        (``tt_actor_choose_action``: the noise is added in the actor kernel's output stage).  ``observation`` must hold one row
+        per environment: the OU state is per env."""
         with torch.cuda.device(self.device):
             obs = torch.as_tensor(observation, device=self.device)
             single = obs.dim() == 1
-            mu = self.actor.forward(obs, out=self._action, precision=self.precision)
-            if not evaluate:
-                n = self.noise
-                check(self.L.tt_ou_step(n.x_prev.data_ptr(), mu.data_ptr(), None, mu.numel(), n.seed, n.global_env_offset,
-                                        n.iter_ptr, stream_ptr()))
-                if n._own_iter:
-                    n._iter += 1
+            if single:
+                obs = obs.reshape(1, -1)
+            if obs.shape[0] != self.num_envs:
+                raise ValueError(f"choose_action: got {obs.shape[0]} observation rows for {self.num_envs} environments")
+            if obs.dtype != torch.float32 or obs.stride(1) != 1:
+                obs = obs.to(torch.float32).contiguous()
+            n = self.noise
+            _, prec = _lib.resolve_precision(self.precision, self.allow_out_of_bar)
+            check(self.L.tt_actor_choose_action(self.actor._h, obs.data_ptr(), obs.stride(0), self.num_envs, n.x_prev.data_ptr(), n.seed,
+                                                n.global_env_offset, n.iter_ptr, int(evaluate), self._action.data_ptr(), None, prec,
+                                                None, stream_ptr()))
+            if not evaluate and n._own_iter:
+                n._iter += 1
+            mu = self._action
         return mu.reshape(-1) if single else mu.reshape(-1, 1)
 
     @staticmethod

@@ -49,9 +49,10 @@
 #ifndef TT_TC4_P1A
 #define TT_TC4_P1A (TT_TC4_LEAD >= 9 ? 0 : TT_TC4_LEAD >= 6 ? 1 : 2)
 #endif
-#ifndef TT_TC4_EPI2
-#define TT_TC4_EPI2 0      // epilogue 2: 0 = one row per thread (tcgen05.ld.32x32b; default), 1 = four rows x two columns per 8-column octet
-                           // (16x256b: a quarter of the parameter-load wavefronts, but two shuffle reductions -- measured 1 % slower)
+// The timing-only ablations and the per-phase cycle counters exist only in the developer build (-DTT_DEV_VARIANTS,
+// profiles/build_variants.sh); the product library carries neither.
+#if !defined(TT_DEV_VARIANTS)
+#undef TT_ABLATE
 #endif
 #ifndef TT_ABLATE
 #define TT_ABLATE 0
@@ -200,7 +201,7 @@ struct Plan4 {
 };
 
 enum { D_W1 = 0, D_XFULL, D_WFULL, D_WFREE, D_A2FULL, D_H2AFULL, D_H2BFULL, D_H2AFREE, D_H2BFREE,
-       D_W2FULL, D_W2EMPTY = D_W2FULL + 6, D_A2FREE = D_W2EMPTY + 6, D_COUNT = D_A2FREE + KB2 };
+       D_W2FULL, D_W2EMPTY = D_W2FULL + 6, D_A2FREE = D_W2EMPTY + 6, D_NOISE = D_A2FREE + KB2, D_COUNT = D_NOISE + 4 };
 static_assert(D_COUNT <= 40, "barrier table");
 
 // kProf: per-phase cycle counters of block 0 (profiles/tc_phase_profile.py); compiled out of the production instantiation
@@ -212,7 +213,7 @@ static_assert(D_COUNT <= 40, "barrier table");
 template <typename OpT, bool kSplit, bool kProf, int kCluster>
 __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restrict__ w1img, const char *__restrict__ w2img,
                                                            tt_actor_dev A, const float *__restrict__ obs, int64_t ld, int64_t n,
-                                                           float *__restrict__ out, TTRingS ring,
+                                                           float *__restrict__ out, TTRingS ring, TTActorTail tail,
                                                            unsigned long long *__restrict__ dbg) {
     using P = Plan4<kSplit>;
     constexpr int kGroups = 4, kEpiThreads = 512, kThreads = 640;
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         mbar_init(bar(D_H2AFULL), 1); mbar_init(bar(D_H2BFULL), 1); mbar_init(bar(D_H2AFREE), kEpiThreads); mbar_init(bar(D_H2BFREE), kEpiThreads);
         for (int i = 0; i < P::kSlots; i++) { mbar_init(bar(D_W2FULL + i), 1); mbar_init(bar(D_W2EMPTY + i), kCluster); }
         for (int i = 0; i < KB2; i++) mbar_init(bar(D_A2FREE + i), 1);
+        for (int i = 0; i < 4; i++) mbar_init(bar(D_NOISE + i), 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kM2Warp) {
@@ -324,12 +326,30 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         // It follows the epilogue's staging counter, so its reads of a tile come right after the epilogue's own prefetch of
         // the same rows and hit L2 (unsynchronised, this warp ran far ahead and every observation row was fetched from
         // DRAM twice: 743 MB instead of 386 MB per launch at N = 2^22).
-        if (ring.S) {
+        // ... and the Ornstein-Uhlenbeck noise of the tile's rows (DDPG/noise.py:12-17): x <- x + theta (0 - x) dt + sigma
+        // sqrt(dt) N(0, 1), four rows per lane, written back to the OU state array; the output stage of the epilogue (group 0)
+        // picks x up from there (D_NOISE: one of four mbarriers per tile, this warp is never more than three tiles ahead of
+        // the output stage because it follows the staging counter) and adds it to mu (DDPG_agent.py:41-43).  The Philox
+        // rounds run on this otherwise idle warp instead of on the epilogue's critical path.
+        if (ring.S || tail.ou_x) {
             uint32_t j = 0;
+            const uint32_t titer = tail.ou_x ? *tail.iter : 0u;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, j++) {
                 while (*staged <= j) __nanosleep(200);
                 const int64_t row0 = tile * kTileM;
                 const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
+                if (tail.ou_x) {
+                    float xv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { const int rr = lane + 32 * i; xv[i] = rr < rows ? __ldcg(tail.ou_x + row0 + rr) : 0.f; }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int rr = lane + 32 * i;
+                        if (rr < rows) __stcg(tail.ou_x + row0 + rr, ttm::ou_advance(xv[i], ttm::rng_normal_ks(tail.keys, tail.gid0 + (uint32_t)(row0 + rr), titer)));
+                    }
+                    mbar_arrive(bar(D_NOISE + (j & 3u)));              // release: this lane's stores are visible to the waiting epilogue threads
+                }
+                if (!ring.S) continue;
                 const int64_t rrow0 = ring.m.row(row0);
                 const float *src = obs + row0 * ld;
                 float *dst = ring.S + rrow0 * IN;
@@ -482,7 +502,6 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             if (prof) { t1 = clock64(); e_st += t1 - t0; }
         };
 
-#if TT_TC4_EPI2 == 0
         // layer-2 side of one tile: LayerNorm + ReLU over H2, dot with mu.weight, tanh.  Column group g owns columns
         // [40 g, 40 g + 40) of half A and [160 + 36 g, 160 + 36 g + 36) of half B.
         const int ca = 40 * grp, cbb = kNA + 36 * grp;
@@ -508,55 +527,6 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             acc(va, 32); acc(vt, 8);
             if (prof) { t1 = clock64(); e_pa += t1 - t0; t0 = t1; }
         };
-#else
-        // layer-2 side of one tile: LayerNorm + ReLU over H2, dot with mu.weight, tanh -- tcgen05.ld.16x256b mapping
-        // (profiles/ld_shape_probe.cu): a thread (lane quarter q = warp % 4, lane t, column group grp) owns the FOUR rows
-        // 32 q + t / 4 + 8 i (i = 0..3) and, of every 8-column octet of its group's ranges, the TWO columns 2 (t % 4), + 1.  One
-        // 8-byte parameter load then serves four rows (a quarter of the shared-memory wavefronts of the row-per-thread mapping;
-        // the four threads of a row combine their partial sums with two shuffles).
-        // Octets per group: half A 5 each (40 columns); half B 5, 5, 4, 4 (144 columns; columns 300, 301 -- group 3, t % 4 == 2 of
-        // its last octet -- are the linear half of the output dot, see the pack).
-        const int tq = lane & 3;
-        const int rw = (warp & 3) * 32 + (lane >> 2);                      // first of this thread's four rows (+ 8 i)
-        const int ca = 40 * grp, cbb = kNA + (grp < 2 ? 40 * grp : 80 + 32 * (grp - 2));
-        const bool b5 = grp < 2;                                           // half B: 5 octets (else 4)
-        const bool islin = grp == kGroups - 1 && tq == 2;
-        const uint32_t trow16 = trow + (16u << 16);
-        float q4[4];                                                       // per-row sum of squares of this thread's columns
-        // value pair of row i (0..3) in octet j (0..3) of a 4-octet load pair (lo: rows +0, +8; hi: rows +16, +24)
-#define TT_X4(lo, hi, j, i) make_float2(__uint_as_float(((i) < 2 ? lo : hi)[4 * (j) + 2 * ((i) & 1)]), __uint_as_float(((i) < 2 ? lo : hi)[4 * (j) + 2 * ((i) & 1) + 1]))
-        auto acc4 = [&](const uint32_t (&lo)[16], const uint32_t (&hi)[16], float2 (&q)[4], int noct) {
-            if (TT_ABLATE & 8) return;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-#pragma unroll
-                for (int i = 0; i < 4; i++) if (j < noct) { const float2 x = TT_X4(lo, hi, j, i); q[i] = __ffma2_rn(x, x, q[i]); }
-        };
-        auto acc1 = [&](const uint32_t (&lo)[4], const uint32_t (&hi)[4], float2 (&q)[4]) {
-            if (TT_ABLATE & 8) return;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t *s = i < 2 ? lo : hi;
-                const float2 x = make_float2(__uint_as_float(s[2 * (i & 1)]), __uint_as_float(s[2 * (i & 1) + 1]));
-                q[i] = __ffma2_rn(x, x, q[i]);
-            }
-        };
-        auto pass1a = [&](uint32_t c2) {                                   // statistics of half A (runs under the rest of half B)
-            if (prof) t0 = clock64();
-            mbar_wait(bar(D_H2AFULL), c2 & 1u);
-            if (prof) { t1 = clock64(); e_wa += t1 - t0; t0 = t1; }
-            tc_fence_after();
-            uint32_t alo[16], ahi[16], tlo[4], thi[4];
-            tmem_ld16x256_x4(trow + (uint32_t)ca, alo); tmem_ld16x256_x4(trow16 + (uint32_t)ca, ahi);
-            tmem_ld16x256_x1(trow + (uint32_t)(ca + 32), tlo); tmem_ld16x256_x1(trow16 + (uint32_t)(ca + 32), thi);
-            tmem_wait();
-            float2 q[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-            acc4(alo, ahi, q, 4); acc1(tlo, thi, q);
-#pragma unroll
-            for (int i = 0; i < 4; i++) q4[i] = q[i].x + q[i].y;
-            if (prof) { t1 = clock64(); e_pa += t1 - t0; t0 = t1; }
-        };
-#endif
 
         // layer-1 side of one tile: statistics -> rstd, then the 3 parts -> A2.  c1 = layer-1 tile counter
         // `with_p1a`: run the statistics pass over half A of the layer-2 tile c2 between part 0 and part 1 -- it fills the
@@ -668,7 +638,6 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             if (prof) { t1 = clock64(); e_1 += t1 - t0; t0 = t1; }
         };
 
-#if TT_TC4_EPI2 == 0
         auto layer2 = [&](int64_t tile, uint32_t c2) {
             const uint32_t ph = c2 & 1u;
             const int64_t row0 = tile * kTileM;
@@ -747,6 +716,11 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
             quad((kQ - 1) & 1, vq[0], vq[1], vq[2], vq[3]);                // columns cbb + 32 .. cbb + 35
             if (prof) { t1 = clock64(); e_2d += t1 - t2; t2 = t1; }
             red3[grp * kTileM + r] = dot2.x + dot2.y;
+            float noise = 0.f;                                             // this row's OU state, advanced by the copy warp (see there)
+            if (grp == 0 && tail.ou_x) {
+                mbar_wait(bar(D_NOISE + (c2 & 3u)), (c2 >> 2) & 1u);
+                if (r < rows) noise = __ldcg(tail.ou_x + row0 + r);
+            }
             if (prof) tw = clock64();
             named_bar_sync(1, kEpiThreads);
             if (prof) e_b2 += clock64() - tw;
@@ -754,125 +728,15 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
                 float d = b3;
 #pragma unroll
                 for (int g = 0; g < kGroups; g++) d += red3[g * kTileM + r];
-                out[row0 + r] = tanhf(d);
+                const float a = tanhf(d) + noise;                          // DDPG_agent.py:41-43: mu + noise, unclipped
+                const int64_t row = row0 + r;
+                out[row] = a;
+                if (tail.scaled) tail.scaled[row] = fminf(fmaxf(a, -1.0f), 1.0f) * 0.78539819f;    // trainv2.py:516
+                if (tail.ring.A && row >= tail.ring.m.first) tail.ring.A[tail.ring.m.row(row)] = a;  // agent.remember keeps the raw action
             }
             if (prof) { t1 = clock64(); e_2 += t1 - t0; t0 = t1; }
         };
 
-#else
-        auto layer2 = [&](int64_t tile, uint32_t c2) {
-            const uint32_t ph = c2 & 1u;
-            const int64_t row0 = tile * kTileM;
-            const int rows = (int)((n - row0) < kTileM ? (n - row0) : kTileM);
-            if (prof) t0 = clock64();
-            mbar_wait(bar(D_H2BFULL), ph);
-            if (prof) { t1 = clock64(); e_wb += t1 - t0; t0 = t1; }
-            tc_fence_after();
-            uint32_t alo[16], ahi[16], tlo[4], thi[4];
-            tmem_ld16x256_x4(trow + (uint32_t)cbb, alo); tmem_ld16x256_x4(trow16 + (uint32_t)cbb, ahi);
-            if (b5) { tmem_ld16x256_x1(trow + (uint32_t)(cbb + 32), tlo); tmem_ld16x256_x1(trow16 + (uint32_t)(cbb + 32), thi); }
-            tmem_wait();
-            float lin[4];                                                  // columns 300, 301: the linear half of the output dot (hi + lo)
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint32_t *s = i < 2 ? alo : ahi;
-                const int k = 12 + 2 * (i & 1);                            // octet 3 of group 3's half-B range = columns 296..303
-                lin[i] = islin ? __uint_as_float(s[k]) + __uint_as_float(s[k + 1]) : 0.f;
-                if (islin) { s[k] = 0u; s[k + 1] = 0u; }
-            }
-            {
-                float2 q[4] = {make_float2(q4[0], 0.f), make_float2(q4[1], 0.f), make_float2(q4[2], 0.f), make_float2(q4[3], 0.f)};
-                acc4(alo, ahi, q, 4);
-                if (b5) acc1(tlo, thi, q);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    float s = q[i].x + q[i].y;
-                    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    q4[i] = s;
-                }
-            }
-            if (prof) { t2 = clock64(); e_2a += t2 - t0; }
-            // statistics exchange between the column groups: red1[row][group]; the thread with t % 4 == i writes row i
-            red1[(rw + 8 * tq) * kGroups + grp] = tq == 0 ? q4[0] : tq == 1 ? q4[1] : tq == 2 ? q4[2] : q4[3];
-            // pass 2 re-reads the accumulators; half A's loads fly while the statistics are exchanged
-            tmem_ld16x256_x4(trow + (uint32_t)ca, alo); tmem_ld16x256_x4(trow16 + (uint32_t)ca, ahi);
-            tmem_ld16x256_x1(trow + (uint32_t)(ca + 32), tlo); tmem_ld16x256_x1(trow16 + (uint32_t)(ca + 32), thi);
-            if (prof) tw = clock64();
-            named_bar_sync(1, kEpiThreads);
-            if (prof) e_b1 += clock64() - tw;
-            float rstd[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const float4 s = *reinterpret_cast<const float4 *>(red1 + (rw + 8 * i) * kGroups);
-                rstd[i] = rsqrtf(((s.x + s.y) + (s.z + s.w)) * (1.0f / H2) + 1e-5f);
-            }
-            float2 dot2[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) dot2[i] = make_float2(rstd[i] * lin[i], 0.f);
-            // parameters of this thread's two columns of an octet: be2 / g2 and w3 |g2| / 2 (8-byte loads, two octets ahead)
-            float2 E[2], W[2];
-            auto loadp = [&](int slot, int col) {
-                if (TT_ABLATE & 2) return;
-                E[slot] = lds64_early(pbe2 + col + 2 * tq); W[slot] = lds64_early(pw3 + col + 2 * tq);
-            };
-            auto oct = [&](int slot, float2 x0, float2 x1, float2 x2, float2 x3) {
-                if (TT_ABLATE & 2) return;
-                const float2 x[4] = {x0, x1, x2, x3};
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float2 y = __ffma2_rn(x[i], make_float2(rstd[i], rstd[i]), E[slot]);
-                    dot2[i] = __ffma2_rn(make_float2(fabsf(y.x), fabsf(y.y)), W[slot], dot2[i]);
-                }
-            };
-            auto oct1 = [&](int slot, const uint32_t (&lo)[4], const uint32_t (&hi)[4]) {
-                oct(slot, make_float2(__uint_as_float(lo[0]), __uint_as_float(lo[1])), make_float2(__uint_as_float(lo[2]), __uint_as_float(lo[3])),
-                    make_float2(__uint_as_float(hi[0]), __uint_as_float(hi[1])), make_float2(__uint_as_float(hi[2]), __uint_as_float(hi[3])));
-            };
-            // octet sequence: half A 0..4, half B 0..3 (4): columns ca + 8 o | cbb + 8 o
-            loadp(0, ca); loadp(1, ca + 8);
-            tmem_wait();
-            if (prof) { t1 = clock64(); e_2b += t1 - t2; t2 = t1; }
-            tc_fence_before();
-            mbar_arrive(bar(D_H2AFREE));                                   // half A is in registers: the next tile's half A may start
-#pragma unroll
-            for (int o = 0; o < 4; o++) {
-                oct(o & 1, TT_X4(alo, ahi, o, 0), TT_X4(alo, ahi, o, 1), TT_X4(alo, ahi, o, 2), TT_X4(alo, ahi, o, 3));
-                loadp(o & 1, o + 2 < 5 ? ca + 8 * (o + 2) : cbb + 8 * (o + 2 - 5));
-            }
-            tmem_ld16x256_x4(trow + (uint32_t)cbb, alo); tmem_ld16x256_x4(trow16 + (uint32_t)cbb, ahi);   // half B flies under the last octet of half A
-            oct1(0, tlo, thi);                                             // half A, octet 4
-            loadp(0, cbb + 8);
-            if (b5) { tmem_ld16x256_x1(trow + (uint32_t)(cbb + 32), tlo); tmem_ld16x256_x1(trow16 + (uint32_t)(cbb + 32), thi); }
-            tmem_wait();
-            tc_fence_before();
-            mbar_arrive(bar(D_H2BFREE));
-            if (prof) { t1 = clock64(); e_2c += t1 - t2; t2 = t1; }
-#pragma unroll
-            for (int o = 0; o < 4; o++) {                                  // half B, octets 0..3: parameter slots 1, 0, 1, 0
-                oct((o + 1) & 1, TT_X4(alo, ahi, o, 0), TT_X4(alo, ahi, o, 1), TT_X4(alo, ahi, o, 2), TT_X4(alo, ahi, o, 3));
-                if (o + 2 < 5) loadp((o + 1) & 1, cbb + 8 * (o + 2));
-            }
-            if (b5) oct1(1, tlo, thi);                                     // half B, octet 4 (groups 0, 1)
-            if (prof) { t1 = clock64(); e_2d += t1 - t2; t2 = t1; }
-            float dsel = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                float s = dot2[i].x + dot2[i].y;
-                s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
-                dsel = tq == i ? s : dsel;
-            }
-            red3[(rw + 8 * tq) * kGroups + grp] = dsel;
-            if (prof) tw = clock64();
-            named_bar_sync(1, kEpiThreads);
-            if (prof) e_b2 += clock64() - tw;
-            if (grp == 0 && rw + 8 * tq < rows) {
-                const float4 s = *reinterpret_cast<const float4 *>(red3 + (rw + 8 * tq) * kGroups);
-                out[row0 + rw + 8 * tq] = tanhf(b3 + ((s.x + s.y) + (s.z + s.w)));
-            }
-            if (prof) { t1 = clock64(); e_2 += t1 - t0; t0 = t1; }
-        };
-#undef TT_X4
-#endif
 
         const int64_t first = blockIdx.x, G = gridDim.x;
         uint32_t c1 = 0, c2 = 0;
@@ -917,16 +781,21 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
 
 template <typename OpT, bool kSplit>
 int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, const float *d_obs, int64_t ld, int64_t n, float *d_mu,
-               const TTRingS *ring, unsigned long long *dbg, cudaStream_t st) {
+               const TTRingS *ring, const TTActorTail *tail, unsigned long long *dbg, cudaStream_t st) {
     TTRingS rs;
     if (ring) rs = *ring; else { rs.S = nullptr; rs.m = tt_make_ring_map(1, 0, 0); }
+    const TTActorTail tl = tail ? *tail : tt_no_tail();
     using P = Plan4<kSplit>;
     static_assert(P::total <= 232448u, "shared-memory plan exceeds 227 KB");
-    static int cluster = -1;      // 2 = CTA pairs with multicast W2 loads (default when 74 pairs are co-resident), 1 = single CTAs
-    if (cluster < 0) {
+    // per device: 2 = CTA pairs with multicast W2 loads (default when 74 pairs are co-resident), 1 = single CTAs, 0 = not probed yet
+    static int cluster_of[tt::kMaxDevices] = {};
+    int &cluster = cluster_of[tt::device_index()];
+    if (cluster == 0) {
+#if defined(TT_DEV_VARIANTS)
         TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
-        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
         TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
+#endif
+        TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
         TT_CUDA(cudaFuncSetAttribute(actor_tc4_kernel<OpT, kSplit, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::total));
         const char *e = getenv("TT_TC_CLUSTER");
         int want = e ? atoi(e) : 2;
@@ -946,7 +815,10 @@ int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, cons
     }
     const int64_t ntiles = (n + kTileM - 1) / kTileM;
     int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
-    if (cluster == 2) {
+#if !defined(TT_DEV_VARIANTS)
+    dbg = nullptr;
+#endif
+    if (cluster == 2 && ntiles > 1) {
         grid = (grid + 1) & ~1;                                  // whole pairs; a CTA without tiles only serves the pair's W2 ring
         if (grid > (tt::sm_count() & ~1)) grid = tt::sm_count() & ~1;
         cudaLaunchConfig_t cfg{};
@@ -954,28 +826,39 @@ int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, cons
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (dbg) TT_CUDA(cudaLaunchKernelEx(&cfg, actor_tc4_kernel<OpT, kSplit, true, 2>, w1img, w2img, A, d_obs, ld, n, d_mu, rs, dbg));
-        else TT_CUDA(cudaLaunchKernelEx(&cfg, actor_tc4_kernel<OpT, kSplit, false, 2>, w1img, w2img, A, d_obs, ld, n, d_mu, rs, dbg));
+#if defined(TT_DEV_VARIANTS)
+        if (dbg) TT_CUDA(cudaLaunchKernelEx(&cfg, actor_tc4_kernel<OpT, kSplit, true, 2>, w1img, w2img, A, d_obs, ld, n, d_mu, rs, tl, dbg));
+        else
+#endif
+        TT_CUDA(cudaLaunchKernelEx(&cfg, actor_tc4_kernel<OpT, kSplit, false, 2>, w1img, w2img, A, d_obs, ld, n, d_mu, rs, tl, dbg));
     } else {
-        auto kern = dbg ? actor_tc4_kernel<OpT, kSplit, true, 1> : actor_tc4_kernel<OpT, kSplit, false, 1>;
-        kern<<<grid, 640, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, rs, dbg);
+#if defined(TT_DEV_VARIANTS)
+        if (dbg) actor_tc4_kernel<OpT, kSplit, true, 1><<<grid, 640, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, rs, tl, dbg);
+        else
+#endif
+        actor_tc4_kernel<OpT, kSplit, false, 1><<<grid, 640, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, rs, tl, dbg);
     }
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
 
+unsigned long long *g_tc_dbg = nullptr;
+
 }  // namespace
 
 namespace tt {
 
-int actor_pack_tc4(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *g1, const float *fc2_w, const float *fc2_b, cudaStream_t s) {
+bool actor_tc_supported(const tt_actor_dev &A) { return A.in_dim == IN && A.h1 == H1 && A.h2 == H2; }
+
+int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *fc2_w, const float *fc2_b, cudaStream_t s) {
     const tt_actor_dev &A = a->dev;
+    if (!actor_tc_supported(A)) return TT_OK;       // the tensor-core path is specialised to 23-400-300; forward() will refuse
     if (!a->scratch_clean) { TT_CUDA(cudaMemsetAsync(A.l1c_scratch, 0, sizeof(double) * 600, s)); a->scratch_clean = true; }
     pack_l1c_gram_kernel<<<kGramBlocks, 576, 0, s>>>(A.l1c_scratch, fc1_w, fc1_b);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     pack_l1c_chol_kernel<<<1, 576, 0, s>>>(A.l1c_scratch, A.l1c_scratch + 600);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    pack_l1c_image_kernel<<<54, 256, 0, s>>>(reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + 600, fc1_w, fc1_b, g1);
+    pack_l1c_image_kernel<<<54, 256, 0, s>>>(reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + 600, fc1_w, fc1_b, A.g1);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     double *st2 = A.l1c_scratch + 1200;
     pack_w2_colstats_kernel<<<KB2, 32 * kStatSlices, 0, s>>>(st2, fc2_w, fc2_b, A.g2, A.w3);
@@ -987,14 +870,24 @@ int actor_pack_tc4(tt_actor *a, const float *fc1_w, const float *fc1_b, const fl
     return TT_OK;
 }
 
-int actor_forward_tc4(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring,
-                      unsigned long long *dbg, cudaStream_t st) {
+int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring,
+                     const TTActorTail *tail, cudaStream_t st) {
     const tt_actor_dev &A = a->dev;
+    if (!actor_tc_supported(A)) {
+        set_error("tensor-core actor is specialised to layer sizes 23-400-300 (got %d-%d-%d); use TT_PREC_FP32", A.in_dim, A.h1, A.h2);
+        return TT_ERR_INVALID;
+    }
     if (precision == TT_PREC_BF16)
-        return launch_tc4<__nv_bfloat16, false>(reinterpret_cast<const char *>(A.w1c_bf16), reinterpret_cast<const char *>(A.w2s_bf16), A, d_obs, ld, n, d_mu, ring, dbg, st);
+        return launch_tc4<__nv_bfloat16, false>(reinterpret_cast<const char *>(A.w1c_bf16), reinterpret_cast<const char *>(A.w2s_bf16), A, d_obs, ld, n, d_mu, ring, tail, g_tc_dbg, st);
     if (precision == TT_PREC_F16_PLAIN)          // plain fp16 first layer: only the hi block of the image is loaded
-        return launch_tc4<__half, false>(reinterpret_cast<const char *>(A.w1c_f16), reinterpret_cast<const char *>(A.w2s_f16), A, d_obs, ld, n, d_mu, ring, dbg, st);
-    return launch_tc4<__half, true>(reinterpret_cast<const char *>(A.w1c_f16), reinterpret_cast<const char *>(A.w2s_f16), A, d_obs, ld, n, d_mu, ring, dbg, st);
+        return launch_tc4<__half, false>(reinterpret_cast<const char *>(A.w1c_f16), reinterpret_cast<const char *>(A.w2s_f16), A, d_obs, ld, n, d_mu, ring, tail, g_tc_dbg, st);
+    return launch_tc4<__half, true>(reinterpret_cast<const char *>(A.w1c_f16), reinterpret_cast<const char *>(A.w2s_f16), A, d_obs, ld, n, d_mu, ring, tail, g_tc_dbg, st);
 }
 
 }  // namespace tt
+
+#if defined(TT_DEV_VARIANTS)
+// Developer build only (not part of the public header): per-phase cycle counters of block 0 of the tensor-core actor.
+// d_buf: device buffer of >= 24 uint64, or NULL to switch profiling off.
+extern "C" void tt_debug_set_tc_profile(unsigned long long *d_buf) { g_tc_dbg = d_buf; }
+#endif

@@ -1,7 +1,7 @@
 // tt_agent.cu -- kernels (b) OU noise and (c) the batched actor forward (fp32 CUDA-core path), plus the
 // weight re-packing.  Replaces Agent.choose_action (DDPG/DDPG_agent.py:36-49), OUActionNoise
 // (DDPG/noise.py:12-20) and ActorNetwork.forward (DDPG/networks.py:138-147) for N observations at once.
-// The tcgen05 (bf16 tensor-core) actor lives in tt_actor_tc.cu and shares tt_actor with this file.
+// The tcgen05 tensor-core actor lives in tt_actor_tc4.cu and shares tt_actor with this file.
 #include <new>
 #include "tt_actor.cuh"
 #include "tt_common.cuh"
@@ -16,7 +16,7 @@ constexpr float kPiOver4F = 0.78539819f;       // float32(pi/4) == env.action_sp
 // (b) OU noise, DDPG/noise.py:12-17 with theta=0.2, sigma=0.15, dt=1e-2, mu=0; optional fused
 //     "mu + noise" (DDPG_agent.py:41-43) and "clip(a,-1,1) * pi/4" (trainv2.py:516)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float ou_advance(float xp, float nrm) { return xp + 0.2f * (0.0f - xp) * 0.01f + 0.15f * 0.1f * nrm; }
+using ttm::ou_advance;
 
 __global__ void __launch_bounds__(kThreads) ou_kernel(float *__restrict__ x, float *__restrict__ action,
                                                       float *__restrict__ scaled, const uint8_t *__restrict__ reset_mask,
@@ -65,11 +65,6 @@ __global__ void __launch_bounds__(kThreads) ou_kernel_x4(float4 *__restrict__ x,
             __stcs(&ring_a[r4], a);
         }
     }
-}
-
-__global__ void __launch_bounds__(kThreads) ou_zero_kernel(float *__restrict__ x, const uint8_t *__restrict__ mask, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i < n && mask[i]) x[i] = 0.0f;
 }
 
 __global__ void __launch_bounds__(kThreads) scale_kernel(const float *__restrict__ a, float *__restrict__ s, int64_t n) {
@@ -192,7 +187,7 @@ __device__ __forceinline__ void bias_ln_relu(float (&acc)[8][CJ], const float *_
 
 template <int CJ1, int CJ2, bool kGuard>
 __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A, const float *__restrict__ obs, int64_t ld,
-                                                                int64_t n, float *__restrict__ out, TTRingS ring) {
+                                                                int64_t n, float *__restrict__ out, TTRingS ring, TTActorTail tail) {
     extern __shared__ __align__(16) float smem[];
     float *xs = smem;                                   // [k1p][RS]
     float *hs = xs + A.k1p * RS;                        // [h1p][RS]
@@ -244,14 +239,29 @@ __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A,
 #pragma unroll
             for (int j = 0; j < CJ2; j++) w3[j] = (!kGuard || lane + 32 * j < A.h2p) ? A.w3[lane + 32 * j] : 0.f;
             const float b3 = A.b3[0];
+            float srow = 0.f;                                   // lane r keeps the output dot of row 8 warp + r
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 float s = 0.f;
 #pragma unroll
                 for (int j = 0; j < CJ2; j++) s = fmaf(acc[r][j], w3[j], s);
                 s = warp_sum_f(s);
-                const int row = warp * 8 + r;
-                if (lane == 0 && row < rows) out[row0 + row] = tanhf(s + b3);
+                if (lane == r) srow = s;
+            }
+            // output stage, one lane per row: tanh, then what Agent.choose_action and the training loop do with it
+            // (DDPG_agent.py:41-43 mu + OU noise, trainv2.py:516 clip * pi / 4, agent.remember of the raw action)
+            const int row = warp * 8 + lane;
+            if (lane < 8 && row < rows) {
+                const int64_t gr = row0 + row;
+                float a = tanhf(srow + b3);
+                if (tail.ou_x) {
+                    const float xn = ou_advance(tail.ou_x[gr], ttm::rng_normal_ks(tail.keys, tail.gid0 + (uint32_t)gr, *tail.iter));
+                    tail.ou_x[gr] = xn;
+                    a += xn;
+                }
+                out[gr] = a;
+                if (tail.scaled) tail.scaled[gr] = fminf(fmaxf(a, -1.0f), 1.0f) * kPiOver4F;
+                if (tail.ring.A && gr >= tail.ring.m.first) tail.ring.A[tail.ring.m.row(gr)] = a;
             }
         }
         __syncthreads();
@@ -268,9 +278,11 @@ size_t actor_fp32_smem(const tt_actor_dev &A) {
 
 namespace tt {
 
-int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, const TTRingS *ring, cudaStream_t s) {
+int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, const TTRingS *ring, const TTActorTail *tail,
+                       cudaStream_t s) {
     TTRingS rs;
     if (ring) rs = *ring; else { rs.S = nullptr; rs.m = tt_make_ring_map(1, 0, 0); }
+    const TTActorTail tl = tail ? *tail : tt_no_tail();
     const tt_actor_dev &A = a->dev;
     const size_t smem = actor_fp32_smem(A);
     const int64_t ntiles = (n + TM - 1) / TM;
@@ -279,11 +291,11 @@ int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_
     if (cj1 == 13 && cj2 == 10) {
         auto kern = actor_fp32_kernel<13, 10, false>;
         TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs);
+        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs, tl);
     } else if (cj1 <= 16 && cj2 <= 16) {
         auto kern = actor_fp32_kernel<16, 16, true>;
         TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs);
+        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs, tl);
     } else {
         set_error("actor: hidden sizes above 512 are not supported (h1=%d h2=%d)", A.h1, A.h2);
         return TT_ERR_INVALID;
@@ -311,10 +323,25 @@ int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_
     return TT_OK;
 }
 
-int launch_ou_zero(float *d_x, const uint8_t *d_mask, int64_t n, cudaStream_t s) {
-    ou_zero_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(d_x, d_mask, n);
-    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    return TT_OK;
+// TT_PREC_AUTO (north_star (c)): tcgen05 tiles only once the batch is a real dense contraction, warp-level fp32 FMA below.
+// Measured on a B200 (profiles/r02_actor_auto_sweep.md): the tensor-core kernel pays a fixed ~12 us per launch (TMEM
+// allocation, W1 image, the W2 stream start-up) and the fp32 kernel ~8 us + 11 us per 64-row tile wave; the two cross between
+// 128 and 256 rows.  Below the threshold the fp32 kernel is also the more accurate one (1e-5 vs 1e-3).
+constexpr int64_t kAutoTcMinRows = 192;
+int actor_resolve_precision(const tt_actor *a, int precision, int64_t n) {
+    if (precision != TT_PREC_AUTO) return precision;
+    const tt_actor_dev &A = a->dev;
+    const bool tc_ok = A.in_dim == 23 && A.h1 == 400 && A.h2 == 300;
+    return tc_ok && n >= kAutoTcMinRows ? TT_PREC_F16 : TT_PREC_FP32;
+}
+
+int actor_forward_any(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring,
+                      const TTActorTail *tail, cudaStream_t s) {
+    precision = actor_resolve_precision(a, precision, n);
+    if (precision == TT_PREC_FP32) return actor_forward_fp32(a, d_obs, ld, n, d_mu, ring, tail, s);
+    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16 || precision == TT_PREC_F16_PLAIN) return actor_forward_tc(a, d_obs, ld, n, d_mu, precision, ring, tail, s);
+    set_error("unknown actor precision %d", precision);
+    return TT_ERR_INVALID;
 }
 
 }  // namespace tt
@@ -386,11 +413,10 @@ int tt_actor_forward(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n,
     TT_REQUIRE(a && d_obs && d_mu, "NULL argument");
     TT_REQUIRE(a->loaded, "tt_actor_load has not been called");
     TT_REQUIRE(n > 0 && ld_obs >= a->dev.in_dim, "bad n / ld_obs");
-    if (precision == TT_PREC_FP32) return tt::actor_forward_fp32(a, d_obs, ld_obs, n, d_mu, nullptr, tt::as_stream(stream));
-    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16 || precision == TT_PREC_F16_PLAIN) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, nullptr, tt::as_stream(stream));
-    tt::set_error("tt_actor_forward: unknown precision %d", precision);
-    return TT_ERR_INVALID;
+    return tt::actor_forward_any(a, d_obs, ld_obs, n, d_mu, precision, nullptr, nullptr, tt::as_stream(stream));
 }
+
+int tt_actor_auto_precision(tt_actor *a, int64_t n) { return a ? tt::actor_resolve_precision(a, TT_PREC_AUTO, n) : TT_ERR_INVALID; }
 
 int tt_actor_forward_store(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n, float *d_mu, int32_t precision,
                            const tt_replay_ring *ring, tt_stream_t stream) {
@@ -399,10 +425,23 @@ int tt_actor_forward_store(tt_actor *a, const float *d_obs, int64_t ld_obs, int6
     TT_REQUIRE(n > 0 && ld_obs >= a->dev.in_dim, "bad n / ld_obs");
     TT_REQUIRE(ring && ring->d_state_mem && ring->mem_size > 0 && ring->mem_cntr >= 0, "bad ring");
     const TTRingS rs = {ring->d_state_mem, tt_make_ring_map(ring->mem_size, ring->mem_cntr, n)};
-    if (precision == TT_PREC_FP32) return tt::actor_forward_fp32(a, d_obs, ld_obs, n, d_mu, &rs, tt::as_stream(stream));
-    if (precision == TT_PREC_BF16 || precision == TT_PREC_F16 || precision == TT_PREC_F16_PLAIN) return tt::actor_forward_tc(a, d_obs, ld_obs, n, d_mu, precision, &rs, tt::as_stream(stream));
-    tt::set_error("tt_actor_forward_store: unknown precision %d", precision);
-    return TT_ERR_INVALID;
+    return tt::actor_forward_any(a, d_obs, ld_obs, n, d_mu, precision, &rs, nullptr, tt::as_stream(stream));
+}
+
+int tt_actor_choose_action(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n, float *d_ou_x, uint64_t seed,
+                           uint64_t global_env_offset, const uint32_t *d_iter, int32_t evaluate, float *d_action, float *d_scaled,
+                           int32_t precision, const tt_replay_ring *ring, tt_stream_t stream) {
+    TT_REQUIRE(a && d_obs && d_action, "NULL argument");
+    TT_REQUIRE(a->loaded, "tt_actor_load has not been called");
+    TT_REQUIRE(n > 0 && ld_obs >= a->dev.in_dim, "bad n / ld_obs");
+    TT_REQUIRE(evaluate || (d_ou_x && d_iter), "noise needs d_ou_x and d_iter");
+    TT_REQUIRE(!ring || (ring->d_state_mem && ring->d_action_mem && ring->mem_size > 0 && ring->mem_cntr >= 0), "bad ring");
+    TTActorTail tl = tt_no_tail();
+    tl.ou_x = evaluate ? nullptr : d_ou_x; tl.scaled = d_scaled; tl.keys = ttm::philox_expand_key(seed);
+    tl.gid0 = (uint32_t)global_env_offset; tl.iter = d_iter;
+    TTRingS rs; rs.S = nullptr; rs.m = tt_make_ring_map(1, 0, 0);
+    if (ring) { rs.S = ring->d_state_mem; rs.m = tt_make_ring_map(ring->mem_size, ring->mem_cntr, n); tl.ring.A = ring->d_action_mem; tl.ring.m = rs.m; }
+    return tt::actor_forward_any(a, d_obs, ld_obs, n, d_action, precision, ring ? &rs : nullptr, &tl, tt::as_stream(stream));
 }
 
 }  // extern "C"

@@ -53,7 +53,9 @@ int cuda_fail(cudaError_t e, const char *what);
 
 inline cudaStream_t as_stream(tt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-int sm_count();
+constexpr int kMaxDevices = 64;
+int device_index();          // the current CUDA device, as an index into per-device caches
+int sm_count();              // SM count of the current device
 
 // number of kernels launched by this library since load (bench.py reports it as gpu_launches)
 extern unsigned long long g_launches;

@@ -46,7 +46,9 @@ struct tt_env {
     EnvPtrs p;
     uint64_t seed;
     uint64_t gid0;
-    bool per_env_goal;   // per-env goals and/or trailer lengths were injected: the step kernel reads goal[] and l2v[]
+    bool goal_injected;  // per-env goals were injected (tt_env_set_state): the step kernel reads goal[] (and l2v[]) until the
+                         // next FULL reset puts every env back on the configured goal
+    bool l2_injected;    // per-env trailer lengths were injected (tt_env_set_l2; like `env.L2 = ...` they persist across resets)
 };
 
 namespace {
@@ -160,12 +162,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // K env steps per launch; state stays in registers across the K steps; persistent over 128-env tiles.
-// kMinBlocks == 7 is a memory-traffic-only probe (no arithmetic) used for roofline analysis.
-template <bool kInfo, bool kGoal, int kMinBlocks, int kStages>
+// kMinBlocks == 7 is a memory-traffic-only probe (no arithmetic) used for roofline analysis (developer build).
+// kRoll: the rollout's form (K == 1, obs != NULL): the driver-side `if done: env.reset(); agent.noise.reset()`
+// (trainv2.py:489-492) happens inside the kernel -- a finished env's TERMINAL observation goes to the ring's new_state row
+// (what trainv2.py:525 stores), its reset observation (new Philox pose of this iteration) to `obs`, its OU state is zeroed
+// -- and the last CTA to finish advances the Philox iteration counter: no separate reset / tick launches.
+template <bool kInfo, bool kGoal, int kMinBlocks, int kStages, bool kRoll>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p, StepConsts k, const float *__restrict__ actions,
                                                                       int K, int auto_reset, float *__restrict__ obs, int64_t ld,
                                                                       float *__restrict__ reward, uint8_t *__restrict__ done,
-                                                                      tt_step_info info, uint64_t seed, uint64_t gid0, TTRingOut rpl) {
+                                                                      tt_step_info info, uint64_t seed, uint64_t gid0, TTRingOut rpl,
+                                                                      float *__restrict__ ou_x) {
     // observation tiles: double buffered; full tiles leave through the bulk-copy engine (cp.async.bulk shared ->
     // global), which drains them while the CTA already computes its next tile
     __shared__ __align__(128) float tiles[2][kBlock * TT_OBS_DIM];
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                     for (int c = 0; c < TT_NCOMP; c++) o.comps[c] = 0.f;
                 } else {
                     const float a = j == 0 ? cur.action : __ldcs(&actions[(int64_t)j * N + i]);
+#if defined(TT_DEV_VARIANTS)
                     if (kMinBlocks == 7) {
                         e.psi1 += a; e.psi2 += a; e.x1 += 1; e.y1 += 2; e.x2 += 3; e.y2 += e.gx;
                         e.closest += a; e.cum += e.sgy; e.first_steer += e.cgy; e.g1 += a; e.g2 += a; e.g3 += a; e.packed += 1;
@@ -240,6 +248,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                         for (int c = 0; c < TT_OBS_DIM; c++) o.obs[c] = (float)e.x1 + (float)c;
                         o.reward = e.closest; o.done = false; o.success = false; o.flags = 0; o.viol = 0;
                     } else
+#endif
                         env_step<kInfo>(k, e, a, o);
                     sa.steps += 1.f; sa.rew += o.reward;
                     if (o.done) {
@@ -265,7 +274,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                     if (info.d_flags) info.d_flags[oi] = (uint8_t)o.flags;
                     if (info.d_success) info.d_success[oi] = o.success ? 1 : 0;
                 }
-                if (o.done && !(e.packed & PK_FINISHED)) {
+                if (!kRoll && o.done && !(e.packed & PK_FINISHED)) {
                     if (auto_reset) {
                         double sx, sy, syaw;
                         rng_pose(k, seed, (uint32_t)(gid0 + i), t0 + (uint32_t)j, sx, sy, syaw);
@@ -274,7 +283,52 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                     } else e.packed |= PK_FINISHED;
                 }
             }
-            if (obs) {
+            if (kRoll) {
+                // tiles[0] = what the ring stores as new_state (terminal rows), tiles[1] = what the next iteration observes (reset
+                // rows for finished envs).  One bulk store each; they drain while the CTA computes its next tile, and the wait for
+                // their shared-memory reads sits here, a whole tile of arithmetic later.
+                float *tileA = tiles[0], *tileB = tiles[1];
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+                if (active) {
+                    if (rpl.S2) {
+#pragma unroll
+                        for (int c = 0; c < TT_OBS_DIM; c++) tileA[threadIdx.x * TT_OBS_DIM + c] = o.obs[c];
+                    }
+                    if (o.done) {                                        // trainv2.py:489-492: env.reset() + agent.noise.reset()
+                        double sx, sy, syaw;
+                        rng_pose(k, seed, (uint32_t)(gid0 + i), t0, sx, sy, syaw);
+                        reset_from_pose(k, e, sx, sy, syaw, k.gx, k.gy, k.gyaw, o.obs);
+                        store_episode_consts(p, i, e, sx, sy, syaw, k.gyaw);
+                        if (ou_x) ou_x[i] = 0.0f;
+                    }
+#pragma unroll
+                    for (int c = 0; c < TT_OBS_DIM; c++) tileB[threadIdx.x * TT_OBS_DIM + c] = o.obs[c];
+                }
+                const int64_t rrow0 = rpl.S2 ? rpl.m.row(row0) : 0;
+                const bool ring_bulk = rpl.S2 && rows == kBlock && !rpl.m.many && row0 >= rpl.m.first && rrow0 + kBlock <= rpl.m.cap &&
+                                       (rrow0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(rpl.S2) & 15) == 0);
+                const bool obs_bulk = bulk_ok && rows == kBlock;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (threadIdx.x == 0 && (obs_bulk || ring_bulk)) {
+                    const uint32_t bytes = (uint32_t)(kBlock * TT_OBS_DIM * sizeof(float));
+                    if (obs_bulk)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(obs + row0 * TT_OBS_DIM), "r"((uint32_t)__cvta_generic_to_shared(tileB)), "r"(bytes) : "memory");
+                    if (ring_bulk)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(rpl.S2 + rrow0 * TT_OBS_DIM), "r"((uint32_t)__cvta_generic_to_shared(tileA)), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (!obs_bulk) store_obs_tile(tileB, obs, ld, row0, rows);
+                if (rpl.S2 && !ring_bulk) {
+                    for (int v = threadIdx.x; v < rows * TT_OBS_DIM; v += kBlock) {
+                        const int r = v / TT_OBS_DIM, c = v - r * TT_OBS_DIM;
+                        if (row0 + r >= rpl.m.first) rpl.S2[rpl.m.row(row0 + r) * TT_OBS_DIM + c] = tileA[v];
+                    }
+                }
+            } else if (obs) {
                 float *tile = tiles[tbuf];
                 __syncthreads();                 // thread 0 has waited for the bulk store that last read this buffer
                 if (active) {
@@ -317,6 +371,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
     }
 
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all bulk stores complete
+    if (kRoll) {
+        // iteration tick: every CTA read *p.iter (t0) when it started, and the last one to get here has seen all others finish
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(p.iter + 1, 1u) == gridDim.x - 1) { p.iter[1] = 0u; *p.iter = t0 + 1u; }
+        }
+    }
 
     // statistics: steps and reward every launch, the episode counters only in warps that finished an episode
     // (one warp-shuffle tree each; one double atomic per warp and statistic).  All lanes of the warp get here.
@@ -538,7 +600,7 @@ int tt_env_create(tt_env **out, const tt_env_cfg *cfg, int64_t n_envs, uint64_t 
     if (tt_device_count() <= 0) { tt::set_error("tt_env_create: no CUDA device (there is no CPU fallback)"); return TT_ERR_CUDA; }
     tt_env *e = new (std::nothrow) tt_env;
     TT_REQUIRE(e, "out of host memory");
-    e->cfg = *cfg; e->k = tt_make_consts(*cfg); e->seed = seed; e->gid0 = global_env_offset; e->per_env_goal = false;
+    e->cfg = *cfg; e->k = tt_make_consts(*cfg); e->seed = seed; e->gid0 = global_env_offset; e->goal_injected = false; e->l2_injected = false;
     env_layout(n_envs, &e->p, static_cast<char *>(d_workspace));
     cudaError_t err = cudaMemset(d_workspace, 0, tt_env_workspace_bytes(n_envs));
     if (err != cudaSuccess) { delete e; return tt::cuda_fail(err, "cudaMemset(workspace)"); }
@@ -574,7 +636,10 @@ static int env_reset_impl(tt_env *env, const uint8_t *d_mask, float *d_obs, int6
         env_reset_kernel<<<(unsigned)grid_for(env->p.N), kBlock, 0, s>>>(env->p, env->k, d_mask, d_obs, ld_obs, env->seed,
                                                                         env->gid0, d_mask ? 0u : 0x80000000u, d_ou_x);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    if (!d_mask) { tick_kernel<<<1, 1, 0, s>>>(env->p.iter, 1u); TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK(); }
+    if (!d_mask) {
+        tick_kernel<<<1, 1, 0, s>>>(env->p.iter, 1u); TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+        env->goal_injected = false;            // every env is back on the configured goal: the step kernel stops reading goal[]
+    }
     return TT_OK;
 }
 
@@ -588,9 +653,11 @@ int tt_env_reset_ou(tt_env *env, const uint8_t *d_mask, float *d_obs, int64_t ld
 }
 
 static int env_step_impl(tt_env *env, const float *d_actions, int32_t K, int32_t auto_reset, float *d_obs, int64_t ld_obs,
-                         float *d_reward, uint8_t *d_done, const tt_step_info *info, const TTRingOut *ring, tt_stream_t stream) {
+                         float *d_reward, uint8_t *d_done, const tt_step_info *info, const TTRingOut *ring, bool roll, float *d_ou_x,
+                         tt_stream_t stream) {
     TT_REQUIRE(env && d_actions, "NULL argument");
     TT_REQUIRE(!ring || (K == 1 && d_obs), "fused replay store needs K == 1 and an observation buffer");
+    TT_REQUIRE(!roll || (K == 1 && d_obs), "fused reset needs K == 1 and an observation buffer");
     TTRingOut ro;
     if (ring) ro = *ring; else { ro.S2 = nullptr; ro.R = nullptr; ro.D = nullptr; ro.m = tt_make_ring_map(1, 0, 0); }
     TT_REQUIRE(K >= 1, "K < 1");
@@ -599,54 +666,63 @@ static int env_step_impl(tt_env *env, const float *d_actions, int32_t K, int32_t
     tt_step_info inf;
     memset(&inf, 0, sizeof inf);
     const bool want = info && (info->d_comps || info->d_violation || info->d_flags || info->d_success);
-    // tuning knob TT_ENV_MINBLOCKS = <CTAs per SM><prefetch stages>: default 42 = 4 CTAs/SM (<=128 regs) with a 2-stage
-    // cp.async shared-memory prefetch; 43/52/53/62 = other combinations; 40/5/6 = register double buffer; 7 = traffic-only probe.
-    // Measured at N = 2^22 (profiles/env_kernel_bench.py): 42: 208 us (70.4 % of the HBM roofline), 43: 210, 52/53: 218,
-    // 40: 264, 62: 276.
-    static const int variant = [] { const char *e = getenv("TT_ENV_MINBLOCKS"); return e ? atoi(e) : TT_ENV_MINBLOCKS_DEFAULT; }();
     const int64_t ntiles = grid_for(env->p.N);
-#define TT_LAUNCH_STEP(INFO, GOAL, MB, ST)                                                                                      \
+    // 4 CTAs / SM (<= 128 registers) with a 2-stage cp.async shared-memory prefetch: measured best of the combinations tried
+    // (profiles/env_kernel_bench.py; the others exist in the developer build only, TT_ENV_MINBLOCKS).  Opt-in shared memory
+    // and occupancy are per device.
+#define TT_LAUNCH_STEP(INFO, GOAL, MB, ST, ROLL)                                                                                \
     do {                                                                                                                        \
-        auto kern = env_step_kernel<INFO, GOAL, MB, ST>;                                                                        \
+        auto kern = env_step_kernel<INFO, GOAL, MB, ST, ROLL>;                                                                  \
         const size_t dsm = (size_t)(ST) * sizeof(RawSlab);                                                                      \
-        static int per_sm = 0;                                                                                                  \
+        static int per_sm_of[tt::kMaxDevices] = {};                                                                            \
+        int &per_sm = per_sm_of[tt::device_index()];                                                                            \
         if (per_sm == 0) {                                                                                                      \
-            if (dsm > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);                     \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, dsm) != cudaSuccess) per_sm = 4;           \
+            if (dsm > 0) TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));            \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, dsm) != cudaSuccess || per_sm <= 0) per_sm = 4; \
         }                                                                                                                       \
-        const int64_t cap = (int64_t)tt::sm_count() * (per_sm > 0 ? per_sm : 4);                                                \
+        const int64_t cap = (int64_t)tt::sm_count() * per_sm;                                                                   \
         kern<<<(unsigned)(ntiles < cap ? ntiles : cap), kBlock, dsm, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs,       \
                                                                          ld_obs, d_reward, d_done, inf, env->seed, env->gid0,  \
-                                                                         ro);                                                  \
+                                                                         ro, d_ou_x);                                          \
     } while (0)
-    const bool goal = env->per_env_goal;
-    if (want) {
+    const bool goal = env->goal_injected || env->l2_injected;
+    if (roll) {
+        if (goal) TT_LAUNCH_STEP(false, true, 4, 2, true); else TT_LAUNCH_STEP(false, false, 4, 2, true);
+    } else if (want) {
         inf = *info;
-        if (goal) TT_LAUNCH_STEP(true, true, 4, 2); else TT_LAUNCH_STEP(true, false, 4, 2);
-    } else if (goal) TT_LAUNCH_STEP(false, true, 4, 2);
-    else if (variant == 5) TT_LAUNCH_STEP(false, false, 5, 0);
-    else if (variant == 6) TT_LAUNCH_STEP(false, false, 6, 0);
-    else if (variant == 7) TT_LAUNCH_STEP(false, false, 7, 0);
-    else if (variant == 40) TT_LAUNCH_STEP(false, false, 4, 0);      /* register double buffer instead of cp.async */
-    else if (variant == 43) TT_LAUNCH_STEP(false, false, 4, 3);
-    else if (variant == 52) TT_LAUNCH_STEP(false, false, 5, 2);
-    else if (variant == 53) TT_LAUNCH_STEP(false, false, 5, 3);
-    else if (variant == 62) TT_LAUNCH_STEP(false, false, 6, 2);
-    else TT_LAUNCH_STEP(false, false, 4, 2);                        /* default: 4 CTAs/SM, 2-stage cp.async prefetch */
+        if (goal) TT_LAUNCH_STEP(true, true, 4, 2, false); else TT_LAUNCH_STEP(true, false, 4, 2, false);
+    } else if (goal) TT_LAUNCH_STEP(false, true, 4, 2, false);
+    else {
+#if defined(TT_DEV_VARIANTS)
+        // tuning knob TT_ENV_MINBLOCKS = <CTAs per SM><prefetch stages>; 40/5/6 = register double buffer; 7 = traffic-only probe.
+        // Measured at N = 2^22: 42: 208 us (70.4 % of the HBM roofline), 43: 210, 52/53: 218, 40: 264, 62: 276.
+        static const int variant = [] { const char *e = getenv("TT_ENV_MINBLOCKS"); return e ? atoi(e) : 42; }();
+        if (variant == 5) TT_LAUNCH_STEP(false, false, 5, 0, false);
+        else if (variant == 6) TT_LAUNCH_STEP(false, false, 6, 0, false);
+        else if (variant == 7) TT_LAUNCH_STEP(false, false, 7, 0, false);
+        else if (variant == 40) TT_LAUNCH_STEP(false, false, 4, 0, false);
+        else if (variant == 43) TT_LAUNCH_STEP(false, false, 4, 3, false);
+        else if (variant == 52) TT_LAUNCH_STEP(false, false, 5, 2, false);
+        else if (variant == 53) TT_LAUNCH_STEP(false, false, 5, 3, false);
+        else if (variant == 62) TT_LAUNCH_STEP(false, false, 6, 2, false);
+        else
+#endif
+        TT_LAUNCH_STEP(false, false, 4, 2, false);
+    }
 #undef TT_LAUNCH_STEP
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    if (auto_reset) { tick_kernel<<<1, 1, 0, s>>>(env->p.iter, (uint32_t)K); TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK(); }
+    if (auto_reset && !roll) { tick_kernel<<<1, 1, 0, s>>>(env->p.iter, (uint32_t)K); TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK(); }
     return TT_OK;
 }
 
 int tt_env_step_k(tt_env *env, const float *d_actions, int32_t K, int32_t auto_reset, float *d_obs, int64_t ld_obs,
                   float *d_reward, uint8_t *d_done, const tt_step_info *info, tt_stream_t stream) {
-    return env_step_impl(env, d_actions, K, auto_reset, d_obs, ld_obs, d_reward, d_done, info, nullptr, stream);
+    return env_step_impl(env, d_actions, K, auto_reset, d_obs, ld_obs, d_reward, d_done, info, nullptr, false, nullptr, stream);
 }
 
 int tt_env_step(tt_env *env, const float *d_action, float *d_obs, int64_t ld_obs, float *d_reward, uint8_t *d_done,
                 const tt_step_info *info, tt_stream_t stream) {
-    return env_step_impl(env, d_action, 1, 0, d_obs, ld_obs, d_reward, d_done, info, nullptr, stream);
+    return env_step_impl(env, d_action, 1, 0, d_obs, ld_obs, d_reward, d_done, info, nullptr, false, nullptr, stream);
 }
 
 int tt_env_step_store(tt_env *env, const float *d_action, float *d_obs, int64_t ld_obs, float *d_reward, uint8_t *d_done,
@@ -655,7 +731,19 @@ int tt_env_step_store(tt_env *env, const float *d_action, float *d_obs, int64_t 
                ring->mem_cntr >= 0, "bad ring");
     const TTRingOut ro = {ring->d_new_state_mem, ring->d_reward_mem, ring->d_terminal_mem,
                           tt_make_ring_map(ring->mem_size, ring->mem_cntr, env->p.N)};
-    return env_step_impl(env, d_action, 1, 0, d_obs, ld_obs, d_reward, d_done, nullptr, &ro, stream);
+    return env_step_impl(env, d_action, 1, 0, d_obs, ld_obs, d_reward, d_done, nullptr, &ro, false, nullptr, stream);
+}
+
+// step + `if done: env.reset(); agent.noise.reset()` (trainv2.py:489-492) + iteration tick in ONE launch: the env half of a
+// rollout iteration.  d_obs rows of finished envs receive the reset observation, the ring (optional) their terminal one.
+int tt_env_step_reset(tt_env *env, const float *d_action, float *d_obs, int64_t ld_obs, float *d_reward, uint8_t *d_done,
+                      float *d_ou_x, const tt_replay_ring *ring, tt_stream_t stream) {
+    TT_REQUIRE(env && d_action && d_obs, "NULL argument");
+    if (!ring) return env_step_impl(env, d_action, 1, 1, d_obs, ld_obs, d_reward, d_done, nullptr, nullptr, true, d_ou_x, stream);
+    TT_REQUIRE(ring->d_new_state_mem && ring->d_reward_mem && ring->d_terminal_mem && ring->mem_size > 0 && ring->mem_cntr >= 0, "bad ring");
+    const TTRingOut ro = {ring->d_new_state_mem, ring->d_reward_mem, ring->d_terminal_mem,
+                          tt_make_ring_map(ring->mem_size, ring->mem_cntr, env->p.N)};
+    return env_step_impl(env, d_action, 1, 1, d_obs, ld_obs, d_reward, d_done, nullptr, &ro, true, d_ou_x, stream);
 }
 
 int tt_env_tick(tt_env *env, uint32_t by, tt_stream_t stream) {
@@ -670,7 +758,7 @@ int tt_env_set_state(tt_env *env, const int64_t *d_idx, int64_t n, const double 
     TT_REQUIRE(env && d_state && d_start && d_goal, "NULL argument");
     TT_REQUIRE(n > 0 && n <= env->p.N, "n out of range");
     TT_REQUIRE(!d_obs || ld_obs >= TT_OBS_DIM, "ld_obs < 23");
-    env->per_env_goal = true;      // injected goals may differ from the configured one: the step kernel reads goal[]
+    env->goal_injected = true;     // injected goals may differ from the configured one: the step kernel reads goal[]
     env_set_state_kernel<<<(unsigned)grid_for(n), kBlock, 0, tt::as_stream(stream)>>>(env->p, env->k, d_idx, n, d_state,
                                                                                      d_start, d_goal, d_obs, ld_obs);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
@@ -691,7 +779,7 @@ int tt_env_set_l2(tt_env *env, const int64_t *d_idx, int64_t n, const double *d_
     TT_REQUIRE(n > 0 && n <= env->p.N, "bad n");
     env_set_l2_kernel<<<(unsigned)grid_for(n), kBlock, 0, tt::as_stream(stream)>>>(env->p, env->cfg.v1x, d_idx, n, d_l2);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    env->per_env_goal = true;      // the step kernel must read l2v[] (and goal[]) from now on
+    env->l2_injected = true;       // the step kernel must read l2v[] (and goal[]) from now on
     return TT_OK;
 }
 

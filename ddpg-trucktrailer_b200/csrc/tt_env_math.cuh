@@ -387,6 +387,19 @@ TT_HD float rng_normal(uint64_t seed, uint32_t gid, uint32_t t) {
 #endif
 }
 
+// OUActionNoise.__call__ (DDPG/noise.py:12-17) with theta = 0.2, mu = 0, dt = 1e-2, sigma = 0.15:
+// x <- x + theta (mu - x) dt + sigma sqrt(dt) N(0, 1).  Explicitly un-contracted (the same roundings wherever it is inlined:
+// the stand-alone noise kernel and the actor kernels' fused output stage must agree bit for bit, and so does the oracle).
+TT_HD float ou_advance(float xp, float nrm) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(__fadd_rn(xp, __fmul_rn(__fmul_rn(0.2f, __fsub_rn(0.0f, xp)), 0.01f)), __fmul_rn(0.15f * 0.1f, nrm));
+#else
+    const float t = (0.2f * (0.0f - xp)) * 0.01f;
+    const float u = xp + t;
+    return u + (0.15f * 0.1f) * nrm;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // one env step: simv2.py:499-545 + reward_functionv1.py (restated in SURVEY.md appendix A)
 // `action` = scaled steering angle as passed to env.step (trainv2.py:516-520)

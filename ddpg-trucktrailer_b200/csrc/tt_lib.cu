@@ -19,14 +19,21 @@ int cuda_fail(cudaError_t e, const char *what) {
     return TT_ERR_CUDA;
 }
 
+// Launch facts are cached PER DEVICE: a process may drive several GPUs (every Python class takes a device argument), and
+// the opt-in shared-memory attributes, occupancy figures and SM counts belong to the device that is current at the launch.
+int device_index() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+    static int n[kMaxDevices] = {};
+    const int dev = device_index();
+    if (n[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 }  // namespace tt

@@ -53,13 +53,18 @@ class VecTruckTrailerEnv:
     global_env_offset : global id of env 0 (multi-GPU sharding: rank * num_envs).
     ld_obs : row stride of observation buffers in floats (>= 23).
     emit_info : also produce the per-step reward components / violation / flags (the reference ``info``).
+    auto_tick : a MASKED ``reset`` (the driver-side reset on done) also advances the Philox iteration counter, so that a
+        hand-written loop ``choose_action -> step -> reset(options={'mask': done})`` is one iteration of the random
+        streams (new start poses and new OU normals every pass).  With ``auto_tick=False`` the driver calls ``tick()``
+        once per iteration itself.  (``RolloutEngine`` / ``tt_rollout_step`` tick inside the env kernel.)
     """
 
     metadata = {"render.modes": ["human", "rgb_array"]}
     reward_range = (-float("inf"), float("inf"))
 
     def __init__(self, num_envs: int, seed: int = 27, global_env_offset: int = 0, cfg: EnvConfig | None = None,
-                 ld_obs: int = TT_OBS_DIM, emit_info: bool = False, device: str | torch.device | None = None):
+                 ld_obs: int = TT_OBS_DIM, emit_info: bool = False, device: str | torch.device | None = None,
+                 auto_tick: bool = True):
         _lib.require_cuda()
         self.L = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -67,6 +72,7 @@ class VecTruckTrailerEnv:
         self.cfg = cfg or EnvConfig()
         self.ld_obs = int(ld_obs)
         self.emit_info = emit_info
+        self.auto_tick = bool(auto_tick)
         self.seed_value = int(seed)
         self.global_env_offset = int(global_env_offset)
         N = self.num_envs
@@ -156,7 +162,8 @@ class VecTruckTrailerEnv:
     def reset(self, seed=None, options=None):
         """simv2.py:459-498.  ``options={'mask': done}`` resets only the envs whose mask is set (the
         driver-side reset on ``done``, trainv2.py:489) and returns the observation batch with those rows
-        replaced; without a mask every env starts a new episode."""
+        replaced; without a mask every env starts a new episode.  A masked reset ends one iteration of the Philox
+        streams (see ``auto_tick``): call it once per loop pass, also when no env has finished."""
         with torch.cuda.device(self.device):
             if seed is not None:
                 self.seed_value = int(seed)
@@ -166,6 +173,8 @@ class VecTruckTrailerEnv:
                 mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
             buf = self._obs[self._cur]
             check(self.L.tt_env_reset(self._h, ptr(mask), buf.data_ptr(), self.ld_obs, stream_ptr()))
+            if mask is not None and self.auto_tick:
+                check(self.L.tt_env_tick(self._h, 1, stream_ptr()))
         return self._obs_view(buf), {}
 
     def step(self, action, emit_info=None):
@@ -297,7 +306,7 @@ class Truck_trailer_Env_2:
     reward_range = VecTruckTrailerEnv.reward_range
 
     def __init__(self, seed: int = 27, device=None):
-        self.vec = VecTruckTrailerEnv(1, seed=seed, emit_info=True, device=device)
+        self.vec = VecTruckTrailerEnv(1, seed=seed, emit_info=True, device=device, auto_tick=False)
         v = self.vec
         self.observation_space, self.action_space = v.observation_space, v.action_space
         self.observation_dim = TT_OBS_DIM

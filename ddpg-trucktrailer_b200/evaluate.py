@@ -82,7 +82,7 @@ def run_sweep(agent, poses, goal=None, precision=None, record_trajectories=False
     tlen = np.ones(len(first), np.int64)
     steps = 0
     while bool(alive.any()) and steps < max_steps_cap:
-        mu = agent.actor.forward(obs, precision=prec)                  # choose_action(obs, evaluate=True), heatmap.py:139
+        mu = agent.actor.forward(obs, precision=prec, allow_out_of_bar=getattr(agent, "allow_out_of_bar", False))                  # choose_action(obs, evaluate=True), heatmap.py:139
         obs, rew, done, info = env.step(VecAgent.scale_action(mu))     # heatmap.py:140-141
         score += torch.where(alive, rew.double(), torch.zeros_like(score))
         newly = alive & done

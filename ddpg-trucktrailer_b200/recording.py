@@ -90,7 +90,7 @@ class EpisodeRecorder:
             raw = agent.choose_action(obs); scaled = agent.scale_action(raw)
             obs2, rew, done, info = env.step(scaled)
             rec.record(raw, scaled, obs2, rew, done, info)    # BEFORE the masked reset
-            obs, _ = env.reset(options={'mask': done}); env.tick()
+            obs, _ = env.reset(options={'mask': done})
             rec.after_reset(obs, done)
 
     Finished episodes accumulate in ``rec.episodes`` (dicts in the save_episode layout plus ``transitions``) and can be

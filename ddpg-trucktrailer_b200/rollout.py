@@ -12,10 +12,11 @@ from ._lib import PRECISIONS, check, ptr, stream_ptr
 
 
 class RolloutEngine:
-    def __init__(self, env, agent, store=True, evaluate=False, precision=None):
+    def __init__(self, env, agent, store=True, evaluate=False, precision=None, allow_out_of_bar=None):
         self.env, self.agent = env, agent
         self.store, self.evaluate = store, evaluate
-        self.precision = precision or agent.precision
+        allow = agent.allow_out_of_bar if allow_out_of_bar is None else allow_out_of_bar
+        self.precision, _ = _lib.resolve_precision(precision or agent.precision, allow)
         self.L = _lib.load()
         agent.noise.bind_env(env)
         N, dev = env.num_envs, env.device
@@ -57,12 +58,24 @@ class RolloutEngine:
         # the capture only recorded the launches: roll the host-side bookkeeping back
         m.mem_cntr, env._cur, self.iterations = cntr0, cur0, it0
         self._graph, self._graph_k = g, k
+        # what the captured launches carry BY VALUE: the Philox seed, the ring write position and the observation buffer
+        # parity.  step_graph() refuses to replay when any of them has moved (reset(seed=...), step() / remember() in between).
+        self._graph_key = (env.seed_value, (m.mem_cntr % m.mem_size) if self.store else 0, env._cur, id(self.agent.actor))
         return k
+
+    def _graph_state(self):
+        env, m = self.env, self.agent.memory
+        return (env.seed_value, (m.mem_cntr % m.mem_size) if self.store else 0, env._cur, id(self.agent.actor))
 
     def step_graph(self):
         """Replay the captured K iterations.  Returns (obs_next, reward, done) of the LAST of them."""
         if self._graph is None:
             raise RuntimeError("call capture() first")
+        if self._graph_state() != self._graph_key:
+            raise RuntimeError("step_graph: the captured launches carry the Philox seed, the ring write position, the observation "
+                               f"buffer parity and the actor by value; they were {self._graph_key} at capture time and are "
+                               f"{self._graph_state()} now (reset(seed=...), or an odd number of step() / a remember() in between) "
+                               "-- call capture() again")
         env, m = self.env, self.agent.memory
         self._graph.replay()
         if self.store:
@@ -71,6 +84,8 @@ class RolloutEngine:
         return env._obs_view(env._obs[env._cur]), self.reward, self.done
 
     def reset(self, seed=None):
+        if seed is not None and int(seed) != self.env.seed_value:
+            self._graph = None                        # the captured launches carry the old seed
         obs, _ = self.env.reset(seed=seed)
         self.agent.noise.bind_env(self.env)
         self.agent.noise.reset()
@@ -93,6 +108,7 @@ class RolloutEngine:
                                  m.new_state_memory.data_ptr() if self.store else None,
                                  m.terminal_memory.data_ptr() if self.store else None, m.mem_size, m.mem_cntr)
             prec = PRECISIONS[self.precision]
+            # (two launches: actor + noise + scaling + store of s, a | env step + store of s', r, done + reset + tick)
             check(self.L.tt_rollout_step(env._h, ag.actor._h, C.byref(b), prec, int(self.evaluate), stream_ptr()))
             if self.store:
                 m.mem_cntr += env.num_envs

@@ -76,6 +76,14 @@ typedef struct tt_step_info {
 } tt_step_info;
 
 typedef struct tt_env tt_env;         /* opaque */
+/* The replay ring (ReplayBuffer, DDPG/replay_buffer.py:4-12) as raw device arrays: dense float32 state / new_state
+ * [mem_size,23], action / reward [mem_size], terminal uint8 [mem_size]; mem_cntr = transitions stored so far.  A batch of n
+ * transitions goes to rows (mem_cntr + i) % mem_size (store_transition semantics).  Members a call does not write may be NULL. */
+typedef struct tt_replay_ring {
+    float   *d_state_mem, *d_action_mem, *d_reward_mem, *d_new_state_mem;
+    uint8_t *d_terminal_mem;
+    int64_t  mem_size, mem_cntr;
+} tt_replay_ring;
 typedef void *tt_stream_t;            /* cudaStream_t */
 
 const char *tt_last_error(void);
@@ -155,12 +163,15 @@ int tt_ou_step(float *d_x, float *d_action, const uint8_t *d_reset_mask, int64_t
 
 /* ---- actor: ActorNetwork.forward (DDPG/networks.py:138-147) ---- */
 typedef struct tt_actor tt_actor;     /* opaque: packed device weights */
-/* TT_PREC_FP32: CUDA-core fp32 (<= 1e-5 of torch fp32, any layer sizes).  Tensor-core paths (tcgen05, layer sizes
- * 23-400-300): TT_PREC_F16_PLAIN = plain fp16 operands in both layers (10 % faster than TT_PREC_F16; 2e-5 on reference-scale
- * weights, 1.2e-3 on strongly amplified ones); TT_PREC_F16 = fp16 operands with an exact (split hi/lo) first layer, fp32 accumulation (<= 1e-3 even
- * for strongly amplified trained weights); TT_PREC_BF16 = plain bf16 operands (fastest; <= 1e-3 for reference-scale
- * weights). */
-enum { TT_PREC_FP32 = 0, TT_PREC_BF16 = 1, TT_PREC_F16 = 2, TT_PREC_F16_PLAIN = 3 };
+/* TT_PREC_FP32: warp-level fp32 FMA on the CUDA cores (<= 1e-5 of torch fp32, any layer sizes).
+ * TT_PREC_F16: tcgen05 tensor cores (layer sizes 23-400-300), fp16 operands with an exact (split hi/lo) first layer, fp32
+ * accumulation: <= 1e-3 even for strongly amplified trained weights -- the tensor-core mode that holds north_star's bar.
+ * TT_PREC_AUTO: TT_PREC_F16 once the batch is a real dense contraction (n >= 192 rows and 23-400-300 layers), TT_PREC_FP32
+ * below (tt_actor_auto_precision tells which).
+ * OUT-OF-BAR modes (faster, plain 16-bit operands in both layers; within 1e-3 on reference-scale weights only, 1.2e-3 /
+ * 1e-2 on strongly amplified ones -- the Python classes refuse them without allow_out_of_bar=True):
+ * TT_PREC_F16_PLAIN = plain fp16 operands, TT_PREC_BF16 = plain bf16 operands. */
+enum { TT_PREC_FP32 = 0, TT_PREC_BF16 = 1, TT_PREC_F16 = 2, TT_PREC_F16_PLAIN = 3, TT_PREC_AUTO = 4 };
 size_t tt_actor_workspace_bytes(int32_t in_dim, int32_t h1, int32_t h2);
 int tt_actor_create(tt_actor **out, int32_t in_dim, int32_t h1, int32_t h2, void *d_workspace,
                     size_t workspace_bytes);
@@ -175,6 +186,18 @@ int tt_actor_load(tt_actor *a, const float *d_fc1_w, const float *d_fc1_b, const
  * clip(mu, -1, 1) * float32(pi/4) (trainv2.py:516).  precision: one of TT_PREC_*. */
 int tt_actor_forward(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n, float *d_mu,
                      int32_t precision, tt_stream_t stream);
+
+/* The concrete precision TT_PREC_AUTO resolves to for a batch of n rows (TT_PREC_FP32 or TT_PREC_F16). */
+int tt_actor_auto_precision(tt_actor *a, int64_t n);
+
+/* Agent.choose_action (DDPG/DDPG_agent.py:36-49) in ONE launch: d_action[n] = mu(obs) + OU noise (unless evaluate; the OU
+ * state d_ou_x[n] is advanced in place with N(0,1) from Philox(seed; global id, *d_iter, stream 1)) -- the UNCLIPPED action
+ * the reference returns -- and, if d_scaled != NULL, clip(action, -1, 1) * float32(pi/4) (trainv2.py:516).  With a ring
+ * (may be NULL) the observation rows and the raw actions are also written as the `state` / `action` part of the n
+ * transitions (agent.remember, DDPG_agent.py:51-52).  Bit-identical to tt_actor_forward + tt_ou_step + tt_scale_action. */
+int tt_actor_choose_action(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n, float *d_ou_x, uint64_t seed,
+                           uint64_t global_env_offset, const uint32_t *d_iter, int32_t evaluate, float *d_action,
+                           float *d_scaled, int32_t precision, const tt_replay_ring *ring, tt_stream_t stream);
 
 /* clip(a, -1, 1) * float32(pi/4): the driver-side scaling at trainv2.py:516 */
 int tt_scale_action(const float *d_action, float *d_scaled, int64_t n, tt_stream_t stream);
@@ -198,17 +221,19 @@ int tt_replay_gather(const float *d_state_mem, const float *d_action_mem, const 
  * calls below are the producers of tt_rollout_step with the store fused in (193 B written per transition, nothing
  * re-read): the actor writes `state` while it reads the observations, the noise kernel writes the raw `action`, the
  * env kernel writes `new_state`, `reward` and `terminal`.  Members that a call does not write may be NULL. */
-typedef struct tt_replay_ring {
-    float   *d_state_mem, *d_action_mem, *d_reward_mem, *d_new_state_mem;
-    uint8_t *d_terminal_mem;
-    int64_t  mem_size, mem_cntr;
-} tt_replay_ring;
 int tt_actor_forward_store(tt_actor *a, const float *d_obs, int64_t ld_obs, int64_t n, float *d_mu, int32_t precision,
                            const tt_replay_ring *ring, tt_stream_t stream);
 int tt_ou_step_store(float *d_x, float *d_action, float *d_scaled, int64_t n, uint64_t seed, uint64_t global_env_offset,
                      const uint32_t *d_iter, int32_t evaluate, const tt_replay_ring *ring, tt_stream_t stream);
 int tt_env_step_store(tt_env *env, const float *d_action, float *d_obs, int64_t ld_obs, float *d_reward,
                       uint8_t *d_done, const tt_replay_ring *ring, tt_stream_t stream);
+/* env.step (simv2.py:499-545) + the driver's `if done: env.reset(); agent.noise.reset()` (trainv2.py:489-492) + the Philox
+ * iteration tick in ONE launch -- the env half of a rollout iteration.  d_obs rows of finished envs receive the RESET
+ * observation of their next episode (pose from Philox(seed; global id, iteration, stream 0)), their TERMINAL observation goes
+ * to the ring's new_state row (ring may be NULL), their OU state d_ou_x[i] (may be NULL) is zeroed; d_done still reports
+ * the finished episode.  Bit-identical to tt_env_step_store + tt_env_reset(mask = done) + zeroing + tt_env_tick. */
+int tt_env_step_reset(tt_env *env, const float *d_action, float *d_obs, int64_t ld_obs, float *d_reward, uint8_t *d_done,
+                      float *d_ou_x, const tt_replay_ring *ring, tt_stream_t stream);
 
 /* ---- one whole rollout iteration (trainv2.py:511-531 without learn()) as one launch sequence ---- */
 typedef struct tt_rollout_bufs {
@@ -225,8 +250,8 @@ typedef struct tt_rollout_bufs {
     uint8_t *d_terminal_mem;
     int64_t  mem_size, mem_cntr;
 } tt_rollout_bufs;
-/* actor -> OU noise (unless evaluate) -> scale -> env step -> reset finished envs, with the replay store fused into
- * the producers (see above).  Advances the env's iteration counter. */
+/* tt_actor_choose_action (actor + OU noise unless evaluate + scaling + store of s, a) -> tt_env_step_reset (env step + store of
+ * s', r, done + reset of finished envs + tick): two launches.  Advances the env's iteration counter. */
 int tt_rollout_step(tt_env *env, tt_actor *actor, const tt_rollout_bufs *b, int32_t precision,
                     int32_t evaluate, tt_stream_t stream);
 

@@ -25,6 +25,28 @@ VIOLATION_NAMES = ("none", "jackknife", "jackknife_warning", "major_boundary", "
                    "past_the_goal", "max_step", "excessive_backward")
 
 
+# threshold margins reported by tto_step_m (positive = flag raised) and the termination flag each one decides
+MARGIN_NAMES = ("jackknife", "out_of_map", "goal_passed", "excessive_backward", "goal_pos", "goal_ori", "max_steps")
+NMARGINS = 7
+# TT_F_* bit -> margins that decide it (goal_reached is the AND of two tests)
+FLAG_MARGINS = {0: (0,), 1: (1,), 2: (6,), 3: (4, 5), 4: (2,), 5: (3,)}
+# Documented epsilons of a "within-epsilon threshold crossing" (DESIGN.md section 3): the CUDA path carries angles in float64
+# (observed error <= 2e-9 rad, growing with the unstable hitch dynamics) and positions in 2^-25 m fixed point with float32
+# stage arithmetic (observed <= 4e-6 relative = 1.6e-4 m at map scale); max_steps is an integer test (no epsilon).
+MARGIN_EPS = (1e-6, 2e-4, 2e-4, 2e-4, 2e-4, 2e-5, 0.0)
+
+
+def explained_by_margin(flags_a, flags_b, margins):
+    """True when every termination bit that differs between two flag bytes is a within-epsilon threshold crossing."""
+    diff = int(flags_a) ^ int(flags_b)
+    if diff == 0:
+        return False
+    for bit, ms in FLAG_MARGINS.items():
+        if diff >> bit & 1 and not any(abs(margins[m]) < MARGIN_EPS[m] for m in ms):
+            return False
+    return True
+
+
 class Cfg(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("L1", "L2", "v1x", "dt", "map_min", "map_max", "max_hitch",
                                            "steer_max", "pos_thr", "ori_thr", "step_len",
@@ -149,6 +171,16 @@ class OracleEnv:
                              _p(out["comps"]), _p(out["viol"]), _p(out["flags"]), _p(out["done"]), _p(out["success"]))
         return {k: v[:n] for k, v in out.items()}
 
+    def replay_m(self, actions):
+        """``replay`` plus the per-step threshold margins [n, 7] (``MARGIN_NAMES``; positive = flag raised)."""
+        actions = np.ascontiguousarray(actions, np.float32).reshape(-1)
+        T = len(actions)
+        out = dict(state=np.zeros((T, 6)), obs=np.zeros((T, 23), np.float32), comps=np.zeros((T, NCOMP)),
+                   flags=np.zeros((T, NFLAGS), np.uint8), done=np.zeros(T, np.uint8), margins=np.zeros((T, NMARGINS)))
+        n = lib().tto_replay_m(C.byref(self.cfg), C.byref(self.e), _p(actions), T, _p(out["state"]), _p(out["obs"]),
+                               _p(out["comps"]), _p(out["flags"]), _p(out["done"]), _p(out["margins"]))
+        return {k: v[:n] for k, v in out.items()}
+
 
 ACTOR_KEYS = ("fc1.weight", "fc1.bias", "bn1.weight", "bn1.bias", "fc2.weight", "fc2.bias", "bn2.weight",
               "bn2.bias", "mu.weight", "mu.bias")
@@ -192,6 +224,22 @@ def rng_normal(seed, gid, t):
 def ou_step(x, action, reset_mask, seed, gid0, t):
     """In-place on x (float32[N]) and action (float32[N] or None)."""
     lib().tto_ou_step(_p(x), _p(action), _p(reset_mask), len(x), C.c_uint64(seed), C.c_uint32(gid0), C.c_uint32(t))
+
+
+def rollout_replay(seed, gid0, a_raw, pose_t0=0x80000000, iter0=1, cfg=None, want_obs=True):
+    """Open-loop oracle replay of a recorded rollout: ``a_raw`` float32 [T, n] = the ring's raw actions of envs
+    gid0 .. gid0 + n - 1.  See tto_rollout_replay.  Returns arrays shaped [T, n, ...]."""
+    cfg = cfg or default_cfg()
+    a_raw = np.ascontiguousarray(a_raw, np.float32)
+    T, n = a_raw.shape
+    out = dict(rew=np.zeros((T, n)), done=np.zeros((T, n), np.uint8), flags=np.zeros((T, n), np.uint8),
+               state=np.zeros((T, n, 6)), margins=np.zeros((T, n, NMARGINS)), ou=np.zeros((T, n), np.float32))
+    if want_obs:
+        out["s"] = np.zeros((T, n, 23), np.float32); out["s2"] = np.zeros((T, n, 23), np.float32)
+    lib().tto_rollout_replay(C.byref(cfg), C.c_uint64(seed), C.c_uint32(gid0), C.c_uint32(pose_t0), C.c_uint32(iter0),
+                             C.c_int64(n), C.c_int(T), _p(a_raw), _p(out.get("s")), _p(out.get("s2")), _p(out["rew"]),
+                             _p(out["done"]), _p(out["flags"]), _p(out["state"]), _p(out["margins"]), _p(out["ou"]))
+    return out
 
 
 def replay_store(S, A, R, S2, D, cntr, s, a, r, s2, d):

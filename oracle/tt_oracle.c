@@ -247,8 +247,14 @@ enum { F_JACKKNIFE = 0, F_OUT_OF_MAP, F_MAX_STEPS, F_GOAL_REACHED, F_GOAL_PASSED
 
 /* simv2.py:499-545 step(); reward_functionv1.py:6-109 (__init__), :442-506 (compute_reward) and parts.
  * action = scaled steering angle (float32, as DDPG/trainv2.py:516 passes it).  Returns done. */
-TTO_API int tto_step(const tto_cfg *c, tto_env *e, float action, float *obs, double *comps, int *viol,
-                     int *flags, int *success_out) {
+/* tto_step_m additionally reports, for the termination tests, how far the float64 state is from each threshold
+ * (`margins`, may be NULL; the sign is "positive = flag raised"):  [0] |theta| - 90 deg (rad), [1] distance of the closest
+ * of x1,y1,x2,y2 beyond the map edge (m), [2] goal_y - y2 (m), [3] d - (closest + 6) (m), [4] pos_thr - d (m),
+ * [5] ori_thr - |orientation error| (rad), [6] steps - max_episode_steps.  The parity tests accept a termination-step
+ * mismatch against the CUDA path only where the differing flag's margin is inside its documented epsilon. */
+enum { M_JACKKNIFE = 0, M_MAP, M_PAST, M_BACKWARD, M_GOAL_POS, M_GOAL_ORI, M_STEPS, M_NMARGINS };
+TTO_API int tto_step_m(const tto_cfg *c, tto_env *e, float action, float *obs, double *comps, int *viol,
+                       int *flags, int *success_out, double *margins) {
     /* simv2.py:504-505 */
     double delta = clipd((double)action, -c->steer_max, c->steer_max);
     double yn[6];
@@ -351,7 +357,19 @@ TTO_API int tto_step(const tto_cfg *c, tto_env *e, float action, float *obs, dou
     fl[F_EXCESSIVE_BACKWARD] = exb;                                 /* :538 */
     int done = 0;
     for (int i = 0; i < F_NFLAGS; i++) { done |= fl[i]; if (flags) flags[i] = fl[i]; }
+    if (margins) {
+        double out = -1e30;
+        for (int i = 2; i < 6; i++) { out = fmax(out, lo - st[i]); out = fmax(out, st[i] - hi); }
+        margins[M_JACKKNIFE] = fabs(st[0] - st[1]) - c->max_hitch; margins[M_MAP] = out; margins[M_PAST] = e->gy - st[5];
+        margins[M_BACKWARD] = cur - (e->closest + 6.0); margins[M_GOAL_POS] = c->pos_thr - cur;
+        margins[M_GOAL_ORI] = c->ori_thr - oerr; margins[M_STEPS] = (double)(e->steps - e->emax);
+    }
     return done;
+}
+
+TTO_API int tto_step(const tto_cfg *c, tto_env *e, float action, float *obs, double *comps, int *viol,
+                     int *flags, int *success_out) {
+    return tto_step_m(c, e, action, obs, comps, viol, flags, success_out, 0);
 }
 
 /* Replays T actions from the env's current state; arrays are [T,...] row-major; stops after `done`
@@ -369,6 +387,24 @@ TTO_API int tto_replay(const tto_cfg *c, tto_env *e, const float *actions, int T
         if (flags) for (int i = 0; i < F_NFLAGS; i++) flags[F_NFLAGS * t + i] = (uint8_t)fl[i];
         if (done) done[t] = (uint8_t)d;
         if (success) success[t] = (uint8_t)su;
+        n = t + 1;
+        if (d) break;
+    }
+    return n;
+}
+
+/* tto_replay plus the per-step threshold margins [T, M_NMARGINS] (see tto_step_m) */
+TTO_API int tto_replay_m(const tto_cfg *c, tto_env *e, const float *actions, int T, double *state, float *obs,
+                         double *comps, uint8_t *flags, uint8_t *done, double *margins) {
+    int n = 0;
+    for (int t = 0; t < T; t++) {
+        float o[23]; double cp[C_NCOMP]; int v, fl[F_NFLAGS], su;
+        int d = tto_step_m(c, e, actions[t], o, cp, &v, fl, &su, margins ? margins + M_NMARGINS * t : 0);
+        if (state) memcpy(state + 6 * t, e->st, 6 * sizeof(double));
+        if (obs) memcpy(obs + 23 * t, o, sizeof o);
+        if (comps) memcpy(comps + C_NCOMP * t, cp, sizeof cp);
+        if (flags) for (int i = 0; i < F_NFLAGS; i++) flags[F_NFLAGS * t + i] = (uint8_t)fl[i];
+        if (done) done[t] = (uint8_t)d;
         n = t + 1;
         if (d) break;
     }
@@ -500,6 +536,43 @@ TTO_API void tto_ou_step(float *x, float *action, const uint8_t *reset_mask, int
         float xn = xp + 0.2f * (0.0f - xp) * 0.01f + 0.15f * 0.1f * n;
         x[i] = xn;
         if (action) action[i] += xn;                                 /* DDPG_agent.py:41-43 */
+    }
+}
+
+/* Open-loop replay of a recorded rollout (tests): envs [0, n) of a shard with global ids gid0 + i, T iterations of the
+ * training-loop body (DDPG/trainv2.py:489-531) driven by the RAW actions a[T, n] that the rollout stored (what
+ * agent.remember keeps): scaled = clip(a, -1, 1) * float32(pi / 4) (trainv2.py:516), env.step, and on `done` a reset from
+ * the env's Philox pose stream at that iteration (iter0 + t) plus noise.reset().  Outputs are [T, n, ...] row-major like the
+ * ring: s (observation before the step), s2 (after, terminal when done), reward, done, termination bits, state after the
+ * step, threshold margins, and the OU state x that choose_action added at that iteration.  Initial poses: the full
+ * reset's salted counter `pose_t0`. */
+TTO_API void tto_rollout_replay(const tto_cfg *c, uint64_t seed, uint32_t gid0, uint32_t pose_t0, uint32_t iter0, int64_t n, int T,
+                                const float *a, float *s, float *s2, double *rew, uint8_t *done, uint8_t *flags,
+                                double *state, double *margins, float *ou) {
+    for (int64_t i = 0; i < n; i++) {
+        tto_env e; float o[23]; double sx, sy, syaw; float x = 0.0f;
+        const uint32_t gid = gid0 + (uint32_t)i;
+        tto_rng_pose(seed, gid, pose_t0, &sx, &sy, &syaw);
+        tto_reset_pose(c, &e, sx, sy, syaw, 0.0, -30.0, 90.0 * M_PI / 180.0, o);
+        for (int t = 0; t < T; t++) {
+            const int64_t r = (int64_t)t * n + i;
+            x = x + 0.2f * (0.0f - x) * 0.01f + 0.15f * 0.1f * tto_rng_normal(seed, gid, iter0 + (uint32_t)t);
+            if (ou) ou[r] = x;
+            if (s) memcpy(s + r * 23, o, sizeof o);
+            const float scaled = fminf(fmaxf(a[r], -1.0f), 1.0f) * 0.78539819f;
+            float o2[23]; double cp[C_NCOMP]; int v, fl[F_NFLAGS], su;
+            const int d = tto_step_m(c, &e, scaled, o2, cp, &v, fl, &su, margins ? margins + r * M_NMARGINS : 0);
+            if (s2) memcpy(s2 + r * 23, o2, sizeof o2);
+            if (rew) rew[r] = cp[C_TOTAL];
+            if (done) done[r] = (uint8_t)d;
+            if (flags) { uint8_t b = 0; for (int k = 0; k < F_NFLAGS; k++) b |= (uint8_t)(fl[k] << k); flags[r] = b; }
+            if (state) memcpy(state + r * 6, e.st, sizeof e.st);
+            if (d) {
+                tto_rng_pose(seed, gid, iter0 + (uint32_t)t, &sx, &sy, &syaw);
+                tto_reset_pose(c, &e, sx, sy, syaw, 0.0, -30.0, 90.0 * M_PI / 180.0, o);
+                x = 0.0f;
+            } else memcpy(o, o2, sizeof o);
+        }
     }
 }
 

@@ -76,14 +76,15 @@ def _oracle_batch(orc, state0, start, actions):
     """Oracle trajectories for a batch: returns per-step arrays padded after done."""
     N, T = actions.shape
     out = dict(state=np.zeros((N, T, 6)), rew=np.zeros((N, T)), done=np.zeros((N, T), np.uint8), length=np.zeros(N, np.int32),
-               flags=np.zeros((N, T), np.uint8), obs_last=np.zeros((N, 23), np.float32))
+               flags=np.zeros((N, T), np.uint8), obs_last=np.zeros((N, 23), np.float32), margins=np.zeros((N, T, orc.NMARGINS)))
     cfg = orc.default_cfg(0)
     for i in range(N):
         e = orc.OracleEnv(cfg)
         e.set_state(state0[i], start[i])
-        o = e.replay(actions[i])
+        o = e.replay_m(actions[i])
         n = len(o["done"])
         out["state"][i, :n] = o["state"]; out["rew"][i, :n] = o["comps"][:, 0]; out["done"][i, :n] = o["done"]
+        out["margins"][i, :n] = o["margins"]
         out["flags"][i, :n] = (o["flags"] * BITS).sum(1); out["length"][i] = n; out["obs_last"][i] = o["obs"][-1]
     return out
 
@@ -113,11 +114,17 @@ def test_against_oracle_random_batch(N, T):
     flags = info.flags.cpu().numpy().T
     ref = _oracle_batch(orc, state0, start, acts)
     L = ref["length"]
-    # done-step agreement; a mismatch is accepted only as a documented epsilon threshold crossing
+    # done-step agreement: termination flags are exact, except where the float64 oracle state sits within the documented
+    # epsilon of the threshold whose flag differs (oracle.MARGIN_EPS) -- every mismatch is checked
+    # against the oracle's margins at the step where the two paths part, none is accepted by count
     first_done = np.where(done.any(1), done.argmax(1) + 1, T + 1)
     ref_done = np.where(ref["done"].any(1), L, T + 1)
     mism = np.nonzero(first_done != ref_done)[0]
-    assert len(mism) <= max(1, N // 2000), f"{len(mism)} termination mismatches"
+    for i in mism:
+        t = min(first_done[i], ref_done[i]) - 1
+        assert orc.explained_by_margin(flags[i, t], ref["flags"][i, t], ref["margins"][i, t]), \
+            f"env {i} step {t}: flags {flags[i, t]:#x} vs oracle {ref['flags'][i, t]:#x}, margins {ref['margins'][i, t]} -- not a within-epsilon crossing"
+    assert len(mism) <= max(1, N // 2000), f"{len(mism)} epsilon crossings is more than a float32-level effect"
     ok = np.setdiff1d(np.arange(N), mism)
     mask = np.arange(T)[None, :] < L[:, None]
     mask[mism] = False
@@ -143,7 +150,7 @@ def test_step_k_equals_single_steps_and_global_ids():
     rs, ds = [], []
     for t in range(K):
         _, r, d, _ = b.step(acts[t]); rs.append(r.clone()); ds.append(d.clone())
-        b.reset(options={"mask": d}); b.tick()
+        b.reset(options={"mask": d})
     assert torch.equal(rk, torch.stack(rs)) and torch.equal(dk.bool(), torch.stack(ds))
     assert torch.equal(a.state, b.state) and dk.sum() > 50
     c = tt.VecTruckTrailerEnv(300, seed=5, global_env_offset=600); c.reset()
@@ -230,7 +237,7 @@ def test_full_size_properties():
         assert torch.equal(r, rk[t]) and torch.equal(d, dk[t].bool())
         rsum += float(r.double().sum()); dsum += int(d.sum())
         steps_before = b.get_state()["episode_steps"]
-        b.reset(options={"mask": d}); b.tick()
+        b.reset(options={"mask": d})
         steps_after = b.get_state()["episode_steps"]
         assert (steps_after[d] == 0).all() and torch.equal(steps_after[~d], steps_before[~d])
     assert torch.equal(a.state, b.state)

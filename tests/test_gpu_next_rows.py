@@ -155,7 +155,6 @@ def test_episode_recorder_roundtrip(tmp_path):
         r.record(raw, scaled, obs2, rew, done, info)
         obs, _ = env.reset(options={"mask": done})
         agent.noise.reset(done)
-        env.tick()
         r.after_reset(obs, done)
         if len(r.episodes) >= 4:
             break
