@@ -107,6 +107,16 @@ SYMBOLS = {
     "tt_ou_step_store": (C.c_int, [_P, _P, _P, _I64, _U64, _U64, _P, _I32, C.POINTER(ReplayRing), _P]),
     "tt_env_step_store": (C.c_int, [_P, _P, _P, _I64, _P, _P, C.POINTER(ReplayRing), _P]),
     "tt_env_step_reset": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, C.POINTER(ReplayRing), _P]),
+    "tt_learner_workspace_bytes": (C.c_size_t, [_I32, _I32, _I32, _I32]),
+    "tt_learner_create": (C.c_int, [C.POINTER(_P), _I32, _I32, _I32, _I32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _U64, _P, C.c_size_t]),
+    "tt_learner_destroy": (C.c_int, [_P]),
+    "tt_learner_params": (_P, [_P, _I32]),
+    "tt_learner_param_count": (_I64, [_P, _I32]),
+    "tt_learner_grads": (_P, [_P, _I32]),
+    "tt_learner_last_q": (_P, [_P]),
+    "tt_learner_last_rows": (_P, [_P]),
+    "tt_learner_reset_optimizer": (C.c_int, [_P, _P]),
+    "tt_learn_step": (C.c_int, [_P, C.POINTER(ReplayRing), _P, _P, _P]),
     "tt_rollout_step": (C.c_int, [_P, _P, C.POINTER(RolloutBufs), _I32, _I32, _P]),
 }
 

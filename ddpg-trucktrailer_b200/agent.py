@@ -2,9 +2,8 @@
 DDPG/DDPG_agent.py:9-52 for N observations at once.
 
 The actor forward (DDPG/networks.py:138-147), the per-env Ornstein-Uhlenbeck noise (DDPG/noise.py) and the
-replay store run as CUDA kernels behind the C ABI.  ``learn()`` (DDPG_agent.py:72-106) is the learner and
-not part of this path; it is provided as a plain torch step on the device ring
-so that the reference driver loop runs end to end.
+replay store run as CUDA kernels behind the C ABI.  ``learn()`` (DDPG_agent.py:72-106)
+is ``tt_learn_step``: hand-written kernels on the device ring (learner.py, csrc/tt_learn.cu).
 """
 from __future__ import annotations
 
@@ -195,13 +194,10 @@ class VecAgent:
     chkpt_dir = "tmp/ddpg"
 
     def _state_dicts(self):
-        sds = {"actor": self.actor.state_dict()}
-        if self._learner is not None:
-            ln = self._learner
-            sds.update(target_actor=ln.target_actor.state_dict(), critic=ln.critic.state_dict(), target_critic=ln.target_critic.state_dict())
-        else:
-            sds["target_actor"] = self.actor.state_dict()        # update_network_parameters(tau=1), DDPG_agent.py:34
-        return sds
+        if self._learner is not None:                            # the learner owns the four networks once it exists
+            return {n: self._learner.state_dict(n) for n in ("actor", "target_actor", "critic", "target_critic")}
+        sd = self.actor.state_dict()
+        return {"actor": sd, "target_actor": sd}                 # update_network_parameters(tau=1), DDPG_agent.py:34
 
     def save_models(self):
         """``Agent.save_models``: <chkpt_dir>/{actor,target_actor,critic,target_critic}_ddpg in the reference's format
@@ -215,32 +211,33 @@ class VecAgent:
 
     def load_models(self):
         """``Agent.load_models``: loads whatever of the four reference checkpoints exists; the actor goes to the CUDA
-        kernels' weight layouts (fp32 + tensor-core images), the others to the learner."""
+        kernels' weight layouts (fp32 + tensor-core images), all four to the learner."""
         from . import checkpoint
         sds = checkpoint.load_models(self.chkpt_dir)
         if "actor" not in sds:
             raise FileNotFoundError(checkpoint.checkpoint_path(self.chkpt_dir, "actor"))
         checkpoint.check_actor_state_dict(sds["actor"], *self.actor.dims)
         self.actor.load_state_dict(sds["actor"])
-        if len(sds) > 1:
-            from .learner import TorchLearner
-            if self._learner is None:
-                self._learner = TorchLearner(self)
-            ln = self._learner
-            ln.actor.load_state_dict(sds["actor"])
-            for name, net in (("target_actor", ln.target_actor), ("critic", ln.critic), ("target_critic", ln.target_critic)):
+        if len(sds) > 1 or self._learner is not None:
+            ln = self.learner
+            for name in ("actor", "target_actor", "critic", "target_critic"):
                 if name in sds:
-                    net.load_state_dict(sds[name])
+                    ln.load_state_dict(name, sds[name])
+            ln.push_actor()
         return sorted(sds)
 
-    learner_graph = False          # True: capture the learner step into one CUDA graph (learner.py)
+    @property
+    def learner(self):
+        """The ``CudaLearner`` (created on first use: critic / targets initialised like the reference ``Agent.__init__``)."""
+        if self._learner is None:
+            from .learner import CudaLearner
+            self._learner = CudaLearner(self)
+        return self._learner
 
     def learn(self):
-        """Learner step (DDPG_agent.py:72-106), not part of the B200 hot path: plain torch on the device ring."""
-        from .learner import TorchLearner
-        if self._learner is None:
-            self._learner = TorchLearner(self, graph=self.learner_graph)
-        return self._learner.learn()
+        """``Agent.learn`` (DDPG_agent.py:72-106): one DDPG update on a batch sampled from the device ring; the new policy is
+        re-packed into the rollout actor.  Hand-written kernels (``tt_learn_step``), no torch autograd."""
+        return self.learner.learn()
 
 
 class Agent(VecAgent):

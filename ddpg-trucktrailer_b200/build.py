@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtt_b200.so")
-SOURCES = ["tt_lib.cu", "tt_env.cu", "tt_agent.cu", "tt_actor_tc4.cu", "tt_replay.cu", "tt_rollout.cu"]
+SOURCES = ["tt_lib.cu", "tt_env.cu", "tt_agent.cu", "tt_actor_tc4.cu", "tt_replay.cu", "tt_rollout.cu", "tt_learn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=default", "--expt-relaxed-constexpr"]
 

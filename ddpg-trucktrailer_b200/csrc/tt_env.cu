@@ -284,16 +284,21 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                 }
             }
             if (kRoll) {
-                // tiles[0] = what the ring stores as new_state (terminal rows), tiles[1] = what the next iteration observes (reset
-                // rows for finished envs).  One bulk store each; they drain while the CTA computes its next tile, and the wait for
-                // their shared-memory reads sits here, a whole tile of arithmetic later.
-                float *tileA = tiles[0], *tileB = tiles[1];
-                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncthreads();
+                // Per WARP (32 envs = 2 944 B of observation rows): tiles[0] = what the ring stores as new_state (terminal rows),
+                // tiles[1] = what the next iteration observes (reset rows for finished envs), one bulk store each.  No block-wide
+                // barrier: a warp that has to reset an env (Philox pose, float64 sin / cos, observation: a few hundred dependent
+                // instructions, ~1 warp in 3) does not hold up the other three.  The bulk stores drain while the warp computes its
+                // next tile; the wait for their shared-memory reads sits here, a whole tile of arithmetic later.
+                const int wib = threadIdx.x >> 5, ln = threadIdx.x & 31;
+                float *tileA = tiles[0] + wib * 32 * TT_OBS_DIM, *tileB = tiles[1] + wib * 32 * TT_OBS_DIM;
+                const int64_t wrow0 = row0 + 32 * wib;
+                const int wrows = rows - 32 * wib < 0 ? 0 : (rows - 32 * wib > 32 ? 32 : rows - 32 * wib);
+                if (ln == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
                 if (active) {
                     if (rpl.S2) {
 #pragma unroll
-                        for (int c = 0; c < TT_OBS_DIM; c++) tileA[threadIdx.x * TT_OBS_DIM + c] = o.obs[c];
+                        for (int c = 0; c < TT_OBS_DIM; c++) tileA[ln * TT_OBS_DIM + c] = o.obs[c];
                     }
                     if (o.done) {                                        // trainv2.py:489-492: env.reset() + agent.noise.reset()
                         double sx, sy, syaw;
@@ -303,29 +308,34 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                         if (ou_x) ou_x[i] = 0.0f;
                     }
 #pragma unroll
-                    for (int c = 0; c < TT_OBS_DIM; c++) tileB[threadIdx.x * TT_OBS_DIM + c] = o.obs[c];
+                    for (int c = 0; c < TT_OBS_DIM; c++) tileB[ln * TT_OBS_DIM + c] = o.obs[c];
                 }
-                const int64_t rrow0 = rpl.S2 ? rpl.m.row(row0) : 0;
-                const bool ring_bulk = rpl.S2 && rows == kBlock && !rpl.m.many && row0 >= rpl.m.first && rrow0 + kBlock <= rpl.m.cap &&
+                const int64_t rrow0 = (rpl.S2 && wrows > 0) ? rpl.m.row(wrow0) : 0;
+                const bool ring_bulk = rpl.S2 && wrows == 32 && !rpl.m.many && wrow0 >= rpl.m.first && rrow0 + 32 <= rpl.m.cap &&
                                        (rrow0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(rpl.S2) & 15) == 0);
-                const bool obs_bulk = bulk_ok && rows == kBlock;
+                const bool obs_bulk = bulk_ok && wrows == 32;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();
-                if (threadIdx.x == 0 && (obs_bulk || ring_bulk)) {
-                    const uint32_t bytes = (uint32_t)(kBlock * TT_OBS_DIM * sizeof(float));
+                __syncwarp();
+                if (ln == 0 && (obs_bulk || ring_bulk)) {
+                    const uint32_t bytes = (uint32_t)(32 * TT_OBS_DIM * sizeof(float));
                     if (obs_bulk)
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(obs + row0 * TT_OBS_DIM), "r"((uint32_t)__cvta_generic_to_shared(tileB)), "r"(bytes) : "memory");
+                                     ::"l"(obs + wrow0 * TT_OBS_DIM), "r"((uint32_t)__cvta_generic_to_shared(tileB)), "r"(bytes) : "memory");
                     if (ring_bulk)
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                      ::"l"(rpl.S2 + rrow0 * TT_OBS_DIM), "r"((uint32_t)__cvta_generic_to_shared(tileA)), "r"(bytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if (!obs_bulk) store_obs_tile(tileB, obs, ld, row0, rows);
-                if (rpl.S2 && !ring_bulk) {
-                    for (int v = threadIdx.x; v < rows * TT_OBS_DIM; v += kBlock) {
+                if (!obs_bulk) {
+                    for (int v = ln; v < wrows * TT_OBS_DIM; v += 32) {
                         const int r = v / TT_OBS_DIM, c = v - r * TT_OBS_DIM;
-                        if (row0 + r >= rpl.m.first) rpl.S2[rpl.m.row(row0 + r) * TT_OBS_DIM + c] = tileA[v];
+                        obs[(wrow0 + r) * ld + c] = tileB[v];
+                    }
+                }
+                if (rpl.S2 && !ring_bulk) {
+                    for (int v = ln; v < wrows * TT_OBS_DIM; v += 32) {
+                        const int r = v / TT_OBS_DIM, c = v - r * TT_OBS_DIM;
+                        if (wrow0 + r >= rpl.m.first) rpl.S2[rpl.m.row(wrow0 + r) * TT_OBS_DIM + c] = tileA[v];
                     }
                 }
             } else if (obs) {
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
         if (active) store_dyn(p, i, e);
     }
 
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all bulk stores complete
+    if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all bulk stores (of this issuing lane) complete
     if (kRoll) {
         // iteration tick: every CTA read *p.iter (t0) when it started, and the last one to get here has seen all others finish
         __syncthreads();

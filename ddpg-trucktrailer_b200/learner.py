@@ -1,136 +1,154 @@
-"""Learner step of the reference (``Agent.learn``, DDPG/DDPG_agent.py:72-131; critic DDPG/networks.py:9-68)
-as plain PyTorch on the device-resident replay ring.  NOT part of the B200 hot path (SURVEY.md section 8f,
-row f1 "next"): it exists so that a driver written against the reference API runs end to end, and it
-hands updated actor weights back to the CUDA actor.
-
-``TorchLearner(agent, graph=True)`` captures the whole step -- index sampling, the ring gather kernel (tt_replay_gather),
-both forward / backward passes, Adam, the soft target update and the re-pack of the new actor weights into the CUDA
-actor's fp32 / tensor-core layouts (tt_actor_load) -- into ONE CUDA graph (fused Adam, multi-tensor soft update): the step is
-~200 tiny launches, i.e. pure launch latency in eager mode (3.0 ms eager, 0.51 ms as a graph on a B200)."""
+"""Learner step of the reference (``Agent.learn``, DDPG/DDPG_agent.py:72-131; networks DDPG/networks.py:9-68, :98-147;
+``ReplayBuffer.sample_buffer`` DDPG/replay_buffer.py:23-34) on the device-resident replay ring: row f1 of SURVEY.md
+section 8.  ``CudaLearner`` binds ``tt_learn_step`` (csrc/tt_learn.cu): 13 hand-written kernels -- sampling + gather, the
+forward passes of the four networks as grouped launches, both backward passes, Adam (critic weight decay 0.01), the soft
+target updates -- followed by the re-pack of the new policy into the rollout actor's operand images.  No torch.nn, no
+autograd, no cuBLAS; every launch goes to the caller's stream and the sequence is graph-capturable.
+"""
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
-import torch.nn as nn
-import torch.nn.functional as F
 
-from .agent import ACTOR_KEYS
+from . import _lib
+from ._lib import check, stream_ptr
 
-
-class _Actor(nn.Module):
-    def __init__(self, i, h1, h2):
-        super().__init__()
-        self.fc1, self.fc2 = nn.Linear(i, h1), nn.Linear(h1, h2)
-        self.bn1, self.bn2 = nn.LayerNorm(h1), nn.LayerNorm(h2)
-        self.mu = nn.Linear(h2, 1)
-
-    def forward(self, s):
-        x = F.relu(self.bn1(self.fc1(s)))
-        x = F.relu(self.bn2(self.fc2(x)))
-        return torch.tanh(self.mu(x))
+ACTOR_KEYS = ("fc1.weight", "fc1.bias", "bn1.weight", "bn1.bias", "fc2.weight", "fc2.bias", "bn2.weight", "bn2.bias",
+              "mu.weight", "mu.bias")
+# the reference CriticNetwork's state_dict order (module registration order, networks.py:20-33)
+CRITIC_KEYS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias",
+               "action_value.weight", "action_value.bias", "q.weight", "q.bias")
+NETS = ("actor", "target_actor", "critic", "target_critic")
 
 
-class _Critic(nn.Module):
-    def __init__(self, i, h1, h2):
-        super().__init__()
-        self.fc1, self.fc2 = nn.Linear(i, h1), nn.Linear(h1, h2)
-        self.bn1, self.bn2 = nn.LayerNorm(h1), nn.LayerNorm(h2)
-        self.action_value, self.q = nn.Linear(1, h2), nn.Linear(h2, 1)
-        for lin, f in ((self.fc1, 1 / np.sqrt(h1)), (self.fc2, 1 / np.sqrt(h2)), (self.q, 0.003), (self.action_value, 1 / np.sqrt(h2))):
-            lin.weight.data.uniform_(-f, f); lin.bias.data.uniform_(-f, f)
-
-    def forward(self, s, a):
-        x = F.relu(self.bn1(self.fc1(s)))
-        x = self.bn2(self.fc2(x))
-        return self.q(F.relu(x + self.action_value(a)))
+def _flat_layout(kind, i, h1, h2):
+    """name -> (offset, shape) inside the flat float32 parameter vector of one network (include/tt_b200.h)."""
+    trunk = [("fc1.weight", (h1, i)), ("fc1.bias", (h1,)), ("bn1.weight", (h1,)), ("bn1.bias", (h1,)),
+             ("fc2.weight", (h2, h1)), ("fc2.bias", (h2,)), ("bn2.weight", (h2,)), ("bn2.bias", (h2,))]
+    tail = [("mu.weight", (1, h2)), ("mu.bias", (1,))] if kind == "actor" else \
+           [("action_value.weight", (h2, 1)), ("action_value.bias", (h2,)), ("q.weight", (1, h2)), ("q.bias", (1,))]
+    out, off = {}, 0
+    for name, shape in trunk + tail:
+        out[name] = (off, shape)
+        off += int(np.prod(shape))
+    return out, off
 
 
-class TorchLearner:
-    def __init__(self, agent, graph=False):
+def init_critic_state_dict(input_dims=23, fc1_dims=400, fc2_dims=300, n_actions=1, seed=None):
+    """Initial critic parameters with the reference's distributions and draw order (networks.py:20-45): fc1 / fc2
+    U(+-1/sqrt(out_features)), q U(+-0.003), action_value U(+-1/sqrt(fc2_dims)), LayerNorm (1, 0)."""
+    import torch.nn as nn
+    if seed is not None:
+        torch.manual_seed(seed)
+    fc1, fc2 = nn.Linear(input_dims, fc1_dims), nn.Linear(fc1_dims, fc2_dims)
+    bn1, bn2 = nn.LayerNorm(fc1_dims), nn.LayerNorm(fc2_dims)
+    av, q = nn.Linear(n_actions, fc2_dims), nn.Linear(fc2_dims, 1)
+    for lin, f in ((fc1, 1.0 / np.sqrt(fc1_dims)), (fc2, 1.0 / np.sqrt(fc2_dims)), (q, 0.003), (av, 1.0 / np.sqrt(fc2_dims))):
+        lin.weight.data.uniform_(-f, f); lin.bias.data.uniform_(-f, f)
+    mods = {"fc1": fc1, "fc2": fc2, "bn1": bn1, "bn2": bn2, "action_value": av, "q": q}
+    return {k: getattr(mods[k.split(".")[0]], k.split(".")[1]).data.clone() for k in CRITIC_KEYS}
+
+
+class CudaLearner:
+    """The four networks of the reference ``Agent`` + both Adam states + the batch workspace in one device workspace;
+    ``learn()`` = one ``Agent.learn()``.  Parameters are exchanged as reference-layout state_dicts."""
+
+    def __init__(self, agent, seed=None, critic_seed=None, critic_weight_decay=0.01):
+        _lib.require_cuda()
         self.agent = agent
-        self.use_graph = bool(graph)
-        self._graph = None
+        self.L = _lib.load()
+        self.device = agent.device
         i, h1, h2 = agent.actor.dims
-        dev = agent.device
-        self.actor, self.target_actor = _Actor(i, h1, h2).to(dev), _Actor(i, h1, h2).to(dev)
-        self.critic, self.target_critic = _Critic(i, h1, h2).to(dev), _Critic(i, h1, h2).to(dev)
-        self.actor.load_state_dict(agent.actor.state_dict())
-        self.target_actor.load_state_dict(self.actor.state_dict())
-        self.target_critic.load_state_dict(self.critic.state_dict())
-        cap = dict(capturable=True, fused=True) if self.use_graph else {}      # one kernel per optimizer step inside the graph
-        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=agent.alpha, **cap)
-        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=agent.beta, weight_decay=0.01, **cap)
+        self.dims, self.batch = (i, h1, h2), int(agent.batch_size)
+        with torch.cuda.device(self.device):
+            nbytes = self.L.tt_learner_workspace_bytes(i, h1, h2, self.batch)
+            if nbytes == 0:
+                raise ValueError("learner: unsupported sizes")
+            self._ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (self._ws.data_ptr() + 255) // 256 * 256
+            h = C.c_void_p()
+            check(self.L.tt_learner_create(C.byref(h), i, h1, h2, self.batch, float(agent.alpha), float(agent.beta), float(agent.gamma),
+                                           float(agent.tau), float(critic_weight_decay), int(agent.noise.seed if seed is None else seed),
+                                           base, nbytes))
+            self._h = h
+            # float32 views of the flat parameter / gradient vectors inside the workspace
+            self._flat, self._params, self._gflat = {}, {}, {}
+            for n, name in enumerate(NETS):
+                kind = "actor" if "actor" in name else "critic"
+                layout, count = _flat_layout(kind, i, h1, h2)
+                assert count == self.L.tt_learner_param_count(h, n)
+                off = self.L.tt_learner_params(h, n) - self._ws.data_ptr()
+                flat = self._ws[off:off + 4 * count].view(torch.float32)
+                self._flat[name] = flat
+                self._params[name] = {k: flat[o:o + int(np.prod(shp))].view(shp) for k, (o, shp) in layout.items()}
+            for which, name in enumerate(("actor", "critic")):
+                off = self.L.tt_learner_grads(h, which) - self._ws.data_ptr()
+                self._gflat[name] = self._ws[off:off + 4 * self._flat[name].numel()].view(torch.float32)
+            # Agent.__init__ (DDPG_agent.py:22-34): targets start as copies (update_network_parameters(tau=1))
+            self.load_state_dict("actor", agent.actor.state_dict())
+            self.load_state_dict("target_actor", agent.actor.state_dict())
+            csd = init_critic_state_dict(i, h1, h2, 1, seed=critic_seed)
+            self.load_state_dict("critic", csd)
+            self.load_state_dict("target_critic", csd)
+        self.steps = 0
 
-    @torch.no_grad()
-    def _soft_update(self, net, target, tau):
-        ps, tps = list(net.parameters()), list(target.parameters())
-        if self.use_graph:                                       # two multi-tensor kernels instead of two per parameter
-            torch._foreach_mul_(tps, 1 - tau)
-            torch._foreach_add_(tps, ps, alpha=tau)
-            return
-        for p, tp in zip(ps, tps):
-            tp.mul_(1 - tau).add_(p, alpha=tau)
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self.L.tt_learner_destroy(h)
+            except Exception:
+                pass
+            self._h = None
 
-    def learn(self):
-        ag = self.agent
-        if ag.memory.mem_cntr < ag.batch_size:
-            return
-        if self.use_graph:
-            return self._learn_graph()
-        s, a, r, s2, d = ag.memory.sample_buffer(ag.batch_size)
-        self._update(s, a, r, s2, d)
-        ag.actor.load_state_dict({k: v.detach() for k, v in self.actor.state_dict().items() if k in ACTOR_KEYS})
+    # ---- parameter exchange (reference state_dict layout) ----
+    def state_dict(self, net):
+        keys = ACTOR_KEYS if "actor" in net else CRITIC_KEYS
+        return {k: self._params[net][k].detach().clone() for k in keys}
 
-    def _update(self, s, a, r, s2, d):
-        """DDPG_agent.py:84-106 on one batch."""
-        ag = self.agent
-        with torch.no_grad():
-            q2 = self.target_critic(s2, self.target_actor(s2))
-            q2 = q2.masked_fill(d.view(-1, 1), 0.0)                         # critic_value_[done] = 0.0
-            target = (r + ag.gamma * q2.view(-1)).view(ag.batch_size, 1)
-        self.critic_opt.zero_grad()
-        F.mse_loss(target, self.critic(s, a)).backward()
-        self.critic_opt.step()
-        self.actor_opt.zero_grad()
-        (-self.critic(s, self.actor(s))).mean().backward()
-        self.actor_opt.step()
-        self._soft_update(self.actor, self.target_actor, ag.tau)
-        self._soft_update(self.critic, self.target_critic, ag.tau)
+    def load_state_dict(self, net, sd):
+        for k, view in self._params[net].items():
+            t = torch.as_tensor(sd[k]).detach().to(device=self.device, dtype=torch.float32)
+            if tuple(t.shape) != tuple(view.shape):
+                raise ValueError(f"{net}.{k}: expected shape {tuple(view.shape)}, got {tuple(t.shape)}")
+            view.copy_(t)
 
-    # ------------------------------------------------------------------ the whole step as one CUDA graph
-    def _graph_body(self):
-        from . import _lib
-        ag, m, B = self.agent, self.agent.memory, self.agent.batch_size
-        rows = (torch.rand(B, device=ag.device) * self._max_mem).long().clamp_(max=m.mem_size - 1)     # replay_buffer.py:26
-        s, a, r, s2, d = self._batch
-        _lib.check(m.L.tt_replay_gather(m.state_memory.data_ptr(), m.action_memory.data_ptr(), m.reward_memory.data_ptr(),
-                                        m.new_state_memory.data_ptr(), m.terminal_memory.data_ptr(), rows.data_ptr(), B, s.data_ptr(),
-                                        a.data_ptr(), r.data_ptr(), s2.data_ptr(), d.data_ptr(), _lib.stream_ptr()))
-        self._update(s, a, r, s2, d.bool())
-        p = dict(self.actor.named_parameters())
-        _lib.check(ag.actor.L.tt_actor_load(ag.actor._h, *[p[k].data_ptr() for k in ACTOR_KEYS], _lib.stream_ptr()))
+    def grads(self, net):
+        """Gradients of the last step (``actor`` or ``critic``) as a name -> tensor dict (diagnostics / tests)."""
+        kind = "actor" if net == "actor" else "critic"
+        layout, _ = _flat_layout(kind, *self.dims)
+        g = self._gflat[kind]
+        return {k: g[o:o + int(np.prod(shp))].view(shp).clone() for k, (o, shp) in layout.items()}
 
-    def _learn_graph(self):
+    def reset_optimizer(self):
+        with torch.cuda.device(self.device):
+            check(self.L.tt_learner_reset_optimizer(self._h, stream_ptr()))
+
+    def push_actor(self, actor=None):
+        """Re-pack the learner's current actor parameters into a rollout actor (default: the agent's)."""
+        actor = actor or self.agent.actor
+        actor.load_state_dict(self._params["actor"])
+        actor._sd = {k: self._params["actor"][k] for k in ACTOR_KEYS}       # the rollout actor's state_dict follows the learner
+
+    # ---- Agent.learn ----
+    def learn(self, rows=None, repack_into="agent"):
+        """One DDPG update on a batch sampled from the agent's ring (``rows``: explicit ring rows instead, int64 [batch]).
+        ``repack_into``: rollout actor that receives the new policy ("agent" = the agent's, None = nobody)."""
         ag, m = self.agent, self.agent.memory
-        with torch.cuda.device(ag.device):
-            if self._graph is None:
-                B, dev = ag.batch_size, ag.device
-                self._max_mem = torch.zeros((), dtype=torch.float32, device=dev)
-                self._batch = (torch.empty(B, 23, device=dev), torch.empty(B, 1, device=dev), torch.empty(B, device=dev),
-                               torch.empty(B, 23, device=dev), torch.empty(B, dtype=torch.uint8, device=dev))
-                self._max_mem.fill_(float(min(m.mem_cntr, m.mem_size)))
-                # the rollout actor reads the learner's parameter tensors from now on (static addresses)
-                ag.actor._sd = {k: v for k, v in self.actor.named_parameters() if k in ACTOR_KEYS}
-                side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):                      # warm-up outside the capture (allocator, Adam state, cuBLAS)
-                    for _ in range(3):
-                        self._graph_body()
-                torch.cuda.current_stream().wait_stream(side)
-                self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph):
-                    self._graph_body()
-                self.graph_warmup_steps = 3
-                return
-            self._max_mem.fill_(float(min(m.mem_cntr, m.mem_size)))
-            self._graph.replay()
+        if m.mem_cntr < self.batch:                                          # DDPG_agent.py:73-74
+            return
+        with torch.cuda.device(self.device):
+            ring = _lib.ReplayRing(m.state_memory.data_ptr(), m.action_memory.data_ptr(), m.reward_memory.data_ptr(),
+                                   m.new_state_memory.data_ptr(), m.terminal_memory.data_ptr(), m.mem_size, m.mem_cntr)
+            if rows is not None:
+                rows = torch.as_tensor(rows, dtype=torch.int64, device=self.device).contiguous()
+                if rows.numel() != self.batch:
+                    raise ValueError(f"rows: expected {self.batch} ring rows")
+            target = ag.actor if repack_into == "agent" else repack_into
+            check(self.L.tt_learn_step(self._h, C.byref(ring), None if rows is None else rows.data_ptr(),
+                                       target._h if target is not None else None, stream_ptr()))
+            if target is not None:
+                target._sd = {k: self._params["actor"][k] for k in ACTOR_KEYS}
+        self.steps += 1

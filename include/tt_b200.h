@@ -255,6 +255,36 @@ typedef struct tt_rollout_bufs {
 int tt_rollout_step(tt_env *env, tt_actor *actor, const tt_rollout_bufs *b, int32_t precision,
                     int32_t evaluate, tt_stream_t stream);
 
+/* ---- learner: Agent.learn (DDPG/DDPG_agent.py:72-131) on the device-resident ring ---- */
+/* One tt_learner holds the four networks of the reference Agent (actor, target_actor, critic, target_critic:
+ * DDPG/networks.py:9-68, :98-147), both Adam states and the batch workspace inside the caller's workspace.  Parameters
+ * of a network are ONE flat float32 vector, tensors in this order (shapes as in the reference state_dict):
+ *   actor  (net 0, target 1): fc1.weight[h1,in] fc1.bias[h1] bn1.weight[h1] bn1.bias[h1] fc2.weight[h2,h1] fc2.bias[h2]
+ *                             bn2.weight[h2] bn2.bias[h2] mu.weight[1,h2] mu.bias[1]
+ *   critic (net 2, target 3): the same eight trunk tensors, then action_value.weight[h2,1] action_value.bias[h2]
+ *                             q.weight[1,h2] q.bias[1]
+ * tt_learner_params returns the device pointer (inside the workspace) the caller reads / writes to exchange weights. */
+typedef struct tt_learner tt_learner;
+size_t tt_learner_workspace_bytes(int32_t in_dim, int32_t h1, int32_t h2, int32_t batch);
+int tt_learner_create(tt_learner **out, int32_t in_dim, int32_t h1, int32_t h2, int32_t batch, float alpha, float beta,
+                      float gamma, float tau, float critic_weight_decay, uint64_t seed, void *d_workspace,
+                      size_t workspace_bytes);
+int tt_learner_destroy(tt_learner *ln);
+float  *tt_learner_params(tt_learner *ln, int32_t net);          /* 0 actor, 1 target_actor, 2 critic, 3 target_critic */
+int64_t tt_learner_param_count(tt_learner *ln, int32_t net);
+float  *tt_learner_grads(tt_learner *ln, int32_t which);         /* gradients of the last step: 0 actor, 1 critic (same layout) */
+const float   *tt_learner_last_q(tt_learner *ln);                /* [batch] critic(s, a) of the last step */
+const int64_t *tt_learner_last_rows(tt_learner *ln);             /* [batch] ring rows of the last step */
+int tt_learner_reset_optimizer(tt_learner *ln, tt_stream_t stream);   /* zero both Adam states and the step counter */
+/* One Agent.learn(): sample `batch` rows uniformly with replacement from the filled part of the ring
+ * (replay_buffer.py:23-34; Philox(seed; b, step, stream 2) -- or the given d_rows[batch] when not NULL), critic update
+ * (MSE on r + gamma Q'(s', pi'(s')) with terminal masking, Adam with weight decay), actor update (ascent on Q(s, pi(s))
+ * through the UPDATED critic, Adam), soft update of both targets (tau).  If repack_into != NULL the new actor parameters are
+ * then re-packed into that rollout actor (tt_actor_load).  13 kernel launches (+ 7 of the re-pack) on `stream`, no
+ * synchronisation, graph-capturable (the step counter lives in device memory), deterministic. */
+int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_rows, tt_actor *repack_into,
+                  tt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

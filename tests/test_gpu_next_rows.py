@@ -200,51 +200,3 @@ def test_save_and_load_models(tmp_path):
         assert torch.equal(a.actor.forward(obs, precision=prec).clone(), b.actor.forward(obs, precision=prec).clone())
     sd = torch.load(os.path.join(a.chkpt_dir, "actor_ddpg"))
     assert list(sd) == list(tt.ACTOR_KEYS) or set(sd) == set(tt.ACTOR_KEYS)
-
-
-def test_learner_graph_equals_eager_and_updates_rollout_actor():
-    """f1: the learner step captured as one CUDA graph == the eager step.  The ring holds one transition repeated, so any
-    sampled batch is the same batch and the two modes (different index RNGs) must agree up to the rounding differences of
-    Adam's capturable code path; the rollout actor follows the learner's weights."""
-    import time
-    import ddpg_trucktrailer_b200 as tt
-    from ddpg_trucktrailer_b200.learner import TorchLearner
-    torch.manual_seed(0)
-    cap, B = 4096, 64
-    s = torch.empty(1, 23, device="cuda").uniform_(-1, 1).expand(cap, 23).contiguous()
-    s2 = torch.empty(1, 23, device="cuda").uniform_(-1, 1).expand(cap, 23).contiguous()
-
-    def make():
-        ag = tt.VecAgent(1e-4, 1e-3, (23,), 1e-3, 1, num_envs=cap, max_size=cap, actor_seed=3, batch_size=B)
-        ag.remember(s, torch.full((cap,), 0.3, device="cuda"), torch.full((cap,), 7.0, device="cuda"), s2,
-                    torch.zeros(cap, dtype=torch.uint8, device="cuda"))
-        return ag
-
-    ag_e, ag_g = make(), make()
-    le, lg = TorchLearner(ag_e, graph=False), TorchLearner(ag_g, graph=True)
-    for name in ("actor", "target_actor", "critic", "target_critic"):           # identical starting networks
-        getattr(lg, name).load_state_dict(getattr(le, name).state_dict())
-    steps = 8
-    for _ in range(steps):
-        le.learn()
-    lg.learn()                                                # capture: runs 3 warm-up steps + records (no replay yet)
-    for _ in range(steps - lg.graph_warmup_steps):
-        lg.learn()
-    for name in ("actor", "target_actor", "critic", "target_critic"):
-        a, b = getattr(le, name).state_dict(), getattr(lg, name).state_dict()
-        for k in a:
-            assert torch.allclose(a[k], b[k], rtol=1e-3, atol=2e-5), (name, k, (a[k] - b[k]).abs().max())
-    moved = (le.actor.fc1.weight - torch.as_tensor(tt.init_actor_state_dict(seed=3)["fc1.weight"], device="cuda")).abs().max()
-    assert moved > 1e-4
-    obs = torch.empty(512, 23, device="cuda").uniform_(-1, 1)
-    out_g = ag_g.actor.forward(obs).clone()
-    with torch.no_grad():
-        want = lg.actor(obs).reshape(-1)
-    assert (out_g - want).abs().max() < 1e-5                  # the CUDA actor was re-packed inside the graph
-    assert set(ag_g.actor.state_dict()) == set(tt.ACTOR_KEYS)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(50): le.learn()
-    torch.cuda.synchronize(); t1 = time.perf_counter()
-    for _ in range(50): lg.learn()
-    torch.cuda.synchronize(); t2 = time.perf_counter()
-    print(f"learner step: eager {(t1 - t0) / 50 * 1e3:.3f} ms, one CUDA graph {(t2 - t1) / 50 * 1e3:.3f} ms")

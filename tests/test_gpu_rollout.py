@@ -269,7 +269,7 @@ def test_choose_action_one_launch_equals_separate_kernels(precision, N, evaluate
 def test_step_reset_one_launch_equals_separate_kernels(N, cap, cntr0, store):
     """tt_env_step_reset (env step + ring store + reset of finished envs + OU zeroing + iteration tick in ONE launch) ==
     tt_env_step_store + tt_env_reset(mask = done) + masked zeroing + tt_env_tick, bit for bit, over 40 iterations in which
-    ~half of the envs finish an episode: observations (reset rows), rewards, done, ring rows (terminal rows), env state,
+    ~10 % of the envs finish an episode: observations (reset rows), rewards, done, ring rows (terminal rows), env state,
     start poses, OU state, statistics, iteration counter."""
     import ctypes as C
     import ddpg_trucktrailer_b200 as tt
@@ -308,7 +308,7 @@ def test_step_reset_one_launch_equals_separate_kernels(N, cap, cntr0, store):
                         d=mem.terminal_memory.clone(), state=st["state"], start=st["start"], steps=st["episode_steps"], x=x.clone(),
                         stats=env.read_stats(), tot=tot))
     a, b = res
-    assert a["tot"] == b["tot"] and a["tot"] > N // 3
+    assert a["tot"] == b["tot"] and a["tot"] > N // 20
     for k in ("obs", "rew", "done", "s2", "r", "d", "state", "start", "steps", "x"):
         assert torch.equal(a[k], b[k]), k
     assert a["stats"] == b["stats"]

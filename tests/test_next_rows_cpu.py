@@ -144,11 +144,12 @@ def test_sweep_poses_and_classification():
 
 
 def test_learner_step_matches_reference_learn(golden_dir):
-    """f1: TorchLearner.learn == the reference's Agent.learn (DDPG_agent.py:72-131: critic MSE on the bootstrapped target
+    """f1 checker: oracle/torch_learner.py (the torch restatement the CUDA learner is tested against on the GPU,
+    tests/test_gpu_learner.py) == the reference's Agent.learn (DDPG_agent.py:72-131: critic MSE on the bootstrapped target
     with terminal masking, Adam (critic weight_decay 0.01), actor ascent on Q, soft target update) -- three consecutive
     steps from the reference's initial weights on the reference's batches (tests/golden/ref_learn.npz, generated by
     oracle/make_golden_learn.py from the untouched reference)."""
-    ln_mod = _load("learner")
+    from oracle import torch_learner as ln_mod
     g = np.load(os.path.join(golden_dir, "ref_learn.npz"))
     dims = tuple(int(v) for v in g["dims"])
     alpha, beta, tau, gamma = (float(v) for v in g["hyper"])
