@@ -83,6 +83,26 @@ class CudaActor:
     def state_dict(self):
         return {k: v.detach().clone() for k, v in self._sd.items()}
 
+    def flat_size(self):
+        i, h1, h2 = self.dims
+        return h1 * i + 3 * h1 + h2 * h1 + 3 * h2 + h2 + 1
+
+    def load_flat(self, flat):
+        """Load from ONE flat float32 CUDA vector holding the ten tensors in ``ACTOR_KEYS`` order (the layout of the learner's
+        actor parameters and of the broadcast message, include/tt_b200.h): no copies, the re-pack kernels read it in place."""
+        i, h1, h2 = self.dims
+        if flat.dtype != torch.float32 or flat.device != self.device or flat.numel() != self.flat_size() or not flat.is_contiguous():
+            raise ValueError("load_flat: need a contiguous float32 vector of flat_size() elements on the actor's device")
+        shapes = ((h1, i), (h1,), (h1,), (h1,), (h2, h1), (h2,), (h2,), (h2,), (1, h2), (1,))
+        views, o = {}, 0
+        for k, shp in zip(ACTOR_KEYS, shapes):
+            n = int(np.prod(shp))
+            views[k] = flat[o:o + n].view(shp)
+            o += n
+        with torch.cuda.device(self.device):
+            check(self.L.tt_actor_load(self._h, *[views[k].data_ptr() for k in ACTOR_KEYS], stream_ptr()))
+        self._sd = views
+
     def auto_precision(self, n):
         """What precision="auto" resolves to for a batch of n rows: "f16" (tcgen05 tiles) once the batch is a real dense
         contraction, "fp32" (warp-level FMA) below."""

@@ -36,7 +36,8 @@ struct EnvPtrs {
     double2 *l2v;        // (L2, v1x / L2) per env (heatmap.py:89 varies the trailer length per trial)
     double *pose;        // [4][N]
     double *stats;       // [16]
-    uint32_t *iter;
+    uint32_t *iter;      // [0] Philox iteration counter, [1] CTAs-finished counter of the rollout kernel's tick
+    uint32_t *done_list; // [N] scratch of the rollout kernel: envs that finished an episode in this launch, per-CTA segments
     int64_t N;
 };
 
@@ -161,12 +162,35 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// reset(): mask == nullptr -> every env; else only where mask[i] != 0.  Also clears the OU state is NOT done
+// here (that is tt_ou_step's reset mask, trainv2.py:492).
+__device__ __forceinline__ void reset_env(const EnvPtrs &p, const StepConsts &k, int64_t i, float *__restrict__ obs, int64_t ld,
+                                          uint64_t seed, uint64_t gid0, uint32_t t, float *__restrict__ ou_x) {
+    if (ou_x) ou_x[i] = 0.0f;                                 // agent.noise.reset() for the new episode (trainv2.py:492)
+    EnvRegs e;
+    { const double2 l = p.l2v[i]; e.L2 = l.x; e.vL2 = l.y; }
+    double sx, sy, syaw;
+    rng_pose(k, seed, (uint32_t)(gid0 + i), t, sx, sy, syaw);
+    float o[TT_OBS_DIM];
+    reset_from_pose(k, e, sx, sy, syaw, k.gx, k.gy, k.gyaw, obs ? o : nullptr);
+    store_dyn(p, i, e);
+    store_episode_consts(p, i, e, sx, sy, syaw, k.gyaw);
+    if (obs) {
+#pragma unroll
+        for (int c = 0; c < TT_OBS_DIM; c++) obs[i * ld + c] = o[c];
+    }
+}
+
 // K env steps per launch; state stays in registers across the K steps; persistent over 128-env tiles.
 // kMinBlocks == 7 is a memory-traffic-only probe (no arithmetic) used for roofline analysis (developer build).
 // kRoll: the rollout's form (K == 1, obs != NULL): the driver-side `if done: env.reset(); agent.noise.reset()`
-// (trainv2.py:489-492) happens inside the kernel -- a finished env's TERMINAL observation goes to the ring's new_state row
-// (what trainv2.py:525 stores), its reset observation (new Philox pose of this iteration) to `obs`, its OU state is zeroed
-// -- and the last CTA to finish advances the Philox iteration counter: no separate reset / tick launches.
+// (trainv2.py:489-492) happens inside the kernel, and the last CTA to finish advances the Philox iteration counter: no
+// separate reset / tick launches.  A finished env's TERMINAL observation goes to the ring's new_state row (what
+// trainv2.py:525 stores) with the tile's bulk store, like every other row.  Its reset is DEFERRED to the end of the kernel:
+// the main loop only appends the env to the CTA's list (~1.4 % of the envs per step, but 84 % of the 128-env tiles and a
+// third of the warps would otherwise run a few hundred extra dependent instructions -- Philox pose, float64 sin / cos,
+// observation -- on one or two lanes: +22 % kernel time, measured); after the tile loop the CTA resets its listed envs one per
+// thread on full warps and overwrites their rows of `obs` with the reset observation (the bulk stores have completed).
 template <bool kInfo, bool kGoal, int kMinBlocks, int kStages, bool kRoll>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p, StepConsts k, const float *__restrict__ actions,
                                                                       int K, int auto_reset, float *__restrict__ obs, int64_t ld,
@@ -176,10 +200,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
     // observation tiles: double buffered; full tiles leave through the bulk-copy engine (cp.async.bulk shared ->
     // global), which drains them while the CTA already computes its next tile
     __shared__ __align__(128) float tiles[2][kBlock * TT_OBS_DIM];
+    __shared__ int s_ndone;                               // kRoll: entries in this CTA's segment of p.done_list
     uint32_t tbuf = 0;
+    if (kRoll) { if (threadIdx.x == 0) s_ndone = 0; __syncthreads(); }
     const bool bulk_ok = obs != nullptr && ld == TT_OBS_DIM && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
     const int64_t N = p.N;
     const int64_t ntiles = (N + kBlock - 1) / kBlock;
+    const int64_t seg0 = (int64_t)blockIdx.x * ((ntiles + gridDim.x - 1) / gridDim.x) * kBlock;   // kRoll: this CTA's list segment
     const uint32_t t0 = *p.iter;
     StatAcc sa;
     sa.steps = sa.episodes = sa.successes = sa.ret = sa.ret2 = sa.rew = 0.f;
@@ -284,31 +311,17 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                 }
             }
             if (kRoll) {
-                // Per WARP (32 envs = 2 944 B of observation rows): tiles[0] = what the ring stores as new_state (terminal rows),
-                // tiles[1] = what the next iteration observes (reset rows for finished envs), one bulk store each.  No block-wide
-                // barrier: a warp that has to reset an env (Philox pose, float64 sin / cos, observation: a few hundred dependent
-                // instructions, ~1 warp in 3) does not hold up the other three.  The bulk stores drain while the warp computes its
-                // next tile; the wait for their shared-memory reads sits here, a whole tile of arithmetic later.
+                // Per WARP (32 envs = 2 944 B of observation rows, double buffered): no block-wide barrier in the tile loop.  The tile
+                // goes out as one bulk store to `obs` and one to the ring's new_state rows; they drain while the warp computes
+                // its next tile.
                 const int wib = threadIdx.x >> 5, ln = threadIdx.x & 31;
-                float *tileA = tiles[0] + wib * 32 * TT_OBS_DIM, *tileB = tiles[1] + wib * 32 * TT_OBS_DIM;
+                float *tile = tiles[tbuf] + wib * 32 * TT_OBS_DIM;
                 const int64_t wrow0 = row0 + 32 * wib;
                 const int wrows = rows - 32 * wib < 0 ? 0 : (rows - 32 * wib > 32 ? 32 : rows - 32 * wib);
-                if (ln == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
                 if (active) {
-                    if (rpl.S2) {
 #pragma unroll
-                        for (int c = 0; c < TT_OBS_DIM; c++) tileA[ln * TT_OBS_DIM + c] = o.obs[c];
-                    }
-                    if (o.done) {                                        // trainv2.py:489-492: env.reset() + agent.noise.reset()
-                        double sx, sy, syaw;
-                        rng_pose(k, seed, (uint32_t)(gid0 + i), t0, sx, sy, syaw);
-                        reset_from_pose(k, e, sx, sy, syaw, k.gx, k.gy, k.gyaw, o.obs);
-                        store_episode_consts(p, i, e, sx, sy, syaw, k.gyaw);
-                        if (ou_x) ou_x[i] = 0.0f;
-                    }
-#pragma unroll
-                    for (int c = 0; c < TT_OBS_DIM; c++) tileB[ln * TT_OBS_DIM + c] = o.obs[c];
+                    for (int c = 0; c < TT_OBS_DIM; c++) tile[ln * TT_OBS_DIM + c] = o.obs[c];
+                    if (o.done) p.done_list[seg0 + atomicAdd(&s_ndone, 1)] = (uint32_t)i;     // reset at the end of the kernel
                 }
                 const int64_t rrow0 = (rpl.S2 && wrows > 0) ? rpl.m.row(wrow0) : 0;
                 const bool ring_bulk = rpl.S2 && wrows == 32 && !rpl.m.many && wrow0 >= rpl.m.first && rrow0 + 32 <= rpl.m.cap &&
@@ -316,28 +329,31 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                 const bool obs_bulk = bulk_ok && wrows == 32;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (ln == 0 && (obs_bulk || ring_bulk)) {
-                    const uint32_t bytes = (uint32_t)(32 * TT_OBS_DIM * sizeof(float));
+                if (ln == 0) {
+                    const uint32_t bytes = (uint32_t)(32 * TT_OBS_DIM * sizeof(float)), src = (uint32_t)__cvta_generic_to_shared(tile);
                     if (obs_bulk)
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(obs + wrow0 * TT_OBS_DIM), "r"((uint32_t)__cvta_generic_to_shared(tileB)), "r"(bytes) : "memory");
+                                     ::"l"(obs + wrow0 * TT_OBS_DIM), "r"(src), "r"(bytes) : "memory");
                     if (ring_bulk)
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(rpl.S2 + rrow0 * TT_OBS_DIM), "r"((uint32_t)__cvta_generic_to_shared(tileA)), "r"(bytes) : "memory");
+                                     ::"l"(rpl.S2 + rrow0 * TT_OBS_DIM), "r"(src), "r"(bytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");       // the OTHER buffer is free again
                 }
                 if (!obs_bulk) {
                     for (int v = ln; v < wrows * TT_OBS_DIM; v += 32) {
                         const int r = v / TT_OBS_DIM, c = v - r * TT_OBS_DIM;
-                        obs[(wrow0 + r) * ld + c] = tileB[v];
+                        obs[(wrow0 + r) * ld + c] = tile[v];
                     }
                 }
                 if (rpl.S2 && !ring_bulk) {
                     for (int v = ln; v < wrows * TT_OBS_DIM; v += 32) {
                         const int r = v / TT_OBS_DIM, c = v - r * TT_OBS_DIM;
-                        if (wrow0 + r >= rpl.m.first) rpl.S2[rpl.m.row(wrow0 + r) * TT_OBS_DIM + c] = tileA[v];
+                        if (wrow0 + r >= rpl.m.first) rpl.S2[rpl.m.row(wrow0 + r) * TT_OBS_DIM + c] = tile[v];
                     }
                 }
+                __syncwarp();                     // (the element-wise paths have read the tile; lane 0 has waited for the other buffer)
+                tbuf ^= 1u;
             } else if (obs) {
                 float *tile = tiles[tbuf];
                 __syncthreads();                 // thread 0 has waited for the bulk store that last read this buffer
@@ -382,6 +398,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
 
     if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all bulk stores (of this issuing lane) complete
     if (kRoll) {
+        // deferred resets (trainv2.py:489-492: env.reset() + agent.noise.reset()): one listed env per thread, full warps.  Every
+        // bulk store of this CTA has completed (wait_group 0 above + the barrier), so the reset observation written here
+        // replaces the terminal row in `obs`; the ring keeps the terminal row.
+        __syncthreads();
+        const int nd = s_ndone;
+        for (int j = threadIdx.x; j < nd; j += kBlock) reset_env(p, k, (int64_t)p.done_list[seg0 + j], obs, ld, seed, gid0, t0, ou_x);
         // iteration tick: every CTA read *p.iter (t0) when it started, and the last one to get here has seen all others finish
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -405,25 +427,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                 if (lane == 0 && r != 0.f) atomicAdd(&p.stats[slot[s]], (double)r);
             }
         }
-    }
-}
-
-// reset(): mask == nullptr -> every env; else only where mask[i] != 0.  Also clears the OU state is NOT done
-// here (that is tt_ou_step's reset mask, trainv2.py:492).
-__device__ __forceinline__ void reset_env(const EnvPtrs &p, const StepConsts &k, int64_t i, float *__restrict__ obs, int64_t ld,
-                                          uint64_t seed, uint64_t gid0, uint32_t t, float *__restrict__ ou_x) {
-    if (ou_x) ou_x[i] = 0.0f;                                 // agent.noise.reset() for the new episode (trainv2.py:492)
-    EnvRegs e;
-    { const double2 l = p.l2v[i]; e.L2 = l.x; e.vL2 = l.y; }
-    double sx, sy, syaw;
-    rng_pose(k, seed, (uint32_t)(gid0 + i), t, sx, sy, syaw);
-    float o[TT_OBS_DIM];
-    reset_from_pose(k, e, sx, sy, syaw, k.gx, k.gy, k.gyaw, obs ? o : nullptr);
-    store_dyn(p, i, e);
-    store_episode_consts(p, i, e, sx, sy, syaw, k.gyaw);
-    if (obs) {
-#pragma unroll
-        for (int c = 0; c < TT_OBS_DIM; c++) obs[i * ld + c] = o[c];
     }
 }
 
@@ -585,13 +588,14 @@ static size_t env_layout(int64_t n, EnvPtrs *p, char *base) {
     auto take = [&](size_t bytes) { size_t o = off; off = tt::align_up(off + bytes, 256); return o; };
     const size_t o_psi = take(sizeof(double2) * n), o_pos = take(sizeof(int4) * n), o_a = take(sizeof(float4) * n),
                  o_b = take(sizeof(float4) * n), o_pk = take(sizeof(uint32_t) * n), o_goal = take(sizeof(int4) * n), o_l2v = take(sizeof(double2) * n),
-                 o_pose = take(sizeof(double) * 4 * n), o_stats = take(sizeof(double) * TT_NSTATS), o_iter = take(256);
+                 o_pose = take(sizeof(double) * 4 * n), o_stats = take(sizeof(double) * TT_NSTATS), o_iter = take(256),
+                 o_list = take(sizeof(uint32_t) * (n + 128));
     if (p) {
         p->psi = reinterpret_cast<double2 *>(base + o_psi); p->pos = reinterpret_cast<int4 *>(base + o_pos);
         p->rsA = reinterpret_cast<float4 *>(base + o_a); p->rsB = reinterpret_cast<float4 *>(base + o_b);
         p->packed = reinterpret_cast<uint32_t *>(base + o_pk); p->goal = reinterpret_cast<int4 *>(base + o_goal); p->l2v = reinterpret_cast<double2 *>(base + o_l2v);
         p->pose = reinterpret_cast<double *>(base + o_pose); p->stats = reinterpret_cast<double *>(base + o_stats);
-        p->iter = reinterpret_cast<uint32_t *>(base + o_iter); p->N = n;
+        p->iter = reinterpret_cast<uint32_t *>(base + o_iter); p->done_list = reinterpret_cast<uint32_t *>(base + o_list); p->N = n;
     }
     return off;
 }

@@ -81,30 +81,63 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// mean / rstd of `rows` rows of width K (two-pass, like torch), one warp per row; out[b] = (mean, rstd)
+// mean / rstd of `rows` rows of width K <= 512 (two-pass, like torch); out[b] = (mean, rstd).  A warp takes FOUR rows at a
+// time with all their values in registers: one round of independent loads (one memory latency per four rows instead of two
+// per row -- the step is latency-bound), the second pass runs from registers.
 __device__ void row_stats(const float *__restrict__ X, int ldx, int rows, int K, float2 *out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int b = warp; b < rows; b += nw) {
-        const float *x = X + (size_t)b * ldx;
-        float s = 0.f;
-        for (int k = lane; k < K; k += 32) s += x[k];
-        const float mean = warp_sum(s) / (float)K;
-        float q = 0.f;
-        for (int k = lane; k < K; k += 32) { const float d = x[k] - mean; q = fmaf(d, d, q); }
-        const float rstd = rsqrtf(warp_sum(q) / (float)K + kLnEps);
-        if (lane == 0) out[b] = make_float2(mean, rstd);
+    for (int b0 = 4 * warp; b0 < rows; b0 += 4 * nw) {
+        float v[4][kMaxH / 32];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int i = 0; i < kMaxH / 32; i++) {
+                const int k = lane + 32 * i;
+                v[r][i] = (b0 + r < rows && k < K) ? X[(size_t)(b0 + r) * ldx + k] : 0.f;
+            }
+        float mean[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < kMaxH / 32; i++) sum += v[r][i];
+            mean[r] = warp_sum(sum) / (float)K;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < kMaxH / 32; i++) { const float d = (lane + 32 * i < K) ? v[r][i] - mean[r] : 0.f; q = fmaf(d, d, q); }
+            const float rstd = rsqrtf(warp_sum(q) / (float)K + kLnEps);
+            if (lane == 0 && b0 + r < rows) out[b0 + r] = make_float2(mean[r], rstd);
+        }
     }
 }
 
 __device__ __forceinline__ float ln_relu(float x, float2 st, float g, float be) { return fmaxf(fmaf((x - st.x) * st.y, g, be), 0.f); }
 
-// Y tile: all B rows x 16 columns [n0, n0 + 16); reduction over K in chunks of 32
+// Y tile: all B rows x 16 columns [n0, n0 + 16); reduction over K in chunks of 32.  The next chunk's operands are fetched
+// into registers while the current one is multiplied (the global-load latency of every chunk would otherwise be exposed).
 __device__ void job_fwd(const Job &J, int cta, float *smem) {
     float (*Xs)[65] = reinterpret_cast<float (*)[65]>(smem);                    // [32][65]  k-major
     float (*Ws)[17] = reinterpret_cast<float (*)[17]>(smem + 32 * 65);          // [32][17]
     float2 *st = reinterpret_cast<float2 *>(smem + 32 * 65 + 32 * 17);          // [64]
     const int tid = threadIdx.x, tn = tid & 15, tb = tid >> 4, n0 = cta * 16;
     const bool ln = J.g != nullptr;
+    float xr[8], wr[2];
+    auto fetch = [&](int k0) {                                                  // raw operands of chunk k0 -> registers
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int e = tid + kT * i, b = e >> 5, k = k0 + (e & 31);
+            xr[i] = (b < J.B && k < J.K) ? J.X[(size_t)b * J.ldx + k] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int e = tid + kT * i, n = e >> 5, k = k0 + (e & 31);
+            wr[i] = (n0 + n < J.N && k < J.K) ? J.W[(size_t)(n0 + n) * J.ldw + k] : 0.f;
+        }
+    };
+    fetch(0);
     if (ln) {
         row_stats(J.X, J.ldx, J.B, J.K, st);
         __syncthreads();
@@ -115,19 +148,14 @@ __device__ void job_fwd(const Job &J, int cta, float *smem) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int e = tid + kT * i, b = e >> 5, kk = e & 31, k = k0 + kk;
-            float x = 0.f;
-            if (b < J.B && k < J.K) {
-                x = J.X[(size_t)b * J.ldx + k];
-                if (ln) x = ln_relu(x, st[b], J.g[k], J.be[k]);
-            }
+            float x = xr[i];
+            if (ln) x = (b < J.B && k < J.K) ? ln_relu(x, st[b], J.g[k], J.be[k]) : 0.f;
             Xs[kk][b] = x;
         }
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int e = tid + kT * i, n = e >> 5, kk = e & 31, k = k0 + kk;
-            Ws[kk][n] = (n0 + n < J.N && k < J.K) ? J.W[(size_t)(n0 + n) * J.ldw + k] : 0.f;
-        }
+        for (int i = 0; i < 2; i++) { const int e = tid + kT * i; Ws[e & 31][e >> 5] = wr[i]; }
         __syncthreads();
+        if (k0 + 32 < J.K) fetch(k0 + 32);
 #pragma unroll
         for (int kk = 0; kk < 32; kk++) {
             const float w = Ws[kk][tn];
@@ -188,24 +216,33 @@ __device__ void job_wgrad(const Job &J, int cta, float *smem) {
     }
 }
 
-// dX tile: all B rows x 16 columns [k0, k0 + 16); reduction over N in chunks of 32
+// dX tile: all B rows x 16 columns [k0, k0 + 16); reduction over N in chunks of 32 (register prefetch like job_fwd)
 __device__ void job_xgrad(const Job &J, int cta, float *smem) {
     float (*Ds)[65] = reinterpret_cast<float (*)[65]>(smem);                    // [32 n][65]  (b)
     float (*Ws)[17] = reinterpret_cast<float (*)[17]>(smem + 32 * 65);          // [32 n][17]  (k)
     const int tid = threadIdx.x, tk = tid & 15, tb = tid >> 4, k0 = cta * 16;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int nb = 0; nb < J.N; nb += 32) {
+    float dr[8], wr[2];
+    auto fetch = [&](int nb) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int e = tid + kT * i, b = e >> 5, nn = e & 31;
-            Ds[nn][b] = (b < J.B && nb + nn < J.N) ? J.D[(size_t)b * J.ldd + nb + nn] : 0.f;
+            dr[i] = (b < J.B && nb + nn < J.N) ? J.D[(size_t)b * J.ldd + nb + nn] : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             const int e = tid + kT * i, nn = e >> 4, kk = e & 15;
-            Ws[nn][kk] = (nb + nn < J.N && k0 + kk < J.K) ? J.W[(size_t)(nb + nn) * J.ldw + k0 + kk] : 0.f;
+            wr[i] = (nb + nn < J.N && k0 + kk < J.K) ? J.W[(size_t)(nb + nn) * J.ldw + k0 + kk] : 0.f;
         }
+    };
+    fetch(0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int nb = 0; nb < J.N; nb += 32) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const int e = tid + kT * i; Ds[e & 31][e >> 5] = dr[i]; }
+#pragma unroll
+        for (int i = 0; i < 2; i++) { const int e = tid + kT * i; Ws[e >> 4][e & 15] = wr[i]; }
         __syncthreads();
+        if (nb + 32 < J.N) fetch(nb + 32);
 #pragma unroll
         for (int nn = 0; nn < 32; nn++) {
             const float w = Ws[nn][tk];
@@ -271,9 +308,19 @@ __global__ void learn_gather_kernel(tt_replay_ring ring, int64_t max_mem, const 
     }
 }
 
-// ---- row-wise stages: one CTA of 512 threads, one warp per batch row with the row in registers ----
-constexpr int kRowT = 512, kPerLane = kMaxH / 32;
+// ---- row-wise stages: a CLUSTER of 8 CTAs x 8 warps, one warp per batch row with the row in registers; after a cluster
+//      barrier the same 2 048 threads take the column sums over the batch (= the parameter gradients), one column each, rows
+//      in order (deterministic).  One warp per row keeps the dependent chain of a row (load -> statistics -> head -> backward)
+//      at one memory latency per network instead of serialising rows.
+constexpr int kRowCtas = 8, kRowT = 256, kRowThreads = kRowCtas * kRowT, kPerLane = kMaxH / 32;
 struct Row { float v[kPerLane]; };
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {        // release / acquire at cluster scope: the rows' global writes are visible
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void load_row(Row &r, const float *__restrict__ p, int H, int lane) {
 #pragma unroll
@@ -320,6 +367,7 @@ struct HeadArgs {
     const float *act, *rew, *done;                                        // batch
     float *dh2;                                                           // out: gradient w.r.t. the fc2 output [B][H2]
     float *sc0, *sc1, *sc2;                                               // scratch [B][H2]
+    float *dv;                                                            // scratch [B]: dL/dq (critic) or dL/d(pre-tanh) (actor) per row
     // gradients (flat-layout pointers)
     float *g_g2, *g_be2, *g_t0, *g_t1, *g_t2, *g_t3;                      // critic: wa, ba, wq, bq | actor: w3, b3, -, -
     float *q_out, *y_out, *a_out;                                         // diagnostics / hand-over: Q(s,a), target, actor(s)
@@ -329,28 +377,30 @@ struct HeadArgs {
 __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
     __shared__ float s_dq[kMaxB], s_act[kMaxB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
-    for (int b = warp; b < A.B; b += kRowT / 32) {
-        Row x;
+    const int b = (int)cluster_rank() * (kRowT / 32) + warp;
+    if (b < A.B) {
+        Row x, xt;
+        load_row(xt, A.h2[JOB_TA] + (size_t)b * H, H, lane);             // the three rows' loads are independent: issue them together
+        Row xc;
+        load_row(xc, A.h2[JOB_TC] + (size_t)b * H, H, lane);
+        load_row(x, A.h2[JOB_C] + (size_t)b * H, H, lane);
         // a' = target_actor(s') head: tanh(mu(relu(LN2(h2))))            (networks.py:142-145)
-        load_row(x, A.h2[JOB_TA] + (size_t)b * H, H, lane);
-        normalize_row(x, H, lane);
+        normalize_row(xt, H, lane);
         float p = 0.f;
 #pragma unroll
-        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; if (j < H) p = fmaf(fmaxf(fmaf(x.v[i], A.ta_g2[j], A.ta_be2[j]), 0.f), A.ta_w3[j], p); }
+        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; if (j < H) p = fmaf(fmaxf(fmaf(xt.v[i], A.ta_g2[j], A.ta_be2[j]), 0.f), A.ta_w3[j], p); }
         const float a2 = tanhf(warp_sum(p) + A.ta_b3[0]);
         // Q'(s', a') = q(relu(LN2(h2) + action_value(a')))                 (networks.py:53-68)
-        load_row(x, A.h2[JOB_TC] + (size_t)b * H, H, lane);
-        normalize_row(x, H, lane);
+        normalize_row(xc, H, lane);
         float q2 = 0.f;
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
-            if (j < H) q2 = fmaf(fmaxf(fmaf(x.v[i], A.tc_g2[j], A.tc_be2[j]) + fmaf(a2, A.tc_wa[j], A.tc_ba[j]), 0.f), A.tc_wq[j], q2);
+            if (j < H) q2 = fmaf(fmaxf(fmaf(xc.v[i], A.tc_g2[j], A.tc_be2[j]) + fmaf(a2, A.tc_wa[j], A.tc_ba[j]), 0.f), A.tc_wq[j], q2);
         }
         q2 = warp_sum(q2) + A.tc_bq[0];
         const float y = A.rew[b] + A.gamma * (A.done[b] != 0.f ? 0.f : q2);       // DDPG_agent.py:90-93
         // Q(s, a) and its backward
-        load_row(x, A.h2[JOB_C] + (size_t)b * H, H, lane);
         const float rstd = normalize_row(x, H, lane);
         const float act = A.act[b];
         Row z;
@@ -375,29 +425,35 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
                 A.dh2[o] = dx.v[i]; A.sc0[o] = dz.v[i]; A.sc1[o] = dz.v[i] * x.v[i]; A.sc2[o] = dq * fmaxf(z.v[i], 0.f);
             }
         }
-        if (lane == 0) { s_dq[b] = dq; s_act[b] = act; if (A.q_out) A.q_out[b] = q; if (A.y_out) A.y_out[b] = y; }
+        if (lane == 0) { A.dv[b] = dq; if (A.q_out) A.q_out[b] = q; if (A.y_out) A.y_out[b] = y; }
     }
+    cluster_barrier();
+    if (threadIdx.x < A.B) { s_dq[threadIdx.x] = A.dv[threadIdx.x]; s_act[threadIdx.x] = A.act[threadIdx.x]; }
     __syncthreads();
     // parameter gradients = column sums over the batch, in row order
-    for (int j = threadIdx.x; j < H; j += kRowT) {
+    const int gt = (int)cluster_rank() * kRowT + threadIdx.x;
+    for (int j = gt; j < H; j += kRowThreads) {
         float gba = 0.f, gwa = 0.f, gg2 = 0.f, gwq = 0.f;
-        for (int b = 0; b < A.B; b++) {
-            const size_t o = (size_t)b * H + j;
+#pragma unroll 8
+        for (int bb = 0; bb < A.B; bb++) {
+            const size_t o = (size_t)bb * H + j;
             const float dz = A.sc0[o];
-            gba += dz; gwa = fmaf(dz, s_act[b], gwa); gg2 += A.sc1[o]; gwq += A.sc2[o];
+            gba += dz; gwa = fmaf(dz, s_act[bb], gwa); gg2 += A.sc1[o]; gwq += A.sc2[o];
         }
         A.g_be2[j] = gba; A.g_g2[j] = gg2; A.g_t0[j] = gwa; A.g_t1[j] = gba; A.g_t2[j] = gwq;
     }
-    if (threadIdx.x == 0) { float s = 0.f; for (int b = 0; b < A.B; b++) s += s_dq[b]; A.g_t3[0] = s; }
+    if (gt == 0) { float sum = 0.f; for (int bb = 0; bb < A.B; bb++) sum += s_dq[bb]; A.g_t3[0] = sum; }
 }
 
 // K9: DDPG_agent.py:99-103  actor_loss = -mean(critic(states, actor(states)))
 __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
     __shared__ float s_dp[kMaxB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
-    for (int b = warp; b < A.B; b += kRowT / 32) {
-        Row x, o2;
+    const int b = (int)cluster_rank() * (kRowT / 32) + warp;
+    if (b < A.B) {
+        Row x, o2, c;
         load_row(x, A.h2[JOB_A] + (size_t)b * H, H, lane);
+        load_row(c, A.h2[JOB_C] + (size_t)b * H, H, lane);
         const float rstd = normalize_row(x, H, lane);
         float p = 0.f;
 #pragma unroll
@@ -408,8 +464,6 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
         }
         const float a = tanhf(warp_sum(p) + A.a_b3[0]);
         // dQ/da through the UPDATED critic: z = LN2(h2') + action_value(a); dq = -1 / B
-        Row c;
-        load_row(c, A.h2[JOB_C] + (size_t)b * H, H, lane);
         normalize_row(c, H, lane);
         float da = 0.f;
         const float dq = -1.0f / (float)A.B;
@@ -435,15 +489,19 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
                 A.dh2[o] = dx.v[i]; A.sc0[o] = dout.v[i]; A.sc1[o] = dout.v[i] * x.v[i]; A.sc2[o] = dp * fmaxf(o2.v[i], 0.f);
             }
         }
-        if (lane == 0) { s_dp[b] = dp; if (A.a_out) A.a_out[b] = a; }
+        if (lane == 0) { A.dv[b] = dp; if (A.a_out) A.a_out[b] = a; }
     }
+    cluster_barrier();
+    if (threadIdx.x < A.B) s_dp[threadIdx.x] = A.dv[threadIdx.x];
     __syncthreads();
-    for (int j = threadIdx.x; j < H; j += kRowT) {
+    const int gt = (int)cluster_rank() * kRowT + threadIdx.x;
+    for (int j = gt; j < H; j += kRowThreads) {
         float gbe = 0.f, gg = 0.f, gw3 = 0.f;
-        for (int b = 0; b < A.B; b++) { const size_t o = (size_t)b * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; gw3 += A.sc2[o]; }
+#pragma unroll 8
+        for (int bb = 0; bb < A.B; bb++) { const size_t o = (size_t)bb * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; gw3 += A.sc2[o]; }
         A.g_be2[j] = gbe; A.g_g2[j] = gg; A.g_t0[j] = gw3;
     }
-    if (threadIdx.x == 0) { float s = 0.f; for (int b = 0; b < A.B; b++) s += s_dp[b]; A.g_t1[0] = s; }
+    if (gt == 0) { float sum = 0.f; for (int bb = 0; bb < A.B; bb++) sum += s_dp[bb]; A.g_t1[0] = sum; }
 }
 
 // K5 / K11: relu + LayerNorm 1 backward (warp = row), then the fc1 backward: dW1[n][k] = sum_b dh1[b][n] x[b][k], db1, dg1, dbe1
@@ -460,11 +518,12 @@ __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
     __shared__ float xs[kMaxB * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H1;
     for (int v = threadIdx.x; v < A.B * A.IN; v += kRowT) xs[v] = A.x[v];
-    for (int b = warp; b < A.B; b += kRowT / 32) {
+    const int b = (int)cluster_rank() * (kRowT / 32) + warp;
+    if (b < A.B) {
         Row x, dout, dx;
         load_row(x, A.h1 + (size_t)b * H, H, lane);
-        const float rstd = normalize_row(x, H, lane);
         load_row(dout, A.da1 + (size_t)b * H, H, lane);
+        const float rstd = normalize_row(x, H, lane);
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
@@ -477,18 +536,22 @@ __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
             if (j < H) { const size_t o = (size_t)b * H + j; A.dh1[o] = dx.v[i]; A.sc0[o] = dout.v[i]; A.sc1[o] = dout.v[i] * x.v[i]; }
         }
     }
+    cluster_barrier();
     __syncthreads();
-    for (int j = threadIdx.x; j < H; j += kRowT) {
+    const int gt = (int)cluster_rank() * kRowT + threadIdx.x;
+    for (int j = gt; j < H; j += kRowThreads) {
         float gbe = 0.f, gg = 0.f, gb = 0.f;
-        for (int b = 0; b < A.B; b++) { const size_t o = (size_t)b * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; gb += A.dh1[o]; }
+#pragma unroll 8
+        for (int bb = 0; bb < A.B; bb++) { const size_t o = (size_t)bb * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; gb += A.dh1[o]; }
         A.g_be1[j] = gbe; A.g_g1[j] = gg; A.g_b1[j] = gb;
     }
-    // dW1[n][k]: thread per element, batch in row order (dh1 written by this CTA above)
-    for (int e = threadIdx.x; e < H * A.IN; e += kRowT) {
+    // dW1[n][k]: thread per element, batch in row order
+    for (int e = gt; e < H * A.IN; e += kRowThreads) {
         const int n = e / A.IN, k = e - n * A.IN;
-        float s = 0.f;
-        for (int b = 0; b < A.B; b++) s = fmaf(A.dh1[(size_t)b * H + n], xs[b * A.IN + k], s);
-        A.g_w1[e] = s;
+        float sum = 0.f;
+#pragma unroll 8
+        for (int bb = 0; bb < A.B; bb++) sum = fmaf(A.dh1[(size_t)bb * H + n], xs[bb * A.IN + k], sum);
+        A.g_w1[e] = sum;
     }
 }
 
@@ -536,7 +599,7 @@ struct tt_learner {
     Batch bt;
     float *h1[NJOBS], *h2[NJOBS], *st1[NJOBS];
     float *dh2, *da1, *dh1, *sc0, *sc1, *sc2;
-    float *q, *y, *aout;
+    float *q, *y, *aout, *dv;
     int *step;                        // number of updates done (Adam's step count and the sampling counter)
 };
 
@@ -555,7 +618,7 @@ size_t learner_layout(const Layout &L, int B, tt_learner *ln, char *base) {
     for (int j = 0; j < NJOBS; j++) { o_h1[j] = take(sizeof(float) * B * L.h1); o_h2[j] = take(sizeof(float) * B * L.h2); o_st[j] = take(sizeof(float) * 2 * B); }
     size_t o_dh2 = take(sizeof(float) * B * L.h2), o_da1 = take(sizeof(float) * B * L.h1), o_dh1 = take(sizeof(float) * B * L.h1);
     size_t o_sc[3] = {take(sizeof(float) * B * hm), take(sizeof(float) * B * hm), take(sizeof(float) * B * hm)};
-    size_t o_q = take(sizeof(float) * B), o_y = take(sizeof(float) * B), o_ao = take(sizeof(float) * B), o_step = take(256);
+    size_t o_q = take(sizeof(float) * B), o_y = take(sizeof(float) * B), o_ao = take(sizeof(float) * B), o_dv = take(sizeof(float) * B), o_step = take(256);
     if (ln) {
         auto f = [&](size_t o) { return reinterpret_cast<float *>(base + o); };
         for (int i = 0; i < 4; i++) ln->p[i] = f(o_p[i]);
@@ -564,7 +627,7 @@ size_t learner_layout(const Layout &L, int B, tt_learner *ln, char *base) {
         ln->bt.rows = reinterpret_cast<int64_t *>(base + o_rows);
         for (int j = 0; j < NJOBS; j++) { ln->h1[j] = f(o_h1[j]); ln->h2[j] = f(o_h2[j]); ln->st1[j] = f(o_st[j]); }
         ln->dh2 = f(o_dh2); ln->da1 = f(o_da1); ln->dh1 = f(o_dh1); ln->sc0 = f(o_sc[0]); ln->sc1 = f(o_sc[1]); ln->sc2 = f(o_sc[2]);
-        ln->q = f(o_q); ln->y = f(o_y); ln->aout = f(o_ao); ln->step = reinterpret_cast<int *>(base + o_step);
+        ln->q = f(o_q); ln->y = f(o_y); ln->aout = f(o_ao); ln->dv = f(o_dv); ln->step = reinterpret_cast<int *>(base + o_step);
     }
     return off;
 }
@@ -574,6 +637,19 @@ Job fwd_job(int B, int N, int K, const float *X, int ldx, const float *W, const 
     j.type = G_FWD; j.ctas = (N + 15) / 16; j.B = B; j.N = N; j.K = K; j.X = X; j.ldx = ldx; j.W = W; j.ldw = K; j.bias = bias; j.g = g; j.be = be;
     j.stats = stats; j.Y = Y; j.ldy = N;
     return j;
+}
+
+// a row-wise stage: one cluster of kRowCtas CTAs
+template <typename Kern, typename Args>
+int launch_rows(Kern kern, const Args &args, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kRowCtas); cfg.blockDim = dim3(kRowT); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kRowCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    TT_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
 }
 
 int launch_jobs(const JobList &L, cudaStream_t s) {
@@ -678,12 +754,11 @@ int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_r
     H.a_g2 = pa + L.g2(); H.a_be2 = pa + L.be2(); H.a_w3 = pa + T; H.a_b3 = pa + T + H2;
     H.act = ln->bt.a; H.rew = ln->bt.r; H.done = ln->bt.d;
     H.dh2 = ln->dh2; H.sc0 = ln->sc0; H.sc1 = ln->sc1; H.sc2 = ln->sc2;
-    H.q_out = ln->q; H.y_out = ln->y; H.a_out = ln->aout;
+    H.q_out = ln->q; H.y_out = ln->y; H.a_out = ln->aout; H.dv = ln->dv;
     {
         HeadArgs C = H;
         C.g_g2 = gc + L.g2(); C.g_be2 = gc + L.be2(); C.g_t0 = gc + T; C.g_t1 = gc + T + H2; C.g_t2 = gc + T + 2 * H2; C.g_t3 = gc + T + 3 * H2;
-        learn_critic_head_kernel<<<1, kRowT, 0, s>>>(C);
-        TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+        if ((rc = launch_rows(learn_critic_head_kernel, C, s)) != TT_OK) return rc;
     }
     // backward through fc2 / LayerNorm 1 / fc1 of one network whose dh2 is in ln->dh2 and whose forward job is `job`
     auto trunk_backward = [&](int job, const float *p, float *g, const float *x) -> int {
@@ -702,9 +777,7 @@ int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_r
         A.B = B; A.IN = IN; A.H1 = H1; A.h1 = ln->h1[job]; A.da1 = ln->da1; A.g1 = p + L.g1(); A.be1 = p + L.be1(); A.x = x;
         A.dh1 = ln->dh1; A.sc0 = ln->sc0; A.sc1 = ln->sc1;
         A.g_w1 = g + L.w1(); A.g_b1 = g + L.b1(); A.g_g1 = g + L.g1(); A.g_be1 = g + L.be1();
-        learn_l1_backward_kernel<<<1, kRowT, 0, s>>>(A);
-        TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-        return TT_OK;
+        return launch_rows(learn_l1_backward_kernel, A, s);
     };
     auto adam = [&](float *p, float *m, float *v, float *target, const float *g, int n, float lr, float wd) -> int {
         AdamArgs A{};
@@ -732,8 +805,7 @@ int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_r
     {
         HeadArgs A = H;
         A.g_g2 = ga + L.g2(); A.g_be2 = ga + L.be2(); A.g_t0 = ga + T; A.g_t1 = ga + T + H2; A.g_t2 = nullptr; A.g_t3 = nullptr;
-        learn_actor_head_kernel<<<1, kRowT, 0, s>>>(A);
-        TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+        if ((rc = launch_rows(learn_actor_head_kernel, A, s)) != TT_OK) return rc;
     }
     // K10, K11, K12 (DDPG_agent.py:99-106)
     if ((rc = trunk_backward(JOB_A, pa, ga, ln->bt.s)) != TT_OK) return rc;

@@ -84,3 +84,86 @@ def broadcast_actor(sd: dict, src: int = 0, device=None) -> dict:
     flat = flatten_actor(sd, device=device)
     dist.broadcast(flat, src=src)
     return unflatten_actor(flat, sd)
+
+
+class OverlappedSync:
+    """The two per-iteration collectives of the rollout, issued asynchronously on a side stream so
+    that they overlap the next iteration's kernels instead of sitting on the rollout stream:
+
+    * ``push_stats(stats)``: sum all-reduce of the 16-double statistics vector.  Returns the all-reduced vector of the
+      PREVIOUS push (None the first time): the consumer is one iteration behind, the rollout stream never waits for the
+      network.
+    * ``push_policy(flat)`` / ``wait_policy()``: one-message broadcast of the flat actor parameter vector from the learner
+      rank (the vector ``tt_learn_step`` updates in place: no torch.cat / unflatten round trip); ``wait_policy`` makes the
+      CALLING stream wait for it -- call it on the stream that re-packs the parameters into the spare packed actor.
+
+    Works with NCCL (side CUDA stream) and with gloo (CPU tests: the same call sequence, ``wait`` blocks the host)."""
+
+    def __init__(self, device=None, src: int = 0):
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.cuda = self.device.type == "cuda"
+        self.on = dist.is_initialized() and dist.get_world_size() > 1
+        self.src = src
+        self._stats = [torch.zeros(TT_NSTATS, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self._swork = [None, None]
+        self._i = 0
+        self._pwork = None
+        if self.cuda:
+            self.stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self._ev = [torch.cuda.Event() for _ in range(2)]
+            self._pev = torch.cuda.Event()
+
+    def _side(self):
+        import contextlib
+        return torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()
+
+    def push_stats(self, stats: torch.Tensor):
+        b = self._i & 1
+        self._i += 1
+        prev = None
+        if self._swork[b ^ 1] is not None:
+            w = self._swork[b ^ 1]
+            if w is not True:
+                w.wait()                       # NCCL: the current stream waits (the collective finished an iteration ago)
+            prev = self._stats[b ^ 1]
+        self._stats[b].copy_(stats)
+        if not self.on:
+            self._swork[b] = True
+            return prev
+        if self.cuda:
+            self._ev[b].record()
+            with self._side():
+                self.stream.wait_event(self._ev[b])
+                self._swork[b] = dist.all_reduce(self._stats[b], op=dist.ReduceOp.SUM, async_op=True)
+        else:
+            self._swork[b] = dist.all_reduce(self._stats[b], op=dist.ReduceOp.SUM, async_op=True)
+        return prev
+
+    def flush_stats(self):
+        """The all-reduced vector of the LAST push (waits for it)."""
+        b = (self._i - 1) & 1
+        w = self._swork[b]
+        if w is None:
+            return None
+        if w is not True:
+            w.wait()
+        return self._stats[b]
+
+    def push_policy(self, flat: torch.Tensor):
+        """Start the broadcast of ``flat`` (in place) from the learner rank; everything queued on the current stream so far
+        (the learner step that produced it) is ordered before it."""
+        if not self.on:
+            self._pwork = True
+            return
+        if self.cuda:
+            self._pev.record()
+            with self._side():
+                self.stream.wait_event(self._pev)
+                self._pwork = dist.broadcast(flat, src=self.src, async_op=True)
+        else:
+            self._pwork = dist.broadcast(flat, src=self.src, async_op=True)
+
+    def wait_policy(self):
+        if self._pwork is not None and self._pwork is not True:
+            self._pwork.wait()
+        self._pwork = None

@@ -47,6 +47,47 @@ def test_world2_gloo_shard_stats_broadcast():
     assert sum0 == float(ttd.flatten_actor(init_actor_state_dict(seed=100)).double().sum())
 
 
+def _worker_overlap(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from ddpg_trucktrailer_b200 import dist as ttd
+    ttd.init_from_env("gloo")
+    sync = ttd.OverlappedSync("cpu", src=0)
+    got = []
+    for it in range(5):                                    # the consumer sees the all-reduced statistics one iteration later
+        st = torch.zeros(16, dtype=torch.float64); st[0] = 100 * (rank + 1) + it; st[1] = it
+        prev = sync.push_stats(st)
+        got.append(None if prev is None else prev.tolist())
+    last = sync.flush_stats().tolist()
+    flat = torch.full((131601,), float(rank + 1))          # rank 0 holds the learner's vector
+    for it in range(3):
+        if rank == 0:
+            flat += 1.0                                    # "learner step"
+        sync.push_policy(flat)
+        sync.wait_policy()
+    q.put((rank, got, last, float(flat[0]), float(flat[-1])))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_overlapped_sync():
+    """OverlappedSync: the per-iteration statistics all-reduce is consumed one iteration behind; the policy broadcast moves
+    the learner rank's flat parameter vector in place."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_overlap, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(30) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    for rank, got, last, f0, f1 in res:
+        assert got[0] is None
+        for it in range(1, 5):
+            assert got[it][0] == 300 + 2 * (it - 1) and got[it][1] == 2 * (it - 1)
+        assert last[0] == 300 + 8 and last[1] == 8
+        assert f0 == f1 == 4.0                              # rank 0's vector after three "learner steps", on both ranks
+
+
 def test_shard_covers_everything():
     from ddpg_trucktrailer_b200 import dist as ttd
     for total in (1, 7, 8, 1 << 22, 12345):

@@ -95,8 +95,10 @@ def test_learner_gradients_match_autograd_float64(dims, B):
     class FakeMem:
         mem_cntr = cap
         def sample_buffer(self, bs): return s[rows], a[rows].reshape(-1, 1), r[rows], s2[rows], d[rows].bool()
+    dims_t = tuple(dims)
+
     class FakeActor:
-        dims = tuple(dims)
+        dims = dims_t
         def state_dict(self): return before["actor"]
         def load_state_dict(self, sd_): pass
     class FakeAgent:
