@@ -92,6 +92,8 @@ class Loop:
 def _worker(mode, seed, warm, chunks, chunk, barrier, out):
     os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    import warnings
+    warnings.filterwarnings("ignore")          # DDPG_agent.py:38 builds a tensor from a list of ndarrays on every call
     try:
         lp = Loop(mode, seed)
         lp.run(warm)

@@ -55,9 +55,12 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("TT_BENCH_PRECISION", "f16"), choices=["fp32", "bf16", "f16"])
     ap.add_argument("--ring", type=int, default=1 << 24, help="replay ring capacity per GPU (transitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--config4", action="store_true", help="also time BASELINE.json configs[3]: rollout + replay store + one DDPG "
-                    "critic/actor update (batch 64) per iteration + stats all-reduce + actor broadcast (extra key `config4`)")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="bounded sample of the oracle C port")
+    ap.add_argument("--ref-steps", type=int, default=20000, help="env steps of the single-process Python reference loop (BASELINE.md section 3)")
+    ap.add_argument("--no-config4", action="store_true", help="skip BASELINE.json configs[3] (rollout + replay store + one DDPG critic/actor "
+                    "update (batch 64) per iteration + stats all-reduce + actor broadcast; key `config4`)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the mini-sweep over envs per GPU (BASELINE.json configs[4]; key `sweep`)")
+    ap.add_argument("--e2e-preroll-s", type=float, default=0.5, help="seconds of the e2e pipeline itself run right before its timed region")
     ap.add_argument("--preroll", type=int, default=256, help="untimed rollout iterations before the warm-up, so that episodes "
                     "terminate and reset at their steady-state rate inside the timed region")
     return ap.parse_args()
@@ -93,6 +96,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
+    def window(self, t0, t1):
+        """Clocks of the samples taken inside [t0, t1] (no fallback); None if there were none."""
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        if not rows:
+            return None
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
     def stop(self, t0, t1, load0=None, load1=None):
         """Clocks inside the timed region [t0, t1] (the region lasts tens of ms, nvidia-smi samples every 20 ms); if no
         sample fell into it, the samples taken under the same load right around it (pre-roll .. end of the e2e run)."""
@@ -113,19 +127,25 @@ class ClockSampler:
                 "samples": len(rows), "reasons": reasons}
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm ----
-def cpu_port(n_envs, seconds, threads, steps=None, warmup=1):
-    """The oracle's CPU port of the whole rollout iteration (kind "port": the reference is pure Python and is
-    not present on the GPU box), all host threads, on a bounded sample of the workload."""
+# ------------------------------------------------------------------------------------------------ CPU arms ----
+WORKLOAD = ("full rollout: actor(23-400-300-1)+OU noise+clip*pi/4+simv2 step+reward_functionv1+replay store+reset of finished "
+            "episodes (DDPG/trainv2.py:489-531 without learn()), 2^22 envs/GPU")
+
+
+def _actor_sd_numpy():
     import numpy as np
-    from oracle import oracle as orc
     rng = np.random.default_rng(0)            # reference init distributions (networks.py:110-131)
     u = lambda shape, f: rng.uniform(-f, f, shape).astype(np.float32)
-    sd = {"fc1.weight": u((400, 23), 0.05), "fc1.bias": u(400, 0.05), "bn1.weight": np.ones(400, np.float32),
-          "bn1.bias": np.zeros(400, np.float32), "fc2.weight": u((300, 400), 300 ** -0.5), "fc2.bias": u(300, 300 ** -0.5),
-          "bn2.weight": np.ones(300, np.float32), "bn2.bias": np.zeros(300, np.float32), "mu.weight": u((1, 300), 0.003),
-          "mu.bias": u(1, 0.003)}
-    port = orc.RolloutPort(n_envs, sd, seed=27, threads=threads, capacity=max(n_envs, 1 << 16))
+    return {"fc1.weight": u((400, 23), 0.05), "fc1.bias": u(400, 0.05), "bn1.weight": np.ones(400, np.float32),
+            "bn1.bias": np.zeros(400, np.float32), "fc2.weight": u((300, 400), 300 ** -0.5), "fc2.bias": u(300, 300 ** -0.5),
+            "bn2.weight": np.ones(300, np.float32), "bn2.bias": np.zeros(300, np.float32), "mu.weight": u((1, 300), 0.003),
+            "mu.bias": u(1, 0.003)}
+
+
+def cpu_port(n_envs, seconds, threads, steps=None, warmup=1):
+    """The oracle's C port of the whole rollout iteration (kind "port"), all host threads, on a bounded sample."""
+    from oracle import oracle as orc
+    port = orc.RolloutPort(n_envs, _actor_sd_numpy(), seed=27, threads=threads, capacity=max(n_envs, 1 << 16))
     for _ in range(warmup):
         port.step()
     t0, it = time.perf_counter(), 0
@@ -137,21 +157,78 @@ def cpu_port(n_envs, seconds, threads, steps=None, warmup=1):
     return n_envs * it / dt, it, dt
 
 
+def python_reference_available():
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import prepare_ref
+    return prepare_ref.available()
+
+
+def python_reference(mode, procs, steps_per_proc, warm=300, chunks=1):
+    """The UNMODIFIED reference Python loop (baseline/_ref, baseline/ref_loop.py): `procs` processes, OMP threads = 1."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_loop
+    return ref_loop.time_loop(mode, procs, steps_per_proc, warm=warm, chunks=chunks)
+
+
+def cpu_baseline_block(args):
+    """cpu_baseline of the b200 arm (rank 0, N = 1): the reference's own Python loop timed on this box's host cores in the same
+    run -- single process and one process per core, full rollout loop and env-only loop -- with the
+    oracle's C port of the same iteration as a second figure."""
+    cores = os.cpu_count() or 1
+    out = {}
+    vp, itp, dtp = cpu_port(1 << 14, args.cpu_seconds, cores)
+    vp1, _, _ = cpu_port(1 << 12, min(args.cpu_seconds, 4.0), 1)
+    port = {"value": vp, "unit": UNIT, "cores": cores, "kind": "port", "single_thread_value": vp1,
+            "sample": f"{1 << 14} envs x {itp} rollout iterations in {dtp:.1f}s on {cores} threads (oracle C port: actor fp32 + OU + float64 "
+                      f"adaptive-RK45 env step + store + reset)"}
+    if not python_reference_available():
+        port["note"] = "baseline/_ref is missing (run __graft_entry__.build() where /root/reference is mounted): the Python reference was not timed"
+        return port
+    single = python_reference("rollout", 1, args.ref_steps, warm=1000)
+    per_proc = max(2000, args.ref_steps // 4)
+    multi = python_reference("rollout", cores, per_proc, warm=300)
+    env1 = python_reference("env", 1, args.ref_steps, warm=1000)
+    envm = python_reference("env", cores, per_proc, warm=300)
+    out = {"value": multi["value"], "unit": UNIT, "cores": cores, "kind": "reference",
+           "sample": f"UNMODIFIED reference Python loop (choose_action -> clip*high -> env.step -> remember, reset on done; actor on the CPU): "
+                     f"{cores} processes (one per core, OMP threads 1) x {per_proc} env steps in {multi['seconds']:.1f}s",
+           "single_process_value": single["value"],
+           "single_process_sample": f"1 process x {single['steps']} env steps in {single['seconds']:.1f}s",
+           "env_only": {"single_process_value": env1["value"], "all_cores_value": envm["value"],
+                        "sample": f"env.step with U(-pi/4, pi/4) steering + reset on done: 1 x {env1['steps']} steps in {env1['seconds']:.1f}s; "
+                                  f"{cores} x {per_proc} steps in {envm['seconds']:.1f}s"},
+           "port": port}
+    return out
+
+
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on all host cores.  One bench "step" = every
+    process advances its own environment by a bounded chunk of env steps of the unmodified Python rollout loop."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n = 1 << 15                                   # bounded sample: 32768 envs per step
+    cores = os.cpu_count() or 1
     t0 = time.perf_counter()
-    val, it, dt = cpu_port(n, 0, threads, steps=args.steps, warmup=max(args.warmup, 1))
-    sample = f"{n} envs x {it} rollout iterations (actor fp32 + OU + env step float64 RK45 + store + reset) in {dt:.1f}s"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / it, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "full rollout: actor(23-400-300-1)+OU+simv2 step+reward_functionv1+replay store+reset, "
-                                   "2^22 envs/GPU (CPU arm: bounded sample)", "envs_per_step_sample": n},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+    W, K = max(args.warmup, 1), args.steps
+    if python_reference_available():
+        chunk = 400                                  # env steps per process and bench step (~0.4 s of the ~1 k steps/s loop)
+        res = python_reference("rollout", cores, chunk * K, warm=chunk * W, chunks=K)
+        val, secs = res["value"], res["seconds"]
+        kind, dtype = "reference", "f64"
+        sample = (f"UNMODIFIED reference Python loop (baseline/_ref: DDPG_agent.choose_action -> clip*high -> simv2 env.step -> remember, "
+                  f"reset on done; actor on the CPU): {cores} processes (one per core, OMP threads 1) x {K} steps x {chunk} env steps "
+                  f"after {W} warm-up steps, {secs:.1f}s")
+        extra = {"envs_per_step_sample": cores * chunk}
+    else:
+        n = 1 << 15
+        val, it, secs = cpu_port(n, 0, cores, steps=K, warmup=W)
+        kind, dtype = "port", "f64"
+        sample = f"baseline/_ref missing -> oracle C port: {n} envs x {it} rollout iterations in {secs:.1f}s"
+        extra = {"envs_per_step_sample": n}
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": dict({"workload": WORKLOAD + " (CPU arm: bounded sample of the same loop)"}, **extra),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
@@ -159,6 +236,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm ----
 def run_b200(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import ddpg_trucktrailer_b200 as tt
@@ -172,88 +250,97 @@ def run_b200(args):
     offset = rank * N
     L = tt.load()
     pk = peaks()
+    W, K = max(args.warmup, 3), args.steps
 
     env = tt.VecTruckTrailerEnv(N, seed=27, global_env_offset=offset, device=dev)
     agent = tt.VecAgent(1e-4, 1e-3, (23,), 1e-3, 1, max_size=args.ring, num_envs=N, device=dev, seed=27, global_env_offset=offset,
-                        precision=args.precision, actor_seed=0)
+                        precision=args.precision, actor_seed=0, allow_out_of_bar=args.precision == "bf16")
     sd = tt.init_actor_state_dict(seed=0)
     if world > 1:   # NCCL over NVLink: the only collectives of the path (actor broadcast, stats all-reduce)
         sd = ttd.broadcast_actor({k: v.to(dev) for k, v in sd.items()}, src=0, device=dev)
     agent.load_actor_state_dict(sd)
     eng = tt.RolloutEngine(env, agent, store=True)
     eng.reset()
+    sync = ttd.OverlappedSync(dev, src=0)            # side-stream collectives (no-ops at world == 1)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def timed(fn, iters):
-        barrier(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize(); barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
-    W, K = max(args.warmup, 3), args.steps
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    t_load0 = time.time()
-    for _ in range(args.preroll):          # population reaches its stationary mix of episode ages (max episode ~ 250 steps)
-        eng.step()
-    env.stats_tensor(clear=True)
-    for _ in range(W):
-        eng.step()
-    torch.cuda.synchronize()
-
-    # ---- headline: K rollout iterations, everything resident in HBM ----
-    launches0 = L.tt_launch_count()
-    t_wall0 = time.time()
-    ms = timed(eng.step, K)
-    t_wall1 = time.time()
-    launches = L.tt_launch_count() - launches0
-    value = world * N * K / (ms * 1e-3)
-    stats = ttd.all_reduce_stats(env.stats_tensor(clear=True).clone())
-
-    # ---- e2e: the same iteration driven from the host with HOST buffers inside the timed region:
-    #      H2D of the step's external input (the current actor parameters from pinned host memory, re-packed on the
-    #      device) and D2H of the step's results the reference driver reads (reward and done of every env + stats)
+    # ---- everything the later phases need is allocated NOW, so that no allocation sits between a pre-roll and its timed region
     flat_host = ttd.flatten_actor(sd).cpu().pin_memory()
-    # the policy of step t + 1 is uploaded and re-packed on a side stream WHILE step t runs (two packed actors, used
-    # alternately): what an asynchronous learner hands over; every byte still moves, every step, inside the timed region
     flat_dev = [torch.empty_like(flat_host, device=dev) for _ in range(2)]
-    views = [ttd.unflatten_actor(f, sd) for f in flat_dev]
     actors = [agent.actor, tt.agent.CudaActor(*agent.actor.dims, device=dev)]
-    up_stream = torch.cuda.Stream(device=dev)
-    packed = [torch.cuda.Event() for _ in range(2)]
-    step_done = torch.cuda.Event()
-
-    def upload(slot):                                                  # H2D + device re-pack of one policy, on up_stream
-        with torch.cuda.stream(up_stream):
-            up_stream.wait_event(step_done)                            # the previous user of this slot's images has finished
-            flat_dev[slot].copy_(flat_host, non_blocking=True)
-            actors[slot].load_state_dict(views[slot])
-            packed[slot].record(up_stream)
-    # results are read back one iteration behind on a copy stream (double-buffered staging), so the PCIe transfer of
-    # step t overlaps the kernels of step t+1; every byte still moves inside the timed region
     rew_host = [torch.empty(N, dtype=torch.float32).pin_memory() for _ in range(2)]
     done_host = [torch.empty(N, dtype=torch.uint8).pin_memory() for _ in range(2)]
     stats_host = [torch.empty(16, dtype=torch.float64).pin_memory() for _ in range(2)]
     rew_stage = [torch.empty(N, dtype=torch.float32, device=dev) for _ in range(2)]
     done_stage = [torch.empty(N, dtype=torch.uint8, device=dev) for _ in range(2)]
     stats_stage = [torch.empty(16, dtype=torch.float64, device=dev) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    up_stream, copy_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, iters):
+        """EXACTLY `iters` steps between a barrier + synchronize on both sides, CUDA events, max over ranks; also the wall-clock
+        window of the region (for the clock samples)."""
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(); w1 = time.time(); barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), (w0, w1)
+
+    def headline_step():
+        eng.step()
+        if world > 1:      # section 8e: the per-iteration statistics all-reduce, issued on the side stream, consumed one iteration behind
+            sync.push_stats(env.stats_tensor(clear=True))
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t_load0 = time.time()
+    for _ in range(args.preroll):          # population reaches its stationary mix of episode ages (max episode ~ 250 steps)
+        headline_step()
+    stats_acc = torch.zeros(16, dtype=torch.float64, device=dev)
+    env.stats_tensor(clear=True)
+    for _ in range(W):
+        headline_step()
+
+    # ---- headline: K rollout iterations, everything resident in HBM ----
+    launches0 = L.tt_launch_count()
+    ms, win_value = timed(headline_step, K)
+    launches = L.tt_launch_count() - launches0
+    value = world * N * K / (ms * 1e-3)
+    if world > 1:
+        stats = sync.flush_stats().clone()
+    else:
+        stats = env.stats_tensor(clear=True).clone()
+
+    # ---- e2e: the same iteration driven from the host with HOST buffers inside the timed region:
+    #      H2D of the step's external input (the current actor parameters from pinned host memory, re-packed on the
+    #      device) and D2H of the step's results the reference driver reads (reward and done of every env + stats).
+    # The policy of step t + 1 is uploaded and re-packed on a side stream WHILE step t runs (two packed actors, used
+    # alternately): what an asynchronous learner hands over; results are read back one iteration behind on a copy stream
+    # (double-buffered staging).  Every byte still moves, every step, inside the timed region.
+    packed = [torch.cuda.Event() for _ in range(2)]
+    step_done = torch.cuda.Event()
     staged = [torch.cuda.Event() for _ in range(2)]
     drained = [torch.cuda.Event() for _ in range(2)]
     for ev in drained:
         ev.record()
     e2e_it = [0]
+
+    def upload(slot):                                                  # H2D + device re-pack of one policy, on up_stream
+        with torch.cuda.stream(up_stream):
+            up_stream.wait_event(step_done)                            # the previous user of this slot's images has finished
+            flat_dev[slot].copy_(flat_host, non_blocking=True)
+            actors[slot].load_flat(flat_dev[slot])
+            packed[slot].record(up_stream)
 
     def e2e_step():
         b = e2e_it[0] & 1
@@ -274,40 +361,46 @@ def run_b200(args):
             stats_host[b].copy_(stats_stage[b], non_blocking=True)
             drained[b].record(copy_stream)
 
-    def e2e_run(iters):
-        for _ in range(iters):
-            e2e_step()
-        copy_stream.synchronize(); up_stream.synchronize()
-
     step_done.record()
     upload(0)                                                          # the first step's policy
-
-    e2e_run(2)
-    torch.cuda.synchronize()
+    # its own pre-roll: the e2e pipeline itself for >= args.e2e_preroll_s, straight into the timed region (same clock / power
+    # state as the region; the only gap is the contract's barrier + synchronize)
+    pre = max(W, int(args.e2e_preroll_s / max(ms / K * 1e-3, 1e-6)))
+    for _ in range(pre):
+        e2e_step()
     barrier(); torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w_e0 = time.time()
     ev0.record()
-    e2e_run(K)
+    for _ in range(K):
+        e2e_step()
     torch.cuda.current_stream().wait_stream(copy_stream)
-    torch.cuda.current_stream().wait_stream(up_stream)               # every upload issued inside the region also ends inside it
+    torch.cuda.current_stream().wait_stream(up_stream)               # every copy issued inside the region also ends inside it
     ev1.record()
-    torch.cuda.synchronize(); barrier()
+    torch.cuda.synchronize(); w_e1 = time.time(); barrier()
     t_e2e = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = float(t_e2e)
     agent.actor = actors[0]
-    clocks = sampler.stop(t_wall0, t_wall1, t_load0, time.time()) if sampler else None     # sampled from the pre-roll to the end of e2e
+    actors[0].load_state_dict(sd)
+    env.stats_tensor(clear=True)
+    clocks = clocks_e2e = None
+    if sampler:
+        # the regions last tens of ms and nvidia-smi samples every 20 ms: take the samples of the region plus the 0.3 s of the
+        # same uninterrupted load right before it
+        clocks = sampler.window(win_value[0] - 0.3, win_value[1]) or sampler.window(t_load0, win_value[1])
+        clocks_e2e = sampler.window(w_e0 - 0.3, w_e1)
     e2e = {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": flat_host.numel() * 4,
-           "d2h_bytes_per_step": N * 5 + 128, "ms_per_step": ms_e2e / K,
-           "note": "host buffers: actor parameters H2D + re-pack every step (side stream, one step ahead, two packed actors); reward/done/stats D2H every step (copy stream, one step behind)"}
+           "d2h_bytes_per_step": N * 5 + 128, "ms_per_step": ms_e2e / K, "preroll_iterations": pre, "clocks": clocks_e2e,
+           "note": "host buffers: actor parameters H2D + re-pack every step (side stream, one step ahead, two packed actors); reward/done/stats D2H "
+                   "every step (copy stream, one step behind); timed right after its own pre-roll of the same pipeline"}
 
     # ---- per-kernel timing (CUDA events on the launching stream) -> roofline of the dominant kernel ----
     s = _lib.stream_ptr()
     cur, nxt = env._obs[env._cur], env._obs[env._cur ^ 1]
     m = agent.memory
     prec = _lib.PRECISIONS[args.precision]
-    import ctypes as C
     ring = _lib.ReplayRing(m.state_memory.data_ptr(), m.action_memory.data_ptr(), m.reward_memory.data_ptr(),
                            m.new_state_memory.data_ptr(), m.terminal_memory.data_ptr(), m.mem_size, m.mem_cntr)
     rp = C.byref(ring)
@@ -318,11 +411,6 @@ def run_b200(args):
                                                              agent.noise.iter_ptr, 0, eng.action.data_ptr(), eng.scaled.data_ptr(), prec, rp, s)),
         "env_step": lambda: _lib.check(L.tt_env_step_reset(env._h, eng.scaled.data_ptr(), nxt.data_ptr(), env.ld_obs, env._reward.data_ptr(),
                                                            env._done.data_ptr(), agent.noise.x_prev.data_ptr(), rp, s)),
-        # for reference only (NOT part of the fused rollout): the stand-alone ring scatter kernel
-        "replay_store_standalone": lambda: _lib.check(L.tt_replay_store(m.state_memory.data_ptr(), m.action_memory.data_ptr(), m.reward_memory.data_ptr(),
-                                                             m.new_state_memory.data_ptr(), m.terminal_memory.data_ptr(), m.mem_size, m.mem_cntr,
-                                                             cur.data_ptr(), env.ld_obs, eng.action.data_ptr(), env._reward.data_ptr(),
-                                                             nxt.data_ptr(), env.ld_obs, env._done.data_ptr(), N, s)),
     }
     # Every kernel is timed IN the running rollout (same power / clock state as the headline: under sustained load a B200
     # settles well below its boost clock): one untimed rollout iteration, then the kernel once more between two events,
@@ -339,17 +427,18 @@ def run_b200(args):
             evs.append((e0, e1))
         torch.cuda.synchronize()
         kms[name] = sum(a.elapsed_time(b) for a, b in evs) / K
-    # algorithmic work per launch: env step 229 B + its share of the fused store (s', r, done: 97 B)
-    algo = {"actor": ("tensor", N * ACTOR_FLOPS / 1e12), "env_step": ("hbm", N * (ENV_BYTES + 97) / 1e9),
-            "replay_store_standalone": ("hbm", N * STORE_BYTES / 1e9)}
+    # algorithmic work per launch: actor 259 000 FLOP / row; env step 229 B + its share of the fused store
+    # (s', r, done: 97 B); the noise state (8 B), the stored action / scaled action and the reset are NOT counted
+    algo = {"actor": ("tensor", N * ACTOR_FLOPS / 1e12), "env_step": ("hbm", N * (ENV_BYTES + 97) / 1e9)}
     kernels = {}
     for name, (bound, work) in algo.items():
         peak = pk["hbm"] if bound == "hbm" else pk["tf_sust"]     # kernels timed inside the running rollout: sustained figure
         ach = work / (kms[name] * 1e-3)
         kernels[name] = {"ms": kms[name], "bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
                          "frac": ach / peak}
+    kernels["env_step"]["frac_of_bare_step_229B"] = N * ENV_BYTES / 1e9 / (kms["env_step"] * 1e-3) / pk["hbm"]
     in_step = ["actor", "env_step"]
-    dom = max([k for k in algo if k in in_step], key=lambda n: kms[n])
+    dom = max(in_step, key=lambda n: kms[n])
     try:      # DRAM bytes per env from the committed `ncu --set full` capture (profiles/), scaled to this launch
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             traffic = json.load(f)["bytes_per_env"].get(dom)
@@ -360,53 +449,97 @@ def run_b200(args):
                 "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": pk["src"],
                 "share_of_step": kms[dom] / sum(kms[k] for k in in_step)}
 
-    # ---- optional: BASELINE.json configs[3] = the rollout iteration + one learner update (batch 64) per iteration ----
+    # ---- BASELINE.json configs[3]: the rollout iteration + one DDPG update (batch 64) per iteration (+ collectives) ----
     config4 = None
-    if args.config4:
-        agent.learner_graph = True                   # learner.py: the whole DDPG update as one CUDA graph, samples rank-local ring
-        for _ in range(3):
-            agent.learn()
-        torch.cuda.synchronize()
-        stats_dev = torch.zeros(16, dtype=torch.float64, device=dev)
+    if not args.no_config4:
+        ln = agent.learner                                           # learner rank = 0; created everywhere so that every rank
+        flat = ln._flat["actor"]                                     # has the flat parameter buffer the broadcast lands in
+        spare = actors[1]
+        pol_ready = torch.cuda.Event()
+        c4_it = [0]
 
         def c4_step():
+            main = torch.cuda.current_stream()
+            if world > 1 and c4_it[0] > 0:
+                main.wait_event(pol_ready)                           # last iteration's policy: broadcast + re-packed on the side stream
+                agent.actor, actors[1] = actors[1], agent.actor
+            c4_it[0] += 1
             eng.step()
-            agent.learn()                                              # replays the graph (incl. the actor re-pack) on the same stream
-            if world > 1:                                              # section 8e: the only collectives of the path
-                stats_dev.copy_(env.stats_tensor(clear=True)); dist.all_reduce(stats_dev)
-                flat = ttd.flatten_actor(agent.actor.state_dict(), device=dev); dist.broadcast(flat, src=0)
-                agent.load_actor_state_dict(ttd.unflatten_actor(flat, sd))
-        for _ in range(3):
+            if world == 1:
+                ln.learn()                                           # tt_learn_step + re-pack into the rollout actor, same stream
+                return
+            if rank == 0:
+                ln.learn(repack_into=None)                           # updates `flat` in place
+            sync.push_stats(env.stats_tensor(clear=True))            # all-reduce on the side stream, consumed one iteration behind
+            sync.push_policy(flat)                                   # broadcast of the 526 KB parameter vector on the side stream ...
+            with torch.cuda.stream(sync.stream):
+                sync.wait_policy()
+                actors[1].load_flat(flat)                            # ... and its re-pack into the spare packed actor
+                pol_ready.record(sync.stream)
+        for _ in range(max(W, 5)):
             c4_step()
-        ms4 = timed(c4_step, K)
-        config4 = {"value": world * N * K / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / K,
-                   "note": "configs[3]: rollout + fused replay store + one DDPG update (batch 64, learner step as one CUDA graph, "
-                           "sequential on the rollout stream)" + (" + stats all-reduce + actor broadcast (NCCL)" if world > 1 else "")}
+        l0 = L.tt_launch_count()
+        ms4, _ = timed(c4_step, K)
+        config4 = {"value": world * N * K / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / K, "gpu_launches": int(L.tt_launch_count() - l0),
+                   "extra_ms_over_rollout": ms4 / K - ms / K,
+                   "note": "configs[3]: rollout + fused replay store + one DDPG update per iteration (batch 64, tt_learn_step: hand-written "
+                           "kernels on the device ring" + (", learner on rank 0; stats all-reduce + broadcast of the flat actor vector on a "
+                           "side NCCL stream, re-pack into the spare packed actor, consumed one iteration behind)" if world > 1 else
+                           " + re-pack of the policy, same stream)")}
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(sync.stream)
+        agent.actor = actors[0]
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ----
+    # ---- BASELINE.json configs[4]: mini-sweep over envs per GPU (the full sweep: profiles/sweep.py) ----
+    sweep = None
+    if not args.no_sweep:
+        sweep = []
+        for n in (1 << 12, 1 << 18):
+            e2 = tt.VecTruckTrailerEnv(n, seed=27, global_env_offset=rank * n, device=dev)
+            a2 = tt.VecAgent(1e-4, 1e-3, (23,), 1e-3, 1, max_size=max(4 * n, 1 << 16), num_envs=n, device=dev, seed=27,
+                             global_env_offset=rank * n, precision=args.precision, actor_seed=0, allow_out_of_bar=args.precision == "bf16")
+            g2 = tt.RolloutEngine(e2, a2, store=True)
+            g2.reset()
+            for _ in range(args.preroll):
+                g2.step()
+            iters = 200 if n <= (1 << 14) else 50
+            l0 = L.tt_launch_count()
+            ms_s, _ = timed(g2.step, iters)
+            row = {"envs_per_gpu": n, "us_per_iteration": 1e3 * ms_s / iters, "value": world * n * iters / (ms_s * 1e-3),
+                   "launches_per_iteration": (L.tt_launch_count() - l0) / iters}
+            if n <= (1 << 14):                                       # launch-bound sizes: K iterations as ONE CUDA graph
+                kk = g2.capture()
+                reps = max(1, iters // kk)
+                ms_g, _ = timed(g2.step_graph, reps)
+                row["us_per_iteration_cuda_graph"] = 1e3 * ms_g / (reps * kk)
+            sweep.append(row)
+            del g2, a2, e2
+        sweep.append({"envs_per_gpu": N, "us_per_iteration": 1e3 * ms / K, "value": value, "launches_per_iteration": launches / K})
+
+    # ---- CPU baseline (rank 0, N = 1 only): the reference's Python loop on the host cores + the oracle's C port ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, it, dt = cpu_port(1 << 14, args.cpu_seconds, threads)
-        v1, it1, dt1 = cpu_port(1 << 12, min(args.cpu_seconds, 6.0), 1)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{1 << 14} envs x {it} rollout iterations in {dt:.1f}s on {threads} threads (oracle C port: actor fp32 + OU + "
-                         f"float64 adaptive-RK45 env step + store + reset)",
-               "single_thread_value": v1}
+        cpu = cpu_baseline_block(args)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "bf16": "bf16", "f16": "f16"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": f"full rollout: actor(23-400-300-1,{args.precision})+OU+simv2 step(f64/f32 DP5)+reward_functionv1+"
-                                       f"replay store (fused into the producers)+auto-reset, {N} envs/GPU", "envs_per_gpu": N, "ring_capacity": args.ring, "preroll_iterations": args.preroll,
+                "config": {"workload": WORKLOAD.replace("2^22 envs/GPU", f"{N} envs/GPU") + f"; actor {args.precision} (tcgen05), env step f64/f32 DP5",
+                           "envs_per_gpu": N, "ring_capacity": args.ring, "preroll_iterations": args.preroll,
+                           "launches_per_iteration": launches / K,
                            "l2": "working set per step (>1.2 GB/GPU) far exceeds the 126 MB L2; no flush needed",
-                           "sharding": "global env id ranges, no data-path collective; NCCL only for actor broadcast + stats all-reduce"},
+                           "sharding": "global env id ranges, no data-path collective" + ("; the per-iteration statistics all-reduce (NCCL, side stream) "
+                                       "is inside the timed step" if world > 1 else "")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
                 "cpu_baseline": cpu, "rollout_stats": ttd.summarize(stats)}
         if config4 is not None:
             line["config4"] = config4
+        if sweep is not None:
+            line["sweep"] = sweep
         print(json.dumps(line), flush=True)
+    if sampler:
+        sampler.stop(0, 0)
     if world > 1:
         dist.destroy_process_group()
 

@@ -11,7 +11,7 @@
 //   packed[N] u32    steps | emax | rmax-emax | stage bits | finished
 //   goal[N] int4     gx gy (fixed point) sin/cos(gyaw) bits -- only READ when per-env goals were injected
 //   l2v[N]  double2  trailer length L2 and v1x / L2 -- only READ by the step kernel after a per-env injection
-//   pose[4][N] f64   startx starty startyaw goalyaw (written on reset only; host-visible attributes)
+//   pose[N][4] f64   startx starty startyaw goalyaw (written on reset only, one 32 B sector; host-visible attributes)
 //   stats[16] f64, iter u32
 // One thread owns one environment.  The step kernel is persistent: a CTA walks over 128-env tiles and issues
 // the loads of its NEXT tile before computing the current one (register double buffer), so the DRAM latency
@@ -37,7 +37,7 @@ struct EnvPtrs {
     double *pose;        // [4][N]
     double *stats;       // [16]
     uint32_t *iter;      // [0] Philox iteration counter, [1] CTAs-finished counter of the rollout kernel's tick
-    uint32_t *done_list; // [N] scratch of the rollout kernel: envs that finished an episode in this launch, per-CTA segments
+    uint32_t *done_list; // [N + slack] scratch of the rollout kernel: overflow of a CTA's shared-memory list of finished envs
     int64_t N;
 };
 
@@ -55,6 +55,8 @@ struct tt_env {
 namespace {
 
 constexpr int kBlock = 128;
+constexpr int kDoneSmem = 512;                 // finished envs a CTA of the rollout kernel lists in shared memory (the rest: global)
+constexpr int64_t kListSlack = 128 * 4096;     // global overflow segments are whole tiles per CTA: <= 4096 CTAs of rounding slack
 #ifndef TT_ENV_MINBLOCKS_DEFAULT
 #define TT_ENV_MINBLOCKS_DEFAULT 4
 #endif
@@ -131,9 +133,9 @@ __device__ __forceinline__ void store_dyn(const EnvPtrs &p, int64_t i, const Env
 
 __device__ __forceinline__ void store_episode_consts(const EnvPtrs &p, int64_t i, const EnvRegs &e, double sx, double sy,
                                                      double syaw, double gyaw) {
-    const int64_t N = p.N;
     p.goal[i] = make_int4(e.gx, e.gy, __float_as_int(e.sgy), __float_as_int(e.cgy));
-    p.pose[i] = sx; p.pose[N + i] = sy; p.pose[2 * N + i] = syaw; p.pose[3 * N + i] = gyaw;
+    double *ps = p.pose + 4 * i;
+    ps[0] = sx; ps[1] = sy; ps[2] = syaw; ps[3] = gyaw;
 }
 
 // coalesced store of a [rows, 23] tile held in shared memory to obs[(row0 + r) * ld + c]
@@ -164,17 +166,21 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // reset(): mask == nullptr -> every env; else only where mask[i] != 0.  Also clears the OU state is NOT done
 // here (that is tt_ou_step's reset mask, trainv2.py:492).
+// kPerEnv = false: no per-env trailer length / goal has been injected -- the configured L2 is used without reading l2v[] (one
+// dependent DRAM round trip less) and goal[] already holds the configured goal.
+template <bool kPerEnv>
 __device__ __forceinline__ void reset_env(const EnvPtrs &p, const StepConsts &k, int64_t i, float *__restrict__ obs, int64_t ld,
                                           uint64_t seed, uint64_t gid0, uint32_t t, float *__restrict__ ou_x) {
     if (ou_x) ou_x[i] = 0.0f;                                 // agent.noise.reset() for the new episode (trainv2.py:492)
     EnvRegs e;
-    { const double2 l = p.l2v[i]; e.L2 = l.x; e.vL2 = l.y; }
+    if (kPerEnv) { const double2 l = p.l2v[i]; e.L2 = l.x; e.vL2 = l.y; } else use_default_l2(k, e);
     double sx, sy, syaw;
     rng_pose(k, seed, (uint32_t)(gid0 + i), t, sx, sy, syaw);
     float o[TT_OBS_DIM];
     reset_from_pose(k, e, sx, sy, syaw, k.gx, k.gy, k.gyaw, obs ? o : nullptr);
     store_dyn(p, i, e);
-    store_episode_consts(p, i, e, sx, sy, syaw, k.gyaw);
+    if (kPerEnv) store_episode_consts(p, i, e, sx, sy, syaw, k.gyaw);
+    else reinterpret_cast<double4 *>(p.pose)[i] = make_double4(sx, sy, syaw, k.gyaw);
     if (obs) {
 #pragma unroll
         for (int c = 0; c < TT_OBS_DIM; c++) obs[i * ld + c] = o[c];
@@ -200,7 +206,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
     // observation tiles: double buffered; full tiles leave through the bulk-copy engine (cp.async.bulk shared ->
     // global), which drains them while the CTA already computes its next tile
     __shared__ __align__(128) float tiles[2][kBlock * TT_OBS_DIM];
-    __shared__ int s_ndone;                               // kRoll: entries in this CTA's segment of p.done_list
+    __shared__ int s_ndone;                               // kRoll: finished envs of this CTA so far ...
+    __shared__ uint32_t s_done[kRoll ? kDoneSmem : 1];    // ... the first kDoneSmem of them (typically all: ~1.4 % of ~7 000 envs)
     uint32_t tbuf = 0;
     if (kRoll) { if (threadIdx.x == 0) s_ndone = 0; __syncthreads(); }
     const bool bulk_ok = obs != nullptr && ld == TT_OBS_DIM && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
@@ -321,7 +328,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                 if (active) {
 #pragma unroll
                     for (int c = 0; c < TT_OBS_DIM; c++) tile[ln * TT_OBS_DIM + c] = o.obs[c];
-                    if (o.done) p.done_list[seg0 + atomicAdd(&s_ndone, 1)] = (uint32_t)i;     // reset at the end of the kernel
+                    if (o.done) {                                            // reset at the end of the kernel
+                        const int slot = atomicAdd(&s_ndone, 1);
+                        if (slot < kDoneSmem) s_done[slot] = (uint32_t)i; else p.done_list[seg0 + slot] = (uint32_t)i;
+                    }
                 }
                 const int64_t rrow0 = (rpl.S2 && wrows > 0) ? rpl.m.row(wrow0) : 0;
                 const bool ring_bulk = rpl.S2 && wrows == 32 && !rpl.m.many && wrow0 >= rpl.m.first && rrow0 + 32 <= rpl.m.cap &&
@@ -403,13 +413,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
         // replaces the terminal row in `obs`; the ring keeps the terminal row.
         __syncthreads();
         const int nd = s_ndone;
-        for (int j = threadIdx.x; j < nd; j += kBlock) reset_env(p, k, (int64_t)p.done_list[seg0 + j], obs, ld, seed, gid0, t0, ou_x);
+        for (int j = threadIdx.x; j < nd; j += kBlock)
+            reset_env<kGoal>(p, k, (int64_t)(j < kDoneSmem ? s_done[j] : p.done_list[seg0 + j]), obs, ld, seed, gid0, t0, ou_x);
         // iteration tick: every CTA read *p.iter (t0) when it started, and the last one to get here has seen all others finish
         __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            if (atomicAdd(p.iter + 1, 1u) == gridDim.x - 1) { p.iter[1] = 0u; *p.iter = t0 + 1u; }
-        }
+        if (threadIdx.x == 0 && atomicAdd(p.iter + 1, 1u) == gridDim.x - 1) { p.iter[1] = 0u; *p.iter = t0 + 1u; }
     }
 
     // statistics: steps and reward every launch, the episode counters only in warps that finished an episode
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(kBlock) env_reset_kernel(EnvPtrs p, StepConsts
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= p.N) return;
     if (mask && !mask[i]) return;
-    reset_env(p, k, i, obs, ld, seed, gid0, *p.iter + t_salt, ou_x);
+    reset_env<true>(p, k, i, obs, ld, seed, gid0, *p.iter + t_salt, ou_x);
 }
 
 // Masked reset for the rollout, where about 1 % of the envs finish per step.  One thread per env spends 20 us at N = 2^22
@@ -475,7 +483,7 @@ __global__ void __launch_bounds__(kBlock) env_reset_sparse_kernel(EnvPtrs p, Ste
         int at = pre - cnt;
         while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; list[wib][at++] = lane * 16 + b; }
         __syncwarp();
-        for (int j = lane; j < total; j += 32) reset_env(p, k, w * kWarpWindow + list[wib][j], obs, ld, seed, gid0, t, ou_x);
+        for (int j = lane; j < total; j += 32) reset_env<true>(p, k, w * kWarpWindow + list[wib][j], obs, ld, seed, gid0, t, ou_x);
         __syncwarp();
     }
 }
@@ -517,8 +525,8 @@ __global__ void __launch_bounds__(kBlock) env_get_state_kernel(EnvPtrs p, double
         state[6 * i + 2] = pos_to_double(q.x); state[6 * i + 3] = pos_to_double(q.y);
         state[6 * i + 4] = pos_to_double(q.z); state[6 * i + 5] = pos_to_double(q.w);
     }
-    if (start) { start[3 * i] = p.pose[i]; start[3 * i + 1] = p.pose[N + i]; start[3 * i + 2] = p.pose[2 * N + i]; }
-    if (goal) { const int4 g = p.goal[i]; goal[3 * i] = pos_to_double(g.x); goal[3 * i + 1] = pos_to_double(g.y); goal[3 * i + 2] = p.pose[3 * N + i]; }
+    if (start) { start[3 * i] = p.pose[4 * i]; start[3 * i + 1] = p.pose[4 * i + 1]; start[3 * i + 2] = p.pose[4 * i + 2]; }
+    if (goal) { const int4 g = p.goal[i]; goal[3 * i] = pos_to_double(g.x); goal[3 * i + 1] = pos_to_double(g.y); goal[3 * i + 2] = p.pose[4 * i + 3]; }
     const uint32_t pk = p.packed[i];
     if (steps) steps[i] = (int32_t)(pk & PK_STEPS_MASK);
     if (max_steps) max_steps[i] = (int32_t)((pk >> PK_EMAX_SHIFT) & PK_EMAX_MASK);
@@ -543,7 +551,7 @@ __global__ void __launch_bounds__(kBlock) env_init_goal_kernel(EnvPtrs p, StepCo
     if (i < p.N) {
         p.goal[i] = make_int4(k.gx_fix, k.gy_fix, __float_as_int(k.sgy0), __float_as_int(k.cgy0));
         p.l2v[i] = make_double2(k.L2, k.vL2);
-        p.pose[3 * p.N + i] = k.gyaw;          // env.goalyaw is valid before the first reset (simv2.py:61-63)
+        p.pose[4 * i + 3] = k.gyaw;            // env.goalyaw is valid before the first reset (simv2.py:61-63)
     }
 }
 
@@ -589,7 +597,7 @@ static size_t env_layout(int64_t n, EnvPtrs *p, char *base) {
     const size_t o_psi = take(sizeof(double2) * n), o_pos = take(sizeof(int4) * n), o_a = take(sizeof(float4) * n),
                  o_b = take(sizeof(float4) * n), o_pk = take(sizeof(uint32_t) * n), o_goal = take(sizeof(int4) * n), o_l2v = take(sizeof(double2) * n),
                  o_pose = take(sizeof(double) * 4 * n), o_stats = take(sizeof(double) * TT_NSTATS), o_iter = take(256),
-                 o_list = take(sizeof(uint32_t) * (n + 128));
+                 o_list = take(sizeof(uint32_t) * (n + kListSlack));
     if (p) {
         p->psi = reinterpret_cast<double2 *>(base + o_psi); p->pos = reinterpret_cast<int4 *>(base + o_pos);
         p->rsA = reinterpret_cast<float4 *>(base + o_a); p->rsB = reinterpret_cast<float4 *>(base + o_b);

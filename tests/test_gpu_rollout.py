@@ -311,7 +311,11 @@ def test_step_reset_one_launch_equals_separate_kernels(N, cap, cntr0, store):
     assert a["tot"] == b["tot"] and a["tot"] > N // 20
     for k in ("obs", "rew", "done", "s2", "r", "d", "state", "start", "steps", "x"):
         assert torch.equal(a[k], b[k]), k
-    assert a["stats"] == b["stats"]
+    for k in a["stats"]:      # counts are exact; the float sums depend on the (atomic) summation order
+        if k in ("return_sum", "return_sq_sum", "reward_sum"):
+            assert abs(a["stats"][k] - b["stats"][k]) <= 1e-9 * abs(b["stats"][k]) + 1e-6, k
+        else:
+            assert a["stats"][k] == b["stats"][k], k
 
 
 def test_auto_precision_picks_the_kernel_by_batch_size():
