@@ -116,15 +116,18 @@ __device__ void row_stats(const float *__restrict__ X, int ldx, int rows, int K,
 
 __device__ __forceinline__ float ln_relu(float x, float2 st, float g, float be) { return fmaxf(fmaf((x - st.x) * st.y, g, be), 0.f); }
 
-// Y tile: all B rows x 16 columns [n0, n0 + 16); reduction over K in chunks of 32.  The next chunk's operands are fetched
-// into registers while the current one is multiplied (the global-load latency of every chunk would otherwise be exposed).
+// Y tile: all B rows x 32 columns [n0, n0 + 32); reduction over K in chunks of 32.  A thread owns 4 rows x 2 columns (one
+// 16 B and one 8 B shared-memory load per 8 FMAs: a 1 x 4 tile is shared-memory-bandwidth bound, 5 loads per 4 FMAs).  The next
+// chunk's operands are fetched into registers while the current one is multiplied (the global-load latency of every chunk
+// would otherwise be exposed).
+constexpr int kXS = 68, kWS = 34;                                                // padded row strides (floats), 16 B / 8 B aligned
 __device__ void job_fwd(const Job &J, int cta, float *smem) {
-    float (*Xs)[65] = reinterpret_cast<float (*)[65]>(smem);                    // [32][65]  k-major
-    float (*Ws)[17] = reinterpret_cast<float (*)[17]>(smem + 32 * 65);          // [32][17]
-    float2 *st = reinterpret_cast<float2 *>(smem + 32 * 65 + 32 * 17);          // [64]
-    const int tid = threadIdx.x, tn = tid & 15, tb = tid >> 4, n0 = cta * 16;
+    float *Xs = smem;                                                           // [32 k][kXS]  (b)
+    float *Ws = smem + 32 * kXS;                                                // [32 k][kWS]  (n)
+    float2 *st = reinterpret_cast<float2 *>(smem + 32 * kXS + 32 * kWS);        // [64]
+    const int tid = threadIdx.x, tn = tid & 15, tb = tid >> 4, n0 = cta * 32;
     const bool ln = J.g != nullptr;
-    float xr[8], wr[2];
+    float xr[8], wr[4];
     auto fetch = [&](int k0) {                                                  // raw operands of chunk k0 -> registers
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -132,7 +135,7 @@ __device__ void job_fwd(const Job &J, int cta, float *smem) {
             xr[i] = (b < J.B && k < J.K) ? J.X[(size_t)b * J.ldx + k] : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 4; i++) {
             const int e = tid + kT * i, n = e >> 5, k = k0 + (e & 31);
             wr[i] = (n0 + n < J.N && k < J.K) ? J.W[(size_t)(n0 + n) * J.ldw + k] : 0.f;
         }
@@ -143,33 +146,40 @@ __device__ void job_fwd(const Job &J, int cta, float *smem) {
         __syncthreads();
         if (cta == 0 && J.stats && tid < J.B) reinterpret_cast<float2 *>(J.stats)[tid] = st[tid];
     }
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[4][2] = {};
     for (int k0 = 0; k0 < J.K; k0 += 32) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int e = tid + kT * i, b = e >> 5, kk = e & 31, k = k0 + kk;
             float x = xr[i];
             if (ln) x = (b < J.B && k < J.K) ? ln_relu(x, st[b], J.g[k], J.be[k]) : 0.f;
-            Xs[kk][b] = x;
+            Xs[kk * kXS + b] = x;
         }
 #pragma unroll
-        for (int i = 0; i < 2; i++) { const int e = tid + kT * i; Ws[e & 31][e >> 5] = wr[i]; }
+        for (int i = 0; i < 4; i++) { const int e = tid + kT * i; Ws[(e & 31) * kWS + (e >> 5)] = wr[i]; }
         __syncthreads();
         if (k0 + 32 < J.K) fetch(k0 + 32);
 #pragma unroll
         for (int kk = 0; kk < 32; kk++) {
-            const float w = Ws[kk][tn];
-#pragma unroll
-            for (int i = 0; i < 4; i++) acc[i] = fmaf(Xs[kk][tb + 16 * i], w, acc[i]);
+            const float4 x = *reinterpret_cast<const float4 *>(Xs + kk * kXS + 4 * tb);
+            const float2 w = *reinterpret_cast<const float2 *>(Ws + kk * kWS + 2 * tn);
+            acc[0][0] = fmaf(x.x, w.x, acc[0][0]); acc[0][1] = fmaf(x.x, w.y, acc[0][1]);
+            acc[1][0] = fmaf(x.y, w.x, acc[1][0]); acc[1][1] = fmaf(x.y, w.y, acc[1][1]);
+            acc[2][0] = fmaf(x.z, w.x, acc[2][0]); acc[2][1] = fmaf(x.z, w.y, acc[2][1]);
+            acc[3][0] = fmaf(x.w, w.x, acc[3][0]); acc[3][1] = fmaf(x.w, w.y, acc[3][1]);
         }
         __syncthreads();
     }
-    if (n0 + tn < J.N) {
-        const float bias = J.bias ? J.bias[n0 + tn] : 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int b = tb + 16 * i;
-            if (b < J.B) J.Y[(size_t)b * J.ldy + n0 + tn] = acc[i] + bias;
+    for (int j = 0; j < 2; j++) {
+        const int n = n0 + 2 * tn + j;
+        if (n < J.N) {
+            const float bias = J.bias ? J.bias[n] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int b = 4 * tb + i;
+                if (b < J.B) J.Y[(size_t)b * J.ldy + n] = acc[i][j] + bias;
+            }
         }
     }
 }
@@ -216,12 +226,12 @@ __device__ void job_wgrad(const Job &J, int cta, float *smem) {
     }
 }
 
-// dX tile: all B rows x 16 columns [k0, k0 + 16); reduction over N in chunks of 32 (register prefetch like job_fwd)
+// dX tile: all B rows x 32 columns [k0, k0 + 32); reduction over N in chunks of 32 (same register tile and prefetch as job_fwd)
 __device__ void job_xgrad(const Job &J, int cta, float *smem) {
-    float (*Ds)[65] = reinterpret_cast<float (*)[65]>(smem);                    // [32 n][65]  (b)
-    float (*Ws)[17] = reinterpret_cast<float (*)[17]>(smem + 32 * 65);          // [32 n][17]  (k)
-    const int tid = threadIdx.x, tk = tid & 15, tb = tid >> 4, k0 = cta * 16;
-    float dr[8], wr[2];
+    float *Ds = smem;                                                           // [32 n][kXS]  (b)
+    float *Ws = smem + 32 * kXS;                                                // [32 n][kWS]  (k)
+    const int tid = threadIdx.x, tk = tid & 15, tb = tid >> 4, k0 = cta * 32;
+    float dr[8], wr[4];
     auto fetch = [&](int nb) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -229,39 +239,46 @@ __device__ void job_xgrad(const Job &J, int cta, float *smem) {
             dr[i] = (b < J.B && nb + nn < J.N) ? J.D[(size_t)b * J.ldd + nb + nn] : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int e = tid + kT * i, nn = e >> 4, kk = e & 15;
+        for (int i = 0; i < 4; i++) {
+            const int e = tid + kT * i, nn = e >> 5, kk = e & 31;
             wr[i] = (nb + nn < J.N && k0 + kk < J.K) ? J.W[(size_t)(nb + nn) * J.ldw + k0 + kk] : 0.f;
         }
     };
     fetch(0);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[4][2] = {};
     for (int nb = 0; nb < J.N; nb += 32) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) { const int e = tid + kT * i; Ds[e & 31][e >> 5] = dr[i]; }
+        for (int i = 0; i < 8; i++) { const int e = tid + kT * i; Ds[(e & 31) * kXS + (e >> 5)] = dr[i]; }
 #pragma unroll
-        for (int i = 0; i < 2; i++) { const int e = tid + kT * i; Ws[e >> 4][e & 15] = wr[i]; }
+        for (int i = 0; i < 4; i++) { const int e = tid + kT * i; Ws[(e >> 5) * kWS + (e & 31)] = wr[i]; }
         __syncthreads();
         if (nb + 32 < J.N) fetch(nb + 32);
 #pragma unroll
         for (int nn = 0; nn < 32; nn++) {
-            const float w = Ws[nn][tk];
-#pragma unroll
-            for (int i = 0; i < 4; i++) acc[i] = fmaf(Ds[nn][tb + 16 * i], w, acc[i]);
+            const float4 x = *reinterpret_cast<const float4 *>(Ds + nn * kXS + 4 * tb);
+            const float2 w = *reinterpret_cast<const float2 *>(Ws + nn * kWS + 2 * tk);
+            acc[0][0] = fmaf(x.x, w.x, acc[0][0]); acc[0][1] = fmaf(x.x, w.y, acc[0][1]);
+            acc[1][0] = fmaf(x.y, w.x, acc[1][0]); acc[1][1] = fmaf(x.y, w.y, acc[1][1]);
+            acc[2][0] = fmaf(x.z, w.x, acc[2][0]); acc[2][1] = fmaf(x.z, w.y, acc[2][1]);
+            acc[3][0] = fmaf(x.w, w.x, acc[3][0]); acc[3][1] = fmaf(x.w, w.y, acc[3][1]);
         }
         __syncthreads();
     }
-    if (k0 + tk < J.K) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int b = tb + 16 * i;
-            if (b < J.B) J.Y[(size_t)b * J.ldy + k0 + tk] = acc[i];
+    for (int j = 0; j < 2; j++) {
+        const int k = k0 + 2 * tk + j;
+        if (k < J.K) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int b = 4 * tb + i;
+                if (b < J.B) J.Y[(size_t)b * J.ldy + k] = acc[i][j];
+            }
         }
     }
 }
 
 __global__ void __launch_bounds__(kT) learn_gemm_kernel(JobList L) {
-    __shared__ __align__(16) float smem[64 * 65 + 64 * 17];
+    __shared__ __align__(16) float smem[64 * 65 + 64 * 17];       // >= 32 * kXS + 32 * kWS + 128 (forward / dX) and the dW layout
     int cta = blockIdx.x;
     for (int i = 0; i < L.n; i++) {
         if (cta < L.j[i].ctas) {
@@ -301,7 +318,19 @@ __global__ void learn_gather_kernel(tt_replay_ring ring, int64_t max_mem, const 
         bt.a[tid] = ring.d_action_mem[row]; bt.r[tid] = ring.d_reward_mem[row]; bt.d[tid] = ring.d_terminal_mem[row] ? 1.f : 0.f;
     }
     __syncthreads();
-    for (int v = tid; v < B * in; v += blockDim.x) {
+    // 1024 threads: at most two elements each, all loads issued before the first store (one DRAM latency)
+    float vs[2], vs2[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int v = tid + (int)blockDim.x * i;
+        if (v < B * in) { const int b = v / in, c = v - b * in; vs[i] = ring.d_state_mem[rows[b] * in + c]; vs2[i] = ring.d_new_state_mem[rows[b] * in + c]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int v = tid + (int)blockDim.x * i;
+        if (v < B * in) { bt.s[v] = vs[i]; bt.s2[v] = vs2[i]; }
+    }
+    for (int v = tid + 2 * (int)blockDim.x; v < B * in; v += blockDim.x) {       // (only for blocks smaller than 1024 threads)
         const int b = v / in, c = v - b * in;
         bt.s[v] = ring.d_state_mem[rows[b] * in + c];
         bt.s2[v] = ring.d_new_state_mem[rows[b] * in + c];
@@ -434,7 +463,7 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
     const int gt = (int)cluster_rank() * kRowT + threadIdx.x;
     for (int j = gt; j < H; j += kRowThreads) {
         float gba = 0.f, gwa = 0.f, gg2 = 0.f, gwq = 0.f;
-#pragma unroll 8
+#pragma unroll 32
         for (int bb = 0; bb < A.B; bb++) {
             const size_t o = (size_t)bb * H + j;
             const float dz = A.sc0[o];
@@ -497,7 +526,7 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
     const int gt = (int)cluster_rank() * kRowT + threadIdx.x;
     for (int j = gt; j < H; j += kRowThreads) {
         float gbe = 0.f, gg = 0.f, gw3 = 0.f;
-#pragma unroll 8
+#pragma unroll 32
         for (int bb = 0; bb < A.B; bb++) { const size_t o = (size_t)bb * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; gw3 += A.sc2[o]; }
         A.g_be2[j] = gbe; A.g_g2[j] = gg; A.g_t0[j] = gw3;
     }
@@ -516,6 +545,7 @@ struct L1Args {
 };
 __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
     __shared__ float xs[kMaxB * 32];
+    __shared__ float ds[kMaxB * (kMaxH / kRowCtas)];      // this CTA's column slice of dh1: [B][H1 / 8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H1;
     for (int v = threadIdx.x; v < A.B * A.IN; v += kRowT) xs[v] = A.x[v];
     const int b = (int)cluster_rank() * (kRowT / 32) + warp;
@@ -541,17 +571,24 @@ __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
     const int gt = (int)cluster_rank() * kRowT + threadIdx.x;
     for (int j = gt; j < H; j += kRowThreads) {
         float gbe = 0.f, gg = 0.f, gb = 0.f;
-#pragma unroll 8
+#pragma unroll 32
         for (int bb = 0; bb < A.B; bb++) { const size_t o = (size_t)bb * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; gb += A.dh1[o]; }
         A.g_be1[j] = gbe; A.g_g1[j] = gg; A.g_b1[j] = gb;
     }
-    // dW1[n][k]: thread per element, batch in row order
-    for (int e = gt; e < H * A.IN; e += kRowThreads) {
-        const int n = e / A.IN, k = e - n * A.IN;
+    // dW1[n][k] = sum_b dh1[b][n] x[b][k]: CTA r owns the columns n of its slice of H1, staged in shared memory with one round
+    // of independent loads (reading dh1 from L2 inside the 64-deep dot product would expose the L2 latency 64 times)
+    const int per = (H + kRowCtas - 1) / kRowCtas, nlo = (int)cluster_rank() * per, nhi = min(H, nlo + per), nw = nhi - nlo;
+    for (int v = threadIdx.x; v < A.B * per; v += kRowT) {
+        const int bb = v / per, c = v - bb * per;
+        ds[v] = c < nw ? A.dh1[(size_t)bb * H + nlo + c] : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nw * A.IN; e += kRowT) {
+        const int c = e / A.IN, k = e - c * A.IN;
         float sum = 0.f;
-#pragma unroll 8
-        for (int bb = 0; bb < A.B; bb++) sum = fmaf(A.dh1[(size_t)bb * H + n], xs[bb * A.IN + k], sum);
-        A.g_w1[e] = sum;
+#pragma unroll 16
+        for (int bb = 0; bb < A.B; bb++) sum = fmaf(ds[bb * per + c], xs[bb * A.IN + k], sum);
+        A.g_w1[(size_t)(nlo + c) * A.IN + k] = sum;
     }
 }
 
@@ -634,7 +671,7 @@ size_t learner_layout(const Layout &L, int B, tt_learner *ln, char *base) {
 
 Job fwd_job(int B, int N, int K, const float *X, int ldx, const float *W, const float *bias, const float *g, const float *be, float *stats, float *Y) {
     Job j{};
-    j.type = G_FWD; j.ctas = (N + 15) / 16; j.B = B; j.N = N; j.K = K; j.X = X; j.ldx = ldx; j.W = W; j.ldw = K; j.bias = bias; j.g = g; j.be = be;
+    j.type = G_FWD; j.ctas = (N + 31) / 32; j.B = B; j.N = N; j.K = K; j.X = X; j.ldx = ldx; j.W = W; j.ldw = K; j.bias = bias; j.g = g; j.be = be;
     j.stats = stats; j.Y = Y; j.ldy = N;
     return j;
 }
@@ -726,7 +763,7 @@ int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_r
     const int T = L.tail();
 
     // K0
-    learn_gather_kernel<<<1, 256, 0, s>>>(*ring, max_mem, d_rows, ln->bt, B, IN, ln->seed, ln->step);
+    learn_gather_kernel<<<1, 1024, 0, s>>>(*ring, max_mem, d_rows, ln->bt, B, IN, ln->seed, ln->step);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     int rc;
     // K1: fc1 of the four forward passes
@@ -768,7 +805,7 @@ int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_r
         w.X = ln->h1[job]; w.ldx = H1; w.g = p + L.g1(); w.be = p + L.be1(); w.stats = ln->st1[job];
         w.D = ln->dh2; w.ldd = H2; w.Y = g + L.w2(); w.ldy = H1; w.db = g + L.b2();
         Job xg{};
-        xg.type = G_XGRAD; xg.B = B; xg.N = H2; xg.K = H1; xg.ctas = (H1 + 15) / 16;
+        xg.type = G_XGRAD; xg.B = B; xg.N = H2; xg.K = H1; xg.ctas = (H1 + 31) / 32;
         xg.D = ln->dh2; xg.ldd = H2; xg.W = p + L.w2(); xg.ldw = H1; xg.Y = ln->da1; xg.ldy = H1;
         J.j[0] = w; J.j[1] = xg;
         int r = launch_jobs(J, s);
