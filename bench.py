@@ -452,42 +452,43 @@ def run_b200(args):
     # ---- BASELINE.json configs[3]: the rollout iteration + one DDPG update (batch 64) per iteration (+ collectives) ----
     config4 = None
     if not args.no_config4:
-        ln = agent.learner                                           # learner rank = 0; created everywhere so that every rank
-        flat = ln._flat["actor"]                                     # has the flat parameter buffer the broadcast lands in
-        spare = actors[1]
-        pol_ready = torch.cuda.Event()
-        c4_it = [0]
+        # the learner (rank 0) runs on a side stream UNDER the rollout kernels of the same iteration (rollout.AsyncTrainer: 2 SMs
+        # are left free for its 13 + 3 small dependent kernels; it samples only rows that earlier iterations completed; its policy is
+        # used one iteration later).  With world > 1 the side stream also carries the broadcast of the flat parameter vector
+        # (526 KB, NCCL) before the re-pack into the spare packed actor, and the statistics all-reduce stays inside the step.
+        def run_c4(reserve):
+            tr = tt.AsyncTrainer(eng, reserve_sms=reserve, sync=sync if world > 1 else None, is_learner=rank == 0)
 
-        def c4_step():
-            main = torch.cuda.current_stream()
-            if world > 1 and c4_it[0] > 0:
-                main.wait_event(pol_ready)                           # last iteration's policy: broadcast + re-packed on the side stream
-                agent.actor, actors[1] = actors[1], agent.actor
-            c4_it[0] += 1
-            eng.step()
-            if world == 1:
-                ln.learn()                                           # tt_learn_step + re-pack into the rollout actor, same stream
-                return
-            if rank == 0:
-                ln.learn(repack_into=None)                           # updates `flat` in place
-            sync.push_stats(env.stats_tensor(clear=True))            # all-reduce on the side stream, consumed one iteration behind
-            sync.push_policy(flat)                                   # broadcast of the 526 KB parameter vector on the side stream ...
-            with torch.cuda.stream(sync.stream):
-                sync.wait_policy()
-                actors[1].load_flat(flat)                            # ... and its re-pack into the spare packed actor
-                pol_ready.record(sync.stream)
+            def c4_step():
+                tr.step()
+                if world > 1:
+                    sync.push_stats(env.stats_tensor(clear=True))
+            for _ in range(max(W, 5) + 60):
+                c4_step()
+            l0 = L.tt_launch_count()
+            ms4, _ = timed(c4_step, K)
+            n_l = int(L.tt_launch_count() - l0)
+            tr.close()
+            if world > 1:
+                torch.cuda.current_stream().wait_stream(sync.stream)
+            return ms4, n_l, tr.updates
+        ms4, n_l, n_upd = run_c4(2)
+        # for reference: the same iteration with the update SERIAL on the rollout stream (no SMs reserved)
+        agent.actor = actors[0]
+        ln = agent.learner
+
+        def c4_serial():
+            eng.step(); ln.learn()
         for _ in range(max(W, 5)):
-            c4_step()
-        l0 = L.tt_launch_count()
-        ms4, _ = timed(c4_step, K)
-        config4 = {"value": world * N * K / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / K, "gpu_launches": int(L.tt_launch_count() - l0),
-                   "extra_ms_over_rollout": ms4 / K - ms / K,
+            c4_serial()
+        ms4s, _ = timed(c4_serial, K)
+        config4 = {"value": world * N * K / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / K, "gpu_launches": n_l,
+                   "extra_ms_over_rollout": ms4 / K - ms / K, "reserved_sms": 2, "learner_updates_so_far": n_upd,
+                   "serial_ms_per_step": ms4s / K,
                    "note": "configs[3]: rollout + fused replay store + one DDPG update per iteration (batch 64, tt_learn_step: hand-written "
-                           "kernels on the device ring" + (", learner on rank 0; stats all-reduce + broadcast of the flat actor vector on a "
-                           "side NCCL stream, re-pack into the spare packed actor, consumed one iteration behind)" if world > 1 else
-                           " + re-pack of the policy, same stream)")}
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(sync.stream)
+                           "kernels on the device ring, hidden on a side stream under the rollout kernels, policy used one iteration later"
+                           + (", learner on rank 0; stats all-reduce + broadcast of the flat actor vector over NCCL on side streams)" if world > 1 else ")")
+                           + "; serial_ms_per_step = the update on the rollout stream instead"}
         agent.actor = actors[0]
 
     # ---- BASELINE.json configs[4]: mini-sweep over envs per GPU (the full sweep: profiles/sweep.py) ----

@@ -11,8 +11,8 @@ from ._lib import TTError, load, lib_path, COMP_NAMES, VIOLATION_NAMES, FLAG_NAM
 from .env import VecTruckTrailerEnv, Truck_trailer_Env_2, EnvConfig  # noqa: F401
 from .replay import DeviceReplayBuffer, ReplayBuffer  # noqa: F401
 from .agent import VecAgent, Agent, OUNoiseState, init_actor_state_dict, ACTOR_KEYS  # noqa: F401
-from .rollout import RolloutEngine  # noqa: F401
+from .rollout import RolloutEngine, AsyncTrainer  # noqa: F401
 from . import checkpoint, recording, evaluate  # noqa: F401
 
 __all__ = ["VecTruckTrailerEnv", "Truck_trailer_Env_2", "EnvConfig", "DeviceReplayBuffer", "ReplayBuffer", "VecAgent",
-           "Agent", "OUNoiseState", "RolloutEngine", "init_actor_state_dict", "TTError", "load", "lib_path"]
+           "Agent", "OUNoiseState", "RolloutEngine", "AsyncTrainer", "init_actor_state_dict", "TTError", "load", "lib_path"]

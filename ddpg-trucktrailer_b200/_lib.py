@@ -117,6 +117,8 @@ SYMBOLS = {
     "tt_learner_last_rows": (_P, [_P]),
     "tt_learner_reset_optimizer": (C.c_int, [_P, _P]),
     "tt_learn_step": (C.c_int, [_P, C.POINTER(ReplayRing), _P, _P, _P]),
+    "tt_learn_step_window": (C.c_int, [_P, C.POINTER(ReplayRing), _P, _P, _I64, _I64, _P]),
+    "tt_reserve_sms": (C.c_int, [_I32]),
     "tt_rollout_step": (C.c_int, [_P, _P, C.POINTER(RolloutBufs), _I32, _I32, _P]),
 }
 

@@ -85,7 +85,8 @@ int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_
 int actor_forward_tc(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring, const TTActorTail *tail, cudaStream_t s);
 int actor_forward_any(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, int precision, const TTRingS *ring, const TTActorTail *tail, cudaStream_t s);
 int actor_resolve_precision(const tt_actor *a, int precision, int64_t n);
-int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *fc2_w, const float *fc2_b, cudaStream_t s);
+int actor_pack_all(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *g1, const float *be1, const float *fc2_w, const float *fc2_b,
+                   const float *g2, const float *be2, const float *mu_w, const float *mu_b, cudaStream_t s);
 int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
                  uint64_t gid0, const uint32_t *d_iter, int evaluate, const TTRingA *ring, cudaStream_t s);
 // per-device launch facts (one entry per CUDA device; a process may drive several GPUs)

@@ -84,9 +84,10 @@ constexpr int kGramBlocks = 16;
 __device__ __forceinline__ double wfull(const float *__restrict__ fc1_w, const float *__restrict__ fc1_b, int c, int k) {
     return (double)(k < IN ? fc1_w[c * IN + k] : fc1_b[c]);
 }
-__global__ void __launch_bounds__(576) pack_l1c_gram_kernel(double *__restrict__ acc, const float *__restrict__ fc1_w, const float *__restrict__ fc1_b) {
+__device__ __forceinline__ void pack_l1c_gram(int bid, double *__restrict__ acc, const float *__restrict__ fc1_w, const float *__restrict__ fc1_b) {
     const int t = threadIdx.x, i = t / 24, j = t - i * 24;
-    const int c0 = blockIdx.x * (H1 / kGramBlocks), c1 = c0 + H1 / kGramBlocks;
+    if (t >= 576) return;
+    const int c0 = bid * (H1 / kGramBlocks), c1 = c0 + H1 / kGramBlocks;
     double si = 0.0, sij = 0.0;
 #pragma unroll 5
     for (int c = c0; c < c1; c++) { const double a = wfull(fc1_w, fc1_b, c, i), b = wfull(fc1_w, fc1_b, c, j); si += a; sij += a * b; }
@@ -119,10 +120,9 @@ __global__ void __launch_bounds__(576) pack_l1c_chol_kernel(double *__restrict__
     out[24 + t] = Lf[i][j];
 }
 
-__global__ void __launch_bounds__(256) pack_l1c_image_kernel(char *__restrict__ img_f16, char *__restrict__ img_bf16, const double *__restrict__ ml,
-                                                             const float *__restrict__ fc1_w, const float *__restrict__ fc1_b,
-                                                             const float *__restrict__ g1) {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < N1I * 32; v += gridDim.x * blockDim.x) {
+__device__ __forceinline__ void pack_l1c_image(int bid, int nblk, char *__restrict__ img_f16, char *__restrict__ img_bf16, const double *__restrict__ ml,
+                                               const float *__restrict__ fc1_w, const float *__restrict__ fc1_b, const float *__restrict__ g1) {
+    for (int v = bid * blockDim.x + threadIdx.x; v < N1I * 32; v += nblk * blockDim.x) {
         const int row = v >> 5, k = v & 31;
         double x = 0.0;
         if (k < 24) {
@@ -148,10 +148,10 @@ __device__ __forceinline__ float wf2(const float *__restrict__ fc2_w, const floa
     return k < H1 ? fc2_w[n * H1 + k] : (k == H1 ? fc2_b[n] : 0.f);
 }
 constexpr int kStatSlices = 32;
-__global__ void __launch_bounds__(32 * kStatSlices) pack_w2_colstats_kernel(double *__restrict__ out /* m2[K2P], l2[K2P] */, const float *__restrict__ fc2_w,
-                                                               const float *__restrict__ fc2_b, const float *__restrict__ g2, const float *__restrict__ w3) {
+__device__ __forceinline__ void pack_w2_colstats(int bid, double *__restrict__ out /* m2[K2P], l2[K2P] */, const float *__restrict__ fc2_w,
+                                                 const float *__restrict__ fc2_b, const float *__restrict__ g2, const float *__restrict__ w3) {
     __shared__ double r1[kStatSlices][33], r2[kStatSlices][33], rg[kStatSlices][33];
-    const int kk = threadIdx.x & 31, sl = threadIdx.x >> 5, k = blockIdx.x * 32 + kk;
+    const int kk = threadIdx.x & 31, sl = threadIdx.x >> 5, k = bid * 32 + kk;
     double s1 = 0.0, s2 = 0.0, sg = 0.0;
     for (int n = sl; n < H2; n += kStatSlices) {
         const double w = (double)wf2(fc2_w, fc2_b, n, k), gw = (double)g2[n] * (double)w3[n];
@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(32 * kStatSlices) pack_w2_colstats_kernel(doub
     }
 }
 template <typename OpT>
-__global__ void pack_w2s_kernel(char *__restrict__ img, const double *__restrict__ st, const float *__restrict__ fc2_w, const float *__restrict__ fc2_b) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+__device__ __forceinline__ void pack_w2s(int bid, int nblk, char *__restrict__ img, const double *__restrict__ st, const float *__restrict__ fc2_w,
+                                         const float *__restrict__ fc2_b) {
+    const int tid = bid * blockDim.x + threadIdx.x, nth = nblk * blockDim.x;
     for (int v = tid; v < KB2 * N2 * 32; v += nth) {
         const int kb = v / (N2 * 32), rem = v - kb * N2 * 32, col = rem / 32, kk = rem - col * 32, k = kb * 32 + kk;
         float x = 0.f;
@@ -181,6 +182,57 @@ __global__ void pack_w2s_kernel(char *__restrict__ img, const double *__restrict
 #pragma unroll
         for (int rep = 0; rep < TT_W2_REPLICAS; rep++) *reinterpret_cast<OpT *>(img + (size_t)rep * kW2ImageB + off) = o;
     }
+}
+
+// fp32 image of the CUDA-core actor kernel (tt_actor.cuh): transposed, zero-padded weights + parameter vectors
+__device__ __forceinline__ void pack_fp32(int bid, int nblk, const tt_actor_dev &A, const float *fc1_w, const float *fc1_b, const float *g1, const float *be1,
+                                          const float *fc2_w, const float *fc2_b, const float *g2, const float *be2, const float *mu_w, const float *mu_b) {
+    const int tid = bid * blockDim.x + threadIdx.x, nth = nblk * blockDim.x;
+    for (int v = tid; v < A.k1p * A.h1p; v += nth) {                    // W1T[k][c] = fc1.weight[c][k]
+        const int k = v / A.h1p, c = v - k * A.h1p;
+        A.w1t[v] = (k < A.in_dim && c < A.h1) ? fc1_w[c * A.in_dim + k] : 0.0f;
+    }
+    for (int v = tid; v < A.h1p * A.h2p; v += nth) {                    // W2T[k][c] = fc2.weight[c][k]
+        const int k = v / A.h2p, c = v - k * A.h2p;
+        A.w2t[v] = (k < A.h1 && c < A.h2) ? fc2_w[c * A.h1 + k] : 0.0f;
+    }
+    for (int c = tid; c < A.h1p; c += nth) {
+        const bool in = c < A.h1;
+        A.b1[c] = in ? fc1_b[c] : 0.0f; A.g1[c] = in ? g1[c] : 0.0f; A.be1[c] = in ? be1[c] : 0.0f;
+    }
+    for (int c = tid; c < A.h2p; c += nth) {
+        const bool in = c < A.h2;
+        A.b2[c] = in ? fc2_b[c] : 0.0f; A.g2[c] = in ? g2[c] : 0.0f; A.be2[c] = in ? be2[c] : 0.0f;
+        A.w3[c] = in ? mu_w[c] : 0.0f;
+    }
+    if (tid == 0) A.b3[0] = mu_b[0];
+}
+
+// The re-pack of a policy (tt_actor_load) is on the end-to-end path: a learner hands over new weights every iteration.  Three
+// launches instead of seven: stage A = everything that only reads the raw weights (Gram partial sums of layer 1, column
+// statistics of layer 2, the fp32 images), one CTA: the Cholesky factor, stage C = the three tensor-core operand images.
+struct PackSrc { const float *fc1_w, *fc1_b, *g1, *be1, *fc2_w, *fc2_b, *g2, *be2, *mu_w, *mu_b; };
+constexpr int kPackFp32Blocks = 16;
+__global__ void __launch_bounds__(1024) pack_stage_a_kernel(tt_actor_dev A, PackSrc w, int tc) {
+    int bid = blockIdx.x;
+    if (tc) {
+        if (bid < kGramBlocks) { pack_l1c_gram(bid, A.l1c_scratch, w.fc1_w, w.fc1_b); return; }
+        bid -= kGramBlocks;
+        if (bid < KB2) { pack_w2_colstats(bid, A.l1c_scratch + 1200, w.fc2_w, w.fc2_b, w.g2, w.mu_w); return; }
+        bid -= KB2;
+    }
+    pack_fp32(bid, kPackFp32Blocks, A, w.fc1_w, w.fc1_b, w.g1, w.be1, w.fc2_w, w.fc2_b, w.g2, w.be2, w.mu_w, w.mu_b);
+}
+constexpr int kImgBlocks = 54, kW2sBlocks = 128;
+__global__ void __launch_bounds__(256) pack_stage_c_kernel(tt_actor_dev A, PackSrc w) {
+    int bid = blockIdx.x;
+    if (bid < kImgBlocks) {
+        pack_l1c_image(bid, kImgBlocks, reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + 600, w.fc1_w, w.fc1_b, w.g1);
+        return;
+    }
+    bid -= kImgBlocks;
+    if (bid < kW2sBlocks) pack_w2s<__half>(bid, kW2sBlocks, reinterpret_cast<char *>(A.w2s_f16), A.l1c_scratch + 1200, w.fc2_w, w.fc2_b);
+    else pack_w2s<__nv_bfloat16>(bid - kW2sBlocks, kW2sBlocks, reinterpret_cast<char *>(A.w2s_bf16), A.l1c_scratch + 1200, w.fc2_w, w.fc2_b);
 }
 
 template <bool kSplit>
@@ -814,13 +866,14 @@ int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, cons
         cluster = want == 2 ? 2 : 1;
     }
     const int64_t ntiles = (n + kTileM - 1) / kTileM;
-    int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
+    const int sms = tt::grid_sms();
+    int grid = (int)(ntiles < sms ? ntiles : sms);
 #if !defined(TT_DEV_VARIANTS)
     dbg = nullptr;
 #endif
     if (cluster == 2 && ntiles > 1) {
         grid = (grid + 1) & ~1;                                  // whole pairs; a CTA without tiles only serves the pair's W2 ring
-        if (grid > (tt::sm_count() & ~1)) grid = tt::sm_count() & ~1;
+        if (grid > (sms & ~1)) grid = sms & ~1;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(640); cfg.dynamicSmemBytes = P::total; cfg.stream = st;
         cudaLaunchAttribute at[1];
@@ -850,22 +903,18 @@ namespace tt {
 
 bool actor_tc_supported(const tt_actor_dev &A) { return A.in_dim == IN && A.h1 == H1 && A.h2 == H2; }
 
-int actor_pack_tc_full(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *fc2_w, const float *fc2_b, cudaStream_t s) {
+int actor_pack_all(tt_actor *a, const float *fc1_w, const float *fc1_b, const float *g1, const float *be1, const float *fc2_w, const float *fc2_b,
+                   const float *g2, const float *be2, const float *mu_w, const float *mu_b, cudaStream_t s) {
     const tt_actor_dev &A = a->dev;
-    if (!actor_tc_supported(A)) return TT_OK;       // the tensor-core path is specialised to 23-400-300; forward() will refuse
-    if (!a->scratch_clean) { TT_CUDA(cudaMemsetAsync(A.l1c_scratch, 0, sizeof(double) * 600, s)); a->scratch_clean = true; }
-    pack_l1c_gram_kernel<<<kGramBlocks, 576, 0, s>>>(A.l1c_scratch, fc1_w, fc1_b);
+    const PackSrc w = {fc1_w, fc1_b, g1, be1, fc2_w, fc2_b, g2, be2, mu_w, mu_b};
+    const int tc = actor_tc_supported(A) ? 1 : 0;       // the tensor-core path is specialised to 23-400-300; forward() refuses otherwise
+    if (tc && !a->scratch_clean) { TT_CUDA(cudaMemsetAsync(A.l1c_scratch, 0, sizeof(double) * 600, s)); a->scratch_clean = true; }
+    pack_stage_a_kernel<<<(tc ? kGramBlocks + KB2 : 0) + kPackFp32Blocks, 1024, 0, s>>>(A, w, tc);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    if (!tc) return TT_OK;
     pack_l1c_chol_kernel<<<1, 576, 0, s>>>(A.l1c_scratch, A.l1c_scratch + 600);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    pack_l1c_image_kernel<<<54, 256, 0, s>>>(reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + 600, fc1_w, fc1_b, A.g1);
-    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    double *st2 = A.l1c_scratch + 1200;
-    pack_w2_colstats_kernel<<<KB2, 32 * kStatSlices, 0, s>>>(st2, fc2_w, fc2_b, A.g2, A.w3);
-    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    pack_w2s_kernel<__half><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_f16), st2, fc2_w, fc2_b);
-    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    pack_w2s_kernel<__nv_bfloat16><<<128, 256, 0, s>>>(reinterpret_cast<char *>(A.w2s_bf16), st2, fc2_w, fc2_b);
+    pack_stage_c_kernel<<<kImgBlocks + 2 * kW2sBlocks, 256, 0, s>>>(A, w);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }

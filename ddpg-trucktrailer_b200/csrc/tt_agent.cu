@@ -73,33 +73,6 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(const float *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// weight packing: reference state_dict layout -> kernel layouts (see tt_actor.cuh)
-// ---------------------------------------------------------------------------------------------------------
-__global__ void pack_fp32_kernel(tt_actor_dev A, const float *fc1_w, const float *fc1_b, const float *g1, const float *be1,
-                                 const float *fc2_w, const float *fc2_b, const float *g2, const float *be2,
-                                 const float *mu_w, const float *mu_b) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int v = tid; v < A.k1p * A.h1p; v += nth) {                    // W1T[k][c] = fc1.weight[c][k]
-        const int k = v / A.h1p, c = v - k * A.h1p;
-        A.w1t[v] = (k < A.in_dim && c < A.h1) ? fc1_w[c * A.in_dim + k] : 0.0f;
-    }
-    for (int v = tid; v < A.h1p * A.h2p; v += nth) {                    // W2T[k][c] = fc2.weight[c][k]
-        const int k = v / A.h2p, c = v - k * A.h2p;
-        A.w2t[v] = (k < A.h1 && c < A.h2) ? fc2_w[c * A.h1 + k] : 0.0f;
-    }
-    for (int c = tid; c < A.h1p; c += nth) {
-        const bool in = c < A.h1;
-        A.b1[c] = in ? fc1_b[c] : 0.0f; A.g1[c] = in ? g1[c] : 0.0f; A.be1[c] = in ? be1[c] : 0.0f;
-    }
-    for (int c = tid; c < A.h2p; c += nth) {
-        const bool in = c < A.h2;
-        A.b2[c] = in ? fc2_b[c] : 0.0f; A.g2[c] = in ? g2[c] : 0.0f; A.be2[c] = in ? be2[c] : 0.0f;
-        A.w3[c] = in ? mu_w[c] : 0.0f;
-    }
-    if (tid == 0) A.b3[0] = mu_b[0];
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // (c) actor forward, fp32 on the CUDA cores.  One CTA = 64 observation rows per tile, persistent over tiles.
 // Warp w owns rows 8w..8w+7; lane l owns output columns l, l+32, ...  Activations live in shared memory
 // transposed ([k][row], row stride 68 floats) so that the 8 row operands of one k are two broadcast LDS.128;
@@ -286,7 +259,7 @@ int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_
     const tt_actor_dev &A = a->dev;
     const size_t smem = actor_fp32_smem(A);
     const int64_t ntiles = (n + TM - 1) / TM;
-    const int grid = (int)(ntiles < tt::sm_count() ? ntiles : tt::sm_count());
+    const int grid = (int)(ntiles < tt::grid_sms() ? ntiles : tt::grid_sms());
     const int cj1 = A.h1p / 32, cj2 = A.h2p / 32;
     if (cj1 == 13 && cj2 == 10) {
         auto kern = actor_fp32_kernel<13, 10, false>;
@@ -398,11 +371,8 @@ int tt_actor_load(tt_actor *a, const float *d_fc1_w, const float *d_fc1_b, const
                   const float *d_mu_w, const float *d_mu_b, tt_stream_t stream) {
     TT_REQUIRE(a && d_fc1_w && d_fc1_b && d_ln1_g && d_ln1_b && d_fc2_w && d_fc2_b && d_ln2_g && d_ln2_b && d_mu_w && d_mu_b,
                "NULL argument");
-    cudaStream_t s = tt::as_stream(stream);
-    pack_fp32_kernel<<<64, 256, 0, s>>>(a->dev, d_fc1_w, d_fc1_b, d_ln1_g, d_ln1_b, d_fc2_w, d_fc2_b, d_ln2_g, d_ln2_b,
-                                        d_mu_w, d_mu_b);
-    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    int rc = tt::actor_pack_tc_full(a, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, s);
+    // fp32 images + the tensor-core operand images (tt_actor_tc4.cu): three launches
+    int rc = tt::actor_pack_all(a, d_fc1_w, d_fc1_b, d_ln1_g, d_ln1_b, d_fc2_w, d_fc2_b, d_ln2_g, d_ln2_b, d_mu_w, d_mu_b, tt::as_stream(stream));
     if (rc != TT_OK) return rc;
     a->loaded = true;
     return TT_OK;

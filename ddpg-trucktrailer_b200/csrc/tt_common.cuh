@@ -56,6 +56,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 constexpr int kMaxDevices = 64;
 int device_index();          // the current CUDA device, as an index into per-device caches
 int sm_count();              // SM count of the current device
+int grid_sms();              // SMs the persistent rollout kernels may occupy: sm_count() minus tt_reserve_sms()
 
 // number of kernels launched by this library since load (bench.py reports it as gpu_launches)
 extern unsigned long long g_launches;

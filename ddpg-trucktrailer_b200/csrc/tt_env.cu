@@ -702,7 +702,7 @@ static int env_step_impl(tt_env *env, const float *d_actions, int32_t K, int32_t
             if (dsm > 0) TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));            \
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, dsm) != cudaSuccess || per_sm <= 0) per_sm = 4; \
         }                                                                                                                       \
-        const int64_t cap = (int64_t)tt::sm_count() * per_sm;                                                                   \
+        const int64_t cap = (int64_t)tt::grid_sms() * per_sm;                                                                   \
         kern<<<(unsigned)(ntiles < cap ? ntiles : cap), kBlock, dsm, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs,       \
                                                                          ld_obs, d_reward, d_done, inf, env->seed, env->gid0,  \
                                                                          ro, d_ou_x);                                          \

@@ -7,14 +7,14 @@
 // The step is latency-bound (batch 64 x 23-400-300 networks = 150 MFLOP): what matters is the length of the dependency
 // chain, not the arithmetic.  Stages (one launch each):
 //   K0  sample 64 ring rows (Philox) and gather s, a, r, s', done
-//   K1  fc1 of target_actor(s'), target_critic(s'), critic(s), actor(s)              -- one grouped launch, 4 jobs
-//   K2  LayerNorm 1 + ReLU (in the GEMM prologue) + fc2 of the same four
+//   K1  fc1 + LayerNorm 1 + ReLU of target_actor(s'), target_critic(s'), critic(s), actor(s)   -- one launch, 4 jobs
+//   K2  fc2 of the same four (grouped GEMM launch, cp.async double-buffered operands)
 //   K3  critic head (one CTA, warp = batch row): a' = target_actor head, y = r + gamma Q'(s', a') (1 - done), q = Q(s, a),
 //       dL/dq = 2 (q - y) / B, back through q / action_value / LayerNorm 2 -> d h2; column sums = their parameter gradients
 //   K4  critic fc2 backward: dW2 = dh2^T a1 (grouped with) da1 = dh2 W2
 //   K5  critic LayerNorm 1 backward (one CTA, warp = row) + fc1 backward dW1 = dh1^T s
 //   K6  Adam (weight decay 0.01) on the critic + soft update of target_critic
-//   K7  fc1, K8 fc2 of the UPDATED critic on s
+//   K7  fc1 + LayerNorm 1 + ReLU, K8 fc2 of the UPDATED critic on s
 //   K9  actor head (one CTA): a = actor head, dL/da = -(1/B) dQ/da through relu / action_value, back through tanh / mu /
 //       LayerNorm 2 -> d h2 of the actor
 //   K10 actor fc2 backward, K11 actor LayerNorm 1 + fc1 backward, K12 Adam on the actor + soft update of target_actor
@@ -54,20 +54,17 @@ struct Layout {
 enum { NET_ACTOR = 0, NET_TARGET_ACTOR = 1, NET_CRITIC = 2, NET_TARGET_CRITIC = 3 };
 enum { JOB_TA = 0, JOB_TC = 1, JOB_C = 2, JOB_A = 3, NJOBS = 4 };     // forward passes whose activations are kept
 
-// ---- grouped GEMM jobs ----
+// ---- grouped GEMM jobs (plain fp32 operands, cp.async staging) ----
 enum { G_FWD = 0, G_WGRAD = 1, G_XGRAD = 2 };
 struct Job {
     int type, ctas;                   // CTAs this job occupies in the launch
     int B, N, K;
-    // G_FWD   : Y[b][n] = bias[n] + sum_k f(X)[b][k] W[n][k];  f = identity, or relu(LayerNorm(X; g, be)) when g != NULL
-    //           (row statistics computed in the prologue, written to `stats` [B][2] by the job's first CTA)
-    // G_WGRAD : dW[n][k] = sum_b D[b][n] f(X)[b][k], db[n] = sum_b D[b][n];  f = identity, or relu(LayerNorm) from `stats`
-    // G_XGRAD : dX[b][k] = sum_n D[b][n] W[n][k]
+    // G_FWD   : Y[b][n] = bias[n] + sum_k X[b][k] W[n][k]                       X [B][K], W [N][K]
+    // G_WGRAD : dW[n][k] = sum_b D[b][n] X[b][k],  db[n] = sum_b D[b][n]          D [B][N], X [B][K]
+    // G_XGRAD : dX[b][k] = sum_n D[b][n] W[n][k]                                 D [B][N], W [N][K]
     const float *X; int ldx;
     const float *W; int ldw;
     const float *bias;
-    const float *g, *be;
-    float *stats;
     const float *D; int ldd;
     float *Y; int ldy;                // output: Y / dW / dX
     float *db;
@@ -81,204 +78,148 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// mean / rstd of `rows` rows of width K <= 512 (two-pass, like torch); out[b] = (mean, rstd).  A warp takes FOUR rows at a
-// time with all their values in registers: one round of independent loads (one memory latency per four rows instead of two
-// per row -- the step is latency-bound), the second pass runs from registers.
-__device__ void row_stats(const float *__restrict__ X, int ldx, int rows, int K, float2 *out) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int b0 = 4 * warp; b0 < rows; b0 += 4 * nw) {
-        float v[4][kMaxH / 32];
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-            for (int i = 0; i < kMaxH / 32; i++) {
-                const int k = lane + 32 * i;
-                v[r][i] = (b0 + r < rows && k < K) ? X[(size_t)(b0 + r) * ldx + k] : 0.f;
-            }
-        float mean[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            float sum = 0.f;
-#pragma unroll
-            for (int i = 0; i < kMaxH / 32; i++) sum += v[r][i];
-            mean[r] = warp_sum(sum) / (float)K;
+// global -> shared staging of a [rows x 32] float block (row r at dst + r * kP, source row r at src + r * ld, columns
+// [c0, c0 + 32) clipped to `cols`; rows >= nrows and columns >= cols are zero-filled).  16 B cp.async when the source rows are
+// 16 B aligned (ld % 4 == 0 and cols % 4 == 0: the production sizes), 4 B cp.async otherwise.  No registers, no per-element
+// arithmetic: the LayerNorm / ReLU of the operands is materialised by the producer kernels.
+constexpr int kP = 36;                                                          // shared-memory row pitch (floats): 16 B aligned, LDS.128 conflict-free
+__device__ __forceinline__ void cp16(float *dst, const float *src, bool ok) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = ok ? 16 : 0;                                                 // src-size 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp4(float *dst, const float *src, bool ok) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = ok ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void stage_block(float *dst, const float *__restrict__ src, int ld, int rows, int nrows, int c0, int cols, bool vec) {
+    if (vec) {
+        for (int e = threadIdx.x; e < rows * 8; e += kT) {
+            const int r = e >> 3, q = e & 7, c = c0 + 4 * q;
+            const bool ok = r < nrows && c < cols;
+            cp16(dst + r * kP + 4 * q, ok ? src + (size_t)r * ld + c : src, ok);
         }
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            float q = 0.f;
-#pragma unroll
-            for (int i = 0; i < kMaxH / 32; i++) { const float d = (lane + 32 * i < K) ? v[r][i] - mean[r] : 0.f; q = fmaf(d, d, q); }
-            const float rstd = rsqrtf(warp_sum(q) / (float)K + kLnEps);
-            if (lane == 0 && b0 + r < rows) out[b0 + r] = make_float2(mean[r], rstd);
+    } else {
+        for (int e = threadIdx.x; e < rows * 32; e += kT) {
+            const int r = e >> 5, q = e & 31, c = c0 + q;
+            const bool ok = r < nrows && c < cols;
+            cp4(dst + r * kP + q, ok ? src + (size_t)r * ld + c : src, ok);
         }
     }
 }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ bool vec_ok(const float *p, int ld, int cols) { return (ld & 3) == 0 && (cols & 3) == 0 && ((uintptr_t)p & 15) == 0; }
 
-__device__ __forceinline__ float ln_relu(float x, float2 st, float g, float be) { return fmaxf(fmaf((x - st.x) * st.y, g, be), 0.f); }
-
-// Y tile: all B rows x 32 columns [n0, n0 + 32); reduction over K in chunks of 32.  A thread owns 4 rows x 2 columns (one
-// 16 B and one 8 B shared-memory load per 8 FMAs: a 1 x 4 tile is shared-memory-bandwidth bound, 5 loads per 4 FMAs).  The next
-// chunk's operands are fetched into registers while the current one is multiplied (the global-load latency of every chunk
-// would otherwise be exposed).
-constexpr int kXS = 68, kWS = 34;                                                // padded row strides (floats), 16 B / 8 B aligned
+// Y tile: all B rows x 16 columns [n0, n0 + 16); K in double-buffered chunks of 32.  Thread = 4 rows x 1 column; per 4 k: four
+// 16 B loads of X and one of W for 16 FMAs.
 __device__ void job_fwd(const Job &J, int cta, float *smem) {
-    float *Xs = smem;                                                           // [32 k][kXS]  (b)
-    float *Ws = smem + 32 * kXS;                                                // [32 k][kWS]  (n)
-    float2 *st = reinterpret_cast<float2 *>(smem + 32 * kXS + 32 * kWS);        // [64]
-    const int tid = threadIdx.x, tn = tid & 15, tb = tid >> 4, n0 = cta * 32;
-    const bool ln = J.g != nullptr;
-    float xr[8], wr[4];
-    auto fetch = [&](int k0) {                                                  // raw operands of chunk k0 -> registers
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = tid + kT * i, b = e >> 5, k = k0 + (e & 31);
-            xr[i] = (b < J.B && k < J.K) ? J.X[(size_t)b * J.ldx + k] : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int e = tid + kT * i, n = e >> 5, k = k0 + (e & 31);
-            wr[i] = (n0 + n < J.N && k < J.K) ? J.W[(size_t)(n0 + n) * J.ldw + k] : 0.f;
-        }
+    float *Xs = smem, *Ws = smem + 2 * 64 * kP;                                 // [2][64][kP], [2][16][kP]
+    const int tid = threadIdx.x, tn = tid & 15, tb = tid >> 4, n0 = cta * 16;
+    const bool vx = vec_ok(J.X, J.ldx, J.K), vw = vec_ok(J.W, J.ldw, J.K);
+    const int nch = (J.K + 31) / 32;
+    auto stage = [&](int ch, int buf) {
+        stage_block(Xs + buf * 64 * kP, J.X, J.ldx, 64, J.B, ch * 32, J.K, vx);
+        stage_block(Ws + buf * 16 * kP, J.W + (size_t)n0 * J.ldw, J.ldw, 16, J.N - n0, ch * 32, J.K, vw);
+        cp_commit();
     };
-    fetch(0);
-    if (ln) {
-        row_stats(J.X, J.ldx, J.B, J.K, st);
+    stage(0, 0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ch = 0; ch < nch; ch++) {
+        if (ch + 1 < nch) { stage(ch + 1, (ch + 1) & 1); cp_wait<1>(); } else cp_wait<0>();
         __syncthreads();
-        if (cta == 0 && J.stats && tid < J.B) reinterpret_cast<float2 *>(J.stats)[tid] = st[tid];
-    }
-    float acc[4][2] = {};
-    for (int k0 = 0; k0 < J.K; k0 += 32) {
+        const float *xs = Xs + (ch & 1) * 64 * kP + 4 * tb * kP, *ws = Ws + (ch & 1) * 16 * kP + tn * kP;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = tid + kT * i, b = e >> 5, kk = e & 31, k = k0 + kk;
-            float x = xr[i];
-            if (ln) x = (b < J.B && k < J.K) ? ln_relu(x, st[b], J.g[k], J.be[k]) : 0.f;
-            Xs[kk * kXS + b] = x;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) { const int e = tid + kT * i; Ws[(e & 31) * kWS + (e >> 5)] = wr[i]; }
-        __syncthreads();
-        if (k0 + 32 < J.K) fetch(k0 + 32);
-#pragma unroll
-        for (int kk = 0; kk < 32; kk++) {
-            const float4 x = *reinterpret_cast<const float4 *>(Xs + kk * kXS + 4 * tb);
-            const float2 w = *reinterpret_cast<const float2 *>(Ws + kk * kWS + 2 * tn);
-            acc[0][0] = fmaf(x.x, w.x, acc[0][0]); acc[0][1] = fmaf(x.x, w.y, acc[0][1]);
-            acc[1][0] = fmaf(x.y, w.x, acc[1][0]); acc[1][1] = fmaf(x.y, w.y, acc[1][1]);
-            acc[2][0] = fmaf(x.z, w.x, acc[2][0]); acc[2][1] = fmaf(x.z, w.y, acc[2][1]);
-            acc[3][0] = fmaf(x.w, w.x, acc[3][0]); acc[3][1] = fmaf(x.w, w.y, acc[3][1]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const int n = n0 + 2 * tn + j;
-        if (n < J.N) {
-            const float bias = J.bias ? J.bias[n] : 0.f;
+        for (int q = 0; q < 8; q++) {
+            const float4 w = *reinterpret_cast<const float4 *>(ws + 4 * q);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int b = 4 * tb + i;
-                if (b < J.B) J.Y[(size_t)b * J.ldy + n] = acc[i][j] + bias;
+                const float4 x = *reinterpret_cast<const float4 *>(xs + i * kP + 4 * q);
+                acc[i] = fmaf(x.x, w.x, acc[i]); acc[i] = fmaf(x.y, w.y, acc[i]); acc[i] = fmaf(x.z, w.z, acc[i]); acc[i] = fmaf(x.w, w.w, acc[i]);
             }
         }
-    }
-}
-
-// dW tile: 16 rows n x 64 columns k; reduction over the batch (B <= 64) in one pass
-__device__ void job_wgrad(const Job &J, int cta, float *smem) {
-    float (*Xs)[65] = reinterpret_cast<float (*)[65]>(smem);                    // [64 b][65]  (k)
-    float (*Ds)[17] = reinterpret_cast<float (*)[17]>(smem + 64 * 65);          // [64 b][17]  (n)
-    const int ktiles = (J.K + 63) / 64;
-    const int nt = cta / ktiles, kt = cta - nt * ktiles, n0 = nt * 16, k0 = kt * 64;
-    const int tid = threadIdx.x, tn = tid & 15, tk = tid >> 4;
-    const bool ln = J.g != nullptr;
-    const float2 *st = reinterpret_cast<const float2 *>(J.stats);
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int e = tid + kT * i, b = e >> 6, kk = e & 63, k = k0 + kk;
-        float x = 0.f;
-        if (b < J.B && k < J.K) {
-            x = J.X[(size_t)b * J.ldx + k];
-            if (ln) x = ln_relu(x, st[b], J.g[k], J.be[k]);
-        }
-        Xs[b][kk] = x;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int e = tid + kT * i, b = e >> 4, n = e & 15;
-        Ds[b][n] = (b < J.B && n0 + n < J.N) ? J.D[(size_t)b * J.ldd + n0 + n] : 0.f;
-    }
-    __syncthreads();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb = 0.f;
-    for (int b = 0; b < J.B; b++) {
-        const float d = Ds[b][tn];
-        accb += d;
-#pragma unroll
-        for (int i = 0; i < 4; i++) acc[i] = fmaf(d, Xs[b][tk + 16 * i], acc[i]);
+        __syncthreads();
     }
     if (n0 + tn < J.N) {
+        const float bias = J.bias ? J.bias[n0 + tn] : 0.f;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int k = k0 + tk + 16 * i;
-            if (k < J.K) J.Y[(size_t)(n0 + tn) * J.ldy + k] = acc[i];
+            const int b = 4 * tb + i;
+            if (b < J.B) J.Y[(size_t)b * J.ldy + n0 + tn] = acc[i] + bias;
         }
-        if (J.db && kt == 0 && tk == 0) J.db[n0 + tn] = accb;
     }
 }
 
-// dX tile: all B rows x 32 columns [k0, k0 + 32); reduction over N in chunks of 32 (same register tile and prefetch as job_fwd)
+// dW tile: 16 rows n x 32 columns k; the reduction runs over the batch (B <= 64) in one stage.  Thread = 1 n x 2 k.
+__device__ void job_wgrad(const Job &J, int cta, float *smem) {
+    float *Xs = smem, *Ds = smem + 64 * kP;                                     // X: [64 b][kP] (32 k), D: [64 b][kP] (16 n used)
+    const int ktiles = (J.K + 31) / 32;
+    const int nt = cta / ktiles, kt = cta - nt * ktiles, n0 = nt * 16, k0 = kt * 32;
+    const int tid = threadIdx.x, tk = tid & 15, tn = tid >> 4;
+    stage_block(Xs, J.X, J.ldx, 64, J.B, k0, J.K, vec_ok(J.X, J.ldx, J.K));
+    // D columns [n0, n0 + 16): a 32-wide block whose upper half is clipped away
+    stage_block(Ds, J.D, J.ldd, 64, J.B, n0, min(J.N, n0 + 16), vec_ok(J.D, J.ldd, J.N) && ((min(J.N, n0 + 16) & 3) == 0));
+    cp_commit(); cp_wait<0>();
+    __syncthreads();
+    float a0 = 0.f, a1 = 0.f, ab = 0.f;
+#pragma unroll 8
+    for (int b = 0; b < 64; b++) {
+        const float d = Ds[b * kP + tn];
+        const float2 x = *reinterpret_cast<const float2 *>(Xs + b * kP + 2 * tk);
+        ab += d; a0 = fmaf(d, x.x, a0); a1 = fmaf(d, x.y, a1);
+    }
+    if (n0 + tn < J.N) {
+        const int k = k0 + 2 * tk;
+        if (k < J.K) J.Y[(size_t)(n0 + tn) * J.ldy + k] = a0;
+        if (k + 1 < J.K) J.Y[(size_t)(n0 + tn) * J.ldy + k + 1] = a1;
+        if (J.db && kt == 0 && tk == 0) J.db[n0 + tn] = ab;
+    }
+}
+
+// dX tile: 32 batch rows x 32 columns [k0, k0 + 32); N in double-buffered chunks of 32.  Thread = 1 row x 4 columns; per 4 n:
+// one 16 B load of D and four of W for 16 FMAs.  (26 CTAs for 64 x 400: the reduction over 300 n is the long chain of the
+// backward pass, so it gets the small tile.)
 __device__ void job_xgrad(const Job &J, int cta, float *smem) {
-    float *Ds = smem;                                                           // [32 n][kXS]  (b)
-    float *Ws = smem + 32 * kXS;                                                // [32 n][kWS]  (k)
-    const int tid = threadIdx.x, tk = tid & 15, tb = tid >> 4, k0 = cta * 32;
-    float dr[8], wr[4];
-    auto fetch = [&](int nb) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = tid + kT * i, b = e >> 5, nn = e & 31;
-            dr[i] = (b < J.B && nb + nn < J.N) ? J.D[(size_t)b * J.ldd + nb + nn] : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int e = tid + kT * i, nn = e >> 5, kk = e & 31;
-            wr[i] = (nb + nn < J.N && k0 + kk < J.K) ? J.W[(size_t)(nb + nn) * J.ldw + k0 + kk] : 0.f;
-        }
+    float *Ds = smem, *Ws = smem + 2 * 32 * kP;                                 // [2][32 b][kP] (32 n), [2][32 n][kP] (32 k)
+    const int ktiles = (J.K + 31) / 32;
+    const int bt = cta / ktiles, kt = cta - bt * ktiles, b0 = bt * 32, k0 = kt * 32;
+    const int tid = threadIdx.x, tk = tid & 7, tb = tid >> 3;
+    const bool vd = vec_ok(J.D, J.ldd, J.N), vw = vec_ok(J.W, J.ldw, J.K);
+    const int nch = (J.N + 31) / 32;
+    auto stage = [&](int ch, int buf) {
+        stage_block(Ds + buf * 32 * kP, J.D + (size_t)b0 * J.ldd, J.ldd, 32, J.B - b0, ch * 32, J.N, vd);
+        stage_block(Ws + buf * 32 * kP, J.W + (size_t)ch * 32 * J.ldw, J.ldw, 32, J.N - ch * 32, k0, J.K, vw);
+        cp_commit();
     };
-    fetch(0);
-    float acc[4][2] = {};
-    for (int nb = 0; nb < J.N; nb += 32) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) { const int e = tid + kT * i; Ds[(e & 31) * kXS + (e >> 5)] = dr[i]; }
-#pragma unroll
-        for (int i = 0; i < 4; i++) { const int e = tid + kT * i; Ws[(e >> 5) * kWS + (e & 31)] = wr[i]; }
+    stage(0, 0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ch = 0; ch < nch; ch++) {
+        if (ch + 1 < nch) { stage(ch + 1, (ch + 1) & 1); cp_wait<1>(); } else cp_wait<0>();
         __syncthreads();
-        if (nb + 32 < J.N) fetch(nb + 32);
+        const float *ds = Ds + (ch & 1) * 32 * kP + tb * kP, *ws = Ws + (ch & 1) * 32 * kP + 4 * tk;
 #pragma unroll
-        for (int nn = 0; nn < 32; nn++) {
-            const float4 x = *reinterpret_cast<const float4 *>(Ds + nn * kXS + 4 * tb);
-            const float2 w = *reinterpret_cast<const float2 *>(Ws + nn * kWS + 2 * tk);
-            acc[0][0] = fmaf(x.x, w.x, acc[0][0]); acc[0][1] = fmaf(x.x, w.y, acc[0][1]);
-            acc[1][0] = fmaf(x.y, w.x, acc[1][0]); acc[1][1] = fmaf(x.y, w.y, acc[1][1]);
-            acc[2][0] = fmaf(x.z, w.x, acc[2][0]); acc[2][1] = fmaf(x.z, w.y, acc[2][1]);
-            acc[3][0] = fmaf(x.w, w.x, acc[3][0]); acc[3][1] = fmaf(x.w, w.y, acc[3][1]);
+        for (int q = 0; q < 8; q++) {
+            const float4 d = *reinterpret_cast<const float4 *>(ds + 4 * q);
+            const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float4 w = *reinterpret_cast<const float4 *>(ws + (4 * q + j) * kP);
+                acc[0] = fmaf(dd[j], w.x, acc[0]); acc[1] = fmaf(dd[j], w.y, acc[1]);
+                acc[2] = fmaf(dd[j], w.z, acc[2]); acc[3] = fmaf(dd[j], w.w, acc[3]);
+            }
         }
         __syncthreads();
     }
+    const int b = b0 + tb;
+    if (b < J.B) {
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const int k = k0 + 2 * tk + j;
-        if (k < J.K) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int b = 4 * tb + i;
-                if (b < J.B) J.Y[(size_t)b * J.ldy + k] = acc[i][j];
-            }
-        }
+        for (int j = 0; j < 4; j++) { const int k = k0 + 4 * tk + j; if (k < J.K) J.Y[(size_t)b * J.ldy + k] = acc[j]; }
     }
 }
 
 __global__ void __launch_bounds__(kT) learn_gemm_kernel(JobList L) {
-    __shared__ __align__(16) float smem[64 * 65 + 64 * 17];       // >= 32 * kXS + 32 * kWS + 128 (forward / dX) and the dW layout
+    __shared__ __align__(16) float smem[2 * 64 * kP + 2 * 32 * kP];            // 27 648 B: the dX layout is the largest
     int cta = blockIdx.x;
     for (int i = 0; i < L.n; i++) {
         if (cta < L.j[i].ctas) {
@@ -297,8 +238,8 @@ struct Batch {
     float *s, *s2, *a, *r, *d;        // [B][in], [B][in], [B], [B], [B] (done as 0 / 1)
     int64_t *rows;                    // [B]
 };
-__global__ void learn_gather_kernel(tt_replay_ring ring, int64_t max_mem, const int64_t *__restrict__ given_rows, Batch bt, int B, int in,
-                                    uint64_t seed, int *__restrict__ step) {
+__global__ void learn_gather_kernel(tt_replay_ring ring, int64_t win_begin, int64_t max_mem, const int64_t *__restrict__ given_rows, Batch bt, int B,
+                                    int in, uint64_t seed, int *__restrict__ step) {
     __shared__ int64_t rows[kMaxB];
     const int tid = threadIdx.x;
     const int t = *step;                               // updates done so far = the sampling counter of this one
@@ -313,6 +254,7 @@ __global__ void learn_gather_kernel(tt_replay_ring ring, int64_t max_mem, const 
             const double u = ((double)w[0] * 4294967296.0 + (double)w[1]) * (1.0 / 18446744073709551616.0);       // [0, 1)
             row = (int64_t)(u * (double)max_mem);
             if (row >= max_mem) row = max_mem - 1;
+            row = (win_begin + row) % ring.mem_size;                  // the sampling window may wrap around the ring
         }
         rows[tid] = row; bt.rows[tid] = row;
         bt.a[tid] = ring.d_action_mem[row]; bt.r[tid] = ring.d_reward_mem[row]; bt.d[tid] = ring.d_terminal_mem[row] ? 1.f : 0.f;
@@ -402,11 +344,76 @@ struct HeadArgs {
     float *q_out, *y_out, *a_out;                                         // diagnostics / hand-over: Q(s,a), target, actor(s)
 };
 
+// K1 / K7: fc1 + LayerNorm 1 + ReLU of up to four networks in one launch.  A CTA takes 8 batch rows of one network (warp = row,
+// the whole fc1 output row -- <= 512 values -- in registers), W1 passes through shared memory in blocks of 128 output columns.
+// Writes h1 (pre-LayerNorm, for the backward pass) and a1 = relu(LN1(h1)) (the operand of fc2 and of its weight gradient).
+struct Fc1Job { const float *x, *w1, *b1, *g1, *be1; float *h1, *a1; };
+struct Fc1Args { Fc1Job j[NJOBS]; int njobs, B, IN, H1; };
+constexpr int kW1P = 25;                                   // shared-memory pitch of a W1 row (IN <= 24 + 1; odd: conflict-free for lane = column)
+__global__ void __launch_bounds__(256) learn_fc1_kernel(Fc1Args A) {
+    extern __shared__ float ws[];                          // W1 [H1][kW1P]: the whole matrix in ONE round of independent loads
+    __shared__ float xs[8 * 32];                           // the CTA's 8 input rows
+    const int per = (A.B + 7) / 8;
+    const int job = blockIdx.x / per, b0 = (blockIdx.x - job * per) * 8;
+    const Fc1Job J = A.j[job];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = b0 + warp, H = A.H1, IN = A.IN;
+    // this lane's columns of the three parameter vectors: loaded up front, together with W1 (one memory latency for everything)
+    float pb[kPerLane], pg[kPerLane], pe[kPerLane];
+#pragma unroll
+    for (int i = 0; i < kPerLane; i++) {
+        const int j = lane + 32 * i;
+        pb[i] = j < H ? J.b1[j] : 0.f; pg[i] = j < H ? J.g1[j] : 0.f; pe[i] = j < H ? J.be1[j] : 0.f;
+    }
+    for (int v = threadIdx.x; v < 8 * IN; v += 256) { const int r = v / IN, k = v - r * IN; xs[r * 32 + k] = b0 + r < A.B ? J.x[(size_t)(b0 + r) * IN + k] : 0.f; }
+    for (int v = threadIdx.x; v < H * IN; v += 256) { const int c = v / IN, k = v - c * IN; ws[c * kW1P + k] = J.w1[v]; }
+    __syncthreads();
+    Row h;
+#pragma unroll
+    for (int i = 0; i < kPerLane; i++) {
+        const int c = lane + 32 * i;
+        float acc = 0.f;
+        if (c < H) {
+            for (int k = 0; k < IN; k++) acc = fmaf(xs[warp * 32 + k], ws[c * kW1P + k], acc);
+            acc += pb[i];
+        }
+        h.v[i] = acc;
+    }
+    if (b < A.B) {
+#pragma unroll
+        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; if (j < H) J.h1[(size_t)b * H + j] = h.v[i]; }
+        normalize_row(h, H, lane);
+#pragma unroll
+        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; if (j < H) J.a1[(size_t)b * H + j] = fmaxf(fmaf(h.v[i], pg[i], pe[i]), 0.f); }
+    }
+}
+
+// The head / LayerNorm-backward kernels read a dozen parameter vectors element by element inside dependent arithmetic; from
+// global memory the compiler issues those loads just in time, one L2 latency after the other (measured: 27 us for 150 k
+// instructions).  All vectors are copied to shared memory first: NV loads per thread in flight at once, one latency in total.
+template <int NV>
+__device__ __forceinline__ void stage_vectors(float (*dst)[kMaxH], const float *const (&src)[NV], int H) {
+    for (int j = threadIdx.x; j < H; j += kRowT) {
+        float t[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) t[v] = src[v][j];
+#pragma unroll
+        for (int v = 0; v < NV; v++) dst[v][j] = t[v];
+    }
+}
+
 // K3: DDPG_agent.py:84-97
 __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
     __shared__ float s_dq[kMaxB], s_act[kMaxB];
+    __shared__ float sp[13][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
     const int b = (int)cluster_rank() * (kRowT / 32) + warp;
+    {
+        const float *const src[13] = {A.ta_g2, A.ta_be2, A.ta_w3, A.tc_g2, A.tc_be2, A.tc_wa, A.tc_ba, A.tc_wq, A.c_g2, A.c_be2, A.c_wa, A.c_ba, A.c_wq};
+        stage_vectors<13>(sp, src, H);
+    }
+    const float *ta_g2 = sp[0], *ta_be2 = sp[1], *ta_w3 = sp[2], *tc_g2 = sp[3], *tc_be2 = sp[4], *tc_wa = sp[5], *tc_ba = sp[6], *tc_wq = sp[7],
+                *c_g2 = sp[8], *c_be2 = sp[9], *c_wa = sp[10], *c_ba = sp[11], *c_wq = sp[12];
+    __syncthreads();
     if (b < A.B) {
         Row x, xt;
         load_row(xt, A.h2[JOB_TA] + (size_t)b * H, H, lane);             // the three rows' loads are independent: issue them together
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
         normalize_row(xt, H, lane);
         float p = 0.f;
 #pragma unroll
-        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; if (j < H) p = fmaf(fmaxf(fmaf(xt.v[i], A.ta_g2[j], A.ta_be2[j]), 0.f), A.ta_w3[j], p); }
+        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; if (j < H) p = fmaf(fmaxf(fmaf(xt.v[i], ta_g2[j], ta_be2[j]), 0.f), ta_w3[j], p); }
         const float a2 = tanhf(warp_sum(p) + A.ta_b3[0]);
         // Q'(s', a') = q(relu(LN2(h2) + action_value(a')))                 (networks.py:53-68)
         normalize_row(xc, H, lane);
@@ -425,7 +432,7 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
-            if (j < H) q2 = fmaf(fmaxf(fmaf(xc.v[i], A.tc_g2[j], A.tc_be2[j]) + fmaf(a2, A.tc_wa[j], A.tc_ba[j]), 0.f), A.tc_wq[j], q2);
+            if (j < H) q2 = fmaf(fmaxf(fmaf(xc.v[i], tc_g2[j], tc_be2[j]) + fmaf(a2, tc_wa[j], tc_ba[j]), 0.f), tc_wq[j], q2);
         }
         q2 = warp_sum(q2) + A.tc_bq[0];
         const float y = A.rew[b] + A.gamma * (A.done[b] != 0.f ? 0.f : q2);       // DDPG_agent.py:90-93
@@ -437,15 +444,15 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
-            z.v[i] = j < H ? fmaf(x.v[i], A.c_g2[j], A.c_be2[j]) + fmaf(act, A.c_wa[j], A.c_ba[j]) : 0.f;
-            if (j < H) q = fmaf(fmaxf(z.v[i], 0.f), A.c_wq[j], q);
+            z.v[i] = j < H ? fmaf(x.v[i], c_g2[j], c_be2[j]) + fmaf(act, c_wa[j], c_ba[j]) : 0.f;
+            if (j < H) q = fmaf(fmaxf(z.v[i], 0.f), c_wq[j], q);
         }
         q = warp_sum(q) + A.c_bq[0];
         const float dq = 2.0f * (q - y) / (float)A.B;                    // d mse_loss(target, q) / dq
         Row dz, dx;
 #pragma unroll
-        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; dz.v[i] = (j < H && z.v[i] > 0.f) ? dq * A.c_wq[j] : 0.f; }
-        ln_backward_row(dz, x, A.c_g2, rstd, H, lane, dx);
+        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; dz.v[i] = (j < H && z.v[i] > 0.f) ? dq * c_wq[j] : 0.f; }
+        ln_backward_row(dz, x, c_g2, rstd, H, lane, dx);
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
@@ -477,8 +484,15 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
 // K9: DDPG_agent.py:99-103  actor_loss = -mean(critic(states, actor(states)))
 __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
     __shared__ float s_dp[kMaxB];
+    __shared__ float sp[8][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
     const int b = (int)cluster_rank() * (kRowT / 32) + warp;
+    {
+        const float *const src[8] = {A.a_g2, A.a_be2, A.a_w3, A.c_g2, A.c_be2, A.c_wa, A.c_ba, A.c_wq};
+        stage_vectors<8>(sp, src, H);
+    }
+    const float *a_g2 = sp[0], *a_be2 = sp[1], *a_w3 = sp[2], *c_g2 = sp[3], *c_be2 = sp[4], *c_wa = sp[5], *c_ba = sp[6], *c_wq = sp[7];
+    __syncthreads();
     if (b < A.B) {
         Row x, o2, c;
         load_row(x, A.h2[JOB_A] + (size_t)b * H, H, lane);
@@ -488,8 +502,8 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
-            o2.v[i] = j < H ? fmaf(x.v[i], A.a_g2[j], A.a_be2[j]) : 0.f;
-            if (j < H) p = fmaf(fmaxf(o2.v[i], 0.f), A.a_w3[j], p);
+            o2.v[i] = j < H ? fmaf(x.v[i], a_g2[j], a_be2[j]) : 0.f;
+            if (j < H) p = fmaf(fmaxf(o2.v[i], 0.f), a_w3[j], p);
         }
         const float a = tanhf(warp_sum(p) + A.a_b3[0]);
         // dQ/da through the UPDATED critic: z = LN2(h2') + action_value(a); dq = -1 / B
@@ -500,16 +514,16 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
             if (j < H) {
-                const float z = fmaf(c.v[i], A.c_g2[j], A.c_be2[j]) + fmaf(a, A.c_wa[j], A.c_ba[j]);
-                if (z > 0.f) da = fmaf(dq * A.c_wq[j], A.c_wa[j], da);
+                const float z = fmaf(c.v[i], c_g2[j], c_be2[j]) + fmaf(a, c_wa[j], c_ba[j]);
+                if (z > 0.f) da = fmaf(dq * c_wq[j], c_wa[j], da);
             }
         }
         da = warp_sum(da);
         const float dp = da * (1.0f - a * a);                             // through tanh
         Row dout, dx;
 #pragma unroll
-        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; dout.v[i] = (j < H && o2.v[i] > 0.f) ? dp * A.a_w3[j] : 0.f; }
-        ln_backward_row(dout, x, A.a_g2, rstd, H, lane, dx);
+        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; dout.v[i] = (j < H && o2.v[i] > 0.f) ? dp * a_w3[j] : 0.f; }
+        ln_backward_row(dout, x, a_g2, rstd, H, lane, dx);
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
@@ -546,8 +560,15 @@ struct L1Args {
 __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
     __shared__ float xs[kMaxB * 32];
     __shared__ float ds[kMaxB * (kMaxH / kRowCtas)];      // this CTA's column slice of dh1: [B][H1 / 8]
+    __shared__ float sp[2][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H1;
     for (int v = threadIdx.x; v < A.B * A.IN; v += kRowT) xs[v] = A.x[v];
+    {
+        const float *const src[2] = {A.g1, A.be1};
+        stage_vectors<2>(sp, src, H);
+    }
+    const float *g1 = sp[0], *be1 = sp[1];
+    __syncthreads();
     const int b = (int)cluster_rank() * (kRowT / 32) + warp;
     if (b < A.B) {
         Row x, dout, dx;
@@ -557,9 +578,9 @@ __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
-            if (!(j < H && fmaf(x.v[i], A.g1[j], A.be1[j]) > 0.f)) dout.v[i] = 0.f;      // relu mask
+            if (!(j < H && fmaf(x.v[i], g1[j], be1[j]) > 0.f)) dout.v[i] = 0.f;      // relu mask
         }
-        ln_backward_row(dout, x, A.g1, rstd, H, lane, dx);
+        ln_backward_row(dout, x, g1, rstd, H, lane, dx);
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
             const int j = lane + 32 * i;
@@ -634,7 +655,7 @@ struct tt_learner {
     float *p[4];                      // flat parameters
     float *m[2], *v[2], *g[2];        // Adam moments / gradients: [0] actor, [1] critic
     Batch bt;
-    float *h1[NJOBS], *h2[NJOBS], *st1[NJOBS];
+    float *h1[NJOBS], *a1[NJOBS], *h2[NJOBS];
     float *dh2, *da1, *dh1, *sc0, *sc1, *sc2;
     float *q, *y, *aout, *dv;
     int *step;                        // number of updates done (Adam's step count and the sampling counter)
@@ -651,8 +672,8 @@ size_t learner_layout(const Layout &L, int B, tt_learner *ln, char *base) {
     size_t o_m[2] = {take(pa), take(pc)}, o_v[2] = {take(pa), take(pc)}, o_g[2] = {take(pa), take(pc)};
     size_t o_s = take(sizeof(float) * B * L.in), o_s2 = take(sizeof(float) * B * L.in), o_a = take(sizeof(float) * B),
            o_r = take(sizeof(float) * B), o_d = take(sizeof(float) * B), o_rows = take(sizeof(int64_t) * B);
-    size_t o_h1[NJOBS], o_h2[NJOBS], o_st[NJOBS];
-    for (int j = 0; j < NJOBS; j++) { o_h1[j] = take(sizeof(float) * B * L.h1); o_h2[j] = take(sizeof(float) * B * L.h2); o_st[j] = take(sizeof(float) * 2 * B); }
+    size_t o_h1[NJOBS], o_h2[NJOBS], o_a1[NJOBS];
+    for (int j = 0; j < NJOBS; j++) { o_h1[j] = take(sizeof(float) * B * L.h1); o_h2[j] = take(sizeof(float) * B * L.h2); o_a1[j] = take(sizeof(float) * B * L.h1); }
     size_t o_dh2 = take(sizeof(float) * B * L.h2), o_da1 = take(sizeof(float) * B * L.h1), o_dh1 = take(sizeof(float) * B * L.h1);
     size_t o_sc[3] = {take(sizeof(float) * B * hm), take(sizeof(float) * B * hm), take(sizeof(float) * B * hm)};
     size_t o_q = take(sizeof(float) * B), o_y = take(sizeof(float) * B), o_ao = take(sizeof(float) * B), o_dv = take(sizeof(float) * B), o_step = take(256);
@@ -662,17 +683,16 @@ size_t learner_layout(const Layout &L, int B, tt_learner *ln, char *base) {
         for (int i = 0; i < 2; i++) { ln->m[i] = f(o_m[i]); ln->v[i] = f(o_v[i]); ln->g[i] = f(o_g[i]); }
         ln->bt.s = f(o_s); ln->bt.s2 = f(o_s2); ln->bt.a = f(o_a); ln->bt.r = f(o_r); ln->bt.d = f(o_d);
         ln->bt.rows = reinterpret_cast<int64_t *>(base + o_rows);
-        for (int j = 0; j < NJOBS; j++) { ln->h1[j] = f(o_h1[j]); ln->h2[j] = f(o_h2[j]); ln->st1[j] = f(o_st[j]); }
+        for (int j = 0; j < NJOBS; j++) { ln->h1[j] = f(o_h1[j]); ln->h2[j] = f(o_h2[j]); ln->a1[j] = f(o_a1[j]); }
         ln->dh2 = f(o_dh2); ln->da1 = f(o_da1); ln->dh1 = f(o_dh1); ln->sc0 = f(o_sc[0]); ln->sc1 = f(o_sc[1]); ln->sc2 = f(o_sc[2]);
         ln->q = f(o_q); ln->y = f(o_y); ln->aout = f(o_ao); ln->dv = f(o_dv); ln->step = reinterpret_cast<int *>(base + o_step);
     }
     return off;
 }
 
-Job fwd_job(int B, int N, int K, const float *X, int ldx, const float *W, const float *bias, const float *g, const float *be, float *stats, float *Y) {
+Job fwd_job(int B, int N, int K, const float *X, const float *W, const float *bias, float *Y) {
     Job j{};
-    j.type = G_FWD; j.ctas = (N + 31) / 32; j.B = B; j.N = N; j.K = K; j.X = X; j.ldx = ldx; j.W = W; j.ldw = K; j.bias = bias; j.g = g; j.be = be;
-    j.stats = stats; j.Y = Y; j.ldy = N;
+    j.type = G_FWD; j.ctas = (N + 15) / 16; j.B = B; j.N = N; j.K = K; j.X = X; j.ldx = K; j.W = W; j.ldw = K; j.bias = bias; j.Y = Y; j.ldy = N;
     return j;
 }
 
@@ -751,10 +771,18 @@ int tt_learner_reset_optimizer(tt_learner *ln, tt_stream_t stream) {
 
 int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_rows, tt_actor *repack_into, tt_stream_t stream) {
     TT_REQUIRE(ln && ring, "NULL argument");
+    const int64_t max_mem = ring->mem_cntr < ring->mem_size ? ring->mem_cntr : ring->mem_size;
+    return tt_learn_step_window(ln, ring, d_rows, repack_into, 0, max_mem, stream);
+}
+
+int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_rows, tt_actor *repack_into, int64_t window_begin,
+                         int64_t window_count, tt_stream_t stream) {
+    TT_REQUIRE(ln && ring, "NULL argument");
     TT_REQUIRE(ring->d_state_mem && ring->d_action_mem && ring->d_reward_mem && ring->d_new_state_mem && ring->d_terminal_mem &&
                ring->mem_size > 0, "bad ring");
-    const int64_t max_mem = ring->mem_cntr < ring->mem_size ? ring->mem_cntr : ring->mem_size;
-    TT_REQUIRE(max_mem >= ln->B || d_rows, "fewer transitions in the ring than the batch size (DDPG_agent.py:73-74)");
+    TT_REQUIRE(window_begin >= 0 && window_begin < ring->mem_size && window_count >= 0 && window_count <= ring->mem_size, "bad sampling window");
+    const int64_t win_begin = window_begin, max_mem = window_count;
+    TT_REQUIRE(max_mem >= ln->B || d_rows, "fewer transitions in the sampling window than the batch size (DDPG_agent.py:73-74)");
     cudaStream_t s = tt::as_stream(stream);
     const Layout &L = ln->L;
     const int B = ln->B, IN = L.in, H1 = L.h1, H2 = L.h2;
@@ -763,22 +791,37 @@ int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_r
     const int T = L.tail();
 
     // K0
-    learn_gather_kernel<<<1, 1024, 0, s>>>(*ring, max_mem, d_rows, ln->bt, B, IN, ln->seed, ln->step);
+    learn_gather_kernel<<<1, 1024, 0, s>>>(*ring, win_begin, max_mem, d_rows, ln->bt, B, IN, ln->seed, ln->step);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     int rc;
-    // K1: fc1 of the four forward passes
+    // K1: fc1 + LayerNorm 1 + ReLU of the four forward passes
     const float *netp[NJOBS] = {pta, ptc, pc, pa};
     const float *netx[NJOBS] = {ln->bt.s2, ln->bt.s2, ln->bt.s, ln->bt.s};
+    auto fc1 = [&](const int *jobs, int njobs) -> int {
+        Fc1Args A{};
+        A.njobs = njobs; A.B = B; A.IN = IN; A.H1 = H1;
+        for (int i = 0; i < njobs; i++) {
+            const int j = jobs[i];
+            A.j[i] = Fc1Job{netx[j], netp[j] + L.w1(), netp[j] + L.b1(), netp[j] + L.g1(), netp[j] + L.be1(), ln->h1[j], ln->a1[j]};
+        }
+        const size_t dsm = sizeof(float) * (size_t)H1 * kW1P;
+        static bool attr_of[tt::kMaxDevices] = {};
+        if (dsm > 48 * 1024 && !attr_of[tt::device_index()]) {
+            TT_CUDA(cudaFuncSetAttribute(learn_fc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kMaxH * kW1P)));
+            attr_of[tt::device_index()] = true;
+        }
+        learn_fc1_kernel<<<njobs * ((B + 7) / 8), 256, dsm, s>>>(A);
+        TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+        return TT_OK;
+    };
     {
-        JobList J{}; J.n = NJOBS;
-        for (int j = 0; j < NJOBS; j++) J.j[j] = fwd_job(B, H1, IN, netx[j], IN, netp[j] + L.w1(), netp[j] + L.b1(), nullptr, nullptr, nullptr, ln->h1[j]);
-        if ((rc = launch_jobs(J, s)) != TT_OK) return rc;
+        const int all[NJOBS] = {JOB_TA, JOB_TC, JOB_C, JOB_A};
+        if ((rc = fc1(all, NJOBS)) != TT_OK) return rc;
     }
-    // K2: LayerNorm 1 + ReLU + fc2
+    // K2: fc2
     {
         JobList J{}; J.n = NJOBS;
-        for (int j = 0; j < NJOBS; j++)
-            J.j[j] = fwd_job(B, H2, H1, ln->h1[j], H1, netp[j] + L.w2(), netp[j] + L.b2(), netp[j] + L.g1(), netp[j] + L.be1(), ln->st1[j], ln->h2[j]);
+        for (int j = 0; j < NJOBS; j++) J.j[j] = fwd_job(B, H2, H1, ln->a1[j], netp[j] + L.w2(), netp[j] + L.b2(), ln->h2[j]);
         if ((rc = launch_jobs(J, s)) != TT_OK) return rc;
     }
     // K3: critic head
@@ -801,11 +844,11 @@ int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_r
     auto trunk_backward = [&](int job, const float *p, float *g, const float *x) -> int {
         JobList J{}; J.n = 2;
         Job w{};
-        w.type = G_WGRAD; w.B = B; w.N = H2; w.K = H1; w.ctas = ((H2 + 15) / 16) * ((H1 + 63) / 64);
-        w.X = ln->h1[job]; w.ldx = H1; w.g = p + L.g1(); w.be = p + L.be1(); w.stats = ln->st1[job];
+        w.type = G_WGRAD; w.B = B; w.N = H2; w.K = H1; w.ctas = ((H2 + 15) / 16) * ((H1 + 31) / 32);
+        w.X = ln->a1[job]; w.ldx = H1;
         w.D = ln->dh2; w.ldd = H2; w.Y = g + L.w2(); w.ldy = H1; w.db = g + L.b2();
         Job xg{};
-        xg.type = G_XGRAD; xg.B = B; xg.N = H2; xg.K = H1; xg.ctas = (H1 + 31) / 32;
+        xg.type = G_XGRAD; xg.B = B; xg.N = H2; xg.K = H1; xg.ctas = ((B + 31) / 32) * ((H1 + 31) / 32);
         xg.D = ln->dh2; xg.ldd = H2; xg.W = p + L.w2(); xg.ldw = H1; xg.Y = ln->da1; xg.ldy = H1;
         J.j[0] = w; J.j[1] = xg;
         int r = launch_jobs(J, s);
@@ -832,10 +875,10 @@ int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_r
     if ((rc = adam(pc, ln->m[1], ln->v[1], ptc, gc, ln->np[NET_CRITIC], ln->beta, ln->wd)) != TT_OK) return rc;
     // K7, K8: the updated critic's trunk on s (into the JOB_C buffers)
     {
+        const int one[1] = {JOB_C};
+        if ((rc = fc1(one, 1)) != TT_OK) return rc;
         JobList J{}; J.n = 1;
-        J.j[0] = fwd_job(B, H1, IN, ln->bt.s, IN, pc + L.w1(), pc + L.b1(), nullptr, nullptr, nullptr, ln->h1[JOB_C]);
-        if ((rc = launch_jobs(J, s)) != TT_OK) return rc;
-        J.j[0] = fwd_job(B, H2, H1, ln->h1[JOB_C], H1, pc + L.w2(), pc + L.b2(), pc + L.g1(), pc + L.be1(), ln->st1[JOB_C], ln->h2[JOB_C]);
+        J.j[0] = fwd_job(B, H2, H1, ln->a1[JOB_C], pc + L.w2(), pc + L.b2(), ln->h2[JOB_C]);
         if ((rc = launch_jobs(J, s)) != TT_OK) return rc;
     }
     // K9: actor head

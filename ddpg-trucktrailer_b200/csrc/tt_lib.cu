@@ -36,9 +36,23 @@ int sm_count() {
     return n[dev];
 }
 
+// SMs the rollout kernels leave free (per device): their persistent grids are sized for grid_sms() instead of sm_count(), so
+// that the small dependent kernels of a learner / of NCCL on a side stream find room while a rollout kernel runs.
+static int g_reserved[kMaxDevices] = {};
+int grid_sms() {
+    const int n = sm_count() - g_reserved[device_index()];
+    return n > 0 ? n : 1;
+}
+
 }  // namespace tt
 
 extern "C" {
+
+int tt_reserve_sms(int32_t n) {
+    if (n < 0 || n > tt::sm_count() / 2) { tt::set_error("tt_reserve_sms: n must be in 0 .. %d", tt::sm_count() / 2); return TT_ERR_INVALID; }
+    tt::g_reserved[tt::device_index()] = n;
+    return TT_OK;
+}
 
 const char *tt_last_error(void) { return tt::g_err; }
 int tt_abi_version(void) { return TT_ABI_VERSION; }

@@ -133,11 +133,13 @@ class CudaLearner:
         actor._sd = {k: self._params["actor"][k] for k in ACTOR_KEYS}       # the rollout actor's state_dict follows the learner
 
     # ---- Agent.learn ----
-    def learn(self, rows=None, repack_into="agent"):
+    def learn(self, rows=None, repack_into="agent", window=None):
         """One DDPG update on a batch sampled from the agent's ring (``rows``: explicit ring rows instead, int64 [batch]).
-        ``repack_into``: rollout actor that receives the new policy ("agent" = the agent's, None = nobody)."""
+        ``repack_into``: rollout actor that receives the new policy ("agent" = the agent's, None = nobody).
+        ``window = (begin, count)``: sample only from `count` ring rows starting at `begin` (wrapping) -- for a learner
+        that runs concurrently with a rollout iteration (``rollout.AsyncTrainer``)."""
         ag, m = self.agent, self.agent.memory
-        if m.mem_cntr < self.batch:                                          # DDPG_agent.py:73-74
+        if (m.mem_cntr if window is None else window[1]) < self.batch:      # DDPG_agent.py:73-74
             return
         with torch.cuda.device(self.device):
             ring = _lib.ReplayRing(m.state_memory.data_ptr(), m.action_memory.data_ptr(), m.reward_memory.data_ptr(),
@@ -147,8 +149,12 @@ class CudaLearner:
                 if rows.numel() != self.batch:
                     raise ValueError(f"rows: expected {self.batch} ring rows")
             target = ag.actor if repack_into == "agent" else repack_into
-            check(self.L.tt_learn_step(self._h, C.byref(ring), None if rows is None else rows.data_ptr(),
-                                       target._h if target is not None else None, stream_ptr()))
+            if window is None:
+                check(self.L.tt_learn_step(self._h, C.byref(ring), None if rows is None else rows.data_ptr(),
+                                           target._h if target is not None else None, stream_ptr()))
+            else:
+                check(self.L.tt_learn_step_window(self._h, C.byref(ring), None if rows is None else rows.data_ptr(),
+                                                  target._h if target is not None else None, int(window[0]), int(window[1]), stream_ptr()))
             if target is not None:
                 target._sd = {k: self._params["actor"][k] for k in ACTOR_KEYS}
         self.steps += 1

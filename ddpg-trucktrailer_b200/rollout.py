@@ -114,3 +114,76 @@ class RolloutEngine:
                 m.mem_cntr += env.num_envs
             self.iterations += 1
         return env._obs_view(nxt), self.reward, self.done
+
+
+class AsyncTrainer:
+    """BASELINE.json configs[3]: one rollout iteration + one DDPG update (``Agent.learn``) per step, with the update HIDDEN
+    under the rollout: the learner's launch sequence (``tt_learn_step``, 13 small dependent kernels), the optional broadcast of
+    the new policy (multi-GPU) and its re-pack into the SPARE packed actor run on a side stream while the rollout kernels of
+    the same iteration run on the caller's stream.
+
+    * The rollout kernels are persistent and fill every SM, so a dependent chain of small kernels would otherwise only advance
+      at kernel boundaries; ``reserve_sms`` SMs are left free for it (``tt_reserve_sms``: -1.4 % rollout throughput per 2 SMs,
+      instead of the whole update time serialised behind every iteration).
+    * The update of iteration t samples only ring rows completed by iterations < t (``tt_learn_step_window``), and its
+      policy is used by iteration t + 1: the usual one-step policy lag of an asynchronous learner.
+    * Two packed actors are used alternately; the side stream re-packs into the one the running iteration does not read.
+
+    ``sync`` (``dist.OverlappedSync``): ranks other than ``learner_rank`` receive the flat parameter vector by broadcast."""
+
+    def __init__(self, engine, reserve_sms=2, sync=None, is_learner=True):
+        from .agent import CudaActor
+        self.eng, self.sync, self.is_learner = engine, sync, bool(is_learner)
+        ag = engine.agent
+        self.dev = ag.device
+        self.ln = ag.learner
+        self.flat = self.ln._flat["actor"]
+        with torch.cuda.device(self.dev):
+            self.actors = [ag.actor, CudaActor(*ag.actor.dims, device=self.dev)]
+            self.actors[1].load_state_dict(ag.actor.state_dict())
+            self.side = torch.cuda.Stream(device=self.dev)
+            self.ev_step, self.ev_pol = torch.cuda.Event(), torch.cuda.Event()
+            check(engine.L.tt_reserve_sms(int(reserve_sms)))
+        self.reserve_sms = int(reserve_sms)
+        self.it = 0
+        self.updates = 0
+
+    def close(self):
+        with torch.cuda.device(self.dev):
+            torch.cuda.current_stream().wait_stream(self.side)
+            check(self.eng.L.tt_reserve_sms(0))
+
+    def _window(self):
+        """Ring rows that are complete and that the iteration about to run does not write: (begin, count)."""
+        m, n = self.eng.agent.memory, self.eng.env.num_envs
+        c, cap = m.mem_cntr, m.mem_size
+        if c + n <= cap:
+            return 0, c
+        if n >= cap:
+            return 0, 0
+        begin = (c + n) % cap
+        return begin, (cap - n if c >= cap else max(0, c - begin))
+
+    def step(self):
+        eng, ag = self.eng, self.eng.agent
+        with torch.cuda.device(self.dev):
+            main = torch.cuda.current_stream()
+            if self.it > 0:
+                main.wait_event(self.ev_pol)                  # the policy the side stream prepared during the previous iteration
+                ag.actor = self.actors[self.it & 1]
+            begin, count = self._window()
+            if self.it > 0:
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(self.ev_step)        # iteration t - 1 has finished: its rows are complete, the spare actor is free
+                    if self.is_learner and count >= self.ln.batch:
+                        self.ln.learn(repack_into=None, window=(begin, count))
+                        self.updates += 1
+                    if self.sync is not None and self.sync.on:
+                        self.sync.push_policy(self.flat)
+                        self.sync.wait_policy()
+                    self.actors[(self.it + 1) & 1].load_flat(self.flat)
+                    self.ev_pol.record(self.side)
+            out = eng.step()
+            self.ev_step.record(main)
+            self.it += 1
+        return out

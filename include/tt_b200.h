@@ -87,6 +87,10 @@ typedef struct tt_replay_ring {
 typedef void *tt_stream_t;            /* cudaStream_t */
 
 const char *tt_last_error(void);
+/* Leave n SMs of the current device free: the persistent rollout kernels (actor, env step) size their grids for the
+ * remaining SMs, so that the small dependent kernels of a learner (tt_learn_step) or of NCCL issued on a side stream run
+ * next to a rollout kernel instead of waiting for its last CTA.  0 (default) = the rollout kernels fill the GPU. */
+int tt_reserve_sms(int32_t n);
 int tt_abi_version(void);
 int tt_device_count(void);            /* 0 when no CUDA device is visible */
 uint64_t tt_launch_count(void);       /* kernels launched by this library since it was loaded */
@@ -280,10 +284,15 @@ int tt_learner_reset_optimizer(tt_learner *ln, tt_stream_t stream);   /* zero bo
  * (replay_buffer.py:23-34; Philox(seed; b, step, stream 2) -- or the given d_rows[batch] when not NULL), critic update
  * (MSE on r + gamma Q'(s', pi'(s')) with terminal masking, Adam with weight decay), actor update (ascent on Q(s, pi(s))
  * through the UPDATED critic, Adam), soft update of both targets (tau).  If repack_into != NULL the new actor parameters are
- * then re-packed into that rollout actor (tt_actor_load).  13 kernel launches (+ 7 of the re-pack) on `stream`, no
+ * then re-packed into that rollout actor (tt_actor_load).  13 kernel launches (+ 3 of the re-pack) on `stream`, no
  * synchronisation, graph-capturable (the step counter lives in device memory), deterministic. */
 int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_rows, tt_actor *repack_into,
                   tt_stream_t stream);
+/* The same update with the batch sampled from `window_count` ring rows starting at row `window_begin` (wrapping around):
+ * a learner that runs on a side stream CONCURRENTLY with a rollout iteration samples only the rows earlier iterations
+ * completed, not the ones the running iteration is writing. */
+int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_rows, tt_actor *repack_into,
+                         int64_t window_begin, int64_t window_count, tt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -184,3 +184,43 @@ def test_learner_samples_uniformly_is_deterministic_and_graph_capturable():
             assert torch.equal(x[k], y[k]), (n, k)
     obs = torch.empty(256, 23, device="cuda").uniform_(-1, 1)
     assert torch.equal(ag1.actor.forward(obs).clone(), a3.actor.forward(obs).clone())      # the re-pack ran inside the graph too
+
+
+def test_async_trainer_hides_the_update_and_keeps_semantics():
+    """rollout.AsyncTrainer: one rollout iteration + one DDPG update per step with the update on a side stream.  Checks the
+    contract: (1) every update samples only ring rows that earlier iterations completed (never the rows being written), also
+    after the ring has wrapped; (2) the rollout of iteration t + 1 runs with the policy the update of iteration t produced
+    (the packed actor equals the learner's parameters of one step ago); (3) the learner made one update per iteration."""
+    import ddpg_trucktrailer_b200 as tt
+    N, cap, iters = 4096, 4096 * 5, 14
+    env = tt.VecTruckTrailerEnv(N, seed=3)
+    ag = tt.VecAgent(1e-4, 1e-3, (23,), 1e-3, 1, num_envs=N, max_size=cap, actor_seed=1, seed=3, precision="f16")
+    eng = tt.RolloutEngine(env, ag, store=True)
+    eng.reset()
+    tr = tt.AsyncTrainer(eng, reserve_sms=2)
+    ln = tr.ln
+    seen_flat = []
+    for it in range(iters):
+        c0 = ag.memory.mem_cntr
+        begin, count = tr._window()
+        tr.step()
+        torch.cuda.synchronize()
+        if it > 0 and count >= 64:
+            off = ln.L.tt_learner_last_rows(ln._h) - ln._ws.data_ptr()
+            rows = ln._ws[off:off + 8 * 64].view(torch.int64).cpu().numpy()
+            written = (c0 + np.arange(N)) % cap                         # the rows iteration `it` was writing
+            assert not np.intersect1d(rows, written).size, it
+            rel = (rows - begin) % cap
+            assert rel.max() < count, it
+            if c0 < cap:
+                assert rows.max() < c0                                   # before the wrap: only rows that exist
+        seen_flat.append(ln._flat["actor"].clone())
+        if it >= 2:
+            # iteration `it` ran with the actor packed from the learner's parameters after update it - 1
+            cur = ag.actor.state_dict()
+            want = seen_flat[it - 1]
+            got = torch.cat([cur[k].reshape(-1) for k in tt.ACTOR_KEYS])
+            assert torch.equal(got, want), it
+    assert tr.updates == iters - 1
+    assert not torch.equal(seen_flat[1], seen_flat[-1])                  # the policy moved
+    tr.close()
