@@ -1,5 +1,5 @@
 // tt_learn.cu -- row f1: one DDPG update (Agent.learn, DDPG/DDPG_agent.py:72-131; CriticNetwork DDPG/networks.py:9-68,
-// ActorNetwork :98-147; ReplayBuffer.sample_buffer DDPG/replay_buffer.py:23-34) as 13 small hand-written kernels on the
+// ActorNetwork :98-147; ReplayBuffer.sample_buffer DDPG/replay_buffer.py:23-34) as 15 small hand-written kernels on the
 // caller's stream, on the device-resident replay ring, followed by the re-pack of the new policy into the rollout actor's
 // operand images.  The whole sequence is capturable into one CUDA graph (nothing synchronises, the Adam step counter and
 // the sampling counter live in device memory).
@@ -9,13 +9,13 @@
 //   K0  sample 64 ring rows (Philox) and gather s, a, r, s', done
 //   K1  fc1 + LayerNorm 1 + ReLU of target_actor(s'), target_critic(s'), critic(s), actor(s)   -- one launch, 4 jobs
 //   K2  fc2 of the same four (grouped GEMM launch, cp.async double-buffered operands)
-//   K3  critic head (one CTA, warp = batch row): a' = target_actor head, y = r + gamma Q'(s', a') (1 - done), q = Q(s, a),
+//   K3  critic head (8 CTAs, warp = batch row; the last CTA sums the columns): a' = target_actor head, y = r + gamma Q'(s', a') (1 - done), q = Q(s, a),
 //       dL/dq = 2 (q - y) / B, back through q / action_value / LayerNorm 2 -> d h2; column sums = their parameter gradients
 //   K4  critic fc2 backward: dW2 = dh2^T a1 (grouped with) da1 = dh2 W2
-//   K5  critic LayerNorm 1 backward (one CTA, warp = row) + fc1 backward dW1 = dh1^T s
+//   K5  critic LayerNorm 1 backward (warp = row), K5b fc1 backward dW1 = dh1^T s (a dW job)
 //   K6  Adam (weight decay 0.01) on the critic + soft update of target_critic
 //   K7  fc1 + LayerNorm 1 + ReLU, K8 fc2 of the UPDATED critic on s
-//   K9  actor head (one CTA): a = actor head, dL/da = -(1/B) dQ/da through relu / action_value, back through tanh / mu /
+//   K9  actor head: a = actor head, dL/da = -(1/B) dQ/da through relu / action_value, back through tanh / mu /
 //       LayerNorm 2 -> d h2 of the actor
 //   K10 actor fc2 backward, K11 actor LayerNorm 1 + fc1 backward, K12 Adam on the actor + soft update of target_actor
 // Every reduction has a fixed order (no atomics): the step is deterministic.
@@ -279,18 +279,27 @@ __global__ void learn_gather_kernel(tt_replay_ring ring, int64_t win_begin, int6
     }
 }
 
-// ---- row-wise stages: a CLUSTER of 8 CTAs x 8 warps, one warp per batch row with the row in registers; after a cluster
-//      barrier the same 2 048 threads take the column sums over the batch (= the parameter gradients), one column each, rows
-//      in order (deterministic).  One warp per row keeps the dependent chain of a row (load -> statistics -> head -> backward)
-//      at one memory latency per network instead of serialising rows.
-constexpr int kRowCtas = 8, kRowT = 256, kRowThreads = kRowCtas * kRowT, kPerLane = kMaxH / 32;
+// ---- row-wise stages: 8 CTAs x 8 warps, one warp per batch row with the row in registers (one warp per row keeps the
+//      dependent chain of a row -- load -> statistics -> head -> backward -- at one memory latency per network instead of
+//      serialising rows); the LAST CTA to finish (a ticket counter) then takes the column sums over the batch (= the parameter
+//      gradients), one column per thread, rows in order (deterministic).  No cluster and no grid barrier: the CTAs need not be
+//      co-resident, so the stage also runs on the two or four SMs that rollout.AsyncTrainer leaves free for the learner.
+constexpr int kRowT = 256, kPerLane = kMaxH / 32;
 struct Row { float v[kPerLane]; };
 
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_barrier() {        // release / acquire at cluster scope: the rows' global writes are visible
+// true in exactly one CTA of the launch: the one that arrives last, after every other CTA's global writes are visible
+__device__ __forceinline__ bool last_cta_done(int *ticket) {
+    __shared__ int s_last;
     __threadfence();
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        s_last = t == (int)gridDim.x - 1;
+        if (s_last) *ticket = 0;                            // ready for the next row-wise stage (stream order)
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
 }
 
 __device__ __forceinline__ void load_row(Row &r, const float *__restrict__ p, int H, int lane) {
@@ -339,6 +348,7 @@ struct HeadArgs {
     float *dh2;                                                           // out: gradient w.r.t. the fc2 output [B][H2]
     float *sc0, *sc1, *sc2;                                               // scratch [B][H2]
     float *dv;                                                            // scratch [B]: dL/dq (critic) or dL/d(pre-tanh) (actor) per row
+    int *ticket;                                                          // last-CTA counter (0 between launches)
     // gradients (flat-layout pointers)
     float *g_g2, *g_be2, *g_t0, *g_t1, *g_t2, *g_t3;                      // critic: wa, ba, wq, bq | actor: w3, b3, -, -
     float *q_out, *y_out, *a_out;                                         // diagnostics / hand-over: Q(s,a), target, actor(s)
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
     __shared__ float s_dq[kMaxB], s_act[kMaxB];
     __shared__ float sp[13][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
-    const int b = (int)cluster_rank() * (kRowT / 32) + warp;
+    const int b = (int)blockIdx.x * (kRowT / 32) + warp;
     {
         const float *const src[13] = {A.ta_g2, A.ta_be2, A.ta_w3, A.tc_g2, A.tc_be2, A.tc_wa, A.tc_ba, A.tc_wq, A.c_g2, A.c_be2, A.c_wa, A.c_ba, A.c_wq};
         stage_vectors<13>(sp, src, H);
@@ -463,12 +473,12 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
         }
         if (lane == 0) { A.dv[b] = dq; if (A.q_out) A.q_out[b] = q; if (A.y_out) A.y_out[b] = y; }
     }
-    cluster_barrier();
+    if (!last_cta_done(A.ticket)) return;
     if (threadIdx.x < A.B) { s_dq[threadIdx.x] = A.dv[threadIdx.x]; s_act[threadIdx.x] = A.act[threadIdx.x]; }
     __syncthreads();
     // parameter gradients = column sums over the batch, in row order
-    const int gt = (int)cluster_rank() * kRowT + threadIdx.x;
-    for (int j = gt; j < H; j += kRowThreads) {
+    const int gt = threadIdx.x;
+    for (int j = gt; j < H; j += kRowT) {
         float gba = 0.f, gwa = 0.f, gg2 = 0.f, gwq = 0.f;
 #pragma unroll 32
         for (int bb = 0; bb < A.B; bb++) {
@@ -486,7 +496,7 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
     __shared__ float s_dp[kMaxB];
     __shared__ float sp[8][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
-    const int b = (int)cluster_rank() * (kRowT / 32) + warp;
+    const int b = (int)blockIdx.x * (kRowT / 32) + warp;
     {
         const float *const src[8] = {A.a_g2, A.a_be2, A.a_w3, A.c_g2, A.c_be2, A.c_wa, A.c_ba, A.c_wq};
         stage_vectors<8>(sp, src, H);
@@ -534,11 +544,11 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
         }
         if (lane == 0) { A.dv[b] = dp; if (A.a_out) A.a_out[b] = a; }
     }
-    cluster_barrier();
+    if (!last_cta_done(A.ticket)) return;
     if (threadIdx.x < A.B) s_dp[threadIdx.x] = A.dv[threadIdx.x];
     __syncthreads();
-    const int gt = (int)cluster_rank() * kRowT + threadIdx.x;
-    for (int j = gt; j < H; j += kRowThreads) {
+    const int gt = threadIdx.x;
+    for (int j = gt; j < H; j += kRowT) {
         float gbe = 0.f, gg = 0.f, gw3 = 0.f;
 #pragma unroll 32
         for (int bb = 0; bb < A.B; bb++) { const size_t o = (size_t)bb * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; gw3 += A.sc2[o]; }
@@ -547,29 +557,27 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
     if (gt == 0) { float sum = 0.f; for (int bb = 0; bb < A.B; bb++) sum += s_dp[bb]; A.g_t1[0] = sum; }
 }
 
-// K5 / K11: relu + LayerNorm 1 backward (warp = row), then the fc1 backward: dW1[n][k] = sum_b dh1[b][n] x[b][k], db1, dg1, dbe1
+// K5 / K11: relu + LayerNorm 1 backward (warp = row) -> dh1, and the LayerNorm parameter gradients dg1, dbe1 (last CTA).  The
+// fc1 weight / bias gradients are a dW job of the next grouped launch (dW1 = dh1^T x, db1 = column sums of dh1).
 struct L1Args {
-    int B, IN, H1;
+    int B, H1;
     const float *h1, *da1;           // fc1 output (pre-LayerNorm) and the gradient w.r.t. relu(LN1(h1)), [B][H1]
     const float *g1, *be1;
-    const float *x;                  // network input [B][IN]
-    float *dh1;                      // scratch [B][H1]
+    float *dh1;                      // out [B][H1]
     float *sc0, *sc1;                // scratch [B][H1]
-    float *g_w1, *g_b1, *g_g1, *g_be1;
+    float *g_g1, *g_be1;
+    int *ticket;
 };
 __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
-    __shared__ float xs[kMaxB * 32];
-    __shared__ float ds[kMaxB * (kMaxH / kRowCtas)];      // this CTA's column slice of dh1: [B][H1 / 8]
     __shared__ float sp[2][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H1;
-    for (int v = threadIdx.x; v < A.B * A.IN; v += kRowT) xs[v] = A.x[v];
     {
         const float *const src[2] = {A.g1, A.be1};
         stage_vectors<2>(sp, src, H);
     }
     const float *g1 = sp[0], *be1 = sp[1];
     __syncthreads();
-    const int b = (int)cluster_rank() * (kRowT / 32) + warp;
+    const int b = (int)blockIdx.x * (kRowT / 32) + warp;
     if (b < A.B) {
         Row x, dout, dx;
         load_row(x, A.h1 + (size_t)b * H, H, lane);
@@ -587,29 +595,12 @@ __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
             if (j < H) { const size_t o = (size_t)b * H + j; A.dh1[o] = dx.v[i]; A.sc0[o] = dout.v[i]; A.sc1[o] = dout.v[i] * x.v[i]; }
         }
     }
-    cluster_barrier();
-    __syncthreads();
-    const int gt = (int)cluster_rank() * kRowT + threadIdx.x;
-    for (int j = gt; j < H; j += kRowThreads) {
-        float gbe = 0.f, gg = 0.f, gb = 0.f;
+    if (!last_cta_done(A.ticket)) return;
+    for (int j = threadIdx.x; j < H; j += kRowT) {
+        float gbe = 0.f, gg = 0.f;
 #pragma unroll 32
-        for (int bb = 0; bb < A.B; bb++) { const size_t o = (size_t)bb * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; gb += A.dh1[o]; }
-        A.g_be1[j] = gbe; A.g_g1[j] = gg; A.g_b1[j] = gb;
-    }
-    // dW1[n][k] = sum_b dh1[b][n] x[b][k]: CTA r owns the columns n of its slice of H1, staged in shared memory with one round
-    // of independent loads (reading dh1 from L2 inside the 64-deep dot product would expose the L2 latency 64 times)
-    const int per = (H + kRowCtas - 1) / kRowCtas, nlo = (int)cluster_rank() * per, nhi = min(H, nlo + per), nw = nhi - nlo;
-    for (int v = threadIdx.x; v < A.B * per; v += kRowT) {
-        const int bb = v / per, c = v - bb * per;
-        ds[v] = c < nw ? A.dh1[(size_t)bb * H + nlo + c] : 0.f;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < nw * A.IN; e += kRowT) {
-        const int c = e / A.IN, k = e - c * A.IN;
-        float sum = 0.f;
-#pragma unroll 16
-        for (int bb = 0; bb < A.B; bb++) sum = fmaf(ds[bb * per + c], xs[bb * A.IN + k], sum);
-        A.g_w1[(size_t)(nlo + c) * A.IN + k] = sum;
+        for (int bb = 0; bb < A.B; bb++) { const size_t o = (size_t)bb * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; }
+        A.g_be1[j] = gbe; A.g_g1[j] = gg;
     }
 }
 
@@ -696,15 +687,10 @@ Job fwd_job(int B, int N, int K, const float *X, const float *W, const float *bi
     return j;
 }
 
-// a row-wise stage: one cluster of kRowCtas CTAs
+// a row-wise stage: ceil(B / 8) CTAs (one warp per batch row), the last one to finish sums the columns
 template <typename Kern, typename Args>
-int launch_rows(Kern kern, const Args &args, cudaStream_t s) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(kRowCtas); cfg.blockDim = dim3(kRowT); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kRowCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    TT_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+int launch_rows(Kern kern, const Args &args, int B, cudaStream_t s) {
+    kern<<<(B + kRowT / 32 - 1) / (kRowT / 32), kRowT, 0, s>>>(args);
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
@@ -834,11 +820,11 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     H.a_g2 = pa + L.g2(); H.a_be2 = pa + L.be2(); H.a_w3 = pa + T; H.a_b3 = pa + T + H2;
     H.act = ln->bt.a; H.rew = ln->bt.r; H.done = ln->bt.d;
     H.dh2 = ln->dh2; H.sc0 = ln->sc0; H.sc1 = ln->sc1; H.sc2 = ln->sc2;
-    H.q_out = ln->q; H.y_out = ln->y; H.a_out = ln->aout; H.dv = ln->dv;
+    H.q_out = ln->q; H.y_out = ln->y; H.a_out = ln->aout; H.dv = ln->dv; H.ticket = ln->step + 1;
     {
         HeadArgs C = H;
         C.g_g2 = gc + L.g2(); C.g_be2 = gc + L.be2(); C.g_t0 = gc + T; C.g_t1 = gc + T + H2; C.g_t2 = gc + T + 2 * H2; C.g_t3 = gc + T + 3 * H2;
-        if ((rc = launch_rows(learn_critic_head_kernel, C, s)) != TT_OK) return rc;
+        if ((rc = launch_rows(learn_critic_head_kernel, C, B, s)) != TT_OK) return rc;
     }
     // backward through fc2 / LayerNorm 1 / fc1 of one network whose dh2 is in ln->dh2 and whose forward job is `job`
     auto trunk_backward = [&](int job, const float *p, float *g, const float *x) -> int {
@@ -854,10 +840,15 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
         int r = launch_jobs(J, s);
         if (r != TT_OK) return r;
         L1Args A{};
-        A.B = B; A.IN = IN; A.H1 = H1; A.h1 = ln->h1[job]; A.da1 = ln->da1; A.g1 = p + L.g1(); A.be1 = p + L.be1(); A.x = x;
-        A.dh1 = ln->dh1; A.sc0 = ln->sc0; A.sc1 = ln->sc1;
-        A.g_w1 = g + L.w1(); A.g_b1 = g + L.b1(); A.g_g1 = g + L.g1(); A.g_be1 = g + L.be1();
-        return launch_rows(learn_l1_backward_kernel, A, s);
+        A.B = B; A.H1 = H1; A.h1 = ln->h1[job]; A.da1 = ln->da1; A.g1 = p + L.g1(); A.be1 = p + L.be1();
+        A.dh1 = ln->dh1; A.sc0 = ln->sc0; A.sc1 = ln->sc1; A.g_g1 = g + L.g1(); A.g_be1 = g + L.be1(); A.ticket = ln->step + 1;
+        if ((r = launch_rows(learn_l1_backward_kernel, A, B, s)) != TT_OK) return r;
+        JobList J1{}; J1.n = 1;
+        Job w1{};
+        w1.type = G_WGRAD; w1.B = B; w1.N = H1; w1.K = IN; w1.ctas = ((H1 + 15) / 16) * ((IN + 31) / 32);
+        w1.X = x; w1.ldx = IN; w1.D = ln->dh1; w1.ldd = H1; w1.Y = g + L.w1(); w1.ldy = IN; w1.db = g + L.b1();
+        J1.j[0] = w1;
+        return launch_jobs(J1, s);
     };
     auto adam = [&](float *p, float *m, float *v, float *target, const float *g, int n, float lr, float wd) -> int {
         AdamArgs A{};
@@ -885,7 +876,7 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     {
         HeadArgs A = H;
         A.g_g2 = ga + L.g2(); A.g_be2 = ga + L.be2(); A.g_t0 = ga + T; A.g_t1 = ga + T + H2; A.g_t2 = nullptr; A.g_t3 = nullptr;
-        if ((rc = launch_rows(learn_actor_head_kernel, A, s)) != TT_OK) return rc;
+        if ((rc = launch_rows(learn_actor_head_kernel, A, B, s)) != TT_OK) return rc;
     }
     // K10, K11, K12 (DDPG_agent.py:99-106)
     if ((rc = trunk_backward(JOB_A, pa, ga, ln->bt.s)) != TT_OK) return rc;

@@ -200,6 +200,8 @@ def test_async_trainer_hides_the_update_and_keeps_semantics():
     tr = tt.AsyncTrainer(eng, reserve_sms=2)
     ln = tr.ln
     seen_flat = []
+    ref = tt.agent.CudaActor()
+    probe = torch.empty(300, 23, device="cuda").uniform_(-1, 1)
     for it in range(iters):
         c0 = ag.memory.mem_cntr
         begin, count = tr._window()
@@ -216,11 +218,11 @@ def test_async_trainer_hides_the_update_and_keeps_semantics():
                 assert rows.max() < c0                                   # before the wrap: only rows that exist
         seen_flat.append(ln._flat["actor"].clone())
         if it >= 2:
-            # iteration `it` ran with the actor packed from the learner's parameters after update it - 1
-            cur = ag.actor.state_dict()
-            want = seen_flat[it - 1]
-            got = torch.cat([cur[k].reshape(-1) for k in tt.ACTOR_KEYS])
-            assert torch.equal(got, want), it
+            # iteration `it` ran with the actor packed from the learner's parameters after update it - 1 (the packed images are
+            # what counts: state_dict() of a load_flat actor is a live view of the learner's vector)
+            ref.load_flat(seen_flat[it - 1])
+            for prec in ("fp32", "f16"):
+                assert torch.equal(ag.actor.forward(probe, precision=prec).clone(), ref.forward(probe, precision=prec).clone()), (it, prec)
     assert tr.updates == iters - 1
     assert not torch.equal(seen_flat[1], seen_flat[-1])                  # the policy moved
     tr.close()
