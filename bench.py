@@ -235,6 +235,35 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm ----
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and thereby its pinned staging buffers, by first touch) to the CPUs of the NUMA node its
+    GPU hangs off -- as far as the process is allowed to: a container cpuset that covers one node only cannot be left.  Returns
+    what was found / done (reported under e2e.host)."""
+    info = {"gpu_numa_node": None, "allowed_cpus": len(os.sched_getaffinity(0)), "bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        sysdir = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        with open(sysdir + "/numa_node") as f:
+            info["gpu_numa_node"] = int(f.read())
+        with open(sysdir + "/local_cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        ok = cpus & os.sched_getaffinity(0)
+        info["gpu_local_cpus_allowed"] = len(ok)
+        if ok and ok != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, ok)
+            info["bound"] = True
+    except Exception as e:                            # no NVML / sysfs entry: nothing to bind to
+        info["note"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
 def run_b200(args):
     import ctypes as C
     import torch
@@ -246,6 +275,8 @@ def run_b200(args):
     rank, world, local = ttd.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # before any pinned allocation (first touch decides where the pages live); single-GPU runs keep the whole host for the CPU baseline
+    numa = bind_to_gpu_numa_node(local) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else {"bound": False, "allowed_cpus": len(os.sched_getaffinity(0))}
     N = args.envs
     offset = rank * N
     L = tt.load()
@@ -361,6 +392,21 @@ def run_b200(args):
             stats_host[b].copy_(stats_stage[b], non_blocking=True)
             drained[b].record(copy_stream)
 
+    # what bounds e2e at 8 GPUs is the host side (21 MB D2H per rank and step through one host): measure the D2H rate every rank
+    # gets while ALL ranks copy at once
+    d2h_probe = None
+    if world > 1:
+        barrier(); torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(20):
+            rew_host[0].copy_(rew_stage[0], non_blocking=True); done_host[0].copy_(done_stage[0], non_blocking=True)
+        p1.record(); torch.cuda.synchronize()
+        gbs = torch.tensor([20 * N * 5 / (p0.elapsed_time(p1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        lo, hi = gbs.clone(), gbs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(gbs)
+        d2h_probe = {"per_rank_min": float(lo), "per_rank_max": float(hi), "aggregate": float(gbs),
+                     "needed_per_rank_at_value": N * 5 / (ms / K * 1e-3) / 1e9}
     step_done.record()
     upload(0)                                                          # the first step's policy
     # its own pre-roll: the e2e pipeline itself for >= args.e2e_preroll_s, straight into the timed region (same clock / power
@@ -393,6 +439,7 @@ def run_b200(args):
         clocks_e2e = sampler.window(w_e0 - 0.3, w_e1)
     e2e = {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": flat_host.numel() * 4,
            "d2h_bytes_per_step": N * 5 + 128, "ms_per_step": ms_e2e / K, "preroll_iterations": pre, "clocks": clocks_e2e,
+           "host": dict(numa, d2h_gbs_all_ranks_copying=d2h_probe),
            "note": "host buffers: actor parameters H2D + re-pack every step (side stream, one step ahead, two packed actors); reward/done/stats D2H "
                    "every step (copy stream, one step behind); timed right after its own pre-roll of the same pipeline"}
 
