@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(const float *__restrict
 // transposed ([k][row], row stride 68 floats) so that the 8 row operands of one k are two broadcast LDS.128;
 // the k-major (pre-transposed) weights stream through a cp.async double buffer in chunks of 16 k.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TM = 64, RS = 68, KC = 16;
+constexpr int RS = 68, KC = 16;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -93,9 +93,11 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// acc[r][j] += sum_k act[k][row0w + r] * wT[k][lane + 32 j]  for k in [0, K); weights streamed from global
-template <int CJ, bool kGuard>
-__device__ __forceinline__ void gemm_stream(float (&acc)[8][CJ], const float *__restrict__ act /*smem [K][RS]*/,
+// acc[r][j] += sum_k act[k][row0w + r] * wT[k][lane + 32 j]  for k in [0, K); weights streamed from global.
+// R = rows per warp (8 for full 64-row tiles; 4 / 2 / 1 for batches of <= 32 / 16 / 8 rows, where the padding rows of a
+// 64-row tile would be 88 ... 98 % of the arithmetic of a kernel that runs on ONE SM)
+template <int CJ, bool kGuard, int R>
+__device__ __forceinline__ void gemm_stream(float (&acc)[R][CJ], const float *__restrict__ act /*smem [K][RS]*/,
                                             const float *__restrict__ wT /*global [K][WP]*/, int K, int WP,
                                             float *wbuf /*smem 2*KC*WP*/, int warp, int lane) {
     const int tid = threadIdx.x;
@@ -116,14 +118,22 @@ __device__ __forceinline__ void gemm_stream(float (&acc)[8][CJ], const float *__
         const int k0 = ch * KC, kn = min(KC, K - k0);
 #pragma unroll 4
         for (int kk = 0; kk < kn; kk++) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(act + (size_t)(k0 + kk) * RS + warp * 8);
-            const float4 a1 = *reinterpret_cast<const float4 *>(act + (size_t)(k0 + kk) * RS + warp * 8 + 4);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float a[R];
+            if (R == 8) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(act + (size_t)(k0 + kk) * RS + warp * 8);
+                const float4 a1 = *reinterpret_cast<const float4 *>(act + (size_t)(k0 + kk) * RS + warp * 8 + 4);
+                const float t[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int r = 0; r < R; r++) a[r] = t[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) a[r] = act[(size_t)(k0 + kk) * RS + warp * R + r];
+            }
             float w[CJ];
 #pragma unroll
             for (int j = 0; j < CJ; j++) w[j] = (!kGuard || lane + 32 * j < WP) ? wb[kk * WP + lane + 32 * j] : 0.f;
 #pragma unroll
-            for (int r = 0; r < 8; r++)
+            for (int r = 0; r < R; r++)
 #pragma unroll
                 for (int j = 0; j < CJ; j++) acc[r][j] = fmaf(a[r], w[j], acc[r][j]);
         }
@@ -132,8 +142,8 @@ __device__ __forceinline__ void gemm_stream(float (&acc)[8][CJ], const float *__
 }
 
 // bias + LayerNorm (eps 1e-5, biased variance: torch.nn.LayerNorm) + ReLU on a warp-distributed row block
-template <int CJ, bool kGuard>
-__device__ __forceinline__ void bias_ln_relu(float (&acc)[8][CJ], const float *__restrict__ bias, const float *__restrict__ g,
+template <int CJ, bool kGuard, int R>
+__device__ __forceinline__ void bias_ln_relu(float (&acc)[R][CJ], const float *__restrict__ bias, const float *__restrict__ g,
                                              const float *__restrict__ be, int H, int HP, int lane) {
     float bj[CJ], gj[CJ], bej[CJ];
 #pragma unroll
@@ -144,7 +154,7 @@ __device__ __forceinline__ void bias_ln_relu(float (&acc)[8][CJ], const float *_
     }
     const float invH = 1.0f / (float)H;
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < R; r++) {
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < CJ; j++) { acc[r][j] += bj[j]; s += acc[r][j]; }      // padded columns are exactly 0
@@ -158,9 +168,10 @@ __device__ __forceinline__ void bias_ln_relu(float (&acc)[8][CJ], const float *_
     }
 }
 
-template <int CJ1, int CJ2, bool kGuard>
+template <int CJ1, int CJ2, bool kGuard, int R>
 __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A, const float *__restrict__ obs, int64_t ld,
                                                                 int64_t n, float *__restrict__ out, TTRingS ring, TTActorTail tail) {
+    constexpr int TM = 8 * R;                           // rows per tile: 8 warps x R rows
     extern __shared__ __align__(16) float smem[];
     float *xs = smem;                                   // [k1p][RS]
     float *hs = xs + A.k1p * RS;                        // [h1p][RS]
@@ -182,39 +193,39 @@ __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A,
         __syncthreads();
         // ---- layer 1: fc1 -> LN -> ReLU (networks.py:139-141) ----
         {
-            float acc[8][CJ1];
+            float acc[R][CJ1];
 #pragma unroll
-            for (int r = 0; r < 8; r++)
+            for (int r = 0; r < R; r++)
 #pragma unroll
                 for (int j = 0; j < CJ1; j++) acc[r][j] = 0.f;
-            gemm_stream<CJ1, kGuard>(acc, xs, A.w1t, A.k1p, A.h1p, wbuf, warp, lane);
-            bias_ln_relu<CJ1, kGuard>(acc, A.b1, A.g1, A.be1, A.h1, A.h1p, lane);
+            gemm_stream<CJ1, kGuard, R>(acc, xs, A.w1t, A.k1p, A.h1p, wbuf, warp, lane);
+            bias_ln_relu<CJ1, kGuard, R>(acc, A.b1, A.g1, A.be1, A.h1, A.h1p, lane);
 #pragma unroll
             for (int j = 0; j < CJ1; j++) {
                 const int c = lane + 32 * j;
                 if (c < A.h1p) {
-                    *reinterpret_cast<float4 *>(hs + (size_t)c * RS + warp * 8) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
-                    *reinterpret_cast<float4 *>(hs + (size_t)c * RS + warp * 8 + 4) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
+#pragma unroll
+                    for (int r = 0; r < R; r++) hs[(size_t)c * RS + warp * R + r] = acc[r][j];
                 }
             }
         }
         __syncthreads();
         // ---- layer 2: fc2 -> LN -> ReLU -> mu -> tanh (networks.py:142-145) ----
         {
-            float acc[8][CJ2];
+            float acc[R][CJ2];
 #pragma unroll
-            for (int r = 0; r < 8; r++)
+            for (int r = 0; r < R; r++)
 #pragma unroll
                 for (int j = 0; j < CJ2; j++) acc[r][j] = 0.f;
-            gemm_stream<CJ2, kGuard>(acc, hs, A.w2t, A.h1, A.h2p, wbuf, warp, lane);
-            bias_ln_relu<CJ2, kGuard>(acc, A.b2, A.g2, A.be2, A.h2, A.h2p, lane);
+            gemm_stream<CJ2, kGuard, R>(acc, hs, A.w2t, A.h1, A.h2p, wbuf, warp, lane);
+            bias_ln_relu<CJ2, kGuard, R>(acc, A.b2, A.g2, A.be2, A.h2, A.h2p, lane);
             float w3[CJ2];
 #pragma unroll
             for (int j = 0; j < CJ2; j++) w3[j] = (!kGuard || lane + 32 * j < A.h2p) ? A.w3[lane + 32 * j] : 0.f;
             const float b3 = A.b3[0];
             float srow = 0.f;                                   // lane r keeps the output dot of row 8 warp + r
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
+            for (int r = 0; r < R; r++) {
                 float s = 0.f;
 #pragma unroll
                 for (int j = 0; j < CJ2; j++) s = fmaf(acc[r][j], w3[j], s);
@@ -223,8 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A,
             }
             // output stage, one lane per row: tanh, then what Agent.choose_action and the training loop do with it
             // (DDPG_agent.py:41-43 mu + OU noise, trainv2.py:516 clip * pi / 4, agent.remember of the raw action)
-            const int row = warp * 8 + lane;
-            if (lane < 8 && row < rows) {
+            const int row = warp * R + lane;
+            if (lane < R && row < rows) {
                 const int64_t gr = row0 + row;
                 float a = tanhf(srow + b3);
                 if (tail.ou_x) {
@@ -251,6 +262,18 @@ size_t actor_fp32_smem(const tt_actor_dev &A) {
 
 namespace tt {
 
+template <int CJ1, int CJ2, bool kGuard, int R>
+static int launch_fp32(const tt_actor_dev &A, const float *d_obs, int64_t ld, int64_t n, float *d_mu, const TTRingS &rs, const TTActorTail &tl,
+                       size_t smem, cudaStream_t s) {
+    auto kern = actor_fp32_kernel<CJ1, CJ2, kGuard, R>;
+    TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (n + 8 * R - 1) / (8 * R);
+    const int grid = (int)(ntiles < tt::grid_sms() ? ntiles : tt::grid_sms());
+    kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs, tl);
+    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    return TT_OK;
+}
+
 int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_t n, float *d_mu, const TTRingS *ring, const TTActorTail *tail,
                        cudaStream_t s) {
     TTRingS rs;
@@ -258,23 +281,16 @@ int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_
     const TTActorTail tl = tail ? *tail : tt_no_tail();
     const tt_actor_dev &A = a->dev;
     const size_t smem = actor_fp32_smem(A);
-    const int64_t ntiles = (n + TM - 1) / TM;
-    const int grid = (int)(ntiles < tt::grid_sms() ? ntiles : tt::grid_sms());
     const int cj1 = A.h1p / 32, cj2 = A.h2p / 32;
-    if (cj1 == 13 && cj2 == 10) {
-        auto kern = actor_fp32_kernel<13, 10, false>;
-        TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs, tl);
-    } else if (cj1 <= 16 && cj2 <= 16) {
-        auto kern = actor_fp32_kernel<16, 16, true>;
-        TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs, tl);
-    } else {
-        set_error("actor: hidden sizes above 512 are not supported (h1=%d h2=%d)", A.h1, A.h2);
-        return TT_ERR_INVALID;
+    if (cj1 == 13 && cj2 == 10) {                        // the reference's 400 / 300: rows per warp by batch size
+        if (n <= 8) return launch_fp32<13, 10, false, 1>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
+        if (n <= 16) return launch_fp32<13, 10, false, 2>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
+        if (n <= 32) return launch_fp32<13, 10, false, 4>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
+        return launch_fp32<13, 10, false, 8>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
     }
-    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    return TT_OK;
+    if (cj1 <= 16 && cj2 <= 16) return launch_fp32<16, 16, true, 8>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
+    set_error("actor: hidden sizes above 512 are not supported (h1=%d h2=%d)", A.h1, A.h2);
+    return TT_ERR_INVALID;
 }
 
 int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_reset_mask, int64_t n, uint64_t seed,
