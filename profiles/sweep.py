@@ -43,7 +43,7 @@ for lg in range(12, hi + 1, 2):
                 _lib.check(L.tt_env_step(env._h, eng.scaled.data_ptr(), env._obs[0].data_ptr(), 23, env._reward.data_ptr(), env._done.data_ptr(), None, s))
                 a1.record(); torch.cuda.synchronize()
                 tot += a0.elapsed_time(a1)
-                _lib.check(L.tt_env_reset(env._h, env._done.data_ptr(), env._obs[0].data_ptr(), 23, s)); env.tick()
+                _lib.check(L.tt_env_reset(env._h, env._done.data_ptr(), env._obs[0].data_ptr(), 23, s)); env.tick()   # (C-level masked reset does not tick)
             env_us = tot / iters * 1e3
         del eng, ag, env
         torch.cuda.empty_cache()
