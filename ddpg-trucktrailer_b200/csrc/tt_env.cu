@@ -197,6 +197,9 @@ __device__ __forceinline__ void reset_env(const EnvPtrs &p, const StepConsts &k,
 // third of the warps would otherwise run a few hundred extra dependent instructions -- Philox pose, float64 sin / cos,
 // observation -- on one or two lanes: +22 % kernel time, measured); after the tile loop the CTA resets its listed envs one per
 // thread on full warps and overwrites their rows of `obs` with the reset observation (the bulk stores have completed).
+// Measured alternatives (N = 2^22, 3.4 % finished envs per step, profiles/env_roll_bench.py; the step + ring store alone: 267 us):
+// reset inside the tile loop 322 us, per-warp 32-env tiles + reset inside the loop 316, per-warp tiles + deferred reset 308,
+// per-warp tiles + per-warp batches of 12 inside the loop 322, this version (128-env tiles + deferred reset) 294 us.
 template <bool kInfo, bool kGoal, int kMinBlocks, int kStages, bool kRoll>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p, StepConsts k, const float *__restrict__ actions,
                                                                       int K, int auto_reset, float *__restrict__ obs, int64_t ld,
@@ -317,54 +320,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                     } else e.packed |= PK_FINISHED;
                 }
             }
-            if (kRoll) {
-                // Per WARP (32 envs = 2 944 B of observation rows, double buffered): no block-wide barrier in the tile loop.  The tile
-                // goes out as one bulk store to `obs` and one to the ring's new_state rows; they drain while the warp computes
-                // its next tile.
-                const int wib = threadIdx.x >> 5, ln = threadIdx.x & 31;
-                float *tile = tiles[tbuf] + wib * 32 * TT_OBS_DIM;
-                const int64_t wrow0 = row0 + 32 * wib;
-                const int wrows = rows - 32 * wib < 0 ? 0 : (rows - 32 * wib > 32 ? 32 : rows - 32 * wib);
-                if (active) {
-#pragma unroll
-                    for (int c = 0; c < TT_OBS_DIM; c++) tile[ln * TT_OBS_DIM + c] = o.obs[c];
-                    if (o.done) {                                            // reset at the end of the kernel
-                        const int slot = atomicAdd(&s_ndone, 1);
-                        if (slot < kDoneSmem) s_done[slot] = (uint32_t)i; else p.done_list[seg0 + slot] = (uint32_t)i;
-                    }
-                }
-                const int64_t rrow0 = (rpl.S2 && wrows > 0) ? rpl.m.row(wrow0) : 0;
-                const bool ring_bulk = rpl.S2 && wrows == 32 && !rpl.m.many && wrow0 >= rpl.m.first && rrow0 + 32 <= rpl.m.cap &&
-                                       (rrow0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(rpl.S2) & 15) == 0);
-                const bool obs_bulk = bulk_ok && wrows == 32;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (ln == 0) {
-                    const uint32_t bytes = (uint32_t)(32 * TT_OBS_DIM * sizeof(float)), src = (uint32_t)__cvta_generic_to_shared(tile);
-                    if (obs_bulk)
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(obs + wrow0 * TT_OBS_DIM), "r"(src), "r"(bytes) : "memory");
-                    if (ring_bulk)
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(rpl.S2 + rrow0 * TT_OBS_DIM), "r"(src), "r"(bytes) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");       // the OTHER buffer is free again
-                }
-                if (!obs_bulk) {
-                    for (int v = ln; v < wrows * TT_OBS_DIM; v += 32) {
-                        const int r = v / TT_OBS_DIM, c = v - r * TT_OBS_DIM;
-                        obs[(wrow0 + r) * ld + c] = tile[v];
-                    }
-                }
-                if (rpl.S2 && !ring_bulk) {
-                    for (int v = ln; v < wrows * TT_OBS_DIM; v += 32) {
-                        const int r = v / TT_OBS_DIM, c = v - r * TT_OBS_DIM;
-                        if (wrow0 + r >= rpl.m.first) rpl.S2[rpl.m.row(wrow0 + r) * TT_OBS_DIM + c] = tile[v];
-                    }
-                }
-                __syncwarp();                     // (the element-wise paths have read the tile; lane 0 has waited for the other buffer)
-                tbuf ^= 1u;
-            } else if (obs) {
+            if (kRoll && active && o.done) {                             // reset at the end of the kernel
+                const int slot = atomicAdd(&s_ndone, 1);
+                if (slot < kDoneSmem) s_done[slot] = (uint32_t)i; else p.done_list[seg0 + slot] = (uint32_t)i;
+            }
+            if (obs) {
                 float *tile = tiles[tbuf];
                 __syncthreads();                 // thread 0 has waited for the bulk store that last read this buffer
                 if (active) {
