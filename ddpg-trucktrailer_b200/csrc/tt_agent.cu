@@ -78,7 +78,11 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(const float *__restrict
 // transposed ([k][row], row stride 68 floats) so that the 8 row operands of one k are two broadcast LDS.128;
 // the k-major (pre-transposed) weights stream through a cp.async double buffer in chunks of 16 k.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int RS = 68, KC = 16;
+// per rows-per-warp variant R: row stride of the transposed activations (8 R rows + 4 pad, 16 B aligned) and k-rows per streamed
+// weight chunk.  A small batch runs on ONE SM and is bound by the round trips of the chunk pipeline (the weights are 526 KB), so the
+// variants with small activation buffers spend their shared memory on 3x larger chunks.
+__host__ __device__ constexpr int rs_of(int R) { return 8 * R + 4; }
+__host__ __device__ constexpr int kc_of(int R) { return R <= 2 ? 48 : (R == 4 ? 32 : 16); }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -100,6 +104,7 @@ template <int CJ, bool kGuard, int R>
 __device__ __forceinline__ void gemm_stream(float (&acc)[R][CJ], const float *__restrict__ act /*smem [K][RS]*/,
                                             const float *__restrict__ wT /*global [K][WP]*/, int K, int WP,
                                             float *wbuf /*smem 2*KC*WP*/, int warp, int lane) {
+    constexpr int RS = rs_of(R), KC = kc_of(R);
     const int tid = threadIdx.x;
     const int nchunks = (K + KC - 1) / KC;
     auto issue = [&](int ch, int buf) {
@@ -171,7 +176,7 @@ __device__ __forceinline__ void bias_ln_relu(float (&acc)[R][CJ], const float *_
 template <int CJ1, int CJ2, bool kGuard, int R>
 __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A, const float *__restrict__ obs, int64_t ld,
                                                                 int64_t n, float *__restrict__ out, TTRingS ring, TTActorTail tail) {
-    constexpr int TM = 8 * R;                           // rows per tile: 8 warps x R rows
+    constexpr int TM = 8 * R, RS = rs_of(R);            // rows per tile: 8 warps x R rows
     extern __shared__ __align__(16) float smem[];
     float *xs = smem;                                   // [k1p][RS]
     float *hs = xs + A.k1p * RS;                        // [h1p][RS]
@@ -252,10 +257,10 @@ __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A,
     }
 }
 
-size_t actor_fp32_smem(const tt_actor_dev &A) {
+size_t actor_fp32_smem(const tt_actor_dev &A, int R) {
     const int wmax = A.h1p > A.h2p ? A.h1p : A.h2p;
-    size_t wb = (size_t)2 * KC * wmax;
-    return sizeof(float) * ((size_t)A.k1p * RS + (size_t)A.h1p * RS + wb);
+    size_t wb = (size_t)2 * kc_of(R) * wmax;
+    return sizeof(float) * ((size_t)A.k1p * rs_of(R) + (size_t)A.h1p * rs_of(R) + wb);
 }
 
 }  // namespace
@@ -264,8 +269,9 @@ namespace tt {
 
 template <int CJ1, int CJ2, bool kGuard, int R>
 static int launch_fp32(const tt_actor_dev &A, const float *d_obs, int64_t ld, int64_t n, float *d_mu, const TTRingS &rs, const TTActorTail &tl,
-                       size_t smem, cudaStream_t s) {
+                       cudaStream_t s) {
     auto kern = actor_fp32_kernel<CJ1, CJ2, kGuard, R>;
+    const size_t smem = actor_fp32_smem(A, R);
     TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (n + 8 * R - 1) / (8 * R);
     const int grid = (int)(ntiles < tt::grid_sms() ? ntiles : tt::grid_sms());
@@ -280,15 +286,14 @@ int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_
     if (ring) rs = *ring; else { rs.S = nullptr; rs.m = tt_make_ring_map(1, 0, 0); }
     const TTActorTail tl = tail ? *tail : tt_no_tail();
     const tt_actor_dev &A = a->dev;
-    const size_t smem = actor_fp32_smem(A);
     const int cj1 = A.h1p / 32, cj2 = A.h2p / 32;
     if (cj1 == 13 && cj2 == 10) {                        // the reference's 400 / 300: rows per warp by batch size
-        if (n <= 8) return launch_fp32<13, 10, false, 1>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
-        if (n <= 16) return launch_fp32<13, 10, false, 2>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
-        if (n <= 32) return launch_fp32<13, 10, false, 4>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
-        return launch_fp32<13, 10, false, 8>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
+        if (n <= 8) return launch_fp32<13, 10, false, 1>(A, d_obs, ld, n, d_mu, rs, tl, s);
+        if (n <= 16) return launch_fp32<13, 10, false, 2>(A, d_obs, ld, n, d_mu, rs, tl, s);
+        if (n <= 32) return launch_fp32<13, 10, false, 4>(A, d_obs, ld, n, d_mu, rs, tl, s);
+        return launch_fp32<13, 10, false, 8>(A, d_obs, ld, n, d_mu, rs, tl, s);
     }
-    if (cj1 <= 16 && cj2 <= 16) return launch_fp32<16, 16, true, 8>(A, d_obs, ld, n, d_mu, rs, tl, smem, s);
+    if (cj1 <= 16 && cj2 <= 16) return launch_fp32<16, 16, true, 8>(A, d_obs, ld, n, d_mu, rs, tl, s);
     set_error("actor: hidden sizes above 512 are not supported (h1=%d h2=%d)", A.h1, A.h2);
     return TT_ERR_INVALID;
 }
