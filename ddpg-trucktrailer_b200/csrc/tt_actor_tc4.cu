@@ -97,6 +97,7 @@ __device__ __forceinline__ void pack_l1c_gram(int bid, double *__restrict__ acc,
 static_assert(H1 % kGramBlocks == 0, "gram slices");
 
 __global__ void __launch_bounds__(576) pack_l1c_chol_kernel(double *__restrict__ acc, double *__restrict__ out /* m[24], L[24][24] */) {
+    chain_enter();
     __shared__ double G[24][25], Lf[24][25];
     __shared__ double gmax;
     const int t = threadIdx.x, i = t / 24, j = t - i * 24;
@@ -214,6 +215,7 @@ __device__ __forceinline__ void pack_fp32(int bid, int nblk, const tt_actor_dev 
 struct PackSrc { const float *fc1_w, *fc1_b, *g1, *be1, *fc2_w, *fc2_b, *g2, *be2, *mu_w, *mu_b; };
 constexpr int kPackFp32Blocks = 16;
 __global__ void __launch_bounds__(1024) pack_stage_a_kernel(tt_actor_dev A, PackSrc w, int tc) {
+    chain_enter();
     int bid = blockIdx.x;
     if (tc) {
         if (bid < kGramBlocks) { pack_l1c_gram(bid, A.l1c_scratch, w.fc1_w, w.fc1_b); return; }
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(1024) pack_stage_a_kernel(tt_actor_dev A, Pack
 }
 constexpr int kImgBlocks = 54, kW2sBlocks = 128;
 __global__ void __launch_bounds__(256) pack_stage_c_kernel(tt_actor_dev A, PackSrc w) {
+    chain_enter();
     int bid = blockIdx.x;
     if (bid < kImgBlocks) {
         pack_l1c_image(bid, kImgBlocks, reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + 600, w.fc1_w, w.fc1_b, w.g1);
@@ -307,6 +310,8 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + P::tmem_slot), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    chain_wait();                                    // (tt_common.cuh: chained launches) the setup above touched no global memory
+    chain_trigger();
     for (int c = threadIdx.x; c < K2P; c += kThreads) pbe1[c] = c < H1 ? A.be1[c] : 0.f;
     for (int c = threadIdx.x; c < H2P; c += kThreads) {
         // LayerNorm 2 + ReLU + mu:  w3 relu(g z + be), z = (h - mean) rstd.  relu(y) = (y + |y|) / 2; the y / 2 half is linear in
@@ -868,6 +873,7 @@ int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, cons
     const int64_t ntiles = (n + kTileM - 1) / kTileM;
     const int sms = tt::grid_sms();
     int grid = (int)(ntiles < sms ? ntiles : sms);
+    const bool chained = tt::chain_rollout(n);
 #if !defined(TT_DEV_VARIANTS)
     dbg = nullptr;
 #endif
@@ -876,9 +882,10 @@ int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, cons
         if (grid > (sms & ~1)) grid = sms & ~1;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(640); cfg.dynamicSmemBytes = P::total; cfg.stream = st;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = chained ? 2 : 1;
 #if defined(TT_DEV_VARIANTS)
         if (dbg) TT_CUDA(cudaLaunchKernelEx(&cfg, actor_tc4_kernel<OpT, kSplit, true, 2>, w1img, w2img, A, d_obs, ld, n, d_mu, rs, tl, dbg));
         else
@@ -889,7 +896,8 @@ int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, cons
         if (dbg) actor_tc4_kernel<OpT, kSplit, true, 1><<<grid, 640, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, rs, tl, dbg);
         else
 #endif
-        actor_tc4_kernel<OpT, kSplit, false, 1><<<grid, 640, P::total, st>>>(w1img, w2img, A, d_obs, ld, n, d_mu, rs, tl, dbg);
+        TT_CUDA(tt::launch_chained(chained, actor_tc4_kernel<OpT, kSplit, false, 1>, dim3((unsigned)grid), dim3(640), P::total, st, w1img, w2img, A, d_obs, ld, n,
+                                   d_mu, rs, tl, dbg));
     }
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
@@ -909,12 +917,12 @@ int actor_pack_all(tt_actor *a, const float *fc1_w, const float *fc1_b, const fl
     const PackSrc w = {fc1_w, fc1_b, g1, be1, fc2_w, fc2_b, g2, be2, mu_w, mu_b};
     const int tc = actor_tc_supported(A) ? 1 : 0;       // the tensor-core path is specialised to 23-400-300; forward() refuses otherwise
     if (tc && !a->scratch_clean) { TT_CUDA(cudaMemsetAsync(A.l1c_scratch, 0, sizeof(double) * 600, s)); a->scratch_clean = true; }
-    pack_stage_a_kernel<<<(tc ? kGramBlocks + KB2 : 0) + kPackFp32Blocks, 1024, 0, s>>>(A, w, tc);
+    TT_CUDA(tt::launch_chained(true, pack_stage_a_kernel, dim3((tc ? kGramBlocks + KB2 : 0) + kPackFp32Blocks), dim3(1024), 0, s, A, w, tc));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     if (!tc) return TT_OK;
-    pack_l1c_chol_kernel<<<1, 576, 0, s>>>(A.l1c_scratch, A.l1c_scratch + 600);
+    TT_CUDA(tt::launch_chained(true, pack_l1c_chol_kernel, dim3(1), dim3(576), 0, s, A.l1c_scratch, A.l1c_scratch + 600));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    pack_stage_c_kernel<<<kImgBlocks + 2 * kW2sBlocks, 256, 0, s>>>(A, w);
+    TT_CUDA(tt::launch_chained(true, pack_stage_c_kernel, dim3(kImgBlocks + 2 * kW2sBlocks), dim3(256), 0, s, A, w));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }

@@ -177,6 +177,7 @@ template <int CJ1, int CJ2, bool kGuard, int R>
 __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A, const float *__restrict__ obs, int64_t ld,
                                                                 int64_t n, float *__restrict__ out, TTRingS ring, TTActorTail tail) {
     constexpr int TM = 8 * R, RS = rs_of(R);            // rows per tile: 8 warps x R rows
+    chain_enter();
     extern __shared__ __align__(16) float smem[];
     float *xs = smem;                                   // [k1p][RS]
     float *hs = xs + A.k1p * RS;                        // [h1p][RS]
@@ -275,7 +276,7 @@ static int launch_fp32(const tt_actor_dev &A, const float *d_obs, int64_t ld, in
     TT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (n + 8 * R - 1) / (8 * R);
     const int grid = (int)(ntiles < tt::grid_sms() ? ntiles : tt::grid_sms());
-    kern<<<grid, kThreads, smem, s>>>(A, d_obs, ld, n, d_mu, rs, tl);
+    TT_CUDA(tt::launch_chained(tt::chain_rollout(n), kern, dim3((unsigned)grid), dim3(kThreads), smem, s, A, d_obs, ld, n, d_mu, rs, tl));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }

@@ -62,4 +62,35 @@ int grid_sms();              // SMs the persistent rollout kernels may occupy: s
 extern unsigned long long g_launches;
 #define TT_COUNT_LAUNCH() (++::tt::g_launches)
 
+// ---- programmatic dependent launch (chains of short kernels: the learner's 15 stages, a rollout iteration at small N) ----
+// A kernel launched through launch_chained() may be SCHEDULED while its predecessor in the stream still runs; its first
+// statement must be chain_enter(): griddepcontrol.wait blocks until the predecessor grid has completed and its writes are
+// visible (so the stream order of all memory accesses is unchanged), launch_dependents then lets the successor be scheduled
+// behind this grid.  Every CTA waits unconditionally and before any global access -- a grid that finished without waiting
+// would release its successor ahead of its own predecessor.  What is hidden is the launch latency between dependent kernels
+// of an EAGER stream: the learner step 153 -> 126 us, a 4 096-env rollout iteration 22.6 -> 20.6 us, i.e. what a CUDA graph
+// of the same launches takes (a graph gains nothing more: 127 -> 127, 20.5 -> 20.1 us).  Triggering BEFORE the wait -- the
+// whole chain resident at once -- was slower (learner graph 127 -> 144 us).  `chained = false` (and TT_NO_PDL=1 in the
+// environment) launches normally.
+bool chained_launches_enabled();
+// The two kernels of a rollout iteration are chained only where the launch gap is a visible share of the iteration; a large
+// batch gains nothing (0.3 %), and early-scheduled CTAs of the next kernel would sit on the SMs tt_reserve_sms() keeps free.
+inline bool chain_rollout(int64_t n_envs) { return n_envs <= 262144 && chained_launches_enabled(); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(bool chained, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = chained && chained_launches_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace tt
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void chain_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void chain_enter() { chain_wait(); chain_trigger(); }
+#endif

@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
     __shared__ int s_ndone;                               // kRoll: finished envs of this CTA so far ...
     __shared__ uint32_t s_done[kRoll ? kDoneSmem : 1];    // ... the first kDoneSmem of them (typically all: ~1.4 % of ~7 000 envs)
     uint32_t tbuf = 0;
+    chain_enter();                                        // (tt_common.cuh: chained launches) before the first global access
     if (kRoll) { if (threadIdx.x == 0) s_ndone = 0; __syncthreads(); }
     const bool bulk_ok = obs != nullptr && ld == TT_OBS_DIM && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
     const int64_t N = p.N;
@@ -663,9 +664,9 @@ static int env_step_impl(tt_env *env, const float *d_actions, int32_t K, int32_t
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, dsm) != cudaSuccess || per_sm <= 0) per_sm = 4; \
         }                                                                                                                       \
         const int64_t cap = (int64_t)tt::grid_sms() * per_sm;                                                                   \
-        kern<<<(unsigned)(ntiles < cap ? ntiles : cap), kBlock, dsm, s>>>(env->p, env->k, d_actions, K, auto_reset, d_obs,       \
-                                                                         ld_obs, d_reward, d_done, inf, env->seed, env->gid0,  \
-                                                                         ro, d_ou_x);                                          \
+        TT_CUDA(tt::launch_chained(tt::chain_rollout(env->p.N), kern, dim3((unsigned)(ntiles < cap ? ntiles : cap)), dim3(kBlock), dsm, s, \
+                                   env->p, env->k, d_actions, (int)K, (int)auto_reset, d_obs, ld_obs, d_reward, d_done, inf, env->seed,     \
+                                   env->gid0, ro, d_ou_x));                                                                               \
     } while (0)
     const bool goal = env->goal_injected || env->l2_injected;
     if (roll) {

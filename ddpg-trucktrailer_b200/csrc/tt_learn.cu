@@ -219,6 +219,7 @@ __device__ void job_xgrad(const Job &J, int cta, float *smem) {
 }
 
 __global__ void __launch_bounds__(kT) learn_gemm_kernel(JobList L) {
+    chain_enter();
     __shared__ __align__(16) float smem[2 * 64 * kP + 2 * 32 * kP];            // 27 648 B: the dX layout is the largest
     int cta = blockIdx.x;
     for (int i = 0; i < L.n; i++) {
@@ -240,6 +241,7 @@ struct Batch {
 };
 __global__ void learn_gather_kernel(tt_replay_ring ring, int64_t win_begin, int64_t max_mem, const int64_t *__restrict__ given_rows, Batch bt, int B,
                                     int in, uint64_t seed, int *__restrict__ step) {
+    chain_enter();
     __shared__ int64_t rows[kMaxB];
     const int tid = threadIdx.x;
     const int t = *step;                               // updates done so far = the sampling counter of this one
@@ -361,6 +363,7 @@ struct Fc1Job { const float *x, *w1, *b1, *g1, *be1; float *h1, *a1; };
 struct Fc1Args { Fc1Job j[NJOBS]; int njobs, B, IN, H1; };
 constexpr int kW1P = 25;                                   // shared-memory pitch of a W1 row (IN <= 24 + 1; odd: conflict-free for lane = column)
 __global__ void __launch_bounds__(256) learn_fc1_kernel(Fc1Args A) {
+    chain_enter();
     extern __shared__ float ws[];                          // W1 [H1][kW1P]: the whole matrix in ONE round of independent loads
     __shared__ float xs[8 * 32];                           // the CTA's 8 input rows
     const int per = (A.B + 7) / 8;
@@ -413,6 +416,7 @@ __device__ __forceinline__ void stage_vectors(float (*dst)[kMaxH], const float *
 
 // K3: DDPG_agent.py:84-97
 __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
+    chain_enter();
     __shared__ float s_dq[kMaxB], s_act[kMaxB];
     __shared__ float sp[13][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
@@ -493,6 +497,7 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
 
 // K9: DDPG_agent.py:99-103  actor_loss = -mean(critic(states, actor(states)))
 __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
+    chain_enter();
     __shared__ float s_dp[kMaxB];
     __shared__ float sp[8][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
@@ -569,6 +574,7 @@ struct L1Args {
     int *ticket;
 };
 __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
+    chain_enter();
     __shared__ float sp[2][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H1;
     {
@@ -614,6 +620,7 @@ struct AdamArgs {
     const int *step;                  // device counter of updates, already advanced by the gather kernel of this update
 };
 __global__ void __launch_bounds__(256) learn_adam_kernel(AdamArgs A) {
+    chain_enter();
     __shared__ float s_step_size, s_bc2_sqrt;
     const int t = *A.step;
     if (threadIdx.x == 0) {
@@ -690,7 +697,7 @@ Job fwd_job(int B, int N, int K, const float *X, const float *W, const float *bi
 // a row-wise stage: ceil(B / 8) CTAs (one warp per batch row), the last one to finish sums the columns
 template <typename Kern, typename Args>
 int launch_rows(Kern kern, const Args &args, int B, cudaStream_t s) {
-    kern<<<(B + kRowT / 32 - 1) / (kRowT / 32), kRowT, 0, s>>>(args);
+    TT_CUDA(tt::launch_chained(true, kern, dim3((B + kRowT / 32 - 1) / (kRowT / 32)), dim3(kRowT), 0, s, args));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
@@ -698,7 +705,7 @@ int launch_rows(Kern kern, const Args &args, int B, cudaStream_t s) {
 int launch_jobs(const JobList &L, cudaStream_t s) {
     int ctas = 0;
     for (int i = 0; i < L.n; i++) ctas += L.j[i].ctas;
-    learn_gemm_kernel<<<ctas, kT, 0, s>>>(L);
+    TT_CUDA(tt::launch_chained(true, learn_gemm_kernel, dim3(ctas), dim3(kT), 0, s, L));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
@@ -777,7 +784,7 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     const int T = L.tail();
 
     // K0
-    learn_gather_kernel<<<1, 1024, 0, s>>>(*ring, win_begin, max_mem, d_rows, ln->bt, B, IN, ln->seed, ln->step);
+    TT_CUDA(tt::launch_chained(true, learn_gather_kernel, dim3(1), dim3(1024), 0, s, *ring, win_begin, max_mem, d_rows, ln->bt, B, IN, ln->seed, ln->step));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     int rc;
     // K1: fc1 + LayerNorm 1 + ReLU of the four forward passes
@@ -796,7 +803,7 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
             TT_CUDA(cudaFuncSetAttribute(learn_fc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kMaxH * kW1P)));
             attr_of[tt::device_index()] = true;
         }
-        learn_fc1_kernel<<<njobs * ((B + 7) / 8), 256, dsm, s>>>(A);
+        TT_CUDA(tt::launch_chained(true, learn_fc1_kernel, dim3(njobs * ((B + 7) / 8)), dim3(256), dsm, s, A));
         TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
         return TT_OK;
     };
@@ -857,7 +864,7 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
         int blocks = (n + 255) / 256;
         const int cap = tt::sm_count() * 2;
         if (blocks > cap) blocks = cap;
-        learn_adam_kernel<<<blocks, 256, 0, s>>>(A);
+        TT_CUDA(tt::launch_chained(true, learn_adam_kernel, dim3(blocks), dim3(256), 0, s, A));
         TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
         return TT_OK;
     };

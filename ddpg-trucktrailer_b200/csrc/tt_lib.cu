@@ -1,5 +1,6 @@
 // tt_lib.cu -- library-wide plumbing of libtt_b200.so: thread-local error text, device probing.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "tt_common.cuh"
 
 namespace tt {
@@ -17,6 +18,11 @@ void set_error(const char *fmt, ...) {
 int cuda_fail(cudaError_t e, const char *what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return TT_ERR_CUDA;
+}
+
+bool chained_launches_enabled() {
+    static const bool on = [] { const char *e = getenv("TT_NO_PDL"); return !(e && e[0] && e[0] != '0'); }();
+    return on;
 }
 
 // Launch facts are cached PER DEVICE: a process may drive several GPUs (every Python class takes a device argument), and
