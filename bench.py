@@ -357,7 +357,7 @@ def run_b200(args):
     #      device) and D2H of the step's results the reference driver reads (reward and done of every env + stats).
     # The policy of step t + 1 is uploaded and re-packed on a side stream WHILE step t runs (two packed actors, used
     # alternately): what an asynchronous learner hands over; results are read back one iteration behind on a copy stream
-    # (double-buffered staging).  Every byte still moves, every step, inside the timed region.
+    # (two pairs of result buffers, written by the kernels alternately).  Every byte still moves, every step, inside the timed region.
     packed = [torch.cuda.Event() for _ in range(2)]
     step_done = torch.cuda.Event()
     staged = [torch.cuda.Event() for _ in range(2)]
@@ -381,9 +381,9 @@ def run_b200(args):
         agent.actor = actors[b]
         step_done.record(main)                                       # (everything before this step, incl. the last user of slot b ^ 1)
         upload(b ^ 1)                                                # H2D + re-pack of the NEXT step's policy, overlapped with this step
-        _, r, d = eng.step()
-        main.wait_event(drained[b])                                  # staging buffer b was read out two steps ago
-        rew_stage[b].copy_(r); done_stage[b].copy_(d); stats_stage[b].copy_(env.stats_tensor(clear=True))
+        main.wait_event(drained[b])                                  # result buffers b were read out two steps ago
+        eng.step(out=(rew_stage[b], done_stage[b]))                  # the kernels write this step's reward / done straight into pair b
+        stats_stage[b].copy_(env.stats_tensor(clear=True))
         staged[b].record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(staged[b])

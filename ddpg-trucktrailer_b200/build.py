@@ -17,6 +17,7 @@ LIB = os.path.join(HERE, "libtt_b200.so")
 SOURCES = ["tt_lib.cu", "tt_env.cu", "tt_agent.cu", "tt_actor_tc4.cu", "tt_replay.cu", "tt_rollout.cu", "tt_learn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=default", "--expt-relaxed-constexpr"]
+NVCC_FLAGS += os.environ.get("TT_NVCC_EXTRA", "").split()      # developer builds, e.g. TT_NVCC_EXTRA=-DTT_LEARN_PROFILE
 
 
 def nvcc() -> str:

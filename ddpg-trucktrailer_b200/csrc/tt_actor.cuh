@@ -27,13 +27,12 @@ struct tt_actor_dev {
     float *w1t, *w2t, *b1, *g1, *be1, *b2, *g2, *be2, *w3, *b3;
     void *w2s_f16, *w2s_bf16;                       // v4 layer-2 images: k-blocks grouped by output-column sweep
     void *w1c_f16, *w1c_bf16;                       // v4 layer-1 images: centred, LayerNorm-scaled rows + statistic rows (tt_actor_tc4.cu)
-    double *l1c_scratch;                            // [2048]: v4 pack: Gram accumulators (600) + column means / Cholesky factor (600) of layer 1, column means / linear column of layer 2 (2 x 416)
+    double *l1c_scratch;                            // [12288]: v4 pack: [1200, 2032) column means / linear column of layer 2 (2 x 416), [2048, 11648) Gram partial sums of layer 1 (16 blocks x 600)
 };
 
 struct tt_actor {
     tt_actor_dev dev;
     bool loaded;
-    bool scratch_clean;      // the Gram accumulators of the v4 pack have been zeroed once (the pack re-zeroes them itself)
 };
 
 static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d, char *base) {
@@ -47,7 +46,7 @@ static inline size_t tt_actor_layout(int in_dim, int h1, int h2, tt_actor_dev *d
     const size_t n1 = (h1 + 15) / 16 * 16, n2 = (h2 + 15) / 16 * 16, kb2 = (h1 + 1 + 31) / 32;
     const size_t o_w2sh = take(TT_W2_REPLICAS * kb2 * n2 * 64), o_w2sb = take(TT_W2_REPLICAS * kb2 * n2 * 64);
     const size_t o_w1ch = take(2 * (n1 + 32) * 64), o_w1cb = take(2 * (n1 + 32) * 64);
-    const size_t o_l1s = take(sizeof(double) * 2048);
+    const size_t o_l1s = take(sizeof(double) * 12288);
     if (d) {
         d->in_dim = in_dim; d->h1 = h1; d->h2 = h2; d->k1p = k1p; d->h1p = h1p; d->h2p = h2p; d->kb1 = kb1;
         auto f = [&](size_t o) { return reinterpret_cast<float *>(base + o); };

@@ -76,60 +76,106 @@ __host__ __device__ constexpr int a2_run_end(int ch) { return ((kA2Waits >> ch) 
 //                sum_j (row_j . x)^2 = x^T Gc x = sum_c (h_c - mean(h))^2;   rows 24..31: 0
 // rows 32..431 : g1[c] * (Wf[c][k] - m[k]),  Wf = [fc1.weight | fc1.bias], m = column means
 // Written as [hi | lo] f16 blocks (lo = rounding residual) and as one bf16 block.
-// Three small kernels (the policy is re-packed after every learner step, so this is on the end-to-end path):
-//   1. partial sums  S_ij = sum_c Wf[c][i] Wf[c][j],  s_i = sum_c Wf[c][i]  over a slice of c per block  -> float64 atomics
-//   2. one block: Gc = S - s s^T / 400, Cholesky, column means                                          -> scratch
-//   3. all blocks: the image rows
+// Two launches (the policy is re-packed after every learner step, so this is on the end-to-end path):
+//   A. partial sums  S_ij = sum_c Wf[c][i] Wf[c][j],  s_i = sum_c Wf[c][i]  over a slice of c per block, each block into its OWN
+//      slot of the scratch (no atomics, nothing to zero, summed in block order: deterministic)
+//   C. every image block: column means m = s / 400 -> rows 32..431;  block 0 alone: Gc = S - s s^T / 400, Cholesky (ONE warp,
+//      lane = row held in registers, no block-wide barrier in the 24 dependent pivot steps) -> rows 0..31.
+//      (A separate 576-thread Cholesky kernel between A and C cost 10 us of the 19 us re-pack: 48 block-wide barriers and a
+//      float64 sqrt + division per pivot, and a launch.)
 constexpr int kGramBlocks = 16;
+constexpr int kGramOff = 2048;                      // l1c_scratch: [1200, 2032) layer-2 column statistics, [2048, 2048 + 16 * 600) Gram partials
 __device__ __forceinline__ double wfull(const float *__restrict__ fc1_w, const float *__restrict__ fc1_b, int c, int k) {
     return (double)(k < IN ? fc1_w[c * IN + k] : fc1_b[c]);
 }
-__device__ __forceinline__ void pack_l1c_gram(int bid, double *__restrict__ acc, const float *__restrict__ fc1_w, const float *__restrict__ fc1_b) {
+__device__ __forceinline__ void pack_l1c_gram(int bid, double *__restrict__ part, const float *__restrict__ fc1_w, const float *__restrict__ fc1_b) {
     const int t = threadIdx.x, i = t / 24, j = t - i * 24;
     if (t >= 576) return;
     const int c0 = bid * (H1 / kGramBlocks), c1 = c0 + H1 / kGramBlocks;
     double si = 0.0, sij = 0.0;
 #pragma unroll 5
     for (int c = c0; c < c1; c++) { const double a = wfull(fc1_w, fc1_b, c, i), b = wfull(fc1_w, fc1_b, c, j); si += a; sij += a * b; }
-    atomicAdd(&acc[t], sij);
-    if (j == 0) atomicAdd(&acc[576 + i], si);
+    part[bid * 600 + t] = sij;
+    if (j == 0) part[bid * 600 + 576 + i] = si;
 }
 static_assert(H1 % kGramBlocks == 0, "gram slices");
 
-__global__ void __launch_bounds__(576) pack_l1c_chol_kernel(double *__restrict__ acc, double *__restrict__ out /* m[24], L[24][24] */) {
-    chain_enter();
-    __shared__ double G[24][25], Lf[24][25];
-    __shared__ double gmax;
-    const int t = threadIdx.x, i = t / 24, j = t - i * 24;
-    G[i][j] = acc[t] - acc[576 + i] * acc[576 + j] / H1;
-    Lf[i][j] = 0.0;
-    if (j == 0) out[i] = acc[576 + i] / H1;
-    __syncthreads();
-    acc[t] = 0.0;                                  // accumulators are clean for the next pack
-    if (t < 24) acc[576 + t] = 0.0;
-    if (t == 0) { double d = 0.0; for (int k = 0; k < 24; k++) d = fmax(d, G[k][k]); gmax = d; }
-    __syncthreads();
-    for (int k = 0; k < 24; k++) {                 // right-looking Cholesky, column k; tiny pivots -> zero column
-        const double d = G[k][k];
-        const bool ok = d > 1e-13 * gmax && d > 0.0;
-        const double piv = ok ? sqrt(d) : 0.0;
-        if (j == k && i >= k) Lf[i][k] = ok ? (i == k ? piv : G[i][k] / piv) : 0.0;
-        __syncthreads();
-        if (i > k && j > k) G[i][j] -= Lf[i][k] * Lf[j][k];
-        __syncthreads();
-    }
-    out[24 + t] = Lf[i][j];
+// sum over the Gram blocks of element e (< 600), in block order; the 16 loads are independent
+__device__ __forceinline__ double gram_total(const double *__restrict__ part, int e) {
+    double v[kGramBlocks];
+#pragma unroll
+    for (int b = 0; b < kGramBlocks; b++) v[b] = __ldcg(part + b * 600 + e);
+    double t = 0.0;
+#pragma unroll
+    for (int b = 0; b < kGramBlocks; b++) t += v[b];
+    return t;
 }
 
-__device__ __forceinline__ void pack_l1c_image(int bid, int nblk, char *__restrict__ img_f16, char *__restrict__ img_bf16, const double *__restrict__ ml,
-                                               const float *__restrict__ fc1_w, const float *__restrict__ fc1_b, const float *__restrict__ g1) {
-    for (int v = bid * blockDim.x + threadIdx.x; v < N1I * 32; v += nblk * blockDim.x) {
-        const int row = v >> 5, k = v & 31;
-        double x = 0.0;
-        if (k < 24) {
-            if (row >= kStatRows) x = (double)g1[row - kStatRows] * (wfull(fc1_w, fc1_b, row - kStatRows, k) - ml[k]);
-            else if (row < 24) x = ml[24 + k * 24 + row];           // row j of the statistic block = column j of L
+// block 0 of stage C (256 threads): the statistic rows 0..31 of the three layer-1 images
+__device__ void pack_l1c_stat_rows(char *__restrict__ img_f16, char *__restrict__ img_bf16, const double *__restrict__ part) {
+    __shared__ double sG[24][25], sL[24][25], sS[24];
+    const int t = threadIdx.x;
+    if (t < 24) sS[t] = gram_total(part, 576 + t);
+    double g[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) { const int e = t + 256 * q; g[q] = e < 576 ? gram_total(part, e) : 0.0; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const int e = t + 256 * q;
+        if (e < 576) { const int i = e / 24, j = e - i * 24; sG[i][j] = g[q] - sS[i] * sS[j] / H1; sL[i][j] = 0.0; }
+    }
+    __syncthreads();
+    if (t < 32) {
+        // right-looking Cholesky of the lower triangle by ONE warp: lane i owns row i (registers) and its diagonal element as a
+        // scalar; column k of L travels through shared memory (broadcast reads).  The dependent chain of a step is only
+        // shuffle(diagonal) -> rsqrt -> L[i][k] -> own diagonal update; the column broadcast runs beside the next pivot's rsqrt.
+        // Tiny pivots -> zero column.
+        const int i = t < 24 ? t : 23;
+        double row[24], gm = 0.0;
+#pragma unroll
+        for (int j = 0; j < 24; j++) { row[j] = sG[i][j]; gm = fmax(gm, sG[j][j]); }
+        double diag = sG[i][i];
+        const double tiny = 1e-13 * gm;
+#pragma unroll
+        for (int k = 0; k < 24; k++) {
+            const double d = __shfl_sync(0xffffffffu, diag, k);                   // G[k][k] as updated so far
+            const bool ok = d > tiny && d > 0.0;
+            double pinv = 0.0;
+            if (ok) {                                                              // 1 / sqrt(d): float seed + two Newton steps (1e-15)
+                const double h = 0.5 * d;
+                pinv = (double)rsqrtf((float)d);
+                pinv = pinv * fma(-h * pinv, pinv, 1.5);
+                pinv = pinv * fma(-h * pinv, pinv, 1.5);
+            }
+            const double lik = i == k ? d * pinv : row[k] * pinv;                  // L[i][k], i >= k
+            if (i > k) diag = fma(-lik, lik, diag);
+            if (t < 24 && i >= k) sL[i][k] = lik;
+            __syncwarp();
+#pragma unroll
+            for (int j = k + 1; j < 24; j++) { const double ljk = sL[j][k]; if (j < i) row[j] = fma(-lik, ljk, row[j]); }
         }
+    }
+    __syncthreads();
+    for (int v = t; v < kStatRows * 32; v += 256) {
+        const int rowi = v >> 5, k = v & 31;
+        const float xf = (rowi < 24 && k < 24) ? (float)sL[k][rowi] : 0.f;        // row j of the statistic block = column j of L
+        const __half hi = __float2half_rn(xf);
+        *reinterpret_cast<__half *>(img_f16 + sw64_off(rowi, k)) = hi;
+        *reinterpret_cast<__half *>(img_f16 + N1I * kRowB + sw64_off(rowi, k)) = __float2half_rn(xf - __half2float(hi));
+        *reinterpret_cast<__nv_bfloat16 *>(img_bf16 + sw64_off(rowi, k)) = __float2bfloat16_rn(xf);
+    }
+}
+
+// blocks 1 .. nblk - 1 of the image part of stage C: rows 32..431 = g1[c] (Wf[c][k] - m[k])
+__device__ __forceinline__ void pack_l1c_image(int bid, int nblk, char *__restrict__ img_f16, char *__restrict__ img_bf16, const double *__restrict__ part,
+                                               const float *__restrict__ fc1_w, const float *__restrict__ fc1_b, const float *__restrict__ g1) {
+    __shared__ double m[24];
+    if (threadIdx.x < 24) m[threadIdx.x] = gram_total(part, 576 + threadIdx.x) / H1;
+    __syncthreads();
+    for (int v = kStatRows * 32 + (bid - 1) * blockDim.x + threadIdx.x; v < N1I * 32; v += (nblk - 1) * blockDim.x) {
+        const int row = v >> 5, k = v & 31;
+        const double x = k < 24 ? (double)g1[row - kStatRows] * (wfull(fc1_w, fc1_b, row - kStatRows, k) - m[k]) : 0.0;
         const float xf = (float)x;
         const __half hi = __float2half_rn(xf);
         *reinterpret_cast<__half *>(img_f16 + sw64_off(row, k)) = hi;
@@ -154,13 +200,23 @@ __device__ __forceinline__ void pack_w2_colstats(int bid, double *__restrict__ o
     __shared__ double r1[kStatSlices][33], r2[kStatSlices][33], rg[kStatSlices][33];
     const int kk = threadIdx.x & 31, sl = threadIdx.x >> 5, k = bid * 32 + kk;
     double s1 = 0.0, s2 = 0.0, sg = 0.0;
-    for (int n = sl; n < H2; n += kStatSlices) {
-        const double w = (double)wf2(fc2_w, fc2_b, n, k), gw = (double)g2[n] * (double)w3[n];
+    constexpr int kIt = (H2 + kStatSlices - 1) / kStatSlices;
+    float wv[kIt], gv[kIt], qv[kIt];                                  // every load first: one memory round trip, not kIt dependent ones
+#pragma unroll
+    for (int it = 0; it < kIt; it++) {
+        const int n = sl + it * kStatSlices;
+        const bool in = n < H2;
+        wv[it] = in ? wf2(fc2_w, fc2_b, n, k) : 0.f; gv[it] = in ? g2[n] : 0.f; qv[it] = in ? w3[n] : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; it++) {
+        const double w = (double)wv[it], gw = (double)gv[it] * (double)qv[it];
         s1 += w; s2 += w * gw; sg += gw;
     }
     r1[sl][kk] = s1; r2[sl][kk] = s2; rg[sl][kk] = sg;
     __syncthreads();
     if (sl == 0) {
+#pragma unroll 8
         for (int i = 1; i < kStatSlices; i++) { s1 += r1[i][kk]; s2 += r2[i][kk]; sg += rg[i][kk]; }
         const double m = s1 / H2;
         out[k] = m;
@@ -209,16 +265,16 @@ __device__ __forceinline__ void pack_fp32(int bid, int nblk, const tt_actor_dev 
     if (tid == 0) A.b3[0] = mu_b[0];
 }
 
-// The re-pack of a policy (tt_actor_load) is on the end-to-end path: a learner hands over new weights every iteration.  Three
+// The re-pack of a policy (tt_actor_load) is on the end-to-end path: a learner hands over new weights every iteration.  Two
 // launches instead of seven: stage A = everything that only reads the raw weights (Gram partial sums of layer 1, column
-// statistics of layer 2, the fp32 images), one CTA: the Cholesky factor, stage C = the three tensor-core operand images.
+// statistics of layer 2, the fp32 images), stage C = the three tensor-core operand images (block 0: the Cholesky factor).
 struct PackSrc { const float *fc1_w, *fc1_b, *g1, *be1, *fc2_w, *fc2_b, *g2, *be2, *mu_w, *mu_b; };
 constexpr int kPackFp32Blocks = 16;
 __global__ void __launch_bounds__(1024) pack_stage_a_kernel(tt_actor_dev A, PackSrc w, int tc) {
     chain_enter();
     int bid = blockIdx.x;
     if (tc) {
-        if (bid < kGramBlocks) { pack_l1c_gram(bid, A.l1c_scratch, w.fc1_w, w.fc1_b); return; }
+        if (bid < kGramBlocks) { pack_l1c_gram(bid, A.l1c_scratch + kGramOff, w.fc1_w, w.fc1_b); return; }
         bid -= kGramBlocks;
         if (bid < KB2) { pack_w2_colstats(bid, A.l1c_scratch + 1200, w.fc2_w, w.fc2_b, w.g2, w.mu_w); return; }
         bid -= KB2;
@@ -229,8 +285,9 @@ constexpr int kImgBlocks = 54, kW2sBlocks = 128;
 __global__ void __launch_bounds__(256) pack_stage_c_kernel(tt_actor_dev A, PackSrc w) {
     chain_enter();
     int bid = blockIdx.x;
+    if (bid == 0) { pack_l1c_stat_rows(reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + kGramOff); return; }
     if (bid < kImgBlocks) {
-        pack_l1c_image(bid, kImgBlocks, reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + 600, w.fc1_w, w.fc1_b, w.g1);
+        pack_l1c_image(bid, kImgBlocks, reinterpret_cast<char *>(A.w1c_f16), reinterpret_cast<char *>(A.w1c_bf16), A.l1c_scratch + kGramOff, w.fc1_w, w.fc1_b, w.g1);
         return;
     }
     bid -= kImgBlocks;
@@ -916,12 +973,12 @@ int actor_pack_all(tt_actor *a, const float *fc1_w, const float *fc1_b, const fl
     const tt_actor_dev &A = a->dev;
     const PackSrc w = {fc1_w, fc1_b, g1, be1, fc2_w, fc2_b, g2, be2, mu_w, mu_b};
     const int tc = actor_tc_supported(A) ? 1 : 0;       // the tensor-core path is specialised to 23-400-300; forward() refuses otherwise
-    if (tc && !a->scratch_clean) { TT_CUDA(cudaMemsetAsync(A.l1c_scratch, 0, sizeof(double) * 600, s)); a->scratch_clean = true; }
     TT_CUDA(tt::launch_chained(true, pack_stage_a_kernel, dim3((tc ? kGramBlocks + KB2 : 0) + kPackFp32Blocks), dim3(1024), 0, s, A, w, tc));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     if (!tc) return TT_OK;
-    TT_CUDA(tt::launch_chained(true, pack_l1c_chol_kernel, dim3(1), dim3(576), 0, s, A.l1c_scratch, A.l1c_scratch + 600));
-    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+#if defined(TT_LEARN_PROFILE)
+    { const char *e_ = getenv("TT_PACK_STOP"); if (e_ && atoi(e_) == 1) return TT_OK; }
+#endif
     TT_CUDA(tt::launch_chained(true, pack_stage_c_kernel, dim3(kImgBlocks + 2 * kW2sBlocks), dim3(256), 0, s, A, w));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;

@@ -381,7 +381,6 @@ int tt_actor_create(tt_actor **out, int32_t in_dim, int32_t h1, int32_t h2, void
     TT_REQUIRE(a, "out of host memory");
     tt_actor_layout(in_dim, h1, h2, &a->dev, static_cast<char *>(d_workspace));
     a->loaded = false;
-    a->scratch_clean = false;
     *out = a;
     return TT_OK;
 }

@@ -69,8 +69,18 @@ struct Job {
     float *Y; int ldy;                // output: Y / dW / dX
     float *db;
 };
+// Column sums over the batch (= the gradients of bias-like parameters), riding in the grouped launch that FOLLOWS the row-wise
+// kernel which produced the rows:  dst[v][j] (and dst2[v][j]) = sum_b src[v][b H + j] * (scale[v] ? scale[v][b] : 1),  v < nv;
+// tot_dst[0] = sum_b tot_src[b].  (The row-wise kernels used to end with a ticket: __threadfence, an atomic, and the LAST CTA
+// summing the columns alone -- 4 us of pure latency per kernel on the critical path; here the sums run beside the GEMM tiles.)
+struct ColSumJob {
+    const float *src[4], *scale[4];
+    float *dst[4], *dst2[4];
+    const float *tot_src; float *tot_dst;
+    int nv, B, H, ctas;                 // ctas = ceil(H / 32), 0 = no such job in this launch
+};
 constexpr int kMaxJobs = 4;
-struct JobList { Job j[kMaxJobs]; int n; };
+struct JobList { Job j[kMaxJobs]; int n; ColSumJob cs; };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -110,44 +120,104 @@ __device__ __forceinline__ void stage_block(float *dst, const float *__restrict_
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// at most `n` of the committed groups still pending (run-time n: every chunk of a tile is in flight at once, see job_fwd)
+__device__ __forceinline__ void cp_wait_n(int n) {
+    switch (n) {
+    case 0: cp_wait<0>(); break;   case 1: cp_wait<1>(); break;   case 2: cp_wait<2>(); break;   case 3: cp_wait<3>(); break;
+    case 4: cp_wait<4>(); break;   case 5: cp_wait<5>(); break;   case 6: cp_wait<6>(); break;   case 7: cp_wait<7>(); break;
+    case 8: cp_wait<8>(); break;   case 9: cp_wait<9>(); break;   case 10: cp_wait<10>(); break; case 11: cp_wait<11>(); break;
+    case 12: cp_wait<12>(); break; case 13: cp_wait<13>(); break; case 14: cp_wait<14>(); break; default: cp_wait<15>(); break;
+    }
+}
 __device__ __forceinline__ bool vec_ok(const float *p, int ld, int cols) { return (ld & 3) == 0 && (cols & 3) == 0 && ((uintptr_t)p & 15) == 0; }
 
-// Y tile: all B rows x 16 columns [n0, n0 + 16); K in double-buffered chunks of 32.  Thread = 4 rows x 1 column; per 4 k: four
-// 16 B loads of X and one of W for 16 FMAs.
+// The two long GEMM tiles (forward: 64 batch rows x 16 outputs over K <= 512; dX: 32 batch rows x 32 inputs over N <= 512) are
+// latency problems, not throughput problems: 1 024 outputs per CTA and a reduction of 300-400 terms.  Both run the same scheme:
+//  * the reduction dimension comes in as chunks of 32, ALL of them in flight at once (one cp.async group per chunk, <= 16 chunks
+//    = 184 KB of shared memory): one memory round trip plus the transfer instead of one round trip per chunk;
+//  * the 8 warps SPLIT the reduction: warp w takes the w-th group of four terms of every chunk, and each lane holds an 8 x 4
+//    register tile of the CTA's outputs: 12 conflict-free 16 B shared-memory loads per 128 FMAs on 32 independent accumulators
+//    (the first version -- thread = 4 outputs, 5 loads per 16 FMAs on 4 dependent chains at 34 registers -- took 20 800 cycles
+//    per tile at 8 warps per SM: pure instruction latency);
+//  * the eight partial tiles meet in shared memory ([warp][register][lane]: conflict-free both ways) and are summed in warp order.
+constexpr int kMaxChunks = 16;                                                  // kMaxH / 32
+constexpr int kRedFloats = 8 * 32 * 32;                                         // the partial tiles of the 8 warps
+
+// sum the 8 warps' partial tiles; thread tid gets outputs idx = tid + 256 q (q < 4) as out[q]; idx = reg * 32 + lane
+__device__ __forceinline__ void reduce_partials(const float (&acc)[8][4], float *red, float (&out)[4]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();                                                            // every warp is done with the staging area `red` aliases
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j2 = 0; j2 < 4; j2++) red[(warp * 32 + i * 4 + j2) * 32 + lane] = acc[i][j2];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += red[w * 1024 + threadIdx.x + 256 * q];
+        out[q] = t;
+    }
+}
+
+// Y tile: all B rows x 16 columns [n0, n0 + 16).  Lane (rg = lane / 4, cg = lane % 4) holds rows 8 i + rg, columns 4 j + cg.
 __device__ void job_fwd(const Job &J, int cta, float *smem) {
-    float *Xs = smem, *Ws = smem + 2 * 64 * kP;                                 // [2][64][kP], [2][16][kP]
-    const int tid = threadIdx.x, tn = tid & 15, tb = tid >> 4, n0 = cta * 16;
-    const bool vx = vec_ok(J.X, J.ldx, J.K), vw = vec_ok(J.W, J.ldw, J.K);
     const int nch = (J.K + 31) / 32;
-    auto stage = [&](int ch, int buf) {
-        stage_block(Xs + buf * 64 * kP, J.X, J.ldx, 64, J.B, ch * 32, J.K, vx);
-        stage_block(Ws + buf * 16 * kP, J.W + (size_t)n0 * J.ldw, J.ldw, 16, J.N - n0, ch * 32, J.K, vw);
-        cp_commit();
-    };
-    stage(0, 0);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float *Xs = smem, *Ws = smem + nch * 64 * kP;                               // [nch][64][kP], [nch][16][kP]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, rg = lane >> 2, cg = lane & 3, n0 = cta * 16;
+    const bool vx = vec_ok(J.X, J.ldx, J.K), vw = vec_ok(J.W, J.ldw, J.K);
+    if (vx && vw) {
+        // production sizes: every thread's source / destination of a chunk is the previous chunk's plus a constant (the generic
+        // stage_block spends ~40 instructions of index arithmetic per 16 B copy: a third of this kernel's instructions)
+        const int q = threadIdx.x & 7, r = threadIdx.x >> 3;                    // 16 B column group, row 0..31
+        const bool rx0 = r < J.B, rx1 = r + 32 < J.B, rw = r < 16 && n0 + r < J.N;
+        const float *x0 = J.X + (size_t)(rx0 ? r : 0) * J.ldx + 4 * q, *x1 = J.X + (size_t)(rx1 ? r + 32 : 0) * J.ldx + 4 * q;
+        const float *w0 = J.W + (size_t)(rw ? n0 + r : 0) * J.ldw + 4 * q;
+        float *dx = Xs + r * kP + 4 * q, *dw = Ws + r * kP + 4 * q;
+        for (int ch = 0; ch < nch; ch++) {
+            const bool in = 32 * ch + 4 * q < J.K;
+            cp16(dx, in ? x0 : J.X, rx0 && in); cp16(dx + 32 * kP, in ? x1 : J.X, rx1 && in);
+            if (r < 16) cp16(dw, in ? w0 : J.W, rw && in);
+            cp_commit();
+            x0 += 32; x1 += 32; w0 += 32; dx += 64 * kP; dw += 16 * kP;
+        }
+    } else {
+        for (int ch = 0; ch < nch; ch++) {
+            stage_block(Xs + ch * 64 * kP, J.X, J.ldx, 64, J.B, ch * 32, J.K, vx);
+            stage_block(Ws + ch * 16 * kP, J.W + (size_t)n0 * J.ldw, J.ldw, 16, J.N - n0, ch * 32, J.K, vw);
+            cp_commit();
+        }
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j2 = 0; j2 < 4; j2++) acc[i][j2] = 0.f;
     for (int ch = 0; ch < nch; ch++) {
-        if (ch + 1 < nch) { stage(ch + 1, (ch + 1) & 1); cp_wait<1>(); } else cp_wait<0>();
+        cp_wait_n(nch - 1 - ch);
         __syncthreads();
-        const float *xs = Xs + (ch & 1) * 64 * kP + 4 * tb * kP, *ws = Ws + (ch & 1) * 16 * kP + tn * kP;
+        const float *xs = Xs + ch * 64 * kP + rg * kP + 4 * warp, *ws = Ws + ch * 16 * kP + cg * kP + 4 * warp;
+        float4 b[4];
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const float4 w = *reinterpret_cast<const float4 *>(ws + 4 * q);
+        for (int j2 = 0; j2 < 4; j2++) b[j2] = *reinterpret_cast<const float4 *>(ws + 4 * j2 * kP);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const float4 x = *reinterpret_cast<const float4 *>(xs + i * kP + 4 * q);
-                acc[i] = fmaf(x.x, w.x, acc[i]); acc[i] = fmaf(x.y, w.y, acc[i]); acc[i] = fmaf(x.z, w.z, acc[i]); acc[i] = fmaf(x.w, w.w, acc[i]);
+        for (int i = 0; i < 8; i++) {
+            const float4 a = *reinterpret_cast<const float4 *>(xs + 8 * i * kP);
+#pragma unroll
+            for (int j2 = 0; j2 < 4; j2++) {
+                acc[i][j2] = fmaf(a.x, b[j2].x, acc[i][j2]); acc[i][j2] = fmaf(a.y, b[j2].y, acc[i][j2]);
+                acc[i][j2] = fmaf(a.z, b[j2].z, acc[i][j2]); acc[i][j2] = fmaf(a.w, b[j2].w, acc[i][j2]);
             }
         }
-        __syncthreads();
     }
-    if (n0 + tn < J.N) {
-        const float bias = J.bias ? J.bias[n0 + tn] : 0.f;
+    float out[4];
+    reduce_partials(acc, smem, out);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int b = 4 * tb + i;
-            if (b < J.B) J.Y[(size_t)b * J.ldy + n0 + tn] = acc[i] + bias;
-        }
+    for (int q = 0; q < 4; q++) {
+        const int idx = threadIdx.x + 256 * q, reg = idx >> 5, ln = idx & 31;
+        const int b_ = 8 * (reg >> 2) + (ln >> 2), n = n0 + 4 * (reg & 3) + (ln & 3);
+        if (b_ < J.B && n < J.N) J.Y[(size_t)b_ * J.ldy + n] = out[q] + (J.bias ? J.bias[n] : 0.f);
     }
 }
 
@@ -177,50 +247,113 @@ __device__ void job_wgrad(const Job &J, int cta, float *smem) {
     }
 }
 
-// dX tile: 32 batch rows x 32 columns [k0, k0 + 32); N in double-buffered chunks of 32.  Thread = 1 row x 4 columns; per 4 n:
-// one 16 B load of D and four of W for 16 FMAs.  (26 CTAs for 64 x 400: the reduction over 300 n is the long chain of the
-// backward pass, so it gets the small tile.)
+// dX tile: 32 batch rows x 32 columns [k0, k0 + 32), reduction over N (see above).  Lane (rg = lane / 8, cg = lane % 8) holds
+// rows 4 i + rg, columns 4 cg .. 4 cg + 3.  (26 CTAs for 64 x 400: the reduction over 300 n is the long chain of the backward
+// pass, so it gets the small tile.)
 __device__ void job_xgrad(const Job &J, int cta, float *smem) {
-    float *Ds = smem, *Ws = smem + 2 * 32 * kP;                                 // [2][32 b][kP] (32 n), [2][32 n][kP] (32 k)
+    const int nch = (J.N + 31) / 32;
+    float *Ds = smem, *Ws = smem + nch * 32 * kP;                               // [nch][32 b][kP] (32 n), [nch][32 n][kP] (32 k)
     const int ktiles = (J.K + 31) / 32;
     const int bt = cta / ktiles, kt = cta - bt * ktiles, b0 = bt * 32, k0 = kt * 32;
-    const int tid = threadIdx.x, tk = tid & 7, tb = tid >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, rg = lane >> 3, cg = lane & 7;
     const bool vd = vec_ok(J.D, J.ldd, J.N), vw = vec_ok(J.W, J.ldw, J.K);
-    const int nch = (J.N + 31) / 32;
-    auto stage = [&](int ch, int buf) {
-        stage_block(Ds + buf * 32 * kP, J.D + (size_t)b0 * J.ldd, J.ldd, 32, J.B - b0, ch * 32, J.N, vd);
-        stage_block(Ws + buf * 32 * kP, J.W + (size_t)ch * 32 * J.ldw, J.ldw, 32, J.N - ch * 32, k0, J.K, vw);
-        cp_commit();
-    };
-    stage(0, 0);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ch = 0; ch < nch; ch++) {
-        if (ch + 1 < nch) { stage(ch + 1, (ch + 1) & 1); cp_wait<1>(); } else cp_wait<0>();
-        __syncthreads();
-        const float *ds = Ds + (ch & 1) * 32 * kP + tb * kP, *ws = Ws + (ch & 1) * 32 * kP + 4 * tk;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const float4 d = *reinterpret_cast<const float4 *>(ds + 4 * q);
-            const float dd[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float4 w = *reinterpret_cast<const float4 *>(ws + (4 * q + j) * kP);
-                acc[0] = fmaf(dd[j], w.x, acc[0]); acc[1] = fmaf(dd[j], w.y, acc[1]);
-                acc[2] = fmaf(dd[j], w.z, acc[2]); acc[3] = fmaf(dd[j], w.w, acc[3]);
-            }
+    if (vd && vw) {
+        const int q = threadIdx.x & 7, r = threadIdx.x >> 3;                    // (see job_fwd) one copy of D and one of W per chunk
+        const bool rd = b0 + r < J.B, cw = k0 + 4 * q < J.K;
+        const float *d0 = J.D + (size_t)(rd ? b0 + r : 0) * J.ldd + 4 * q, *w0 = J.W + (size_t)r * J.ldw + (cw ? k0 + 4 * q : 0);
+        float *dd = Ds + r * kP + 4 * q, *dw = Ws + r * kP + 4 * q;
+        for (int ch = 0; ch < nch; ch++) {
+            const bool cd = 32 * ch + 4 * q < J.N, rw = 32 * ch + r < J.N;
+            cp16(dd, cd ? d0 : J.D, rd && cd);
+            cp16(dw, rw ? w0 : J.W, rw && cw);
+            cp_commit();
+            d0 += 32; w0 += (size_t)32 * J.ldw; dd += 32 * kP; dw += 32 * kP;
         }
-        __syncthreads();
+    } else {
+        for (int ch = 0; ch < nch; ch++) {
+            stage_block(Ds + ch * 32 * kP, J.D + (size_t)b0 * J.ldd, J.ldd, 32, J.B - b0, ch * 32, J.N, vd);
+            stage_block(Ws + ch * 32 * kP, J.W + (size_t)ch * 32 * J.ldw, J.ldw, 32, J.N - ch * 32, k0, J.K, vw);
+            cp_commit();
+        }
     }
-    const int b = b0 + tb;
-    if (b < J.B) {
+    float acc[8][4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { const int k = k0 + 4 * tk + j; if (k < J.K) J.Y[(size_t)b * J.ldy + k] = acc[j]; }
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j2 = 0; j2 < 4; j2++) acc[i][j2] = 0.f;
+    for (int ch = 0; ch < nch; ch++) {
+        cp_wait_n(nch - 1 - ch);
+        __syncthreads();
+        const float *ds = Ds + ch * 32 * kP + rg * kP + 4 * warp, *ws = Ws + ch * 32 * kP + 4 * warp * kP + 4 * cg;
+        float4 w[4];                                                            // W[n = 4 warp + e][k0 + 4 cg .. + 3]
+#pragma unroll
+        for (int e = 0; e < 4; e++) w[e] = *reinterpret_cast<const float4 *>(ws + e * kP);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 d = *reinterpret_cast<const float4 *>(ds + 4 * i * kP);  // D[b = 4 i + rg][n = 4 warp .. + 3]
+            acc[i][0] = fmaf(d.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(d.x, w[0].y, acc[i][1]); acc[i][2] = fmaf(d.x, w[0].z, acc[i][2]); acc[i][3] = fmaf(d.x, w[0].w, acc[i][3]);
+            acc[i][0] = fmaf(d.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(d.y, w[1].y, acc[i][1]); acc[i][2] = fmaf(d.y, w[1].z, acc[i][2]); acc[i][3] = fmaf(d.y, w[1].w, acc[i][3]);
+            acc[i][0] = fmaf(d.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(d.z, w[2].y, acc[i][1]); acc[i][2] = fmaf(d.z, w[2].z, acc[i][2]); acc[i][3] = fmaf(d.z, w[2].w, acc[i][3]);
+            acc[i][0] = fmaf(d.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(d.w, w[3].y, acc[i][1]); acc[i][2] = fmaf(d.w, w[3].z, acc[i][2]); acc[i][3] = fmaf(d.w, w[3].w, acc[i][3]);
+        }
     }
+    float out[4];
+    reduce_partials(acc, smem, out);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int idx = threadIdx.x + 256 * q, reg = idx >> 5, ln = idx & 31;
+        const int b_ = b0 + 4 * (reg >> 2) + (ln >> 3), k = k0 + 4 * (ln & 7) + (reg & 3);
+        if (b_ < J.B && k < J.K) J.Y[(size_t)b_ * J.ldy + k] = out[q];
+    }
+}
+
+// 32 columns x 8 groups of 8 batch rows per CTA: 8 nv independent loads per thread (one memory round trip), the groups meet in
+// shared memory and are added in order (deterministic)
+__device__ void job_colsum(const ColSumJob &C, int cta, float *smem) {
+    const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5, j = cta * 32 + cl;
+    // every load first (nvcc otherwise keeps load -> use -> load order: 8 nv dependent L2 round trips), then the arithmetic
+    float x[4][8], sc[4][8];
+#pragma unroll
+    for (int v = 0; v < 4; v++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int b = rg * 8 + i;
+            const bool in = v < C.nv && b < C.B && j < C.H;
+            x[v][i] = in ? __ldcg(C.src[v] + (size_t)b * C.H + j) : 0.f;
+            sc[v][i] = (in && C.scale[v]) ? __ldcg(C.scale[v] + b) : 1.f;
+        }
+    float tot = 0.f;
+    const bool do_tot = cta == 0 && rg == 7 && C.tot_dst;                       // warp 7 of the first CTA: sum of tot_src (B <= 64)
+    if (do_tot) tot = (cl < C.B ? __ldcg(C.tot_src + cl) : 0.f) + (cl + 32 < C.B ? __ldcg(C.tot_src + cl + 32) : 0.f);
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) part = C.scale[v] ? fmaf(x[v][i], sc[v][i], part) : part + x[v][i];
+        smem[(v * 8 + rg) * 32 + cl] = part;
+    }
+    __syncthreads();
+    if (rg < C.nv && j < C.H) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; g++) t += smem[(rg * 8 + g) * 32 + cl];
+        C.dst[rg][j] = t;
+        if (C.dst2[rg]) C.dst2[rg][j] = t;
+    }
+    if (do_tot) { tot = warp_sum(tot); if (cl == 0) C.tot_dst[0] = tot; }
+}
+
+// shared memory (floats) a job's CTAs need
+__host__ __device__ inline int job_smem_floats(const Job &J) {
+    int f = (64 + 64) * kP;
+    if (J.type == G_FWD) f = ((J.K + 31) / 32) * (64 + 16) * kP;
+    if (J.type == G_XGRAD) f = ((J.N + 31) / 32) * (32 + 32) * kP;
+    return J.type != G_WGRAD && f < kRedFloats ? kRedFloats : f;
 }
 
 __global__ void __launch_bounds__(kT) learn_gemm_kernel(JobList L) {
     chain_enter();
-    __shared__ __align__(16) float smem[2 * 64 * kP + 2 * 32 * kP];            // 27 648 B: the dX layout is the largest
+    extern __shared__ __align__(16) float smem[];                              // max over the launch's jobs of job_smem_floats()
     int cta = blockIdx.x;
     for (int i = 0; i < L.n; i++) {
         if (cta < L.j[i].ctas) {
@@ -232,6 +365,7 @@ __global__ void __launch_bounds__(kT) learn_gemm_kernel(JobList L) {
         }
         cta -= L.j[i].ctas;
     }
+    if (cta < L.cs.ctas) job_colsum(L.cs, cta, smem);
 }
 
 // ---- K0: sampling + gather (replay_buffer.py:23-34: uniform with replacement over the filled part of the ring) ----
@@ -283,26 +417,11 @@ __global__ void learn_gather_kernel(tt_replay_ring ring, int64_t win_begin, int6
 
 // ---- row-wise stages: 8 CTAs x 8 warps, one warp per batch row with the row in registers (one warp per row keeps the
 //      dependent chain of a row -- load -> statistics -> head -> backward -- at one memory latency per network instead of
-//      serialising rows); the LAST CTA to finish (a ticket counter) then takes the column sums over the batch (= the parameter
-//      gradients), one column per thread, rows in order (deterministic).  No cluster and no grid barrier: the CTAs need not be
-//      co-resident, so the stage also runs on the two or four SMs that rollout.AsyncTrainer leaves free for the learner.
+//      serialising rows).  The column sums over the batch (= the parameter gradients) are ColSumJobs of the grouped launch that
+//      follows.  No cluster and no grid barrier: the CTAs need not be co-resident, so the stage also runs on the two or four
+//      SMs that rollout.AsyncTrainer leaves free for the learner.
 constexpr int kRowT = 256, kPerLane = kMaxH / 32;
 struct Row { float v[kPerLane]; };
-
-// true in exactly one CTA of the launch: the one that arrives last, after every other CTA's global writes are visible
-__device__ __forceinline__ bool last_cta_done(int *ticket) {
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int t = atomicAdd(ticket, 1);
-        s_last = t == (int)gridDim.x - 1;
-        if (s_last) *ticket = 0;                            // ready for the next row-wise stage (stream order)
-    }
-    __syncthreads();
-    if (s_last) __threadfence();
-    return s_last != 0;
-}
 
 __device__ __forceinline__ void load_row(Row &r, const float *__restrict__ p, int H, int lane) {
 #pragma unroll
@@ -350,53 +469,105 @@ struct HeadArgs {
     float *dh2;                                                           // out: gradient w.r.t. the fc2 output [B][H2]
     float *sc0, *sc1, *sc2;                                               // scratch [B][H2]
     float *dv;                                                            // scratch [B]: dL/dq (critic) or dL/d(pre-tanh) (actor) per row
-    int *ticket;                                                          // last-CTA counter (0 between launches)
-    // gradients (flat-layout pointers)
-    float *g_g2, *g_be2, *g_t0, *g_t1, *g_t2, *g_t3;                      // critic: wa, ba, wq, bq | actor: w3, b3, -, -
     float *q_out, *y_out, *a_out;                                         // diagnostics / hand-over: Q(s,a), target, actor(s)
 };
 
-// K1 / K7: fc1 + LayerNorm 1 + ReLU of up to four networks in one launch.  A CTA takes 8 batch rows of one network (warp = row,
-// the whole fc1 output row -- <= 512 values -- in registers), W1 passes through shared memory in blocks of 128 output columns.
-// Writes h1 (pre-LayerNorm, for the backward pass) and a1 = relu(LN1(h1)) (the operand of fc2 and of its weight gradient).
+// K1 / K7: fc1 + LayerNorm 1 + ReLU of up to four networks in one launch.  A CTA takes 8 batch rows of one network; a THREAD owns
+// one or two output columns for all 8 rows: W1 comes in as one flat 16 B cp.async copy (no index arithmetic, every element read
+// from shared memory by exactly one thread of the CTA), the 8 input rows are broadcast reads, and the LayerNorm statistics are
+// two block-wide reductions.  (The first version gave every WARP a row: each warp then read the whole of W1 from shared
+// memory -- 3 300 instructions per warp and 16 us for 0.6 MFLOP.)  Writes h1 (pre-LayerNorm, for the backward pass) and
+// a1 = relu(LN1(h1)) (the operand of fc2 and of its weight gradient).
 struct Fc1Job { const float *x, *w1, *b1, *g1, *be1; float *h1, *a1; };
 struct Fc1Args { Fc1Job j[NJOBS]; int njobs, B, IN, H1; };
-constexpr int kW1P = 25;                                   // shared-memory pitch of a W1 row (IN <= 24 + 1; odd: conflict-free for lane = column)
-__global__ void __launch_bounds__(256) learn_fc1_kernel(Fc1Args A) {
+constexpr int kFc1T = 256, kFc1Cols = kMaxH / kFc1T, kFc1Rows = 8, kXP = 24;    // kXP: pitch of an input row (IN <= 24)
+__global__ void __launch_bounds__(kFc1T, 1) learn_fc1_kernel(Fc1Args A) {
     chain_enter();
-    extern __shared__ float ws[];                          // W1 [H1][kW1P]: the whole matrix in ONE round of independent loads
-    __shared__ float xs[8 * 32];                           // the CTA's 8 input rows
-    const int per = (A.B + 7) / 8;
-    const int job = blockIdx.x / per, b0 = (blockIdx.x - job * per) * 8;
+    extern __shared__ __align__(16) float ws[];            // W1 flat [H1 * IN] (row c at c * IN: an odd IN is conflict-free for lane = column)
+    __shared__ __align__(16) float xs[kFc1Rows * kXP];     // the CTA's 8 input rows, zero padded
+    __shared__ float red[2][kFc1T / 32][kFc1Rows];
+    const int per = (A.B + kFc1Rows - 1) / kFc1Rows;
+    const int job = blockIdx.x / per, b0 = (blockIdx.x - job * per) * kFc1Rows;
     const Fc1Job J = A.j[job];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = b0 + warp, H = A.H1, IN = A.IN;
-    // this lane's columns of the three parameter vectors: loaded up front, together with W1 (one memory latency for everything)
-    float pb[kPerLane], pg[kPerLane], pe[kPerLane];
-#pragma unroll
-    for (int i = 0; i < kPerLane; i++) {
-        const int j = lane + 32 * i;
-        pb[i] = j < H ? J.b1[j] : 0.f; pg[i] = j < H ? J.g1[j] : 0.f; pe[i] = j < H ? J.be1[j] : 0.f;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, H = A.H1, IN = A.IN, nw = H * IN;
+    if ((nw & 3) == 0 && (reinterpret_cast<uintptr_t>(J.w1) & 15) == 0) {
+        for (int v = tid; v < nw / 4; v += kFc1T) cp16(ws + 4 * v, J.w1 + 4 * v, true);
+    } else {
+        for (int v = tid; v < nw; v += kFc1T) cp4(ws + v, J.w1 + v, true);
     }
-    for (int v = threadIdx.x; v < 8 * IN; v += 256) { const int r = v / IN, k = v - r * IN; xs[r * 32 + k] = b0 + r < A.B ? J.x[(size_t)(b0 + r) * IN + k] : 0.f; }
-    for (int v = threadIdx.x; v < H * IN; v += 256) { const int c = v / IN, k = v - c * IN; ws[c * kW1P + k] = J.w1[v]; }
+    cp_commit();
+    // this thread's columns of the three parameter vectors and the input rows: in flight together with W1
+    float pb[kFc1Cols], pg[kFc1Cols], pe[kFc1Cols];
+#pragma unroll
+    for (int i = 0; i < kFc1Cols; i++) {
+        const int c = tid + kFc1T * i;
+        pb[i] = c < H ? J.b1[c] : 0.f; pg[i] = c < H ? J.g1[c] : 0.f; pe[i] = c < H ? J.be1[c] : 0.f;
+    }
+    if (tid < kFc1Rows * kXP) {
+        const int r = tid / kXP, k = tid - r * kXP;
+        xs[tid] = (k < IN && b0 + r < A.B) ? J.x[(size_t)(b0 + r) * IN + k] : 0.f;
+    }
+    cp_wait<0>();
     __syncthreads();
-    Row h;
+    float h[kFc1Cols][kFc1Rows];
 #pragma unroll
-    for (int i = 0; i < kPerLane; i++) {
-        const int c = lane + 32 * i;
-        float acc = 0.f;
+    for (int i = 0; i < kFc1Cols; i++) {
+        const int c = tid + kFc1T * i;
+#pragma unroll
+        for (int r = 0; r < kFc1Rows; r++) h[i][r] = 0.f;
         if (c < H) {
-            for (int k = 0; k < IN; k++) acc = fmaf(xs[warp * 32 + k], ws[c * kW1P + k], acc);
-            acc += pb[i];
+            const float *w = ws + c * IN;
+#pragma unroll
+            for (int k4 = 0; k4 < kXP / 4; k4++) {
+                float wk[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) wk[e] = 4 * k4 + e < IN ? w[4 * k4 + e] : 0.f;
+#pragma unroll
+                for (int r = 0; r < kFc1Rows; r++) {
+                    const float4 x = *reinterpret_cast<const float4 *>(xs + r * kXP + 4 * k4);
+                    h[i][r] = fmaf(x.x, wk[0], h[i][r]); h[i][r] = fmaf(x.y, wk[1], h[i][r]);
+                    h[i][r] = fmaf(x.z, wk[2], h[i][r]); h[i][r] = fmaf(x.w, wk[3], h[i][r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kFc1Rows; r++) h[i][r] += pb[i];
         }
-        h.v[i] = acc;
     }
-    if (b < A.B) {
+    // LayerNorm statistics of the 8 rows: mean, then the centred sum of squares (two passes, like normalize_row)
+    float stat[kFc1Rows];
 #pragma unroll
-        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; if (j < H) J.h1[(size_t)b * H + j] = h.v[i]; }
-        normalize_row(h, H, lane);
+    for (int pass = 0; pass < 2; pass++) {
 #pragma unroll
-        for (int i = 0; i < kPerLane; i++) { const int j = lane + 32 * i; if (j < H) J.a1[(size_t)b * H + j] = fmaxf(fmaf(h.v[i], pg[i], pe[i]), 0.f); }
+        for (int r = 0; r < kFc1Rows; r++) {
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < kFc1Cols; i++) {
+                const bool in = tid + kFc1T * i < H;
+                if (pass == 0) v += in ? h[i][r] : 0.f;
+                else { const float d = in ? h[i][r] - stat[r] : 0.f; v = fmaf(d, d, v); }
+            }
+            v = warp_sum(v);
+            if (lane == 0) red[pass][warp][r] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kFc1Rows; r++) {
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < kFc1T / 32; w8++) t += red[pass][w8][r];
+            if (pass == 0) stat[r] = t / (float)H;                                   // mean
+            else {
+                const float mean = stat[r], rstd = rsqrtf(t / (float)H + kLnEps);
+#pragma unroll
+                for (int i = 0; i < kFc1Cols; i++) {
+                    const int c = tid + kFc1T * i;
+                    if (c < H && b0 + r < A.B) {
+                        J.h1[(size_t)(b0 + r) * H + c] = h[i][r];
+                        J.a1[(size_t)(b0 + r) * H + c] = fmaxf(fmaf((h[i][r] - mean) * rstd, pg[i], pe[i]), 0.f);
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -417,10 +588,15 @@ __device__ __forceinline__ void stage_vectors(float (*dst)[kMaxH], const float *
 // K3: DDPG_agent.py:84-97
 __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
     chain_enter();
-    __shared__ float s_dq[kMaxB], s_act[kMaxB];
     __shared__ float sp[13][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
     const int b = (int)blockIdx.x * (kRowT / 32) + warp;
+    Row x, xt, xc;                                                       // the three rows' loads and the 13 vectors: one memory latency together
+    if (b < A.B) {
+        load_row(xt, A.h2[JOB_TA] + (size_t)b * H, H, lane);
+        load_row(xc, A.h2[JOB_TC] + (size_t)b * H, H, lane);
+        load_row(x, A.h2[JOB_C] + (size_t)b * H, H, lane);
+    }
     {
         const float *const src[13] = {A.ta_g2, A.ta_be2, A.ta_w3, A.tc_g2, A.tc_be2, A.tc_wa, A.tc_ba, A.tc_wq, A.c_g2, A.c_be2, A.c_wa, A.c_ba, A.c_wq};
         stage_vectors<13>(sp, src, H);
@@ -429,11 +605,6 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
                 *c_g2 = sp[8], *c_be2 = sp[9], *c_wa = sp[10], *c_ba = sp[11], *c_wq = sp[12];
     __syncthreads();
     if (b < A.B) {
-        Row x, xt;
-        load_row(xt, A.h2[JOB_TA] + (size_t)b * H, H, lane);             // the three rows' loads are independent: issue them together
-        Row xc;
-        load_row(xc, A.h2[JOB_TC] + (size_t)b * H, H, lane);
-        load_row(x, A.h2[JOB_C] + (size_t)b * H, H, lane);
         // a' = target_actor(s') head: tanh(mu(relu(LN2(h2))))            (networks.py:142-145)
         normalize_row(xt, H, lane);
         float p = 0.f;
@@ -477,31 +648,19 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
         }
         if (lane == 0) { A.dv[b] = dq; if (A.q_out) A.q_out[b] = q; if (A.y_out) A.y_out[b] = y; }
     }
-    if (!last_cta_done(A.ticket)) return;
-    if (threadIdx.x < A.B) { s_dq[threadIdx.x] = A.dv[threadIdx.x]; s_act[threadIdx.x] = A.act[threadIdx.x]; }
-    __syncthreads();
-    // parameter gradients = column sums over the batch, in row order
-    const int gt = threadIdx.x;
-    for (int j = gt; j < H; j += kRowT) {
-        float gba = 0.f, gwa = 0.f, gg2 = 0.f, gwq = 0.f;
-#pragma unroll 32
-        for (int bb = 0; bb < A.B; bb++) {
-            const size_t o = (size_t)bb * H + j;
-            const float dz = A.sc0[o];
-            gba += dz; gwa = fmaf(dz, s_act[bb], gwa); gg2 += A.sc1[o]; gwq += A.sc2[o];
-        }
-        A.g_be2[j] = gba; A.g_g2[j] = gg2; A.g_t0[j] = gwa; A.g_t1[j] = gba; A.g_t2[j] = gwq;
-    }
-    if (gt == 0) { float sum = 0.f; for (int bb = 0; bb < A.B; bb++) sum += s_dq[bb]; A.g_t3[0] = sum; }
 }
 
 // K9: DDPG_agent.py:99-103  actor_loss = -mean(critic(states, actor(states)))
 __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
     chain_enter();
-    __shared__ float s_dp[kMaxB];
     __shared__ float sp[8][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H2;
     const int b = (int)blockIdx.x * (kRowT / 32) + warp;
+    Row x, c;
+    if (b < A.B) {
+        load_row(x, A.h2[JOB_A] + (size_t)b * H, H, lane);
+        load_row(c, A.h2[JOB_C] + (size_t)b * H, H, lane);
+    }
     {
         const float *const src[8] = {A.a_g2, A.a_be2, A.a_w3, A.c_g2, A.c_be2, A.c_wa, A.c_ba, A.c_wq};
         stage_vectors<8>(sp, src, H);
@@ -509,9 +668,7 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
     const float *a_g2 = sp[0], *a_be2 = sp[1], *a_w3 = sp[2], *c_g2 = sp[3], *c_be2 = sp[4], *c_wa = sp[5], *c_ba = sp[6], *c_wq = sp[7];
     __syncthreads();
     if (b < A.B) {
-        Row x, o2, c;
-        load_row(x, A.h2[JOB_A] + (size_t)b * H, H, lane);
-        load_row(c, A.h2[JOB_C] + (size_t)b * H, H, lane);
+        Row o2;
         const float rstd = normalize_row(x, H, lane);
         float p = 0.f;
 #pragma unroll
@@ -549,45 +706,35 @@ __global__ void __launch_bounds__(kRowT) learn_actor_head_kernel(HeadArgs A) {
         }
         if (lane == 0) { A.dv[b] = dp; if (A.a_out) A.a_out[b] = a; }
     }
-    if (!last_cta_done(A.ticket)) return;
-    if (threadIdx.x < A.B) s_dp[threadIdx.x] = A.dv[threadIdx.x];
-    __syncthreads();
-    const int gt = threadIdx.x;
-    for (int j = gt; j < H; j += kRowT) {
-        float gbe = 0.f, gg = 0.f, gw3 = 0.f;
-#pragma unroll 32
-        for (int bb = 0; bb < A.B; bb++) { const size_t o = (size_t)bb * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; gw3 += A.sc2[o]; }
-        A.g_be2[j] = gbe; A.g_g2[j] = gg; A.g_t0[j] = gw3;
-    }
-    if (gt == 0) { float sum = 0.f; for (int bb = 0; bb < A.B; bb++) sum += s_dp[bb]; A.g_t1[0] = sum; }
 }
 
-// K5 / K11: relu + LayerNorm 1 backward (warp = row) -> dh1, and the LayerNorm parameter gradients dg1, dbe1 (last CTA).  The
-// fc1 weight / bias gradients are a dW job of the next grouped launch (dW1 = dh1^T x, db1 = column sums of dh1).
+// K5 / K11: relu + LayerNorm 1 backward (warp = row) -> dh1.  The fc1 weight / bias gradients (dW1 = dh1^T x, db1 = column sums of
+// dh1) and the LayerNorm parameter gradients dg1, dbe1 (column sums of sc1, sc0) are jobs of the next grouped launch.
 struct L1Args {
     int B, H1;
     const float *h1, *da1;           // fc1 output (pre-LayerNorm) and the gradient w.r.t. relu(LN1(h1)), [B][H1]
     const float *g1, *be1;
     float *dh1;                      // out [B][H1]
     float *sc0, *sc1;                // scratch [B][H1]
-    float *g_g1, *g_be1;
-    int *ticket;
 };
 __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
     chain_enter();
     __shared__ float sp[2][kMaxH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, H = A.H1;
+    const int b = (int)blockIdx.x * (kRowT / 32) + warp;
+    Row x, dout;
+    if (b < A.B) {
+        load_row(x, A.h1 + (size_t)b * H, H, lane);
+        load_row(dout, A.da1 + (size_t)b * H, H, lane);
+    }
     {
         const float *const src[2] = {A.g1, A.be1};
         stage_vectors<2>(sp, src, H);
     }
     const float *g1 = sp[0], *be1 = sp[1];
     __syncthreads();
-    const int b = (int)blockIdx.x * (kRowT / 32) + warp;
     if (b < A.B) {
-        Row x, dout, dx;
-        load_row(x, A.h1 + (size_t)b * H, H, lane);
-        load_row(dout, A.da1 + (size_t)b * H, H, lane);
+        Row dx;
         const float rstd = normalize_row(x, H, lane);
 #pragma unroll
         for (int i = 0; i < kPerLane; i++) {
@@ -600,13 +747,6 @@ __global__ void __launch_bounds__(kRowT) learn_l1_backward_kernel(L1Args A) {
             const int j = lane + 32 * i;
             if (j < H) { const size_t o = (size_t)b * H + j; A.dh1[o] = dx.v[i]; A.sc0[o] = dout.v[i]; A.sc1[o] = dout.v[i] * x.v[i]; }
         }
-    }
-    if (!last_cta_done(A.ticket)) return;
-    for (int j = threadIdx.x; j < H; j += kRowT) {
-        float gbe = 0.f, gg = 0.f;
-#pragma unroll 32
-        for (int bb = 0; bb < A.B; bb++) { const size_t o = (size_t)bb * H + j; gbe += A.sc0[o]; gg += A.sc1[o]; }
-        A.g_be1[j] = gbe; A.g_g1[j] = gg;
     }
 }
 
@@ -703,9 +843,16 @@ int launch_rows(Kern kern, const Args &args, int B, cudaStream_t s) {
 }
 
 int launch_jobs(const JobList &L, cudaStream_t s) {
-    int ctas = 0;
-    for (int i = 0; i < L.n; i++) ctas += L.j[i].ctas;
-    TT_CUDA(tt::launch_chained(true, learn_gemm_kernel, dim3(ctas), dim3(kT), 0, s, L));
+    int ctas = 0, fl = 0;
+    for (int i = 0; i < L.n; i++) { ctas += L.j[i].ctas; const int f = job_smem_floats(L.j[i]); if (f > fl) fl = f; }
+    ctas += L.cs.ctas;
+    if (L.cs.ctas && fl < 4 * 8 * 32) fl = 4 * 8 * 32;
+    static bool attr_of[tt::kMaxDevices] = {};
+    if (!attr_of[tt::device_index()]) {
+        TT_CUDA(cudaFuncSetAttribute(learn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kMaxChunks * (64 + 16) * kP)));
+        attr_of[tt::device_index()] = true;
+    }
+    TT_CUDA(tt::launch_chained(true, learn_gemm_kernel, dim3(ctas), dim3(kT), sizeof(float) * (size_t)fl, s, L));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
     return TT_OK;
 }
@@ -777,6 +924,13 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     const int64_t win_begin = window_begin, max_mem = window_count;
     TT_REQUIRE(max_mem >= ln->B || d_rows, "fewer transitions in the sampling window than the batch size (DDPG_agent.py:73-74)");
     cudaStream_t s = tt::as_stream(stream);
+    // developer build (-DTT_LEARN_PROFILE, profiles/learner_stage_times.py): TT_LEARN_STOP=k ends the sequence after k launches
+#if defined(TT_LEARN_PROFILE)
+    const char *e_ = getenv("TT_LEARN_STOP"); const int stop_at = e_ ? atoi(e_) : 0; int nl_ = 0;
+#define TT_STAGE_END(ret) do { if (++nl_ == stop_at) return ret; } while (0)
+#else
+#define TT_STAGE_END(ret) do { } while (0)
+#endif
     const Layout &L = ln->L;
     const int B = ln->B, IN = L.in, H1 = L.h1, H2 = L.h2;
     float *pa = ln->p[NET_ACTOR], *pta = ln->p[NET_TARGET_ACTOR], *pc = ln->p[NET_CRITIC], *ptc = ln->p[NET_TARGET_CRITIC];
@@ -786,6 +940,7 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     // K0
     TT_CUDA(tt::launch_chained(true, learn_gather_kernel, dim3(1), dim3(1024), 0, s, *ring, win_begin, max_mem, d_rows, ln->bt, B, IN, ln->seed, ln->step));
     TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+    TT_STAGE_END(TT_OK);
     int rc;
     // K1: fc1 + LayerNorm 1 + ReLU of the four forward passes
     const float *netp[NJOBS] = {pta, ptc, pc, pa};
@@ -797,25 +952,27 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
             const int j = jobs[i];
             A.j[i] = Fc1Job{netx[j], netp[j] + L.w1(), netp[j] + L.b1(), netp[j] + L.g1(), netp[j] + L.be1(), ln->h1[j], ln->a1[j]};
         }
-        const size_t dsm = sizeof(float) * (size_t)H1 * kW1P;
+        const size_t dsm = sizeof(float) * (size_t)H1 * IN + 16;
         static bool attr_of[tt::kMaxDevices] = {};
         if (dsm > 48 * 1024 && !attr_of[tt::device_index()]) {
-            TT_CUDA(cudaFuncSetAttribute(learn_fc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kMaxH * kW1P)));
+            TT_CUDA(cudaFuncSetAttribute(learn_fc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kMaxH * kXP + 16)));
             attr_of[tt::device_index()] = true;
         }
-        TT_CUDA(tt::launch_chained(true, learn_fc1_kernel, dim3(njobs * ((B + 7) / 8)), dim3(256), dsm, s, A));
+        TT_CUDA(tt::launch_chained(true, learn_fc1_kernel, dim3(njobs * ((B + kFc1Rows - 1) / kFc1Rows)), dim3(kFc1T), dsm, s, A));
         TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
         return TT_OK;
     };
     {
         const int all[NJOBS] = {JOB_TA, JOB_TC, JOB_C, JOB_A};
         if ((rc = fc1(all, NJOBS)) != TT_OK) return rc;
+        TT_STAGE_END(TT_OK);
     }
     // K2: fc2
     {
         JobList J{}; J.n = NJOBS;
         for (int j = 0; j < NJOBS; j++) J.j[j] = fwd_job(B, H2, H1, ln->a1[j], netp[j] + L.w2(), netp[j] + L.b2(), ln->h2[j]);
         if ((rc = launch_jobs(J, s)) != TT_OK) return rc;
+        TT_STAGE_END(TT_OK);
     }
     // K3: critic head
     HeadArgs H{};
@@ -827,15 +984,15 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     H.a_g2 = pa + L.g2(); H.a_be2 = pa + L.be2(); H.a_w3 = pa + T; H.a_b3 = pa + T + H2;
     H.act = ln->bt.a; H.rew = ln->bt.r; H.done = ln->bt.d;
     H.dh2 = ln->dh2; H.sc0 = ln->sc0; H.sc1 = ln->sc1; H.sc2 = ln->sc2;
-    H.q_out = ln->q; H.y_out = ln->y; H.a_out = ln->aout; H.dv = ln->dv; H.ticket = ln->step + 1;
+    H.q_out = ln->q; H.y_out = ln->y; H.a_out = ln->aout; H.dv = ln->dv;
     {
-        HeadArgs C = H;
-        C.g_g2 = gc + L.g2(); C.g_be2 = gc + L.be2(); C.g_t0 = gc + T; C.g_t1 = gc + T + H2; C.g_t2 = gc + T + 2 * H2; C.g_t3 = gc + T + 3 * H2;
-        if ((rc = launch_rows(learn_critic_head_kernel, C, B, s)) != TT_OK) return rc;
+        if ((rc = launch_rows(learn_critic_head_kernel, H, B, s)) != TT_OK) return rc;
+        TT_STAGE_END(TT_OK);
     }
     // backward through fc2 / LayerNorm 1 / fc1 of one network whose dh2 is in ln->dh2 and whose forward job is `job`
-    auto trunk_backward = [&](int job, const float *p, float *g, const float *x) -> int {
-        JobList J{}; J.n = 2;
+    // (`head`: the column sums that turn the head kernel's per-row terms sc0 / sc1 / sc2 / dv into its parameter gradients)
+    auto trunk_backward = [&](int job, const float *p, float *g, const float *x, const ColSumJob &head) -> int {
+        JobList J{}; J.n = 2; J.cs = head;
         Job w{};
         w.type = G_WGRAD; w.B = B; w.N = H2; w.K = H1; w.ctas = ((H2 + 15) / 16) * ((H1 + 31) / 32);
         w.X = ln->a1[job]; w.ldx = H1;
@@ -846,16 +1003,24 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
         J.j[0] = w; J.j[1] = xg;
         int r = launch_jobs(J, s);
         if (r != TT_OK) return r;
+        TT_STAGE_END(77);
         L1Args A{};
         A.B = B; A.H1 = H1; A.h1 = ln->h1[job]; A.da1 = ln->da1; A.g1 = p + L.g1(); A.be1 = p + L.be1();
-        A.dh1 = ln->dh1; A.sc0 = ln->sc0; A.sc1 = ln->sc1; A.g_g1 = g + L.g1(); A.g_be1 = g + L.be1(); A.ticket = ln->step + 1;
+        A.dh1 = ln->dh1; A.sc0 = ln->sc0; A.sc1 = ln->sc1;
         if ((r = launch_rows(learn_l1_backward_kernel, A, B, s)) != TT_OK) return r;
+        TT_STAGE_END(77);
         JobList J1{}; J1.n = 1;
         Job w1{};
         w1.type = G_WGRAD; w1.B = B; w1.N = H1; w1.K = IN; w1.ctas = ((H1 + 15) / 16) * ((IN + 31) / 32);
         w1.X = x; w1.ldx = IN; w1.D = ln->dh1; w1.ldd = H1; w1.Y = g + L.w1(); w1.ldy = IN; w1.db = g + L.b1();
         J1.j[0] = w1;
-        return launch_jobs(J1, s);
+        ColSumJob c1{};                                     // LayerNorm 1: d be1 = column sums of sc0, d g1 = of sc1
+        c1.nv = 2; c1.B = B; c1.H = H1; c1.ctas = (H1 + 31) / 32;
+        c1.src[0] = ln->sc0; c1.dst[0] = g + L.be1(); c1.src[1] = ln->sc1; c1.dst[1] = g + L.g1();
+        J1.cs = c1;
+        r = launch_jobs(J1, s); if (r != TT_OK) return r;
+        TT_STAGE_END(77);
+        return TT_OK;
     };
     auto adam = [&](float *p, float *m, float *v, float *target, const float *g, int n, float lr, float wd) -> int {
         AdamArgs A{};
@@ -869,24 +1034,43 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
         return TT_OK;
     };
     // K4, K5, K6: critic backward + optimizer (DDPG_agent.py:95-98)
-    if ((rc = trunk_backward(JOB_C, pc, gc, ln->bt.s)) != TT_OK) return rc;
+    {
+        ColSumJob c{};                                      // critic head: d be2 = d action_value.bias = sum dz, d action_value.weight = sum dz a,
+        c.nv = 4; c.B = B; c.H = H2; c.ctas = (H2 + 31) / 32;  // d g2 = sum dz xhat, d q.weight = sum dq relu(z), d q.bias = sum dq
+        c.src[0] = ln->sc0; c.dst[0] = gc + L.be2(); c.dst2[0] = gc + T + H2;
+        c.src[1] = ln->sc0; c.scale[1] = ln->bt.a; c.dst[1] = gc + T;
+        c.src[2] = ln->sc1; c.dst[2] = gc + L.g2();
+        c.src[3] = ln->sc2; c.dst[3] = gc + T + 2 * H2;
+        c.tot_src = ln->dv; c.tot_dst = gc + T + 3 * H2;
+        if ((rc = trunk_backward(JOB_C, pc, gc, ln->bt.s, c)) != TT_OK) return rc == 77 ? TT_OK : rc;
+    }
     if ((rc = adam(pc, ln->m[1], ln->v[1], ptc, gc, ln->np[NET_CRITIC], ln->beta, ln->wd)) != TT_OK) return rc;
+    TT_STAGE_END(TT_OK);
     // K7, K8: the updated critic's trunk on s (into the JOB_C buffers)
     {
         const int one[1] = {JOB_C};
         if ((rc = fc1(one, 1)) != TT_OK) return rc;
+        TT_STAGE_END(TT_OK);
         JobList J{}; J.n = 1;
         J.j[0] = fwd_job(B, H2, H1, ln->a1[JOB_C], pc + L.w2(), pc + L.b2(), ln->h2[JOB_C]);
         if ((rc = launch_jobs(J, s)) != TT_OK) return rc;
+        TT_STAGE_END(TT_OK);
     }
     // K9: actor head
     {
-        HeadArgs A = H;
-        A.g_g2 = ga + L.g2(); A.g_be2 = ga + L.be2(); A.g_t0 = ga + T; A.g_t1 = ga + T + H2; A.g_t2 = nullptr; A.g_t3 = nullptr;
-        if ((rc = launch_rows(learn_actor_head_kernel, A, B, s)) != TT_OK) return rc;
+        if ((rc = launch_rows(learn_actor_head_kernel, H, B, s)) != TT_OK) return rc;
+        TT_STAGE_END(TT_OK);
     }
     // K10, K11, K12 (DDPG_agent.py:99-106)
-    if ((rc = trunk_backward(JOB_A, pa, ga, ln->bt.s)) != TT_OK) return rc;
+    {
+        ColSumJob c{};                                      // actor head: d be2 = sum dout, d g2 = sum dout xhat, d mu.weight = sum dp relu(o2), d mu.bias = sum dp
+        c.nv = 3; c.B = B; c.H = H2; c.ctas = (H2 + 31) / 32;
+        c.src[0] = ln->sc0; c.dst[0] = ga + L.be2();
+        c.src[1] = ln->sc1; c.dst[1] = ga + L.g2();
+        c.src[2] = ln->sc2; c.dst[2] = ga + T;
+        c.tot_src = ln->dv; c.tot_dst = ga + T + H2;
+        if ((rc = trunk_backward(JOB_A, pa, ga, ln->bt.s, c)) != TT_OK) return rc == 77 ? TT_OK : rc;
+    }
     if ((rc = adam(pa, ln->m[0], ln->v[0], pta, ga, ln->np[NET_ACTOR], ln->alpha, 0.f)) != TT_OK) return rc;
     // hand the new policy to the rollout actor (re-pack into the fp32 / tensor-core operand images)
     if (repack_into) {
@@ -895,6 +1079,7 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
                              a + T, a + T + H2, stream);
     }
     return TT_OK;
+#undef TT_STAGE_END
 }
 
 }  // extern "C"

@@ -29,9 +29,8 @@ class RolloutEngine:
 
     # ------------------------------------------------------------------ CUDA graph of K iterations
     def capture(self, k=None):
-        """Capture K consecutive rollout iterations (5 kernel launches each) into ONE CUDA graph; ``step_graph()`` replays
-        it.  Small batches are launch-bound (5 launches ~ 30 us per iteration at N = 4096), a graph removes the per-launch
-        host cost.  Every launch of the C ABI goes to the caller's stream and never synchronises, so the sequence is
+        """Capture K consecutive rollout iterations (2 kernel launches each) into ONE CUDA graph; ``step_graph()`` replays
+        it.  Small batches are launch-bound, a graph removes the per-launch host cost.  Every launch of the C ABI goes to the caller's stream and never synchronises, so the sequence is
         capturable as is; the Philox iteration counter lives in device memory.  The ring write position is a by-value
         argument of the captured launches, so K must bring it back to where it started: K * N % mem_size == 0, and K must
         be even (observation double buffer).  Default: the smallest such K."""
@@ -91,17 +90,25 @@ class RolloutEngine:
         self.agent.noise.reset()
         return obs
 
-    def step(self):
+    def step(self, out=None):
         """One iteration for all envs.  Returns (obs_next, reward, done) views of device buffers; finished envs'
-        rows of obs_next already hold the reset observation (their terminal observation went to the ring)."""
+        rows of obs_next already hold the reset observation (their terminal observation went to the ring).
+        ``out = (reward, done)``: float32 [N] / uint8 [N] device tensors that receive this iteration's reward and done instead
+        of the engine's own buffers -- a caller that reads results back asynchronously alternates two pairs and needs no
+        staging copy."""
         env, ag = self.env, self.agent
+        reward, done = (self.reward, self.done) if out is None else out
+        if out is not None:
+            for t, dt in ((reward, torch.float32), (done, torch.uint8)):
+                if t.dtype != dt or t.numel() != env.num_envs or t.device != self.reward.device or not t.is_contiguous():
+                    raise ValueError("step(out=(reward, done)): float32 [N] and uint8 [N] contiguous tensors on the engine's device")
         with torch.cuda.device(env.device):
             cur = env._obs[env._cur]
             env._cur ^= 1
             nxt = env._obs[env._cur]
             m = ag.memory
             b = _lib.RolloutBufs(cur.data_ptr(), nxt.data_ptr(), env.ld_obs, ag.noise.x_prev.data_ptr(), self.action.data_ptr(),
-                                 self.scaled.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                 self.scaled.data_ptr(), reward.data_ptr(), done.data_ptr(),
                                  m.state_memory.data_ptr() if self.store else None,
                                  m.action_memory.data_ptr() if self.store else None,
                                  m.reward_memory.data_ptr() if self.store else None,
@@ -113,12 +120,12 @@ class RolloutEngine:
             if self.store:
                 m.mem_cntr += env.num_envs
             self.iterations += 1
-        return env._obs_view(nxt), self.reward, self.done
+        return env._obs_view(nxt), reward, done
 
 
 class AsyncTrainer:
     """BASELINE.json configs[3]: one rollout iteration + one DDPG update (``Agent.learn``) per step, with the update HIDDEN
-    under the rollout: the learner's launch sequence (``tt_learn_step``, 13 small dependent kernels), the optional broadcast of
+    under the rollout: the learner's launch sequence (``tt_learn_step``, 15 small dependent kernels), the optional broadcast of
     the new policy (multi-GPU) and its re-pack into the SPARE packed actor run on a side stream while the rollout kernels of
     the same iteration run on the caller's stream.
 
@@ -164,7 +171,7 @@ class AsyncTrainer:
         begin = (c + n) % cap
         return begin, (cap - n if c >= cap else max(0, c - begin))
 
-    def step(self):
+    def step(self, out=None):
         eng, ag = self.eng, self.eng.agent
         with torch.cuda.device(self.dev):
             main = torch.cuda.current_stream()
@@ -183,7 +190,7 @@ class AsyncTrainer:
                         self.sync.wait_policy()
                     self.actors[(self.it + 1) & 1].load_flat(self.flat)
                     self.ev_pol.record(self.side)
-            out = eng.step()
+            res = eng.step(out=out)
             self.ev_step.record(main)
             self.it += 1
-        return out
+        return res

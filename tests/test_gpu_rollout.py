@@ -45,6 +45,25 @@ def test_rollout_step_equals_manual_loop():
     assert s1 == s2 and s1["steps"] == N * iters and s1["episodes"] == tot_done
 
 
+def test_step_out_buffers_receive_reward_and_done():
+    """``RolloutEngine.step(out=(reward, done))``: the kernels write the step's results into the caller's buffers (two pairs
+    used alternately by an asynchronous reader, bench.py e2e) -- same values as the engine's own buffers get."""
+    import ddpg_trucktrailer_b200 as tt
+    N, cap = 3000, 10000
+    env1, ag1 = _mk(tt, N, cap); e1 = tt.RolloutEngine(env1, ag1); e1.reset()
+    env2, ag2 = _mk(tt, N, cap); e2 = tt.RolloutEngine(env2, ag2); e2.reset()
+    pairs = [(torch.full((N,), 7.0, device="cuda"), torch.full((N,), 9, dtype=torch.uint8, device="cuda")) for _ in range(2)]
+    for it in range(40):
+        o1, r1, d1 = e1.step()
+        o2, r2, d2 = e2.step(out=pairs[it & 1])
+        assert r2 is pairs[it & 1][0] and d2 is pairs[it & 1][1]
+        assert torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(o1, o2), it
+    for f in ("new_state_memory", "reward_memory", "terminal_memory"):
+        assert torch.equal(getattr(ag1.memory, f), getattr(ag2.memory, f)), f
+    with pytest.raises(ValueError):
+        e2.step(out=(torch.zeros(N, device="cuda"), torch.zeros(N - 1, dtype=torch.uint8, device="cuda")))
+
+
 def test_rollout_vs_oracle_small():
     """Closed loop (actor in the loop) against the float64 oracle on 64 envs, evaluate=True (no noise)."""
     import ddpg_trucktrailer_b200 as tt
