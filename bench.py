@@ -299,10 +299,11 @@ def run_b200(args):
     flat_dev = [torch.empty_like(flat_host, device=dev) for _ in range(2)]
     actors = [agent.actor, tt.agent.CudaActor(*agent.actor.dims, device=dev)]
     rew_host = [torch.empty(N, dtype=torch.float32).pin_memory() for _ in range(2)]
-    done_host = [torch.empty(N, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    nbits = (N + 31) // 32                                            # done is read back bit-packed (tt_env_set_done_bits): 1 bit per env over PCIe
+    done_host = [torch.empty(nbits, dtype=torch.int32).pin_memory() for _ in range(2)]
     stats_host = [torch.empty(16, dtype=torch.float64).pin_memory() for _ in range(2)]
     rew_stage = [torch.empty(N, dtype=torch.float32, device=dev) for _ in range(2)]
-    done_stage = [torch.empty(N, dtype=torch.uint8, device=dev) for _ in range(2)]
+    done_stage = [torch.zeros(nbits, dtype=torch.int32, device=dev) for _ in range(2)]
     stats_stage = [torch.empty(16, dtype=torch.float64, device=dev) for _ in range(2)]
     up_stream, copy_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
@@ -354,7 +355,7 @@ def run_b200(args):
 
     # ---- e2e: the same iteration driven from the host with HOST buffers inside the timed region:
     #      H2D of the step's external input (the current actor parameters from pinned host memory, re-packed on the
-    #      device) and D2H of the step's results the reference driver reads (reward and done of every env + stats).
+    #      device) and D2H of the step's results the reference driver reads (reward and done -- bit-packed -- of every env + stats).
     # The policy of step t + 1 is uploaded and re-packed on a side stream WHILE step t runs (two packed actors, used
     # alternately): what an asynchronous learner hands over; results are read back one iteration behind on a copy stream
     # (two pairs of result buffers, written by the kernels alternately).  Every byte still moves, every step, inside the timed region.
@@ -382,7 +383,7 @@ def run_b200(args):
         step_done.record(main)                                       # (everything before this step, incl. the last user of slot b ^ 1)
         upload(b ^ 1)                                                # H2D + re-pack of the NEXT step's policy, overlapped with this step
         main.wait_event(drained[b])                                  # result buffers b were read out two steps ago
-        eng.step(out=(rew_stage[b], done_stage[b]))                  # the kernels write this step's reward / done straight into pair b
+        eng.step(out=(rew_stage[b], None, done_stage[b]))            # the kernels write this step's reward / bit-packed done straight into pair b
         stats_stage[b].copy_(env.stats_tensor(clear=True))
         staged[b].record(main)
         with torch.cuda.stream(copy_stream):
@@ -392,8 +393,9 @@ def run_b200(args):
             stats_host[b].copy_(stats_stage[b], non_blocking=True)
             drained[b].record(copy_stream)
 
-    # what bounds e2e at 8 GPUs is the host side (21 MB D2H per rank and step through one host): measure the D2H rate every rank
+    # what bounds e2e at 8 GPUs is the host side (17 MB D2H per rank and step through one host): measure the D2H rate every rank
     # gets while ALL ranks copy at once
+    d2h_bytes = N * 4 + nbits * 4                                     # reward + bit-packed done per step (+ 128 B of statistics)
     d2h_probe = None
     if world > 1:
         barrier(); torch.cuda.synchronize()
@@ -402,11 +404,11 @@ def run_b200(args):
         for _ in range(20):
             rew_host[0].copy_(rew_stage[0], non_blocking=True); done_host[0].copy_(done_stage[0], non_blocking=True)
         p1.record(); torch.cuda.synchronize()
-        gbs = torch.tensor([20 * N * 5 / (p0.elapsed_time(p1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        gbs = torch.tensor([20 * d2h_bytes / (p0.elapsed_time(p1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
         lo, hi = gbs.clone(), gbs.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(gbs)
         d2h_probe = {"per_rank_min": float(lo), "per_rank_max": float(hi), "aggregate": float(gbs),
-                     "needed_per_rank_at_value": N * 5 / (ms / K * 1e-3) / 1e9}
+                     "needed_per_rank_at_value": d2h_bytes / (ms / K * 1e-3) / 1e9}
     step_done.record()
     upload(0)                                                          # the first step's policy
     # its own pre-roll: the e2e pipeline itself for >= args.e2e_preroll_s, straight into the timed region (same clock / power
@@ -430,6 +432,7 @@ def run_b200(args):
     ms_e2e = float(t_e2e)
     agent.actor = actors[0]
     actors[0].load_state_dict(sd)
+    env.set_done_bits(None)
     env.stats_tensor(clear=True)
     clocks = clocks_e2e = None
     if sampler:
@@ -438,9 +441,9 @@ def run_b200(args):
         clocks = sampler.window(win_value[0] - 0.3, win_value[1]) or sampler.window(t_load0, win_value[1])
         clocks_e2e = sampler.window(w_e0 - 0.3, w_e1)
     e2e = {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": flat_host.numel() * 4,
-           "d2h_bytes_per_step": N * 5 + 128, "ms_per_step": ms_e2e / K, "preroll_iterations": pre, "clocks": clocks_e2e,
+           "d2h_bytes_per_step": d2h_bytes + 128, "ms_per_step": ms_e2e / K, "preroll_iterations": pre, "clocks": clocks_e2e,
            "host": dict(numa, d2h_gbs_all_ranks_copying=d2h_probe),
-           "note": "host buffers: actor parameters H2D + re-pack every step (side stream, one step ahead, two packed actors); reward/done/stats D2H "
+           "note": "host buffers: actor parameters H2D + re-pack every step (side stream, one step ahead, two packed actors); reward / bit-packed done / stats D2H "
                    "every step (copy stream, one step behind); timed right after its own pre-roll of the same pipeline"}
 
     # ---- per-kernel timing (CUDA events on the launching stream) -> roofline of the dominant kernel ----

@@ -86,6 +86,7 @@ SYMBOLS = {
     "tt_env_get_reward_state": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "tt_env_set_l2": (C.c_int, [_P, _P, _I64, _P, _P]),
     "tt_env_get_l2": (C.c_int, [_P, _P, _P]),
+    "tt_env_set_done_bits": (C.c_int, [_P, _P]),
     "tt_env_tick": (C.c_int, [_P, _U32, _P]),
     "tt_env_iter_ptr": (_P, [_P]),
     "tt_env_seed_value": (_U64, [_P]),

@@ -38,6 +38,7 @@ struct EnvPtrs {
     double *stats;       // [16]
     uint32_t *iter;      // [0] Philox iteration counter, [1] CTAs-finished counter of the rollout kernel's tick
     uint32_t *done_list; // [N + slack] scratch of the rollout kernel: overflow of a CTA's shared-memory list of finished envs
+    uint32_t *done_bits; // optional (tt_env_set_done_bits): bit i % 32 of word i / 32 = done of env i, written by single-step launches
     int64_t N;
 };
 
@@ -321,6 +322,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) env_step_kernel(EnvPtrs p,
                     } else e.packed |= PK_FINISHED;
                 }
             }
+            if (p.done_bits && K == 1) {                                 // warp-uniform: 32 consecutive envs = one word (a tile starts at a multiple of 128)
+                const uint32_t bits = __ballot_sync(0xffffffffu, active && o.done);
+                if ((threadIdx.x & 31) == 0 && i < N) p.done_bits[i >> 5] = bits;
+            }
             if (kRoll && active && o.done) {                             // reset at the end of the kernel
                 const int slot = atomicAdd(&s_ndone, 1);
                 if (slot < kDoneSmem) s_done[slot] = (uint32_t)i; else p.done_list[seg0 + slot] = (uint32_t)i;
@@ -564,7 +569,7 @@ static size_t env_layout(int64_t n, EnvPtrs *p, char *base) {
         p->rsA = reinterpret_cast<float4 *>(base + o_a); p->rsB = reinterpret_cast<float4 *>(base + o_b);
         p->packed = reinterpret_cast<uint32_t *>(base + o_pk); p->goal = reinterpret_cast<int4 *>(base + o_goal); p->l2v = reinterpret_cast<double2 *>(base + o_l2v);
         p->pose = reinterpret_cast<double *>(base + o_pose); p->stats = reinterpret_cast<double *>(base + o_stats);
-        p->iter = reinterpret_cast<uint32_t *>(base + o_iter); p->done_list = reinterpret_cast<uint32_t *>(base + o_list); p->N = n;
+        p->iter = reinterpret_cast<uint32_t *>(base + o_iter); p->done_list = reinterpret_cast<uint32_t *>(base + o_list); p->done_bits = nullptr; p->N = n;
     }
     return off;
 }
@@ -727,6 +732,13 @@ int tt_env_step_reset(tt_env *env, const float *d_action, float *d_obs, int64_t 
     const TTRingOut ro = {ring->d_new_state_mem, ring->d_reward_mem, ring->d_terminal_mem,
                           tt_make_ring_map(ring->mem_size, ring->mem_cntr, env->p.N)};
     return env_step_impl(env, d_action, 1, 1, d_obs, ld_obs, d_reward, d_done, nullptr, &ro, true, d_ou_x, stream);
+}
+
+int tt_env_set_done_bits(tt_env *env, uint32_t *d_bits) {
+    TT_REQUIRE(env, "env is NULL");
+    TT_REQUIRE((reinterpret_cast<uintptr_t>(d_bits) & 3) == 0, "d_bits must be 4 B aligned");
+    env->p.done_bits = d_bits;
+    return TT_OK;
 }
 
 int tt_env_tick(tt_env *env, uint32_t by, tt_stream_t stream) {

@@ -89,6 +89,7 @@ class VecTruckTrailerEnv:
             self._cur = 0
             self._reward = torch.zeros(N, dtype=torch.float32, device=self.device)
             self._done = torch.zeros(N, dtype=torch.uint8, device=self.device)
+            self._done_bits = None
             self._scaled = torch.zeros(N, dtype=torch.float32, device=self.device)
             self._stats = torch.zeros(TT_NSTATS, dtype=torch.float64, device=self.device)
             self._info_bufs = None
@@ -194,6 +195,23 @@ class VecTruckTrailerEnv:
                                      self._done.data_ptr(), C.byref(info_struct) if emit else None, stream_ptr()))
         info = self._make_info() if emit else {}
         return self._obs_view(buf), self._reward, self._done.bool(), info
+
+    def set_done_bits(self, bits):
+        """Optional bit-packed copy of ``done`` (``tt_env_set_done_bits``): while set, every single-step launch also writes
+        bit i % 32 of word i // 32 = done of env i into ``bits`` (int32 / uint32 [ceil(N / 32)], CUDA) -- 1 bit instead of 1 byte
+        per env for a host that reads the flags back every step.  ``None`` switches it off.  ``unpack_done_bits`` decodes."""
+        if bits is not None:
+            if bits.device != self._done.device or bits.element_size() != 4 or bits.numel() < (self.num_envs + 31) // 32 or not bits.is_contiguous():
+                raise ValueError("done bits: a contiguous 32-bit integer CUDA tensor with ceil(num_envs / 32) elements")
+        self._done_bits = bits                          # keeps the buffer alive while the env points at it
+        check(self.L.tt_env_set_done_bits(self._h, None if bits is None else bits.data_ptr()))
+
+    @staticmethod
+    def unpack_done_bits(bits, n):
+        """bool [n] from the bit-packed words (numpy array or CPU / CUDA tensor)."""
+        import numpy as np
+        a = bits.detach().cpu().numpy() if hasattr(bits, "detach") else np.asarray(bits)
+        return np.unpackbits(a.view(np.uint8), bitorder="little")[:n].astype(bool)
 
     def tick(self, by: int = 1):
         """Advance the Philox iteration counter (once per step+reset iteration when driving by hand)."""

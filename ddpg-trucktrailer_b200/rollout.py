@@ -57,14 +57,16 @@ class RolloutEngine:
         # the capture only recorded the launches: roll the host-side bookkeeping back
         m.mem_cntr, env._cur, self.iterations = cntr0, cur0, it0
         self._graph, self._graph_k = g, k
-        # what the captured launches carry BY VALUE: the Philox seed, the ring write position and the observation buffer
-        # parity.  step_graph() refuses to replay when any of them has moved (reset(seed=...), step() / remember() in between).
-        self._graph_key = (env.seed_value, (m.mem_cntr % m.mem_size) if self.store else 0, env._cur, id(self.agent.actor))
+        # what the captured launches carry BY VALUE: the Philox seed, the ring write position, the observation buffer
+        # parity, the actor and the optional done-bits buffer.  step_graph() refuses to replay when any of them has moved (reset(seed=...), step() / remember() in between).
+        self._graph_key = self._graph_state()
         return k
 
     def _graph_state(self):
         env, m = self.env, self.agent.memory
-        return (env.seed_value, (m.mem_cntr % m.mem_size) if self.store else 0, env._cur, id(self.agent.actor))
+        bits = env._done_bits
+        return (env.seed_value, (m.mem_cntr % m.mem_size) if self.store else 0, env._cur, id(self.agent.actor),
+                None if bits is None else bits.data_ptr())
 
     def step_graph(self):
         """Replay the captured K iterations.  Returns (obs_next, reward, done) of the LAST of them."""
@@ -95,13 +97,19 @@ class RolloutEngine:
         rows of obs_next already hold the reset observation (their terminal observation went to the ring).
         ``out = (reward, done)``: float32 [N] / uint8 [N] device tensors that receive this iteration's reward and done instead
         of the engine's own buffers -- a caller that reads results back asynchronously alternates two pairs and needs no
-        staging copy."""
+        staging copy.  ``out = (reward, done, done_bits)``: additionally the bit-packed flags (``env.set_done_bits``; int32
+        [ceil(N / 32)]) -- what such a caller copies to the host instead of the byte array; ``done`` may then be None (the
+        engine's own byte buffer)."""
         env, ag = self.env, self.agent
-        reward, done = (self.reward, self.done) if out is None else out
+        reward, done = self.reward, self.done
         if out is not None:
+            reward = out[0]
+            done = out[1] if out[1] is not None else self.done
             for t, dt in ((reward, torch.float32), (done, torch.uint8)):
                 if t.dtype != dt or t.numel() != env.num_envs or t.device != self.reward.device or not t.is_contiguous():
                     raise ValueError("step(out=(reward, done)): float32 [N] and uint8 [N] contiguous tensors on the engine's device")
+            if len(out) > 2:
+                env.set_done_bits(out[2])
         with torch.cuda.device(env.device):
             cur = env._obs[env._cur]
             env._cur ^= 1

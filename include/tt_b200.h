@@ -144,6 +144,13 @@ int tt_env_get_reward_state(tt_env *env, float *d_closest, float *d_cum_backward
 int tt_env_set_l2(tt_env *env, const int64_t *d_idx, int64_t n, const double *d_l2, tt_stream_t stream);
 int tt_env_get_l2(tt_env *env, double *d_l2, tt_stream_t stream);
 
+/* Optional bit-packed copy of `done` for hosts that read the flags back every step (1 bit instead of 1 byte per env over PCIe):
+ * while d_bits != NULL every single-step launch (tt_env_step, tt_env_step_store, tt_env_step_reset, tt_rollout_step; not
+ * tt_env_step_k with K > 1) also writes word i / 32, bit i % 32 = done of env i (what np.packbits(done, bitorder='little') of the
+ * byte array gives, read as little-endian uint32).  d_bits: ceil(n_envs / 32) uint32; NULL switches it off.  The pointer is a
+ * by-value launch argument: set it before the launches are captured into a CUDA graph. */
+int tt_env_set_done_bits(tt_env *env, uint32_t *d_bits);
+
 /* Iteration counter of the Philox streams (device-resident so that launch sequences stay graph-capturable).
  * tt_env_step does not advance it; a driver that steps and resets by hand calls tt_env_tick once per
  * iteration (tt_rollout_step, tt_env_step_k with auto_reset and a full tt_env_reset do it themselves). */

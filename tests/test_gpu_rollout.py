@@ -64,6 +64,35 @@ def test_step_out_buffers_receive_reward_and_done():
         e2.step(out=(torch.zeros(N, device="cuda"), torch.zeros(N - 1, dtype=torch.uint8, device="cuda")))
 
 
+@pytest.mark.parametrize("N", [77, 1000, 3000, 4096 + 33])
+def test_done_bits_equal_packed_done_bytes(N):
+    """``tt_env_set_done_bits``: every single-step launch also writes done as one bit per env (what a host that reads the flags
+    back every step copies): equal to np.packbits(done, bitorder='little') for the rollout's kernel and for ``env.step``."""
+    import ddpg_trucktrailer_b200 as tt
+    env, ag = _mk(tt, N, 4 * N)
+    eng = tt.RolloutEngine(env, ag); eng.reset()
+    nw = (N + 31) // 32
+    bits = [torch.full((nw,), -1, dtype=torch.int32, device="cuda") for _ in range(2)]
+    rew = [torch.empty(N, device="cuda") for _ in range(2)]
+    seen = 0
+    for it in range(80):
+        _, r, d = eng.step(out=(rew[it & 1], None, bits[it & 1]))
+        want = np.packbits(d.cpu().numpy().astype(bool), bitorder="little")
+        got = bits[it & 1].cpu().numpy().view(np.uint8)[:want.size]
+        assert np.array_equal(got, want), it
+        assert np.array_equal(tt.VecTruckTrailerEnv.unpack_done_bits(bits[it & 1], N), d.cpu().numpy().astype(bool))
+        seen += int(d.sum())
+    assert seen > 0
+    # the plain step kernel (terminal observation, no reset) writes them too; None switches it off
+    env.set_done_bits(bits[0])
+    _, _, d, _ = env.step(torch.zeros(N, device="cuda"))
+    assert np.array_equal(tt.VecTruckTrailerEnv.unpack_done_bits(bits[0], N), d.cpu().numpy())
+    env.set_done_bits(None)
+    bits[0].fill_(-1)
+    env.reset(options={"mask": d}); env.step(torch.zeros(N, device="cuda"))
+    assert int((bits[0] != -1).sum()) == 0
+
+
 def test_rollout_vs_oracle_small():
     """Closed loop (actor in the loop) against the float64 oracle on 64 envs, evaluate=True (no noise)."""
     import ddpg_trucktrailer_b200 as tt
