@@ -934,7 +934,10 @@ int launch_tc4(const char *w1img, const char *w2img, const tt_actor_dev &A, cons
 #if !defined(TT_DEV_VARIANTS)
     dbg = nullptr;
 #endif
-    if (cluster == 2 && ntiles > 1) {
+    // CTA pairs (multicast W2 stream) pay off only when every SM runs many tiles: measured per rollout iteration, pairs / single
+    // CTAs: 2^12 envs 20.0 / 18.0 us, 2^16 41.6 / 39.0, 2^18 98.5 / 96.6, 2^20 354 / 357, 2^22 - 1.7 % with pairs (the pair's set-up --
+    // cluster barrier, remote mbarrier arrivals -- is pure latency for a CTA that sees one or a few tiles)
+    if (cluster == 2 && ntiles > 2048) {
         grid = (grid + 1) & ~1;                                  // whole pairs; a CTA without tiles only serves the pair's W2 ring
         if (grid > (sms & ~1)) grid = sms & ~1;
         cudaLaunchConfig_t cfg{};

@@ -183,6 +183,8 @@ def test_actor_tc_full_size_position_independence(golden_dir, precision):
     full = out[: (N // B) * B].view(N // B, B)
     assert torch.equal(full, full[0:1].expand_as(full))
     assert torch.equal(out[(N // B) * B:], out[: N - (N // B) * B])
+    # CTA pairs with the multicast W2 stream (batches above 2^18 rows) against single CTAs (the block alone): same bits
+    assert torch.equal(out[:B], actor.forward(block, precision=precision, allow_out_of_bar=True))
 
 
 @pytest.mark.parametrize("precision,tol", [("f16", 1e-3), ("f16_plain", 1.5e-3)])
