@@ -369,6 +369,38 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     }
     chain_wait();                                    // (tt_common.cuh: chained launches) the setup above touched no global memory
     chain_trigger();
+    // The first tile's observation loads (epilogue threads: 8 inputs of the thread's own row) and the loads of the output constant
+    // are issued HERE, in front of the parameter loops and the set-up barrier, so that their memory round trips overlap with
+    // everything below instead of following it (a batch of one tile per CTA is all latency: 9.3 -> 8.8 us per launch in a CUDA graph).
+    float xreg0[8];
+    if (warp < 16) {
+        const int grp0 = warp >> 2, r0 = (warp & 3) * 32 + lane, kk0 = 8 * grp0;
+        const int64_t gr = (int64_t)blockIdx.x * kTileM + r0;
+        const bool ok = gr < n && grp0 < 3;
+        const float *p = obs + gr * ld + kk0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) xreg0[i] = (kk0 + i < IN) ? (ok ? __ldg(p + i) : 0.f) : (kk0 + i == IN ? 1.0f : 0.f);
+    }
+    // constant part of the output: mu.bias + 1/2 sum be2 w3 (every warp computes it, once).  All 30 loads of a lane are issued
+    // before the first use: nvcc otherwise keeps load -> FMA order, ten dependent L2 round trips (2.6 us) in front of the first tile.
+    float b3 = 0.f;
+    {
+        constexpr int kIt = (H2 + 31) / 32;
+        float be[kIt], w[kIt], g[kIt];
+#pragma unroll
+        for (int i = 0; i < kIt; i++) {
+            const int c = lane + 32 * i;
+            const bool in = c < H2;
+            be[i] = in ? __ldg(A.be2 + c) : 0.f; w[i] = in ? __ldg(A.w3 + c) : 0.f; g[i] = in ? __ldg(A.g2 + c) : 1.f;
+        }
+        const float mub = __ldg(A.b3);
+#pragma unroll
+        for (int i = 0; i < kIt; i++) b3 = fmaf(fabsf(g[i]) > 1e-30f ? 0.5f * be[i] : fmaxf(be[i], 0.f), w[i], b3);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) b3 += __shfl_xor_sync(0xffffffffu, b3, o);
+        b3 += mub;
+    }
+
     for (int c = threadIdx.x; c < K2P; c += kThreads) pbe1[c] = c < H1 ? A.be1[c] : 0.f;
     for (int c = threadIdx.x; c < H2P; c += kThreads) {
         // LayerNorm 2 + ReLU + mu:  w3 relu(g z + be), z = (h - mean) rstd.  relu(y) = (y + |y|) / 2; the y / 2 half is linear in
@@ -395,16 +427,6 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
     if (kCluster > 1) cluster_sync_all();            // the partner's mbarriers are initialised before anything multicasts into them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // constant part of the output: mu.bias + 1/2 sum be2 w3 (every warp computes it: 30 loads per lane, once)
-    float b3 = 0.f;
-    for (int c = lane; c < H2; c += 32) {
-        const float be = A.be2[c], w = A.w3[c];
-        b3 = fmaf(fabsf(A.g2[c]) > 1e-30f ? 0.5f * be : fmaxf(be, 0.f), w, b3);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) b3 += __shfl_xor_sync(0xffffffffu, b3, o);
-    b3 += A.b3[0];
-
     if (warp == kProdWarp) {
         // ================= bulk-copy producer: W1 once, then per tile 13 half k-blocks of sweep A and 13 of sweep B =================
         // (warp-uniform control flow; one elected lane issues the copies)
@@ -855,7 +877,8 @@ __global__ void __launch_bounds__(640, 1) actor_tc4_kernel(const char *__restric
         const int64_t first = blockIdx.x, G = gridDim.x;
         uint32_t c1 = 0, c2 = 0;
         if (first < ntiles) {
-            load_x(first);
+#pragma unroll
+            for (int i = 0; i < 8; i++) xreg[i] = xreg0[i];                // tile `first`: loaded during the set-up
             stage(); load_x(first + G);                                    // X(0); registers <- tile 1
             layer1(c1++, -1, 0u);
             if (first + G < ntiles) { stage(); load_x(first + 2 * G); }    // X(1)
