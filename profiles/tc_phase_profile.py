@@ -8,7 +8,7 @@ actor = tt.agent.CudaActor(); actor.load_state_dict(tt.init_actor_state_dict(see
 obs = torch.empty(N,23,device='cuda').uniform_(-1,1)
 dbg = torch.zeros(24, dtype=torch.int64, device='cuda')
 L.tt_debug_set_tc_profile.argtypes=[C.c_void_p]
-for prec in ("f16", "bf16"):
+for prec in ("f16",):
     for _ in range(3): actor.forward(obs, precision=prec)
     L.tt_debug_set_tc_profile(dbg.data_ptr())
     torch.cuda.synchronize()

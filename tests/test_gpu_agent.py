@@ -208,3 +208,26 @@ def test_actor_tc_zero_and_negative_layernorm2_weights(golden_dir, precision, to
     ref = orc.OracleActor(w1).forward(obs)
     assert np.abs(actor.forward(torch.from_numpy(obs).cuda()).cpu().numpy() - ref).max() < 1e-5
     assert np.abs(actor.forward(torch.from_numpy(obs).cuda(), precision=precision, allow_out_of_bar=True).cpu().numpy() - ref).max() < tol
+
+
+def test_actor_tc_rank_deficient_first_layer(golden_dir):
+    """LayerNorm 1's variance comes out of the layer-1 GEMM as |L^T x|^2 with L the Cholesky factor of the centred Gram matrix of
+    [fc1.weight | fc1.bias] (computed by one warp at tt_actor_load).  Inputs the first layer ignores (zero columns), duplicated
+    columns and a constant bias make that matrix singular: the zero-pivot columns of L must be dropped, not divided by."""
+    import ddpg_trucktrailer_b200 as tt
+    from oracle import oracle as orc
+    g = np.load(os.path.join(golden_dir, "ref_actor.npz"))
+    w0, _ = _sets(g)
+    w = {k: v.copy() for k, v in w0.items()}
+    w["fc1.weight"][:, 3] = 0.0                       # an input the network ignores
+    w["fc1.weight"][:, 7] = w["fc1.weight"][:, 5]     # two identical columns
+    w["fc1.weight"][:, 11] = -2.0 * w["fc1.weight"][:, 9]
+    w["fc1.bias"][:] = 0.25                           # constant bias: its centred column is zero
+    rng = np.random.default_rng(11)
+    obs = rng.uniform(-2, 2, (1000, 23)).astype(np.float32)
+    actor = tt.agent.CudaActor(); actor.load_state_dict(w)
+    ref = orc.OracleActor(w).forward(obs)
+    x = torch.from_numpy(obs).cuda()
+    assert np.abs(actor.forward(x, precision="fp32").cpu().numpy() - ref).max() < 1e-5
+    out = actor.forward(x, precision="f16").cpu().numpy()
+    assert np.isfinite(out).all() and np.abs(out - ref).max() < 1e-3
