@@ -503,7 +503,7 @@ def run_b200(args):
     config4 = None
     if not args.no_config4:
         # the learner (rank 0) runs on a side stream UNDER the rollout kernels of the same iteration (rollout.AsyncTrainer: 2 SMs
-        # are left free for its 15 + 2 small dependent kernels; it samples only rows that earlier iterations completed; its policy is
+        # are left free for its 14 + 2 small dependent kernels; it samples only rows that earlier iterations completed; its policy is
         # used one iteration later).  With world > 1 the side stream also carries the broadcast of the flat parameter vector
         # (526 KB, NCCL) before the re-pack into the spare packed actor, and the statistics all-reduce stays inside the step.
         def run_c4(reserve):

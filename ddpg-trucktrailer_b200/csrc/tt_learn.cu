@@ -1,18 +1,18 @@
 // tt_learn.cu -- row f1: one DDPG update (Agent.learn, DDPG/DDPG_agent.py:72-131; CriticNetwork DDPG/networks.py:9-68,
-// ActorNetwork :98-147; ReplayBuffer.sample_buffer DDPG/replay_buffer.py:23-34) as 15 small hand-written kernels on the
+// ActorNetwork :98-147; ReplayBuffer.sample_buffer DDPG/replay_buffer.py:23-34) as 14 small hand-written kernels on the
 // caller's stream, on the device-resident replay ring, followed by the re-pack of the new policy into the rollout actor's
 // operand images.  The whole sequence is capturable into one CUDA graph (nothing synchronises, the Adam step counter and
 // the sampling counter live in device memory).
 //
 // The step is latency-bound (batch 64 x 23-400-300 networks = 150 MFLOP): what matters is the length of the dependency
 // chain, not the arithmetic.  Stages (one launch each):
-//   K0  sample 64 ring rows (Philox) and gather s, a, r, s', done
-//   K1  fc1 + LayerNorm 1 + ReLU of target_actor(s'), target_critic(s'), critic(s), actor(s)   -- one launch, 4 jobs
-//   K2  fc2 of the same four (grouped GEMM launch, cp.async double-buffered operands)
-//   K3  critic head (8 CTAs, warp = batch row; the last CTA sums the columns): a' = target_actor head, y = r + gamma Q'(s', a') (1 - done), q = Q(s, a),
-//       dL/dq = 2 (q - y) / B, back through q / action_value / LayerNorm 2 -> d h2; column sums = their parameter gradients
-//   K4  critic fc2 backward: dW2 = dh2^T a1 (grouped with) da1 = dh2 W2
-//   K5  critic LayerNorm 1 backward (warp = row), K5b fc1 backward dW1 = dh1^T s (a dW job)
+//   K1  sample 64 ring rows (Philox), gather s, a, r, s', done and fc1 + LayerNorm 1 + ReLU of target_actor(s'), target_critic(s'),
+//       critic(s), actor(s)   -- one launch, 4 jobs, every CTA samples the rows it needs
+//   K2  fc2 of the same four (grouped GEMM launch, the whole reduction in flight, split over the warps)
+//   K3  critic head (8 CTAs, warp = batch row): a' = target_actor head, y = r + gamma Q'(s', a') (1 - done), q = Q(s, a),
+//       dL/dq = 2 (q - y) / B, back through q / action_value / LayerNorm 2 -> d h2 and the per-row terms of the parameter gradients
+//   K4  critic fc2 backward: dW2 = dh2^T a1 (grouped with) da1 = dh2 W2 (and with) the column sums of K3's per-row terms
+//   K5  critic LayerNorm 1 backward (warp = row), K5b fc1 backward dW1 = dh1^T s (a dW job) + the column sums of K5
 //   K6  Adam (weight decay 0.01) on the critic + soft update of target_critic
 //   K7  fc1 + LayerNorm 1 + ReLU, K8 fc2 of the UPDATED critic on s
 //   K9  actor head: a = actor head, dL/da = -(1/B) dQ/da through relu / action_value, back through tanh / mu /
@@ -368,51 +368,32 @@ __global__ void __launch_bounds__(kT) learn_gemm_kernel(JobList L) {
     if (cta < L.cs.ctas) job_colsum(L.cs, cta, smem);
 }
 
-// ---- K0: sampling + gather (replay_buffer.py:23-34: uniform with replacement over the filled part of the ring) ----
+// ---- K0 (inside K1): sampling + gather (replay_buffer.py:23-34: uniform with replacement over the filled part of the ring) ----
 struct Batch {
     float *s, *s2, *a, *r, *d;        // [B][in], [B][in], [B], [B], [B] (done as 0 / 1)
     int64_t *rows;                    // [B]
 };
-__global__ void learn_gather_kernel(tt_replay_ring ring, int64_t win_begin, int64_t max_mem, const int64_t *__restrict__ given_rows, Batch bt, int B,
-                                    int in, uint64_t seed, int *__restrict__ step) {
-    chain_enter();
-    __shared__ int64_t rows[kMaxB];
-    const int tid = threadIdx.x;
-    const int t = *step;                               // updates done so far = the sampling counter of this one
-    __syncthreads();
-    if (tid == 0) *step = t + 1;                       // the optimizer kernels of this update read t + 1 (Adam's step number)
-    if (tid < B) {
-        int64_t row;
-        if (given_rows) row = given_rows[tid];
-        else {
-            uint32_t w[4];
-            ttm::philox4x32_10((uint32_t)tid, (uint32_t)t, 2u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
-            const double u = ((double)w[0] * 4294967296.0 + (double)w[1]) * (1.0 / 18446744073709551616.0);       // [0, 1)
-            row = (int64_t)(u * (double)max_mem);
-            if (row >= max_mem) row = max_mem - 1;
-            row = (win_begin + row) % ring.mem_size;                  // the sampling window may wrap around the ring
-        }
-        rows[tid] = row; bt.rows[tid] = row;
-        bt.a[tid] = ring.d_action_mem[row]; bt.r[tid] = ring.d_reward_mem[row]; bt.d[tid] = ring.d_terminal_mem[row] ? 1.f : 0.f;
-    }
-    __syncthreads();
-    // 1024 threads: at most two elements each, all loads issued before the first store (one DRAM latency)
-    float vs[2], vs2[2];
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        const int v = tid + (int)blockDim.x * i;
-        if (v < B * in) { const int b = v / in, c = v - b * in; vs[i] = ring.d_state_mem[rows[b] * in + c]; vs2[i] = ring.d_new_state_mem[rows[b] * in + c]; }
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        const int v = tid + (int)blockDim.x * i;
-        if (v < B * in) { bt.s[v] = vs[i]; bt.s2[v] = vs2[i]; }
-    }
-    for (int v = tid + 2 * (int)blockDim.x; v < B * in; v += blockDim.x) {       // (only for blocks smaller than 1024 threads)
-        const int b = v / in, c = v - b * in;
-        bt.s[v] = ring.d_state_mem[rows[b] * in + c];
-        bt.s2[v] = ring.d_new_state_mem[rows[b] * in + c];
-    }
+// The first fc1 launch of an update samples its own rows: every CTA derives the ring rows of its 8 batch rows from the update
+// counter (Philox stream 2) and reads its inputs straight from the ring; the CTAs of the critic(s) job also write the batch
+// (s, a, r, done, rows) that the later stages read, those of the target-critic job s'.  A separate gather launch in front cost
+// 4 us of the chain.  The counter is advanced by the critic-head kernel, after every CTA here has read it.
+struct Gather {
+    tt_replay_ring ring;
+    int64_t win_begin, max_mem;       // sampling window: `max_mem` rows starting at `win_begin` (wrapping)
+    const int64_t *given_rows;        // explicit rows instead of sampling (tests), or NULL
+    Batch bt;
+    uint64_t seed;
+    const int *step;                  // updates done so far = the sampling counter of this one
+    int on;
+};
+__device__ __forceinline__ int64_t sample_row(const Gather &G, int b, int t) {
+    if (G.given_rows) return G.given_rows[b];
+    uint32_t w[4];
+    ttm::philox4x32_10((uint32_t)b, (uint32_t)t, 2u, 0u, (uint32_t)G.seed, (uint32_t)(G.seed >> 32), w);
+    const double u = ((double)w[0] * 4294967296.0 + (double)w[1]) * (1.0 / 18446744073709551616.0);       // [0, 1)
+    int64_t row = (int64_t)(u * (double)G.max_mem);
+    if (row >= G.max_mem) row = G.max_mem - 1;
+    return (G.win_begin + row) % G.ring.mem_size;                  // the sampling window may wrap around the ring
 }
 
 // ---- row-wise stages: 8 CTAs x 8 warps, one warp per batch row with the row in registers (one warp per row keeps the
@@ -469,6 +450,7 @@ struct HeadArgs {
     float *dh2;                                                           // out: gradient w.r.t. the fc2 output [B][H2]
     float *sc0, *sc1, *sc2;                                               // scratch [B][H2]
     float *dv;                                                            // scratch [B]: dL/dq (critic) or dL/d(pre-tanh) (actor) per row
+    int *step;                                                            // update counter (advanced by the critic head)
     float *q_out, *y_out, *a_out;                                         // diagnostics / hand-over: Q(s,a), target, actor(s)
 };
 
@@ -478,8 +460,8 @@ struct HeadArgs {
 // two block-wide reductions.  (The first version gave every WARP a row: each warp then read the whole of W1 from shared
 // memory -- 3 300 instructions per warp and 16 us for 0.6 MFLOP.)  Writes h1 (pre-LayerNorm, for the backward pass) and
 // a1 = relu(LN1(h1)) (the operand of fc2 and of its weight gradient).
-struct Fc1Job { const float *x, *w1, *b1, *g1, *be1; float *h1, *a1; };
-struct Fc1Args { Fc1Job j[NJOBS]; int njobs, B, IN, H1; };
+struct Fc1Job { const float *x, *w1, *b1, *g1, *be1; float *h1, *a1; int from_s2, writes_batch; };   // (the last two: gather mode)
+struct Fc1Args { Fc1Job j[NJOBS]; int njobs, B, IN, H1; Gather G; };
 constexpr int kFc1T = 256, kFc1Cols = kMaxH / kFc1T, kFc1Rows = 8, kXP = 24;    // kXP: pitch of an input row (IN <= 24)
 __global__ void __launch_bounds__(kFc1T, 1) learn_fc1_kernel(Fc1Args A) {
     chain_enter();
@@ -496,7 +478,7 @@ __global__ void __launch_bounds__(kFc1T, 1) learn_fc1_kernel(Fc1Args A) {
         for (int v = tid; v < nw; v += kFc1T) cp4(ws + v, J.w1 + v, true);
     }
     cp_commit();
-    // this thread's columns of the three parameter vectors and the input rows: in flight together with W1
+    // this thread's columns of the three parameter vectors and the input rows (gather mode: found by sampling): in flight together with W1
     float pb[kFc1Cols], pg[kFc1Cols], pe[kFc1Cols];
 #pragma unroll
     for (int i = 0; i < kFc1Cols; i++) {
@@ -504,8 +486,23 @@ __global__ void __launch_bounds__(kFc1T, 1) learn_fc1_kernel(Fc1Args A) {
         pb[i] = c < H ? J.b1[c] : 0.f; pg[i] = c < H ? J.g1[c] : 0.f; pe[i] = c < H ? J.be1[c] : 0.f;
     }
     if (tid < kFc1Rows * kXP) {
-        const int r = tid / kXP, k = tid - r * kXP;
-        xs[tid] = (k < IN && b0 + r < A.B) ? J.x[(size_t)(b0 + r) * IN + k] : 0.f;
+        const int r = tid / kXP, k = tid - r * kXP, b = b0 + r;
+        float x = 0.f;
+        if (A.G.on) {
+            if (b < A.B) {
+                const int64_t row = sample_row(A.G, b, *A.G.step);
+                const float *src = J.from_s2 ? A.G.ring.d_new_state_mem : A.G.ring.d_state_mem;
+                if (k < IN) x = src[row * IN + k];
+                if (J.writes_batch) {
+                    if (k < IN) (J.from_s2 ? A.G.bt.s2 : A.G.bt.s)[(size_t)b * IN + k] = x;
+                    if (k == 0 && !J.from_s2) {
+                        A.G.bt.rows[b] = row; A.G.bt.a[b] = A.G.ring.d_action_mem[row]; A.G.bt.r[b] = A.G.ring.d_reward_mem[row];
+                        A.G.bt.d[b] = A.G.ring.d_terminal_mem[row] ? 1.f : 0.f;
+                    }
+                }
+            }
+        } else if (k < IN && b < A.B) x = J.x[(size_t)b * IN + k];
+        xs[tid] = x;
     }
     cp_wait<0>();
     __syncthreads();
@@ -648,6 +645,7 @@ __global__ void __launch_bounds__(kRowT) learn_critic_head_kernel(HeadArgs A) {
         }
         if (lane == 0) { A.dv[b] = dq; if (A.q_out) A.q_out[b] = q; if (A.y_out) A.y_out[b] = y; }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *A.step = *A.step + 1;     // this update's rows are sampled (learn_fc1): Adam reads t + 1
 }
 
 // K9: DDPG_agent.py:99-103  actor_loss = -mean(critic(states, actor(states)))
@@ -937,21 +935,19 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     float *ga = ln->g[0], *gc = ln->g[1];
     const int T = L.tail();
 
-    // K0
-    TT_CUDA(tt::launch_chained(true, learn_gather_kernel, dim3(1), dim3(1024), 0, s, *ring, win_begin, max_mem, d_rows, ln->bt, B, IN, ln->seed, ln->step));
-    TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
-    TT_STAGE_END(TT_OK);
     int rc;
-    // K1: fc1 + LayerNorm 1 + ReLU of the four forward passes
+    // K0 + K1: sampling + gather inside fc1 + LayerNorm 1 + ReLU of the four forward passes
     const float *netp[NJOBS] = {pta, ptc, pc, pa};
     const float *netx[NJOBS] = {ln->bt.s2, ln->bt.s2, ln->bt.s, ln->bt.s};
-    auto fc1 = [&](const int *jobs, int njobs) -> int {
+    auto fc1 = [&](const int *jobs, int njobs, bool gather) -> int {
         Fc1Args A{};
         A.njobs = njobs; A.B = B; A.IN = IN; A.H1 = H1;
         for (int i = 0; i < njobs; i++) {
             const int j = jobs[i];
-            A.j[i] = Fc1Job{netx[j], netp[j] + L.w1(), netp[j] + L.b1(), netp[j] + L.g1(), netp[j] + L.be1(), ln->h1[j], ln->a1[j]};
+            A.j[i] = Fc1Job{netx[j], netp[j] + L.w1(), netp[j] + L.b1(), netp[j] + L.g1(), netp[j] + L.be1(), ln->h1[j], ln->a1[j],
+                            j == JOB_TA || j == JOB_TC, j == JOB_C || j == JOB_TC};
         }
+        if (gather) A.G = Gather{*ring, win_begin, max_mem, d_rows, ln->bt, ln->seed, ln->step, 1};
         const size_t dsm = sizeof(float) * (size_t)H1 * IN + 16;
         static bool attr_of[tt::kMaxDevices] = {};
         if (dsm > 48 * 1024 && !attr_of[tt::device_index()]) {
@@ -964,7 +960,7 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     };
     {
         const int all[NJOBS] = {JOB_TA, JOB_TC, JOB_C, JOB_A};
-        if ((rc = fc1(all, NJOBS)) != TT_OK) return rc;
+        if ((rc = fc1(all, NJOBS, true)) != TT_OK) return rc;
         TT_STAGE_END(TT_OK);
     }
     // K2: fc2
@@ -984,7 +980,7 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     H.a_g2 = pa + L.g2(); H.a_be2 = pa + L.be2(); H.a_w3 = pa + T; H.a_b3 = pa + T + H2;
     H.act = ln->bt.a; H.rew = ln->bt.r; H.done = ln->bt.d;
     H.dh2 = ln->dh2; H.sc0 = ln->sc0; H.sc1 = ln->sc1; H.sc2 = ln->sc2;
-    H.q_out = ln->q; H.y_out = ln->y; H.a_out = ln->aout; H.dv = ln->dv;
+    H.q_out = ln->q; H.y_out = ln->y; H.a_out = ln->aout; H.dv = ln->dv; H.step = ln->step;
     {
         if ((rc = launch_rows(learn_critic_head_kernel, H, B, s)) != TT_OK) return rc;
         TT_STAGE_END(TT_OK);
@@ -1049,7 +1045,7 @@ int tt_learn_step_window(tt_learner *ln, const tt_replay_ring *ring, const int64
     // K7, K8: the updated critic's trunk on s (into the JOB_C buffers)
     {
         const int one[1] = {JOB_C};
-        if ((rc = fc1(one, 1)) != TT_OK) return rc;
+        if ((rc = fc1(one, 1, false)) != TT_OK) return rc;
         TT_STAGE_END(TT_OK);
         JobList J{}; J.n = 1;
         J.j[0] = fwd_job(B, H2, H1, ln->a1[JOB_C], pc + L.w2(), pc + L.b2(), ln->h2[JOB_C]);

@@ -1,6 +1,6 @@
 """Learner step of the reference (``Agent.learn``, DDPG/DDPG_agent.py:72-131; networks DDPG/networks.py:9-68, :98-147;
 ``ReplayBuffer.sample_buffer`` DDPG/replay_buffer.py:23-34) on the device-resident replay ring: row f1 of SURVEY.md
-section 8.  ``CudaLearner`` binds ``tt_learn_step`` (csrc/tt_learn.cu): 15 hand-written kernels -- sampling + gather, the
+section 8.  ``CudaLearner`` binds ``tt_learn_step`` (csrc/tt_learn.cu): 14 hand-written kernels -- sampling + gather, the
 forward passes of the four networks as grouped launches, both backward passes, Adam (critic weight decay 0.01), the soft
 target updates -- followed by the re-pack of the new policy into the rollout actor's operand images.  No torch.nn, no
 autograd, no cuBLAS; every launch goes to the caller's stream and the sequence is graph-capturable.

@@ -133,7 +133,7 @@ class RolloutEngine:
 
 class AsyncTrainer:
     """BASELINE.json configs[3]: one rollout iteration + one DDPG update (``Agent.learn``) per step, with the update HIDDEN
-    under the rollout: the learner's launch sequence (``tt_learn_step``, 15 small dependent kernels), the optional broadcast of
+    under the rollout: the learner's launch sequence (``tt_learn_step``, 14 small dependent kernels), the optional broadcast of
     the new policy (multi-GPU) and its re-pack into the SPARE packed actor run on a side stream while the rollout kernels of
     the same iteration run on the caller's stream.
 

@@ -291,7 +291,7 @@ int tt_learner_reset_optimizer(tt_learner *ln, tt_stream_t stream);   /* zero bo
  * (replay_buffer.py:23-34; Philox(seed; b, step, stream 2) -- or the given d_rows[batch] when not NULL), critic update
  * (MSE on r + gamma Q'(s', pi'(s')) with terminal masking, Adam with weight decay), actor update (ascent on Q(s, pi(s))
  * through the UPDATED critic, Adam), soft update of both targets (tau).  If repack_into != NULL the new actor parameters are
- * then re-packed into that rollout actor (tt_actor_load).  15 kernel launches (+ 2 of the re-pack) on `stream`, no
+ * then re-packed into that rollout actor (tt_actor_load).  14 kernel launches (+ 2 of the re-pack) on `stream`, no
  * synchronisation, graph-capturable (the step counter lives in device memory), deterministic. */
 int tt_learn_step(tt_learner *ln, const tt_replay_ring *ring, const int64_t *d_rows, tt_actor *repack_into,
                   tt_stream_t stream);

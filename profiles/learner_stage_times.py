@@ -1,5 +1,5 @@
-"""Marginal cost of each of the learner's 15 launches in the warm, pipelined state: a CUDA graph of the first k launches for
-k = 1..15 (+ the three re-pack launches), differences of consecutive graph times.  Needs the developer knobs TT_LEARN_STOP /
+"""Marginal cost of each of the learner's 14 launches in the warm, pipelined state: a CUDA graph of the first k launches for
+k = 1..14 (+ the two re-pack launches), differences of consecutive graph times.  Needs the developer knobs TT_LEARN_STOP /
 TT_PACK_STOP, which only a -DTT_LEARN_PROFILE build has:
     TT_NVCC_EXTRA=-DTT_LEARN_PROFILE python ddpg-trucktrailer_b200/build.py --force && python profiles/learner_stage_times.py
 (rebuild without the flag afterwards)."""
@@ -13,7 +13,7 @@ ag = tt.VecAgent(1e-4, 1e-3, (23,), 1e-3, 1, max_size=cap, batch_size=B, num_env
 u = lambda *s: torch.empty(*s, device="cuda").uniform_(-1, 1)
 ag.remember(u(cap, 23), u(cap), u(cap) * 20, u(cap, 23), (u(cap) > 0.9).to(torch.uint8))
 ln = ag.learner
-names = ["gather", "fc1 x4", "fc2 x4 (gemm)", "critic head", "critic dW2+da1 (gemm)", "critic LN1 backward", "critic dW1 (gemm)", "Adam critic",
+names = ["sampling + gather + fc1 x4", "fc2 x4 (gemm)", "critic head", "critic dW2+da1 (gemm)", "critic LN1 backward", "critic dW1 (gemm)", "Adam critic",
          "fc1 critic", "fc2 critic (gemm)", "actor head", "actor dW2+da1 (gemm)", "actor LN1 backward", "actor dW1 (gemm)", "Adam actor"]
 
 
@@ -28,7 +28,7 @@ def timed(fn, n=300):
 
 
 prev = 0.0
-for k in range(1, 16):
+for k in range(1, 15):
     os.environ["TT_LEARN_STOP"] = str(k)
     ln.learn(repack_into=None)
     g = torch.cuda.CUDAGraph()
@@ -46,5 +46,5 @@ for k, name in ((1, "re-pack stage A (Gram, W2 column statistics, fp32 images)")
     with torch.cuda.graph(g):
         ln.learn(repack_into="agent")
     t = timed(g.replay)
-    print(f"{15 + k:2d} {name:58s} cumulative {t:7.1f} us   this launch {t - prev:6.1f} us")
+    print(f"{14 + k:2d} {name:58s} cumulative {t:7.1f} us   this launch {t - prev:6.1f} us")
     prev = t
