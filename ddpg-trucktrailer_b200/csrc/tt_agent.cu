@@ -258,6 +258,207 @@ __global__ void __launch_bounds__(kThreads, 1) actor_fp32_kernel(tt_actor_dev A,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// (c') the same fp32 forward for SMALL batches (<= 64 rows), split over a thread-block CLUSTER: 8 CTAs share 8 rows, each CTA
+// owns one eighth of the hidden units of both layers.  The kernel above runs such a batch on ONE SM, which has to pull all
+// 526 KB of fp32 weights through its chunk pipeline (29 us for one row); here every SM fetches its 66 KB slice of W2 with
+// cp.async at kernel start -- in flight under layer 1 -- and the layers meet through distributed shared memory:
+//   layer 1 (unit slice) -> per-CTA (mean, M2) of the slice -> all peers -> exact merge (Chan) -> LayerNorm + ReLU ->
+//   all-gather of the activation slice into every peer's shared memory -> layer 2 (unit slice, K split over the 4 thread
+//   groups) -> (mean, M2) exchange -> LayerNorm + ReLU + partial output dot -> CTA 0 -> tanh + the choose_action tail.
+// Four cluster barriers; the arithmetic is fp32 FMA in k order like the big kernel (LayerNorm statistics merged pairwise).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kClu = 8, kCluRows = 8, kCluT = 256, kCluMaxU = 64, kCluMaxK1 = 32;
+__device__ __forceinline__ uint32_t clu_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void clu_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (own shared memory) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t clu_map(const void *p, uint32_t rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void clu_st2(uint32_t addr, float x, float y) { asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ void clu_st1(uint32_t addr, float x) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory"); }
+
+// (mean, M2) of `cnt` values merged into the running (n, mean, M2)
+__device__ __forceinline__ void chan_merge(float &n, float &mean, float &m2, float cnt, float mean_c, float m2_c) {
+    if (cnt <= 0.f) return;
+    const float nt = n + cnt, d = mean_c - mean;
+    mean += d * (cnt / nt);
+    m2 += m2_c + d * d * (n * cnt / nt);
+    n = nt;
+}
+
+// (mean, M2) over the units of this CTA's slice for the thread's two rows: the 64 threads of a row pair are two warps; two-pass
+// (mean, then centred squares) with warp shuffles and one shared-memory hand-over per pass.  Every thread gets the result.
+__device__ __forceinline__ void slice_stats(float v0, float v1, bool valid, float cnt, float (*red)[2], float &m0, float &m1, float &q0, float &q1) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, w0 = warp & ~1;
+    float s0 = warp_sum_f(valid ? v0 : 0.f), s1 = warp_sum_f(valid ? v1 : 0.f);
+    if (lane == 0) { red[warp][0] = s0; red[warp][1] = s1; }
+    __syncthreads();
+    const float inv = cnt > 0.f ? 1.0f / cnt : 0.f;
+    m0 = (red[w0][0] + red[w0 + 1][0]) * inv; m1 = (red[w0][1] + red[w0 + 1][1]) * inv;
+    __syncthreads();
+    const float d0 = valid ? v0 - m0 : 0.f, d1 = valid ? v1 - m1 : 0.f;
+    s0 = warp_sum_f(d0 * d0); s1 = warp_sum_f(d1 * d1);
+    if (lane == 0) { red[warp][0] = s0; red[warp][1] = s1; }
+    __syncthreads();
+    q0 = red[w0][0] + red[w0 + 1][0]; q1 = red[w0][1] + red[w0 + 1][1];
+}
+
+__global__ void __cluster_dims__(kClu, 1, 1) __launch_bounds__(kCluT, 1)
+actor_fp32_cluster_kernel(tt_actor_dev A, const float *__restrict__ obs, int64_t ld, int64_t n, float *__restrict__ out, TTRingS ring, TTActorTail tail) {
+    chain_enter();
+    extern __shared__ __align__(16) float w2s[];                 // this CTA's slice of W2^T: [h1p][U2]
+    __shared__ __align__(16) float xs[kCluRows][kCluMaxK1];      // the cluster's observation rows
+    __shared__ __align__(16) float a1s[512 * kCluRows];          // layer-1 activations of ALL units, [k][row] (filled by every CTA of the cluster)
+    __shared__ __align__(16) float part[4][kCluMaxU][kCluRows];  // layer-2 partial sums of the four K groups
+    __shared__ __align__(8) float st1[kClu][kCluRows][2], st2[kClu][kCluRows][2];   // per-CTA (mean, M2) of both layers, from every peer
+    __shared__ float outp[kClu][kCluRows];                       // CTA 0: the peers' partial output dots
+    __shared__ float red[kCluT / 32][2];
+    const uint32_t rank = clu_rank();
+    const int t = threadIdx.x, u = t & 63, grp = t >> 6;
+    const int U1 = A.h1p / kClu, U2 = A.h2p / kClu;
+    const int64_t row0 = (int64_t)(blockIdx.x / kClu) * kCluRows;
+    const int rows = (int)min((int64_t)kCluRows, n - row0);
+    // W2 slice: all of it in flight now, needed after two cluster barriers
+    {
+        const int vecs = U2 / 4;                                 // U2 % 4 == 0 (h2p is a multiple of 32)
+        for (int v = t; v < A.h1p * vecs; v += kCluT) {
+            const int k = v / vecs, q = v - k * vecs;
+            cp_async16(w2s + (size_t)k * U2 + 4 * q, A.w2t + (size_t)k * A.h2p + rank * U2 + 4 * q);
+        }
+        cp_async_commit();
+    }
+    // layer-1 weights of this thread's unit (independent of the observation: issued first) and its parameters
+    const int c1 = (int)rank * U1 + u;
+    const bool on1 = u < U1;
+    float w1[kCluMaxK1];
+#pragma unroll
+    for (int k = 0; k < kCluMaxK1; k++) w1[k] = (on1 && k < A.in_dim) ? __ldg(A.w1t + (size_t)k * A.h1p + c1) : 0.f;
+    const float b1 = on1 ? __ldg(A.b1 + c1) : 0.f, g1 = on1 ? __ldg(A.g1 + c1) : 0.f, be1 = on1 ? __ldg(A.be1 + c1) : 0.f;
+    for (int v = t; v < kCluRows * kCluMaxK1; v += kCluT) {
+        const int r = v / kCluMaxK1, k = v - r * kCluMaxK1;
+        float x = 0.f;
+        if (r < rows && k < A.in_dim) {
+            x = __ldcs(obs + (row0 + r) * ld + k);
+            if (rank == 0 && ring.S && row0 + r >= ring.m.first) ring.S[ring.m.row(row0 + r) * A.in_dim + k] = x;     // fused replay store of s
+        }
+        xs[r][k] = x;
+    }
+    __syncthreads();
+    // ---- layer 1: this thread = unit u of the slice, rows 2 grp and 2 grp + 1 ----
+    float h0 = 0.f, h1v = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCluMaxK1; k++) { h0 = fmaf(xs[2 * grp][k], w1[k], h0); h1v = fmaf(xs[2 * grp + 1][k], w1[k], h1v); }
+    h0 += b1; h1v += b1;
+    {
+        const float cnt1 = (float)max(0, min(U1, A.h1 - (int)rank * U1));       // real (unpadded) units of this slice
+        float m0, m1, q0, q1;
+        slice_stats(h0, h1v, on1 && c1 < A.h1, cnt1, red, m0, m1, q0, q1);
+        if (u < kClu) {                                          // thread u of each row pair tells peer u
+            clu_st2(clu_map(&st1[rank][2 * grp][0], (uint32_t)u), m0, q0);
+            clu_st2(clu_map(&st1[rank][2 * grp + 1][0], (uint32_t)u), m1, q1);
+        }
+    }
+    clu_sync();                                                  // (1) every CTA has every slice's statistics
+    {
+        float mean[2], rstd[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            float nn = 0.f, mm = 0.f, m2 = 0.f;
+            for (int p = 0; p < kClu; p++) chan_merge(nn, mm, m2, (float)max(0, min(U1, A.h1 - p * U1)), st1[p][2 * grp + i][0], st1[p][2 * grp + i][1]);
+            mean[i] = mm; rstd[i] = rsqrtf(m2 / (float)A.h1 + 1e-5f);
+        }
+        if (on1) {
+            const bool real = c1 < A.h1;
+            const float y0 = real ? fmaxf(fmaf((h0 - mean[0]) * rstd[0], g1, be1), 0.f) : 0.f;
+            const float y1 = real ? fmaxf(fmaf((h1v - mean[1]) * rstd[1], g1, be1), 0.f) : 0.f;
+            for (uint32_t p = 0; p < kClu; p++) clu_st2(clu_map(&a1s[(size_t)c1 * kCluRows + 2 * grp], p), y0, y1);
+        }
+    }
+    cp_async_wait<0>();
+    clu_sync();                                                  // (2) the full activation block is in every CTA; own W2 slice has landed
+    __syncthreads();
+    // ---- layer 2: unit u of the slice, K group grp, all 8 rows ----
+    const int c2 = (int)rank * U2 + u;
+    const bool on2 = u < U2;
+    {
+        float acc[kCluRows];
+#pragma unroll
+        for (int r = 0; r < kCluRows; r++) acc[r] = 0.f;
+        const int kq = A.h1p / 4, k0 = grp * kq;
+        if (on2) {
+#pragma unroll 4
+            for (int k = k0; k < k0 + kq; k++) {
+                const float w = w2s[(size_t)k * U2 + u];
+                const float4 a0 = *reinterpret_cast<const float4 *>(a1s + (size_t)k * kCluRows), a1 = *reinterpret_cast<const float4 *>(a1s + (size_t)k * kCluRows + 4);
+                acc[0] = fmaf(a0.x, w, acc[0]); acc[1] = fmaf(a0.y, w, acc[1]); acc[2] = fmaf(a0.z, w, acc[2]); acc[3] = fmaf(a0.w, w, acc[3]);
+                acc[4] = fmaf(a1.x, w, acc[4]); acc[5] = fmaf(a1.y, w, acc[5]); acc[6] = fmaf(a1.z, w, acc[6]); acc[7] = fmaf(a1.w, w, acc[7]);
+            }
+#pragma unroll
+            for (int r = 0; r < kCluRows; r++) part[grp][u][r] = acc[r];
+        }
+    }
+    __syncthreads();
+    // thread = (unit u, rows 2 grp, 2 grp + 1) again: sum the K groups in order
+    float z0 = 0.f, z1 = 0.f;
+    if (on2) {
+        const float b2 = __ldg(A.b2 + c2);
+        z0 = ((part[0][u][2 * grp] + part[1][u][2 * grp]) + part[2][u][2 * grp]) + part[3][u][2 * grp] + b2;
+        z1 = ((part[0][u][2 * grp + 1] + part[1][u][2 * grp + 1]) + part[2][u][2 * grp + 1]) + part[3][u][2 * grp + 1] + b2;
+    }
+    {
+        const float cnt2 = (float)max(0, min(U2, A.h2 - (int)rank * U2));
+        float m0, m1, q0, q1;
+        slice_stats(z0, z1, on2 && c2 < A.h2, cnt2, red, m0, m1, q0, q1);
+        if (u < kClu) {
+            clu_st2(clu_map(&st2[rank][2 * grp][0], (uint32_t)u), m0, q0);
+            clu_st2(clu_map(&st2[rank][2 * grp + 1][0], (uint32_t)u), m1, q1);
+        }
+    }
+    clu_sync();                                                  // (3)
+    {
+        float y[2] = {0.f, 0.f};
+        if (on2 && c2 < A.h2) {
+            const float g2 = __ldg(A.g2 + c2), be2 = __ldg(A.be2 + c2), w3 = __ldg(A.w3 + c2);
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                float nn = 0.f, mm = 0.f, m2 = 0.f;
+                for (int p = 0; p < kClu; p++) chan_merge(nn, mm, m2, (float)max(0, min(U2, A.h2 - p * U2)), st2[p][2 * grp + i][0], st2[p][2 * grp + i][1]);
+                const float rstd = rsqrtf(m2 / (float)A.h2 + 1e-5f);
+                y[i] = fmaxf(fmaf(((i ? z1 : z0) - mm) * rstd, g2, be2), 0.f) * w3;
+            }
+        }
+        // partial output dot of this slice: sum over the 64 threads of a row pair (two warps), through shared memory
+        y[0] = warp_sum_f(y[0]); y[1] = warp_sum_f(y[1]);
+        if ((t & 31) == 0) { part[0][t >> 5][0] = y[0]; part[0][t >> 5][1] = y[1]; }
+    }
+    __syncthreads();
+    if (t < kCluRows) {
+        const int g = t >> 1, i = t & 1;                         // row t = rows 2 g + i: warps 2 g and 2 g + 1
+        clu_st1(clu_map(&outp[rank][t], 0), part[0][2 * g][i] + part[0][2 * g + 1][i]);
+    }
+    clu_sync();                                                  // (4) CTA 0 has every slice's partial dot
+    if (rank == 0 && t < rows) {
+        float d = 0.f;
+        for (int p = 0; p < kClu; p++) d += outp[p][t];
+        const int64_t gr = row0 + t;
+        float a = tanhf(d + __ldg(A.b3));
+        if (tail.ou_x) {
+            const float xn = ou_advance(tail.ou_x[gr], ttm::rng_normal_ks(tail.keys, tail.gid0 + (uint32_t)gr, *tail.iter));
+            tail.ou_x[gr] = xn;
+            a += xn;
+        }
+        out[gr] = a;
+        if (tail.scaled) tail.scaled[gr] = fminf(fmaxf(a, -1.0f), 1.0f) * kPiOver4F;
+        if (tail.ring.A && gr >= tail.ring.m.first) tail.ring.A[tail.ring.m.row(gr)] = a;
+    }
+}
+
 size_t actor_fp32_smem(const tt_actor_dev &A, int R) {
     const int wmax = A.h1p > A.h2p ? A.h1p : A.h2p;
     size_t wb = (size_t)2 * kc_of(R) * wmax;
@@ -288,6 +489,33 @@ int actor_forward_fp32(const tt_actor *a, const float *d_obs, int64_t ld, int64_
     const TTActorTail tl = tail ? *tail : tt_no_tail();
     const tt_actor_dev &A = a->dev;
     const int cj1 = A.h1p / 32, cj2 = A.h2p / 32;
+    // small batches: 8-CTA clusters, each CTA one eighth of the hidden units (see actor_fp32_cluster_kernel)
+    if (n <= 256 && A.in_dim <= kCluMaxK1 && A.h1p <= 512 && A.h2p <= 512) {
+        const size_t smem = sizeof(float) * (size_t)A.h1p * (A.h2p / kClu);
+        static int ok_of[kMaxDevices] = {};               // per device: 0 = not probed, > 0 = co-resident clusters of 8 at this size, -1 = none
+        static size_t smem_of[kMaxDevices] = {};
+        static bool attr_of[kMaxDevices] = {};
+        const int dev = device_index();
+        int &ok = ok_of[dev];
+        const unsigned grid = (unsigned)(kClu * ((n + kCluRows - 1) / kCluRows));
+        if (ok == 0 || smem_of[dev] != smem) {
+            ok = -1; smem_of[dev] = smem;
+            if (!attr_of[dev]) attr_of[dev] = cudaFuncSetAttribute(actor_fp32_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                   (int)(sizeof(float) * 512 * (512 / kClu))) == cudaSuccess;
+            if (attr_of[dev]) {
+                cudaLaunchConfig_t q{};
+                q.gridDim = dim3(kClu); q.blockDim = dim3(kCluT); q.dynamicSmemBytes = smem;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, actor_fp32_cluster_kernel, &q) == cudaSuccess && ncl >= 1) ok = ncl;
+            }
+            (void)cudaGetLastError();
+        }
+        if (ok > 0 && grid <= (unsigned)(kClu * ok)) {          // one wave of clusters (37 at 400 / 300: every batch of the AUTO fp32 range)
+            TT_CUDA(launch_chained(chain_rollout(n), actor_fp32_cluster_kernel, dim3(grid), dim3(kCluT), smem, s, A, d_obs, ld, n, d_mu, rs, tl));
+            TT_COUNT_LAUNCH(); TT_LAUNCH_CHECK();
+            return TT_OK;
+        }
+    }
     if (cj1 == 13 && cj2 == 10) {                        // the reference's 400 / 300: rows per warp by batch size
         if (n <= 8) return launch_fp32<13, 10, false, 1>(A, d_obs, ld, n, d_mu, rs, tl, s);
         if (n <= 16) return launch_fp32<13, 10, false, 2>(A, d_obs, ld, n, d_mu, rs, tl, s);
