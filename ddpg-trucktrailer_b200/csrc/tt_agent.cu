@@ -547,9 +547,9 @@ int launch_noise(float *d_x, float *d_action, float *d_scaled, const uint8_t *d_
 }
 
 // TT_PREC_AUTO (north_star (c)): tcgen05 tiles only once the batch is a real dense contraction, warp-level fp32 FMA below.
-// Measured on a B200 (profiles/r02_actor_auto_sweep.md): the tensor-core kernel pays a fixed ~12 us per launch (TMEM
-// allocation, W1 image, the W2 stream start-up) and the fp32 kernel ~8 us + 11 us per 64-row tile wave; the two cross between
-// 128 and 256 rows.  Below the threshold the fp32 kernel is also the more accurate one (1e-5 vs 1e-3).
+// Measured on a B200 (profiles/r02_actor_auto_sweep.md, per launch inside a CUDA graph): the tensor-core kernel 8.7-9.1 us from 1 to
+// 4 096 rows; the fp32 cluster kernel 13 us up to 64 rows, 17 / 19 us at 128 / 192.  There is no latency crossover -- the threshold
+// is an accuracy policy: below it the batch is less than 1.5 tiles and the fp32 kernel is the more accurate one (1e-5 vs 1e-3).
 constexpr int64_t kAutoTcMinRows = 192;
 int actor_resolve_precision(const tt_actor *a, int precision, int64_t n) {
     if (precision != TT_PREC_AUTO) return precision;
