@@ -33,7 +33,7 @@ def test_actor_fp32_matches_reference_torch(golden_dir, ld):
         assert np.abs(out - ref).max() < 1e-5
 
 
-@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 20000])
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 63, 64, 65, 191, 256, 257, 1000, 20000])
 def test_actor_fp32_ragged_sizes_vs_oracle(golden_dir, n):
     import ddpg_trucktrailer_b200 as tt
     from oracle import oracle as orc
@@ -54,6 +54,22 @@ def test_actor_other_hidden_sizes():
     actor = tt.agent.CudaActor(23, 256, 128); actor.load_state_dict(sd)
     obs = np.random.default_rng(0).uniform(-1, 1, (777, 23)).astype(np.float32)
     out = actor.forward(torch.from_numpy(obs).cuda()).cpu().numpy()
+    ref = orc.OracleActor({k: v.numpy() for k, v in sd.items()}).forward(obs)
+    assert np.abs(out - ref).max() < 1e-5
+
+
+@pytest.mark.parametrize("dims", [(23, 256, 128), (23, 130, 77), (23, 512, 512), (23, 33, 31)])
+@pytest.mark.parametrize("n", [1, 5, 70])
+def test_actor_fp32_small_batches_other_hidden_sizes(dims, n):
+    """Small batches take the cluster-split fp32 kernel (one eighth of the hidden units per CTA, statistics and activations
+    exchanged through distributed shared memory): padded and ragged unit slices, slices without any real unit."""
+    import ddpg_trucktrailer_b200 as tt
+    from oracle import oracle as orc
+    sd = tt.init_actor_state_dict(*dims, 1, seed=4)
+    sd["mu.weight"] *= 30
+    actor = tt.agent.CudaActor(*dims); actor.load_state_dict(sd)
+    obs = np.random.default_rng(n).uniform(-1, 1, (n, 23)).astype(np.float32)
+    out = actor.forward(torch.from_numpy(obs).cuda(), precision="fp32").cpu().numpy()
     ref = orc.OracleActor({k: v.numpy() for k, v in sd.items()}).forward(obs)
     assert np.abs(out - ref).max() < 1e-5
 
