@@ -518,11 +518,17 @@ def run_b200(args):
             l0 = L.tt_launch_count()
             ms4, _ = timed(c4_step, K)
             n_l = int(L.tt_launch_count() - l0)
+            # the rollout alone right behind it: same clock / thermal state, same reserved SMs (the headline region ran much earlier)
+            torch.cuda.current_stream().wait_stream(tr.side)
+            for _ in range(max(W, 5) + 20):
+                headline_step()
+            ms_plain, _ = timed(headline_step, K)
             tr.close()
             if world > 1:
                 torch.cuda.current_stream().wait_stream(sync.stream)
-            return ms4, n_l, tr.updates
-        ms4, n_l, n_upd = run_c4(2)
+                sync.flush_stats()
+            return ms4, n_l, tr.updates, ms_plain
+        ms4, n_l, n_upd, ms_plain = run_c4(2)
         # for reference: the same iteration with the update SERIAL on the rollout stream (no SMs reserved)
         agent.actor = actors[0]
         ln = agent.learner
@@ -533,12 +539,14 @@ def run_b200(args):
             c4_serial()
         ms4s, _ = timed(c4_serial, K)
         config4 = {"value": world * N * K / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / K, "gpu_launches": n_l,
-                   "extra_ms_over_rollout": ms4 / K - ms / K, "reserved_sms": 2, "learner_updates_so_far": n_upd,
+                   "extra_ms_over_rollout": ms4 / K - ms_plain / K, "rollout_ms_per_step_same_state": ms_plain / K,
+                   "extra_ms_over_headline": ms4 / K - ms / K, "reserved_sms": 2, "learner_updates_so_far": n_upd,
                    "serial_ms_per_step": ms4s / K,
                    "note": "configs[3]: rollout + fused replay store + one DDPG update per iteration (batch 64, tt_learn_step: hand-written "
                            "kernels on the device ring, hidden on a side stream under the rollout kernels, policy used one iteration later"
                            + (", learner on rank 0; stats all-reduce + broadcast of the flat actor vector over NCCL on side streams)" if world > 1 else ")")
-                           + "; serial_ms_per_step = the update on the rollout stream instead"}
+                           + "; serial_ms_per_step = the update on the rollout stream instead; extra_ms_over_rollout is against rollout_ms_per_step_same_state "
+                             "(the rollout alone timed right behind the config4 region, same reserved SMs)"}
         agent.actor = actors[0]
 
     # ---- BASELINE.json configs[4]: mini-sweep over envs per GPU (the full sweep: profiles/sweep.py) ----
