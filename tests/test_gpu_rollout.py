@@ -385,3 +385,55 @@ def test_auto_precision_picks_the_kernel_by_batch_size():
         actor.forward(torch.zeros(4, 23, device="cuda"), precision="f16_plain")
     with pytest.raises(ValueError):
         ag.choose_action(torch.zeros(9, 23, device="cuda"))               # one observation row per environment
+
+
+def test_full_size_rollout_properties():
+    """BASELINE.json's full size (2^22 envs per GPU), the bench path itself (tcgen05 actor + OU noise + fused ring store + in-kernel
+    reset, two launches per iteration): size-independent properties instead of an oracle replay.  (1) what the ring holds is what
+    the kernels handed over: new_state == the next observation for every env that continues, state(t + 1) == the observation the
+    actor of t + 1 read, action / reward / terminal rows == the step's outputs; (2) clip * pi / 4 is exact; (3) the bit-packed flags
+    equal the bytes; (4) the device statistics count every step; (5) a 4 096-env shard with the matching global offset reproduces
+    its slice of rewards and flags bit for bit (Philox streams are keyed by the global env id, the actor is position independent)."""
+    import ddpg_trucktrailer_b200 as tt
+    N, cap, K, warm = 1 << 22, 1 << 23, 4, 40
+    sd = tt.init_actor_state_dict(seed=0); sd["mu.weight"] *= 100
+
+    def mk(n, offset, ring):
+        env = tt.VecTruckTrailerEnv(n, seed=13, global_env_offset=offset)
+        ag = tt.VecAgent(1e-4, 1e-3, (23,), 1e-3, 1, num_envs=n, max_size=ring, actor_seed=0, seed=13, global_env_offset=offset, precision="f16")
+        ag.load_actor_state_dict(sd)
+        eng = tt.RolloutEngine(env, ag); eng.reset()
+        return env, ag, eng
+
+    env, ag, eng = mk(N, 0, cap)
+    S = 4096
+    env_s, ag_s, eng_s = mk(S, N - S, 4 * S)
+    for _ in range(warm):
+        eng.step(); eng_s.step()
+    env.read_stats()
+    m = ag.memory
+    bits = torch.zeros((N + 31) // 32, dtype=torch.int32, device="cuda")
+    env.set_done_bits(bits)
+    prev_obs, ndone = None, 0
+    for t in range(K):
+        c0 = m.mem_cntr % m.mem_size
+        obs, r, d = eng.step()
+        _, r_s, d_s = eng_s.step()
+        rows = slice(c0, c0 + N)                                        # cap is a multiple of N: no wrap inside an iteration
+        db = d.bool()
+        assert torch.equal(m.reward_memory[rows], r) and torch.equal(m.terminal_memory[rows].bool(), db)
+        assert torch.equal(m.action_memory[rows].reshape(-1), eng.action)
+        assert torch.equal(eng.scaled, eng.action.clamp(-1, 1) * np.float32(0.78539819))
+        ns = m.new_state_memory[rows]
+        assert torch.equal(ns[~db], obs[~db]) and not torch.equal(ns[db], obs[db])          # finished envs: terminal row vs reset observation
+        if prev_obs is not None:
+            assert torch.equal(m.state_memory[rows], prev_obs)
+        prev_obs = obs.clone()
+        got = bits.cpu().numpy().view(np.uint8)
+        assert np.array_equal(got, np.packbits(db.cpu().numpy(), bitorder="little"))
+        assert torch.equal(r[N - S:], r_s) and torch.equal(d[N - S:], d_s)
+        assert torch.isfinite(r).all()
+        ndone += int(db.sum())
+    env.set_done_bits(None)
+    st = env.read_stats()
+    assert st["steps"] == N * K and st["episodes"] == ndone and ndone > N // 200
