@@ -77,6 +77,7 @@ def run_sweep(agent, poses, goal=None, precision=None, record_trajectories=False
     alive = torch.ones(n, dtype=torch.bool, device=dev)
     flags = torch.zeros(n, dtype=torch.uint8, device=dev)
     success = torch.zeros(n, dtype=torch.bool, device=dev)
+    ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
     first = np.arange(0, n, poses["trials"])
     traj = [[st[first, 4].copy()], [st[first, 5].copy()]] if record_trajectories else None
     tlen = np.ones(len(first), np.int64)
@@ -85,6 +86,7 @@ def run_sweep(agent, poses, goal=None, precision=None, record_trajectories=False
         mu = agent.actor.forward(obs, precision=prec, allow_out_of_bar=getattr(agent, "allow_out_of_bar", False))                  # choose_action(obs, evaluate=True), heatmap.py:139
         obs, rew, done, info = env.step(VecAgent.scale_action(mu))     # heatmap.py:140-141
         score += torch.where(alive, rew.double(), torch.zeros_like(score))
+        ep_len += alive
         newly = alive & done
         flags = torch.where(newly, info["termination_flags"], flags)
         success = torch.where(newly, info["success"], success)
@@ -105,7 +107,8 @@ def run_sweep(agent, poses, goal=None, precision=None, record_trajectories=False
                trajectory_endpoints=[{"end_x": float(end[i, 4]), "end_y": float(end[i, 5]), "start_x": float(poses["start_x"][i]),
                                       "start_y": float(poses["start_y"][i]), "violation_type": TERMINATION_CLASSES[cls[i]],
                                       "score": float(sc[i])} for i in range(n)],
-               trials=dict(score=sc, success=su, flags=fl, termination_class=cls, end_state=end, steps=steps))
+               trials=dict(score=sc, success=su, flags=fl, termination_class=cls, end_state=end, steps=steps,
+                           episode_steps=ep_len.cpu().numpy()))
     if record_trajectories:
         tx, ty = np.stack(traj[0], 1), np.stack(traj[1], 1)
         out["trajectories"] = [{"trailer_x": tx[c, :tlen[c]].tolist(), "trailer_y": ty[c, :tlen[c]].tolist(),
